@@ -1,0 +1,254 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as ginger-lib's
+  * `VariableBaseMSM::multi_scalar_mul(bases, scalars) -> G::Projective`
+    (algebra/src/msm/variable_base.rs:85-90), and
+  * `EvaluationDomain<F>` with `new`, `size`, `fft[_in_place]`, `ifft[_in_place]`,
+    `coset_fft[_in_place]`, `coset_ifft[_in_place]` (algebra/src/fft/domain.rs:65-179),
+so the parity tests read like the reference's own tests.  All arithmetic happens in
+libg753.so on the GPU; this file only shapes buffers (numpy uint64, the reference's raw limb
+layout: 12 little-endian u64 per Fq, Montgomery form for field/point coordinates, canonical
+integers for MSM scalars).
+"""
+import ctypes
+
+import numpy as np
+
+from . import ffi
+
+LIMBS = 12
+
+
+class Context:
+    """One GPU (device index) with its stream, scratch memory and twiddle tables."""
+
+    def __init__(self, device=0, library=None):
+        self.lib = library or ffi.default_library()
+        h = ctypes.c_void_p()
+        self.lib.check(self.lib.ctx_create(int(device), ctypes.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- proving-key bases ------------------------------------------------------------
+    def upload_bases(self, group, coords, infinity=None):
+        return Bases(self, group, coords, infinity)
+
+    def sync(self):
+        self.lib.check(self.lib.sync(self.handle))
+
+    @property
+    def launches(self):
+        return int(self.lib.launch_count(self.handle))
+
+    def last_msm_phases(self):
+        buf = (ctypes.c_float * 8)()
+        k = self.lib.last_msm_phases(self.handle, buf, 8)
+        names = ["digits", "sort", "accumulate", "reduce", "combine"]
+        return {names[i]: float(buf[i]) for i in range(k)}
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class Bases:
+    """Device-resident affine bases (`&[G::Affine]`), uploaded once per proving key."""
+
+    def __init__(self, ctx, group, coords, infinity=None):
+        k = ffi.GROUP_K[group]
+        coords = ffi.as_u64(coords).reshape(-1, 2 * k * LIMBS)
+        n = coords.shape[0]
+        inf = None
+        if infinity is not None:
+            inf = np.ascontiguousarray(infinity, dtype=np.uint8).reshape(-1)
+            if inf.shape[0] != n:
+                raise ValueError("infinity flags length mismatch")
+        self.ctx, self.group, self.k, self.n = ctx, group, k, n
+        h = ctypes.c_void_p()
+        ctx.lib.check(ctx.lib.bases_upload(ctx.handle, group, ffi.ptr(coords), ffi.ptr(inf), n, ctypes.byref(h)))
+        self.handle = h
+
+    def __len__(self):
+        return self.n
+
+    def free(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.bases_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class VariableBaseMSM:
+    """algebra/src/msm/variable_base.rs:7-90."""
+
+    @staticmethod
+    def multi_scalar_mul(bases, scalars, group=None, infinity=None, ctx=None, first=0):
+        """sum_i scalars[i] * bases[i] over zip(bases, scalars) -> projective (X, Y, Z) limbs.
+
+        `bases` is either a resident `Bases` handle (the proving-key case; `first` selects
+        the sub-slice view `bases[first..]` the prover takes, groth16/mod.rs:318-350) or a
+        numpy array of affine coordinates (+ `infinity` flags, + `group`), which is the
+        reference's one-shot signature.  `scalars`: (m, 12) uint64 canonical `BigInteger768`.
+        Returns a (3, k*12) uint64 array: the reference's GroupProjective {x, y, z}.
+        """
+        scalars = ffi.as_u64(scalars).reshape(-1, LIMBS)
+        if isinstance(bases, Bases):
+            ctx = bases.ctx
+            k = bases.k
+            avail = len(bases) - first
+            if avail < 0:
+                raise ValueError("slice start beyond the bases")
+            count = min(avail, scalars.shape[0])       # zip semantics, variable_base.rs:36
+            out = np.zeros((3, k * LIMBS), dtype=np.uint64)
+            ctx.lib.check(ctx.lib.msm(ctx.handle, bases.handle, first, count, ffi.ptr(scalars), ffi.ptr(out)))
+            return out
+        if group is None:
+            raise ValueError("group id required with host bases")
+        ctx = ctx or default_context()
+        k = ffi.GROUP_K[group]
+        coords = ffi.as_u64(bases).reshape(-1, 2 * k * LIMBS)[first:]
+        inf = None
+        if infinity is not None:
+            inf = np.ascontiguousarray(infinity, dtype=np.uint8).reshape(-1)[first:]
+        out = np.zeros((3, k * LIMBS), dtype=np.uint64)
+        ctx.lib.check(ctx.lib.msm_host(ctx.handle, group, ffi.ptr(coords), ffi.ptr(inf), coords.shape[0],
+                                       ffi.ptr(scalars), scalars.shape[0], ffi.ptr(out)))
+        return out
+
+
+class EvaluationDomain:
+    """algebra/src/fft/domain.rs:24-179 for the two 753-bit scalar fields.
+
+    `field` is ffi.FIELD_MNT4_FR (two-adicity 30) or ffi.FIELD_MNT6_FR (two-adicity 15).
+    """
+
+    def __init__(self, field, size, log_size, ctx):
+        self.field = field
+        self.size_ = size
+        self.log_size_of_group = log_size
+        self.ctx = ctx
+
+    @staticmethod
+    def new(field, num_coeffs, ctx=None):
+        """`EvaluationDomain::new`: None when 2^ceil(log2 n) is too large for the field
+        (domain.rs:65-72)."""
+        size = 1
+        while size < num_coeffs:
+            size <<= 1
+        log_size = size.bit_length() - 1
+        lib = (ctx.lib if ctx else ffi.default_library())
+        rc = lib.domain_check(field, log_size)
+        if rc == ffi.ERR_DOMAIN:
+            return None
+        lib.check(rc)
+        return EvaluationDomain(field, size, log_size, ctx or default_context())
+
+    @staticmethod
+    def compute_size_of_domain(field, num_coeffs, library=None):
+        size = 1
+        while size < num_coeffs:
+            size <<= 1
+        lib = library or ffi.default_library()
+        return size if lib.domain_check(field, size.bit_length() - 1) == ffi.OK else None
+
+    def size(self):
+        return self.size_
+
+    def _resized(self, v):
+        """Vec::resize(size, zero): truncate or zero-pad (domain.rs:121)."""
+        v = ffi.as_u64(v).reshape(-1, LIMBS)
+        out = np.zeros((self.size_, LIMBS), dtype=np.uint64)
+        m = min(self.size_, v.shape[0])
+        out[:m] = v[:m]
+        return out
+
+    def _run(self, v, mode):
+        buf = self._resized(v)
+        self.ctx.lib.check(self.ctx.lib.ntt(self.ctx.handle, self.field, ffi.ptr(buf), self.log_size_of_group, mode))
+        return buf
+
+    def fft(self, coeffs):
+        return self._run(coeffs, ffi.FFT)
+
+    def ifft(self, evals):
+        return self._run(evals, ffi.IFFT)
+
+    def coset_fft(self, coeffs):
+        return self._run(coeffs, ffi.COSET_FFT)
+
+    def coset_ifft(self, evals):
+        return self._run(evals, ffi.COSET_IFFT)
+
+    # numpy arrays cannot be resized in place; the *_in_place forms return the resized vector
+    fft_in_place = fft
+    ifft_in_place = ifft
+    coset_fft_in_place = coset_fft
+    coset_ifft_in_place = coset_ifft
+
+
+class DeviceVector:
+    """A vector of field elements resident in HBM, for chaining transforms the way
+    R1CStoQAP::witness_map does (r1cs_to_qap.rs:121-161) without host round trips."""
+
+    def __init__(self, ctx, field, n, host=None):
+        self.ctx, self.field, self.n = ctx, field, n
+        p = ctypes.c_void_p()
+        ctx.lib.check(ctx.lib.dev_alloc(ctx.handle, n * 96, ctypes.byref(p)))
+        self.ptr = p
+        if host is not None:
+            self.upload(host)
+
+    def upload(self, host):
+        host = ffi.as_u64(host).reshape(-1, LIMBS)
+        assert host.shape[0] == self.n
+        self.ctx.lib.check(self.ctx.lib.h2d(self.ctx.handle, self.ptr, ffi.ptr(host), self.n * 96))
+
+    def download(self):
+        out = np.empty((self.n, LIMBS), dtype=np.uint64)
+        self.ctx.lib.check(self.ctx.lib.d2h(self.ctx.handle, ffi.ptr(out), self.ptr, self.n * 96))
+        return out
+
+    def ntt(self, mode):
+        log_n = self.n.bit_length() - 1
+        assert 1 << log_n == self.n
+        self.ctx.lib.check(self.ctx.lib.ntt_dev(self.ctx.handle, self.field, self.ptr, log_n, mode))
+
+    def op(self, op, other=None):
+        self.ctx.lib.check(self.ctx.lib.vec_op_dev(self.ctx.handle, self.field, op, self.ptr,
+                                                   other.ptr if other is not None else None, self.n))
+
+    def scale(self, k_mont):
+        k = ffi.as_u64(k_mont).reshape(LIMBS)
+        self.ctx.lib.check(self.ctx.lib.vec_scale_dev(self.ctx.handle, self.field, self.ptr, ffi.ptr(k), self.n))
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.ctx.lib.dev_free(self.ctx.handle, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

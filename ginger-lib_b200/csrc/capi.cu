@@ -1,0 +1,613 @@
+// C ABI of libg753.so (see include/g753.h for the contract and the reference call sites).
+//
+// Built two ways: nvcc for sm_100a (the product) and, with G753_HOST_EMUL, by g++ into a
+// test-only library that runs the barrier-free kernels sequentially on the host so that
+// indexing and orchestration can be checked without a GPU (tests/host_emul).
+#include <map>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "device.cuh"
+#include "ec.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace g753 {
+#if !defined(G753_HOST_EMUL)
+thread_local char g_last_error[512] = "";
+#else
+static thread_local char g_last_error[512] = "";
+#endif
+static int fail(int code, const char* msg) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
+  return code;
+}
+}  // namespace g753
+
+using namespace g753;
+
+enum { MSM_PHASES = 5 };
+
+struct g753_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Scratch scratch;      // MSM workspace
+  Scratch scratch_io;   // host-API staging (scalars / NTT ping-pong)
+  std::map<unsigned, NttTables> tables[2];  // per field, keyed by log_n
+  uint64_t launches = 0;
+  float phase_ms[MSM_PHASES] = {0, 0, 0, 0, 0};
+  int forced_c = 0;
+  std::mutex mu;
+#if !defined(G753_HOST_EMUL)
+  cudaEvent_t ev[MSM_PHASES + 1];
+  bool ev_ok = false;
+#endif
+};
+
+struct g753_bases {
+  int group = 0;
+  size_t n = 0;
+  void* d_points = nullptr;
+  uint8_t* d_inf = nullptr;
+};
+
+static int group_k(int group) {
+  switch (group) {
+    case G753_MNT4_G1: return 1;
+    case G753_MNT4_G2: return 2;
+    case G753_MNT6_G1: return 1;
+    case G753_MNT6_G2: return 3;
+    default: return 0;
+  }
+}
+
+#if !defined(G753_HOST_EMUL)
+static int use_device(g753_ctx* ctx) {
+  cudaError_t e = cudaSetDevice(ctx->device);
+  return e == cudaSuccess ? G753_OK : cuda_fail(e, "cudaSetDevice");
+}
+static void phase_mark(void* user, int phase) {
+  g753_ctx* ctx = (g753_ctx*)user;
+  if (ctx->ev_ok && phase <= MSM_PHASES) cudaEventRecord(ctx->ev[phase], ctx->stream);
+}
+static bool g_consts_loaded[64] = {false};
+static int load_constants(int device) {
+  if (device < 64 && g_consts_loaded[device]) return G753_OK;
+  cudaError_t e = cudaMemcpyToSymbol(d_fc, G753_FIELD_CONSTANTS, sizeof(G753_FIELD_CONSTANTS));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyToSymbol(field constants)");
+  if (device < 64) g_consts_loaded[device] = true;
+  return G753_OK;
+}
+#else
+static int use_device(g753_ctx*) { return G753_OK; }
+#endif
+
+#define CHECK_CTX(ctx)                                              \
+  do {                                                              \
+    if (!(ctx)) return fail(G753_ERR_BAD_ARG, "null context");      \
+    G753_TRY(use_device(ctx));                                      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------
+// dispatch helpers
+// ------------------------------------------------------------------------------------
+template <class C>
+static int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
+                        const uint32_t* d_scalars, void* d_out) {
+  MsmHooks hooks;
+  hooks.launches = &ctx->launches;
+#if !defined(G753_HOST_EMUL)
+  hooks.mark = phase_mark;
+  hooks.user = ctx;
+#endif
+  const Affine<C>* pts = (const Affine<C>*)b->d_points + first;
+  const uint8_t* inf = b->d_inf ? b->d_inf + first : nullptr;
+  int rc = msm_run<C>(ctx->scratch, ctx->stream, pts, inf, d_scalars, count, (typename C::F*)d_out,
+                      ctx->forced_c, hooks);
+  return rc;
+}
+
+static int msm_any(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
+                   const uint32_t* d_scalars, void* d_out) {
+  switch (b->group) {
+    case G753_MNT4_G1: return msm_dispatch<CurveM4G1>(ctx, b, first, count, d_scalars, d_out);
+    case G753_MNT4_G2: return msm_dispatch<CurveM4G2>(ctx, b, first, count, d_scalars, d_out);
+    case G753_MNT6_G1: return msm_dispatch<CurveM6G1>(ctx, b, first, count, d_scalars, d_out);
+    case G753_MNT6_G2: return msm_dispatch<CurveM6G2>(ctx, b, first, count, d_scalars, d_out);
+  }
+  return fail(G753_ERR_BAD_ARG, "unknown group");
+}
+
+template <class C>
+static void sanitize_launch(g753_ctx* ctx, g753_bases* b) {
+  G753_LAUNCH(k_bases_sanitize<C>, div_up(b->n, 256), 256, ctx->stream, (Affine<C>*)b->d_points, b->d_inf,
+              (unsigned)b->n);
+  ctx->launches++;
+}
+
+template <int FID>
+static int ntt_field(g753_ctx* ctx, Fq* d_data, Fq* d_tmp, unsigned log_n, int mode) {
+  std::map<unsigned, NttTables>& m = ctx->tables[FID];
+  auto it = m.find(log_n);
+  if (it == m.end()) {
+    NttTables T;
+    int rc = ntt_tables_build<FID>(T, log_n, ctx->stream, &ctx->launches);
+    if (rc != G753_OK) {
+      T.release();
+      return rc;
+    }
+    it = m.emplace(log_n, T).first;
+  }
+  return ntt_run<FID>(it->second, ctx->stream, d_data, d_tmp, mode, &ctx->launches);
+}
+
+// ------------------------------------------------------------------------------------
+// test kernels: group law / field ops through the real device code
+// ------------------------------------------------------------------------------------
+template <class C>
+__global__ void k_point_op(int op, const Affine<C>* a, const Affine<C>* b, const uint32_t* scalar,
+                           typename C::F* out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Xyzz<C> r;
+  if (op == 0) {
+    r = xyzz_from_affine<C>(*a);
+    xyzz_madd<C>(r, *b);
+  } else if (op == 1) {
+    r = xyzz_from_affine<C>(*a);
+    xyzz_dbl<C>(r);
+  } else {
+    r = xyzz_scalar_mul<C>(*a, scalar);
+  }
+  typename C::F X, Y, Z;
+  xyzz_to_projective<C>(r, X, Y, Z);
+  out[0] = X;
+  out[1] = Y;
+  out[2] = Z;
+}
+
+template <class C>
+static int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+  typedef typename C::F F;
+  const size_t aff = sizeof(Affine<C>), prj = 3 * sizeof(F);
+  G753_TRY(ctx->scratch_io.reserve(2 * aff + 96 + prj + 1024));
+  Carver cv(ctx->scratch_io.ptr);
+  Affine<C>* da = cv.take<Affine<C>>(1);
+  Affine<C>* db = cv.take<Affine<C>>(1);
+  uint32_t* ds = cv.take<uint32_t>(NL);
+  F* dout = cv.take<F>(3);
+  G753_TRY(h2d(da, a, aff, ctx->stream));
+  if (op == 0) G753_TRY(h2d(db, b, aff, ctx->stream));
+  if (op == 2) G753_TRY(h2d(ds, b, 96, ctx->stream));
+  G753_LAUNCH(k_point_op<C>, 1, 1, ctx->stream, op, da, db, ds, dout);
+  ctx->launches++;
+  G753_TRY(launch_check("k_point_op"));
+  G753_TRY(d2h(out, dout, prj, ctx->stream));
+  return stream_sync(ctx->stream);
+}
+
+#if !defined(G753_HOST_EMUL)
+// integer-pipe roofline probe: dependent Montgomery products per thread
+template <int VARIANT>
+__global__ void __launch_bounds__(256) k_mac_probe(const Fq* seed, Fq* sink, int iters) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  Fq x = seed[t & 255];
+  Fq y = seed[(t + 7) & 255];
+  if (VARIANT == 0) {
+    for (int k = 0; k < iters; k++) x = fq_mul<1>(x, y);
+  } else if (VARIANT == 1) {
+    for (int k = 0; k < iters; k++) x = fq_sqr<1>(x);
+  } else {
+    // 24 independent 64-bit accumulators, each a dependent IMAD.WIDE chain: 576 wide MACs / iter
+    unsigned long long acc[NL];
+#pragma unroll
+    for (int i = 0; i < NL; i++) acc[i] = x.l[i];
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+      for (int r = 0; r < NL; r++) {
+#pragma unroll
+        for (int i = 0; i < NL; i++) acc[i] = (unsigned long long)y.l[r] * (unsigned)(acc[i]) + acc[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NL; i++) x.l[i] = (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32);
+  }
+  if (x.l[0] == 0x12345678u && x.l[5] == 0x9abcdef0u) sink[t & 255] = x;  // keep the chain live
+}
+#endif
+
+// ------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------
+extern "C" {
+
+const char* g753_last_error(void) { return g_last_error; }
+const char* g753_version(void) { return "g753 0.1 (sm_100a)"; }
+
+int g753_device_count(int* count) {
+  if (!count) return fail(G753_ERR_BAD_ARG, "null count");
+#if defined(G753_HOST_EMUL)
+  *count = 1;
+  return G753_OK;
+#else
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return cuda_fail(e, "cudaGetDeviceCount");
+  }
+  return G753_OK;
+#endif
+}
+
+int g753_ctx_create(int device, g753_ctx** out) {
+  if (!out) return fail(G753_ERR_BAD_ARG, "null out");
+  *out = nullptr;
+#if !defined(G753_HOST_EMUL)
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(G753_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= count) return fail(G753_ERR_BAD_ARG, "device index out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  G753_TRY(load_constants(device));
+#endif
+  g753_ctx* ctx = new (std::nothrow) g753_ctx();
+  if (!ctx) return fail(G753_ERR_OOM, "host allocation failed");
+  ctx->device = device;
+#if !defined(G753_HOST_EMUL)
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return cuda_fail(e, "cudaStreamCreate");
+  }
+  ctx->ev_ok = true;
+  for (int i = 0; i <= MSM_PHASES; i++)
+    if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) ctx->ev_ok = false;
+#endif
+  const char* fc = getenv("G753_MSM_C");
+  if (fc) ctx->forced_c = atoi(fc);
+  *out = ctx;
+  return G753_OK;
+}
+
+int g753_ctx_destroy(g753_ctx* ctx) {
+  if (!ctx) return G753_OK;
+  use_device(ctx);
+  stream_sync(ctx->stream);
+  ctx->scratch.release();
+  ctx->scratch_io.release();
+  for (int f = 0; f < 2; f++)
+    for (auto& kv : ctx->tables[f]) kv.second.release();
+#if !defined(G753_HOST_EMUL)
+  if (ctx->ev_ok)
+    for (int i = 0; i <= MSM_PHASES; i++) cudaEventDestroy(ctx->ev[i]);
+  cudaStreamDestroy(ctx->stream);
+#endif
+  delete ctx;
+  return G753_OK;
+}
+
+int g753_group_coord_limbs(int group) { return 12 * group_k(group); }
+
+int g753_bases_upload(g753_ctx* ctx, int group, const uint64_t* coords, const uint8_t* infinity, size_t n,
+                      g753_bases** out) {
+  CHECK_CTX(ctx);
+  if (!out) return fail(G753_ERR_BAD_ARG, "null out");
+  *out = nullptr;
+  const int k = group_k(group);
+  if (k == 0) return fail(G753_ERR_BAD_ARG, "unknown group");
+  if (n && !coords) return fail(G753_ERR_BAD_ARG, "null coords");
+  if (n > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "too many bases");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  g753_bases* b = new (std::nothrow) g753_bases();
+  if (!b) return fail(G753_ERR_OOM, "host allocation failed");
+  b->group = group;
+  b->n = n;
+  const size_t pt_bytes = (size_t)2 * k * 96;
+  int rc = dev_alloc(&b->d_points, pt_bytes * n);
+  if (rc == G753_OK && n) rc = h2d(b->d_points, coords, pt_bytes * n, ctx->stream);
+  if (rc == G753_OK && infinity && n) {
+    rc = dev_alloc((void**)&b->d_inf, n);
+    if (rc == G753_OK) rc = h2d(b->d_inf, infinity, n, ctx->stream);
+    if (rc == G753_OK) {
+      switch (group) {
+        case G753_MNT4_G1: sanitize_launch<CurveM4G1>(ctx, b); break;
+        case G753_MNT4_G2: sanitize_launch<CurveM4G2>(ctx, b); break;
+        case G753_MNT6_G1: sanitize_launch<CurveM6G1>(ctx, b); break;
+        case G753_MNT6_G2: sanitize_launch<CurveM6G2>(ctx, b); break;
+      }
+      rc = launch_check("k_bases_sanitize");
+    }
+  }
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  if (rc != G753_OK) {
+    dev_free(b->d_points);
+    dev_free(b->d_inf);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return G753_OK;
+}
+
+int g753_bases_free(g753_ctx* ctx, g753_bases* b) {
+  if (!b) return G753_OK;
+  if (ctx) {
+    use_device(ctx);
+    stream_sync(ctx->stream);
+  }
+  dev_free(b->d_points);
+  dev_free(b->d_inf);
+  delete b;
+  return G753_OK;
+}
+
+size_t g753_bases_len(const g753_bases* b) { return b ? b->n : 0; }
+
+static int msm_check(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count) {
+  if (!b) return fail(G753_ERR_BAD_ARG, "null bases");
+  if (first > b->n || count > b->n - first) return fail(G753_ERR_BAD_ARG, "bases slice out of range");
+  (void)ctx;
+  return G753_OK;
+}
+
+#if !defined(G753_HOST_EMUL)
+static void collect_phases(g753_ctx* ctx) {
+  if (!ctx->ev_ok) return;
+  for (int i = 0; i < MSM_PHASES; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->phase_ms[i] = ms;
+  }
+}
+#endif
+
+int g753_msm_dev(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, const void* d_scalars,
+                 void* d_out_xyz) {
+  CHECK_CTX(ctx);
+  G753_TRY(msm_check(ctx, b, first, count));
+  if ((count && !d_scalars) || !d_out_xyz) return fail(G753_ERR_BAD_ARG, "null pointer");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return msm_any(ctx, b, first, count, (const uint32_t*)d_scalars, d_out_xyz);
+}
+
+int g753_msm(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, const uint64_t* scalars,
+             uint64_t* out_xyz) {
+  CHECK_CTX(ctx);
+  G753_TRY(msm_check(ctx, b, first, count));
+  if ((count && !scalars) || !out_xyz) return fail(G753_ERR_BAD_ARG, "null pointer");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t out_bytes = (size_t)3 * group_k(b->group) * 96;
+  G753_TRY(ctx->scratch_io.reserve(count * 96 + out_bytes + 1024));
+  Carver cv(ctx->scratch_io.ptr);
+  uint32_t* d_scalars = cv.take<uint32_t>(count * NL);
+  uint32_t* d_out = cv.take<uint32_t>(out_bytes / 4);
+  if (count) G753_TRY(h2d(d_scalars, scalars, count * 96, ctx->stream));
+  G753_TRY(msm_any(ctx, b, first, count, d_scalars, d_out));
+  G753_TRY(d2h(out_xyz, d_out, out_bytes, ctx->stream));
+  G753_TRY(stream_sync(ctx->stream));
+#if !defined(G753_HOST_EMUL)
+  if (count) collect_phases(ctx);
+#endif
+  return G753_OK;
+}
+
+int g753_msm_host(g753_ctx* ctx, int group, const uint64_t* coords, const uint8_t* infinity, size_t n_bases,
+                  const uint64_t* scalars, size_t n_scalars, uint64_t* out_xyz) {
+  CHECK_CTX(ctx);
+  // zip-truncation of the reference: scalars.iter().zip(bases) (variable_base.rs:36)
+  const size_t count = n_bases < n_scalars ? n_bases : n_scalars;
+  g753_bases* b = nullptr;
+  G753_TRY(g753_bases_upload(ctx, group, coords, infinity, count, &b));
+  int rc = g753_msm(ctx, b, 0, count, scalars, out_xyz);
+  g753_bases_free(ctx, b);
+  return rc;
+}
+
+int g753_points_sum_dev(g753_ctx* ctx, int group, const void* d_points_xyz, size_t count, void* d_out_xyz) {
+  CHECK_CTX(ctx);
+  if (!d_points_xyz || !d_out_xyz || count > 0xffffffffull) return fail(G753_ERR_BAD_ARG, "bad argument");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  switch (group) {
+    case G753_MNT4_G1:
+      G753_LAUNCH(k_points_sum<CurveM4G1>, 1, 1, ctx->stream, (const FqM4*)d_points_xyz, (unsigned)count, (FqM4*)d_out_xyz);
+      break;
+    case G753_MNT4_G2:
+      G753_LAUNCH(k_points_sum<CurveM4G2>, 1, 1, ctx->stream, (const Fq2M4*)d_points_xyz, (unsigned)count, (Fq2M4*)d_out_xyz);
+      break;
+    case G753_MNT6_G1:
+      G753_LAUNCH(k_points_sum<CurveM6G1>, 1, 1, ctx->stream, (const FqM6*)d_points_xyz, (unsigned)count, (FqM6*)d_out_xyz);
+      break;
+    case G753_MNT6_G2:
+      G753_LAUNCH(k_points_sum<CurveM6G2>, 1, 1, ctx->stream, (const Fq3M6*)d_points_xyz, (unsigned)count, (Fq3M6*)d_out_xyz);
+      break;
+    default: return fail(G753_ERR_BAD_ARG, "unknown group");
+  }
+  ctx->launches++;
+  return launch_check("k_points_sum");
+}
+
+// ---- NTT ---------------------------------------------------------------------------------
+int g753_domain_check(int field, unsigned log_n) {
+  if (field != 0 && field != 1) return fail(G753_ERR_BAD_ARG, "unknown field");
+  if (log_n >= G753_FIELD_CONSTANTS[field].two_adicity || log_n > NTT_MAX_LOG)
+    return fail(G753_ERR_DOMAIN, "domain too large for this field (EvaluationDomain::new -> None)");
+  return G753_OK;
+}
+
+static int ntt_any(g753_ctx* ctx, int field, Fq* d_data, Fq* d_tmp, unsigned log_n, int mode) {
+  if (mode < G753_FFT || mode > G753_COSET_IFFT) return fail(G753_ERR_BAD_ARG, "unknown transform");
+  G753_TRY(g753_domain_check(field, log_n));
+  return field == 0 ? ntt_field<0>(ctx, d_data, d_tmp, log_n, mode) : ntt_field<1>(ctx, d_data, d_tmp, log_n, mode);
+}
+
+int g753_ntt_dev(g753_ctx* ctx, int field, void* d_data, unsigned log_n, int mode) {
+  CHECK_CTX(ctx);
+  if (!d_data) return fail(G753_ERR_BAD_ARG, "null data");
+  G753_TRY(g753_domain_check(field, log_n));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t bytes = sizeof(Fq) << log_n;
+  G753_TRY(ctx->scratch_io.reserve(bytes + 1024));
+  return ntt_any(ctx, field, (Fq*)d_data, (Fq*)ctx->scratch_io.ptr, log_n, mode);
+}
+
+int g753_ntt(g753_ctx* ctx, int field, uint64_t* data, unsigned log_n, int mode) {
+  CHECK_CTX(ctx);
+  if (!data) return fail(G753_ERR_BAD_ARG, "null data");
+  G753_TRY(g753_domain_check(field, log_n));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t bytes = sizeof(Fq) << log_n;
+  G753_TRY(ctx->scratch_io.reserve(2 * Carver::pad(bytes) + 1024));
+  Carver cv(ctx->scratch_io.ptr);
+  Fq* d_data = cv.take<Fq>((size_t)1 << log_n);
+  Fq* d_tmp = cv.take<Fq>((size_t)1 << log_n);
+  G753_TRY(h2d(d_data, data, bytes, ctx->stream));
+  G753_TRY(ntt_any(ctx, field, d_data, d_tmp, log_n, mode));
+  G753_TRY(d2h(data, d_data, bytes, ctx->stream));
+  return stream_sync(ctx->stream);
+}
+
+int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n) {
+  CHECK_CTX(ctx);
+  if (!d_a || (field != 0 && field != 1)) return fail(G753_ERR_BAD_ARG, "bad argument");
+  if (n == 0) return G753_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  if (field == 0)
+    G753_LAUNCH(k_vec_op<0>, div_up(n, 256), 256, ctx->stream, (Fq*)d_a, (const Fq*)d_b, op, n);
+  else
+    G753_LAUNCH(k_vec_op<1>, div_up(n, 256), 256, ctx->stream, (Fq*)d_a, (const Fq*)d_b, op, n);
+  ctx->launches++;
+  return launch_check("k_vec_op");
+}
+
+int g753_vec_scale_dev(g753_ctx* ctx, int field, void* d_a, const uint64_t* k_mont, size_t n) {
+  CHECK_CTX(ctx);
+  if (!d_a || !k_mont || (field != 0 && field != 1)) return fail(G753_ERR_BAD_ARG, "bad argument");
+  if (n == 0) return G753_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  // the constant travels through a small dedicated device slot (kept out of the scratch
+  // buffers, which may hold the caller's chained data)
+  Fq* d_k = nullptr;
+  G753_TRY(dev_alloc((void**)&d_k, sizeof(Fq)));
+  int rc = h2d(d_k, k_mont, sizeof(Fq), ctx->stream);
+  if (rc == G753_OK) {
+    if (field == 0)
+      G753_LAUNCH(k_vec_scale<0>, div_up(n, 256), 256, ctx->stream, (Fq*)d_a, d_k, n);
+    else
+      G753_LAUNCH(k_vec_scale<1>, div_up(n, 256), 256, ctx->stream, (Fq*)d_a, d_k, n);
+    ctx->launches++;
+    rc = launch_check("k_vec_scale");
+  }
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d_k);
+  return rc;
+}
+
+// ---- plumbing ------------------------------------------------------------------------------
+int g753_dev_alloc(g753_ctx* ctx, size_t bytes, void** d_ptr) {
+  CHECK_CTX(ctx);
+  if (!d_ptr) return fail(G753_ERR_BAD_ARG, "null out");
+  return dev_alloc(d_ptr, bytes);
+}
+int g753_dev_free(g753_ctx* ctx, void* d_ptr) {
+  CHECK_CTX(ctx);
+  stream_sync(ctx->stream);
+  dev_free(d_ptr);
+  return G753_OK;
+}
+int g753_h2d(g753_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  CHECK_CTX(ctx);
+  G753_TRY(h2d(d_dst, h_src, bytes, ctx->stream));
+  return stream_sync(ctx->stream);
+}
+int g753_d2h(g753_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  CHECK_CTX(ctx);
+  G753_TRY(d2h(h_dst, d_src, bytes, ctx->stream));
+  return stream_sync(ctx->stream);
+}
+int g753_sync(g753_ctx* ctx) {
+  CHECK_CTX(ctx);
+  return stream_sync(ctx->stream);
+}
+void* g753_stream(g753_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ---- introspection -------------------------------------------------------------------------
+int g753_field_op(g753_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                  size_t n) {
+  CHECK_CTX(ctx);
+  if (!a || !out || (field != 0 && field != 1)) return fail(G753_ERR_BAD_ARG, "bad argument");
+  if (n == 0) return G753_OK;
+  void *d_a = nullptr, *d_b = nullptr;
+  int rc = dev_alloc(&d_a, n * 96);
+  if (rc == G753_OK && b) rc = dev_alloc(&d_b, n * 96);
+  if (rc == G753_OK) rc = h2d(d_a, a, n * 96, ctx->stream);
+  if (rc == G753_OK && b) rc = h2d(d_b, b, n * 96, ctx->stream);
+  if (rc == G753_OK) rc = g753_vec_op_dev(ctx, field, op, d_a, d_b, n);
+  if (rc == G753_OK) rc = d2h(out, d_a, n * 96, ctx->stream);
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d_a);
+  dev_free(d_b);
+  return rc;
+}
+
+int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uint64_t* b, uint64_t* out_xyz) {
+  CHECK_CTX(ctx);
+  if (!a || !out_xyz || (op != 1 && !b)) return fail(G753_ERR_BAD_ARG, "null pointer");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  switch (group) {
+    case G753_MNT4_G1: return point_op_impl<CurveM4G1>(ctx, op, a, b, out_xyz);
+    case G753_MNT4_G2: return point_op_impl<CurveM4G2>(ctx, op, a, b, out_xyz);
+    case G753_MNT6_G1: return point_op_impl<CurveM6G1>(ctx, op, a, b, out_xyz);
+    case G753_MNT6_G2: return point_op_impl<CurveM6G2>(ctx, op, a, b, out_xyz);
+  }
+  return fail(G753_ERR_BAD_ARG, "unknown group");
+}
+
+int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms) {
+  CHECK_CTX(ctx);
+  if (!ms || blocks <= 0 || threads <= 0 || threads > 256 || iters <= 0) return fail(G753_ERR_BAD_ARG, "bad argument");
+#if defined(G753_HOST_EMUL)
+  (void)variant;
+  return fail(G753_ERR_NO_DEVICE, "probe needs a GPU");
+#else
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  Fq* d_seed = nullptr;
+  G753_TRY(dev_alloc((void**)&d_seed, sizeof(Fq) * 512));
+  std::vector<uint32_t> h(256 * NL);
+  uint64_t s = 0x9E3779B97F4A7C15ull;
+  for (size_t i = 0; i < h.size(); i++) {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    h[i] = (uint32_t)(s >> 33);
+    if (i % NL == NL - 1) h[i] &= 0xffff;  // < p
+  }
+  int rc = h2d(d_seed, h.data(), h.size() * 4, ctx->stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  if (rc == G753_OK) {
+    cudaEventRecord(e0, ctx->stream);
+    if (variant == 0) k_mac_probe<0><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
+    else if (variant == 1) k_mac_probe<1><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
+    else k_mac_probe<2><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
+    cudaEventRecord(e1, ctx->stream);
+    ctx->launches++;
+    rc = launch_check("k_mac_probe");
+  }
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  if (rc == G753_OK) cudaEventElapsedTime(ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  dev_free(d_seed);
+  return rc;
+#endif
+}
+
+uint64_t g753_launch_count(const g753_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int g753_last_msm_phases(const g753_ctx* ctx, float* ms, int cap) {
+  if (!ctx || !ms) return 0;
+  int k = cap < MSM_PHASES ? cap : MSM_PHASES;
+  for (int i = 0; i < k; i++) ms[i] = ctx->phase_ms[i];
+  return k;
+}
+
+}  // extern "C"

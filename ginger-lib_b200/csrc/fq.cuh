@@ -1,0 +1,401 @@
+// 753-bit prime-field arithmetic for sm_100a: 24 x 32-bit limbs, Montgomery radix R = 2^768.
+//
+// Replaces (reference, relative to /root/reference/algebra/src):
+//   fields/models/fp_768.rs:1009-1185  Fp768::mul_assign      -> fq_mul
+//   fields/models/fp_768.rs:339-548    Fp768::square_in_place -> fq_sqr
+//   fields/models/fp_768.rs:929-949    add_assign/sub_assign  -> fq_add / fq_sub
+//   fields/models/fp_768.rs:870-883    neg                    -> fq_neg
+//   fields/models/fp_768.rs:303-309    double_in_place        -> fq_dbl
+//   fields/models/fp_768.rs:551-605    inverse                -> fq_inv (Fermat; same value)
+// Limbs are the reference's own in-memory form (BigInteger768 = 12 x u64 little endian,
+// biginteger/mod.rs:20) re-read as 24 x u32, so raw buffers cross the C ABI unconverted.
+// All results are canonical (< p), as the reference's are (fp_768.rs:39-48).
+//
+// The multiplier is an interleaved (CIOS-style) Montgomery product laid out so that every
+// 32x32->64 partial product is one mad.lo.cc/madc.hi.cc pair on a single carry chain: the
+// products of the even-indexed limbs of `a` land on columns (j, j+1) and form one chain,
+// those of the odd-indexed limbs form a second chain one column up.  The two accumulators
+// swap roles after each one-limb Montgomery shift, so no partial product ever has to be
+// re-aligned.  ptxas turns each lo/hi pair into IMAD.WIDE.U32 with carry-in/out (checked
+// with cuobjdump, see DESIGN.md "Field multiplier").
+//
+// The same source compiles for the host (tests/host_emul) with the carry flag emulated in
+// a thread-local variable: that build exists only to test the limb logic without a GPU and
+// is never linked into the product library.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define G753_HD __host__ __device__ __forceinline__
+#define G753_D __device__ __forceinline__
+#define G753_NI __host__ __device__ __noinline__
+#else
+#define G753_HD inline
+#define G753_D inline
+#define G753_NI
+#ifndef __align__
+#define __align__(n) alignas(n)
+#endif
+#endif
+
+namespace g753 {
+
+constexpr int NL = 24;  // 32-bit limbs per base-field element (768 / 32)
+
+struct FieldConstants {
+  uint32_t p[NL];        // modulus
+  uint32_t one[NL];      // R mod p      (Montgomery form of 1)
+  uint32_t r2[NL];       // R^2 mod p    (to-Montgomery multiplier)
+  uint32_t r3[NL];       // R^3 mod p    (Montgomery inverse fix-up)
+  uint32_t gen[NL];      // 17 * R       (multiplicative generator, FpParameters::GENERATOR)
+  uint32_t gen_inv[NL];  // 17^-1 * R
+  uint32_t root[NL];     // 2^s-th root of unity * R (FpParameters::ROOT_OF_UNITY)
+  uint32_t p_minus_2[NL];
+  uint32_t curve_b[NL];  // G1 coefficient b * R of the curve whose base field this is
+  uint32_t inv32;        // -p^-1 mod 2^32
+  uint32_t two_adicity;
+};
+
+#include "constants.inc"
+
+#if defined(__CUDACC__)
+__constant__ FieldConstants d_fc[2];
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define G753_FC(FID) (d_fc[FID])
+#else
+#define G753_FC(FID) (G753_FIELD_CONSTANTS[FID])
+static thread_local uint32_t g_host_cf = 0;  // emulated CC.CF (host test build only)
+#endif
+
+// ------------------------------------------------------------------------------------
+// carry-chain primitives.  Each maps to exactly one PTX instruction on the device.
+// ------------------------------------------------------------------------------------
+G753_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+G753_HD uint32_t mul_hi(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+#define G753_ASM3(name, ins)                                                         \
+  G753_HD uint32_t name(uint32_t a, uint32_t b) {                                    \
+    uint32_t r;                                                                      \
+    asm volatile(ins " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));                    \
+    return r;                                                                        \
+  }
+#define G753_ASM4(name, ins)                                                         \
+  G753_HD uint32_t name(uint32_t a, uint32_t b, uint32_t c) {                        \
+    uint32_t r;                                                                      \
+    asm volatile(ins " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));        \
+    return r;                                                                        \
+  }
+G753_ASM3(add_cc, "add.cc.u32")
+G753_ASM3(addc_cc, "addc.cc.u32")
+G753_ASM3(addc, "addc.u32")
+G753_ASM3(sub_cc, "sub.cc.u32")
+G753_ASM3(subc_cc, "subc.cc.u32")
+G753_ASM3(subc, "subc.u32")
+G753_ASM4(mad_lo_cc, "mad.lo.cc.u32")
+G753_ASM4(madc_lo_cc, "madc.lo.cc.u32")
+G753_ASM4(mad_hi_cc, "mad.hi.cc.u32")
+G753_ASM4(madc_hi_cc, "madc.hi.cc.u32")
+G753_ASM4(madc_hi, "madc.hi.u32")
+G753_ASM4(madc_lo, "madc.lo.u32")
+#undef G753_ASM3
+#undef G753_ASM4
+#else
+G753_HD uint32_t add_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b;
+  g_host_cf = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+}
+G753_HD uint32_t addc_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b + g_host_cf;
+  g_host_cf = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+}
+G753_HD uint32_t addc(uint32_t a, uint32_t b) { return a + b + g_host_cf; }
+G753_HD uint32_t sub_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b;
+  g_host_cf = (uint32_t)((t >> 32) & 1);  // borrow (PTX keeps the borrow in CC.CF for sub)
+  return (uint32_t)t;
+}
+G753_HD uint32_t subc_cc(uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b - g_host_cf;
+  g_host_cf = (uint32_t)((t >> 32) & 1);
+  return (uint32_t)t;
+}
+G753_HD uint32_t subc(uint32_t a, uint32_t b) { return a - b - g_host_cf; }
+G753_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint64_t t = (uint64_t)(uint32_t)(a * b) + c;
+  g_host_cf = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+}
+G753_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint64_t t = (uint64_t)(uint32_t)(a * b) + c + g_host_cf;
+  g_host_cf = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+}
+G753_HD uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint64_t t = (((uint64_t)a * b) >> 32) + c;
+  g_host_cf = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+}
+G753_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) {
+  uint64_t t = (((uint64_t)a * b) >> 32) + c + g_host_cf;
+  g_host_cf = (uint32_t)(t >> 32);
+  return (uint32_t)t;
+}
+G753_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
+  return (uint32_t)((((uint64_t)a * b) >> 32) + c + g_host_cf);
+}
+G753_HD uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c + g_host_cf; }
+#endif
+
+// ------------------------------------------------------------------------------------
+// element type
+// ------------------------------------------------------------------------------------
+struct __align__(16) Fq {
+  uint32_t l[NL];
+};
+
+template <int FID>
+G753_HD Fq fq_zero() {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.l[i] = 0;
+  return r;
+}
+template <int FID>
+G753_HD Fq fq_one() {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.l[i] = G753_FC(FID).one[i];
+  return r;
+}
+G753_HD bool fq_is_zero(const Fq& a) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) t |= a.l[i];
+  return t == 0;
+}
+G753_HD bool fq_eq(const Fq& a, const Fq& b) {
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) t |= a.l[i] ^ b.l[i];
+  return t == 0;
+}
+
+// r = (x >= p) ? x - p : x, for x < 2p
+template <int FID>
+G753_HD void fq_reduce_once(uint32_t* x) {
+  uint32_t t[NL];
+  t[0] = sub_cc(x[0], G753_FC(FID).p[0]);
+#pragma unroll
+  for (int i = 1; i < NL; i++) t[i] = subc_cc(x[i], G753_FC(FID).p[i]);
+  uint32_t borrow = subc(0, 0);  // 0 - 0 - CF : 0xffffffff when x < p
+#pragma unroll
+  for (int i = 0; i < NL; i++) x[i] = borrow ? x[i] : t[i];
+}
+
+template <int FID>
+G753_HD Fq fq_add(const Fq& a, const Fq& b) {
+  Fq r;
+  r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+  r.l[NL - 1] = addc(a.l[NL - 1], b.l[NL - 1]);  // 2p < 2^768: no carry out
+  fq_reduce_once<FID>(r.l);
+  return r;
+}
+
+template <int FID>
+G753_HD Fq fq_sub(const Fq& a, const Fq& b) {
+  Fq r;
+  r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < NL; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+  uint32_t mask = subc(0, 0);  // all ones when a < b
+  r.l[0] = add_cc(r.l[0], G753_FC(FID).p[0] & mask);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) r.l[i] = addc_cc(r.l[i], G753_FC(FID).p[i] & mask);
+  r.l[NL - 1] = addc(r.l[NL - 1], G753_FC(FID).p[NL - 1] & mask);
+  return r;
+}
+
+template <int FID>
+G753_HD Fq fq_dbl(const Fq& a) {
+  return fq_add<FID>(a, a);
+}
+
+template <int FID>
+G753_HD Fq fq_neg(const Fq& a) {
+  if (fq_is_zero(a)) return a;
+  Fq r;
+  r.l[0] = sub_cc(G753_FC(FID).p[0], a.l[0]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) r.l[i] = subc_cc(G753_FC(FID).p[i], a.l[i]);
+  r.l[NL - 1] = subc(G753_FC(FID).p[NL - 1], a.l[NL - 1]);
+  return r;
+}
+
+// k * a for a small compile-time k (curve / non-residue constants 2, 11, 13, 26, 121 are
+// tiny once de-Montgomerised - SURVEY.md appendix A - so the reference's full-width
+// constant multiplications become short addition chains with the same value).
+template <int FID, unsigned K>
+G753_HD Fq fq_mul_small(const Fq& a) {
+  static_assert(K >= 1 && K < 256, "small constant");
+  Fq acc = a;
+  int top = 0;
+  for (int i = 7; i >= 0; i--)
+    if ((K >> i) & 1) {
+      top = i;
+      break;
+    }
+#pragma unroll
+  for (int i = top - 1; i >= 0; i--) {
+    acc = fq_dbl<FID>(acc);
+    if ((K >> i) & 1) acc = fq_add<FID>(acc, a);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------
+// Montgomery multiplication
+// ------------------------------------------------------------------------------------
+// acc[j], acc[j+1] = a[j] * bi   for j = 0, 2, ..., NL-2   (a may be offset by one limb)
+G753_HD void row_mul(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < NL; j += 2) {
+    acc[j] = mul_lo(a[j], bi);
+    acc[j + 1] = mul_hi(a[j], bi);
+  }
+}
+// acc[0..NL) += sum_j a[j] * bi << (32 j), j even: one carry chain; carry out left in CC.CF
+G753_HD void row_mad(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+  acc[0] = mad_lo_cc(a[0], bi, acc[0]);
+  acc[1] = madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+  for (int j = 2; j < NL; j += 2) {
+    acc[j] = madc_lo_cc(a[j], bi, acc[j]);
+    acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 1]);
+  }
+}
+// acc[j] = a[j]*bi (lo/hi as above) + acc[j+2] + CF : multiply-accumulate that also drops the
+// accumulator two limbs (the one-limb Montgomery shift seen from the "odd" array)
+G753_HD void row_mad_shift(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < NL - 2; j += 2) {
+    acc[j] = madc_lo_cc(a[j], bi, acc[j + 2]);
+    acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 3]);
+  }
+  acc[NL - 2] = madc_lo_cc(a[NL - 2], bi, 0);
+  acc[NL - 1] = madc_hi(a[NL - 1 - 1], bi, 0);
+}
+
+// One outer iteration: E holds columns 0..NL-1; O holds, at index k, column k-1 (index 0 dead).
+// On exit E[0] == 0 and (E, O) are to be read swapped (O -> columns 0.., E index k -> column k-1).
+template <int FID, bool FIRST>
+G753_HD void mont_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
+  if (FIRST) {
+    row_mul(O, a + 1, bi);
+    row_mul(E, a, bi);
+  } else {
+    E[0] = add_cc(E[0], O[1]);
+    row_mad_shift(O, a + 1, bi);
+    row_mad(E, a, bi);
+    O[NL - 1] = addc(O[NL - 1], 0);
+  }
+  uint32_t m = mul_lo(E[0], G753_FC(FID).inv32);
+  row_mad(O, G753_FC(FID).p + 1, m);
+  row_mad(E, G753_FC(FID).p, m);
+  O[NL - 1] = addc(O[NL - 1], 0);
+}
+
+template <int FID>
+G753_HD Fq fq_mul(const Fq& a, const Fq& b) {
+  uint32_t even[NL], odd[NL];
+  mont_step<FID, true>(even, odd, a.l, b.l[0]);
+#pragma unroll
+  for (int i = 1; i < NL; i += 2) {
+    mont_step<FID, false>(odd, even, a.l, b.l[i]);
+    if (i + 1 < NL) mont_step<FID, false>(even, odd, a.l, b.l[i + 1]);
+  }
+  // NL is even: after the last step `even` holds columns 0.. and odd[k] column k-1
+  Fq r;
+  r.l[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) r.l[i] = addc_cc(even[i], odd[i + 1]);
+  r.l[NL - 1] = addc(even[NL - 1], 0);
+  fq_reduce_once<FID>(r.l);
+  return r;
+}
+
+template <int FID>
+G753_HD Fq fq_sqr(const Fq& a) {
+  return fq_mul<FID>(a, a);
+}
+
+// Out-of-line entry points: the curve code calls the multiplier hundreds of times per group
+// operation; one shared body per field keeps kernels small (and ptxas time sane) at the cost
+// of a call per product (~5% of its ~1400 instructions).
+template <int FID>
+G753_NI void fq_mul_ni(Fq& r, const Fq& a, const Fq& b) {
+  r = fq_mul<FID>(a, b);
+}
+template <int FID>
+G753_HD Fq fq_mulc(const Fq& a, const Fq& b) {
+  Fq r;
+  fq_mul_ni<FID>(r, a, b);
+  return r;
+}
+template <int FID>
+G753_HD Fq fq_sqrc(const Fq& a) {
+  Fq r;
+  fq_mul_ni<FID>(r, a, a);
+  return r;
+}
+
+// a^e for a 768-bit exponent given as limbs (used for Fermat inversion; not on the hot loop)
+template <int FID>
+G753_NI Fq fq_pow(const Fq& a, const uint32_t* e) {
+  Fq r = fq_one<FID>();
+  bool started = false;
+  for (int i = NL * 32 - 1; i >= 0; i--) {
+    if (started) r = fq_sqrc<FID>(r);
+    if ((e[i >> 5] >> (i & 31)) & 1) {
+      r = started ? fq_mulc<FID>(r, a) : a;
+      started = true;
+    }
+  }
+  return r;
+}
+
+// a^-1 (Montgomery form in, Montgomery form out).  The reference uses a binary extended
+// Euclid (fp_768.rs:551-605); the inverse is unique, so Fermat gives identical limbs.
+template <int FID>
+G753_HD Fq fq_inv(const Fq& a) {
+  return fq_pow<FID>(a, G753_FC(FID).p_minus_2);
+}
+
+template <int FID>
+G753_HD Fq fq_to_mont(const Fq& a) {
+  Fq r2;
+#pragma unroll
+  for (int i = 0; i < NL; i++) r2.l[i] = G753_FC(FID).r2[i];
+  return fq_mul<FID>(a, r2);
+}
+template <int FID>
+G753_HD Fq fq_from_mont(const Fq& a) {
+  Fq one;
+#pragma unroll
+  for (int i = 0; i < NL; i++) one.l[i] = (i == 0) ? 1u : 0u;
+  return fq_mul<FID>(a, one);
+}
+
+}  // namespace g753

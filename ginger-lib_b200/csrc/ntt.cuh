@@ -1,0 +1,217 @@
+// Radix-2 number-theoretic transforms behind EvaluationDomain.
+//
+// Replaces (reference, relative to /root/reference/algebra/src/fft/domain.rs):
+//   :65-94    EvaluationDomain::new          -> ntt_tables_build (omega, omega^-1, n^-1, 17^+-i)
+//   :120-123  fft_in_place   -> best_fft :305-313 -> serial_fft :315-358 / parallel_fft :360-416
+//   :134-138  ifft_in_place  (omega^-1, then * size_inv)
+//   :140-152  distribute_powers, :163-166 coset_fft_in_place, :176-179 coset_ifft_in_place
+//   :245-256, :289-302  element-wise helpers used by R1CStoQAP::witness_map
+// Output convention is the reference's: natural order, out[i] = sum_j in[j] * omega^(i j),
+// omega = ROOT_OF_UNITY^(2^(TWO_ADICITY - log_n)).
+//
+// Algorithm: Stockham autosort (natural order in and out, no bit-reversal pass), twiddles
+// omega^j (j < n/2) and coset powers 17^i / 17^-i * n^-1 from tables that are built once per
+// (field, log_n) and stay resident in HBM.  The coset scaling and the 1/n factor are fused
+// into the first / last butterfly pass.
+#pragma once
+#include "device.cuh"
+#include "fqk.cuh"
+
+namespace g753 {
+
+constexpr unsigned NTT_MAX_LOG = 29;
+
+struct NttTables {
+  unsigned log_n = 0;
+  Fq* tw_fwd = nullptr;     // omega^j,        j < max(n/2, 1)
+  Fq* tw_inv = nullptr;     // omega^-j
+  Fq* coset = nullptr;      // g^i,            i < n       (g = 17)
+  Fq* coset_inv = nullptr;  // g^-i * n^-1
+  Fq* consts = nullptr;     // [0] = n^-1, then the four squaring chains
+  void release() {
+    dev_free(tw_fwd);
+    dev_free(tw_inv);
+    dev_free(coset);
+    dev_free(coset_inv);
+    dev_free(consts);
+    tw_fwd = tw_inv = coset = coset_inv = consts = nullptr;
+  }
+};
+
+// consts layout: [0] n^-1 ; [1 + l] omega^(2^l) ; [1 + L + l] omega^-(2^l) ; [1 + 2L + l] g^(2^l) ;
+// [1 + 3L + l] g^-(2^l), L = max(log_n, 1), l < L
+template <int FID>
+__global__ void k_ntt_setup(unsigned log_n, Fq* consts) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const unsigned L = log_n ? log_n : 1;
+  Fq w;
+#pragma unroll
+  for (int i = 0; i < NL; i++) w.l[i] = G753_FC(FID).root[i];
+  for (unsigned k = log_n; k < G753_FC(FID).two_adicity; k++) w = fq_sqr<FID>(w);  // domain.rs:76-79
+  Fq wi = fq_inv<FID>(w);
+  Fq g, gi;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    g.l[i] = G753_FC(FID).gen[i];
+    gi.l[i] = G753_FC(FID).gen_inv[i];
+  }
+  // n^-1 = (2^-1)^log_n, with 2^-1 = (p + 1) / 2
+  Fq two = fq_dbl<FID>(fq_one<FID>());
+  Fq half = fq_inv<FID>(two);
+  Fq ninv = fq_one<FID>();
+  for (unsigned k = 0; k < log_n; k++) ninv = fq_mul<FID>(ninv, half);
+  consts[0] = ninv;
+  for (unsigned l = 0; l < L; l++) {
+    consts[1 + l] = w;
+    consts[1 + L + l] = wi;
+    consts[1 + 2 * L + l] = g;
+    consts[1 + 3 * L + l] = gi;
+    w = fq_sqr<FID>(w);
+    wi = fq_sqr<FID>(wi);
+    g = fq_sqr<FID>(g);
+    gi = fq_sqr<FID>(gi);
+  }
+}
+
+// tab[0] = *first (or one)
+template <int FID>
+__global__ void k_table_init(Fq* tab, const Fq* first) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  tab[0] = first ? *first : fq_one<FID>();
+}
+// tab[len + t] = tab[t] * (*step) for t < len  (doubles the table: step = base^len)
+template <int FID>
+__global__ void k_table_double(Fq* tab, const Fq* step, unsigned len, unsigned cap) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len || len + t >= cap) return;
+  tab[len + t] = fq_mul<FID>(tab[t], *step);
+}
+
+template <int FID>
+static int ntt_tables_build(NttTables& T, unsigned log_n, cudaStream_t stream, uint64_t* launches) {
+  T.log_n = log_n;
+  const size_t n = (size_t)1 << log_n;
+  const size_t half = n > 1 ? n / 2 : 1;
+  const unsigned L = log_n ? log_n : 1;
+  G753_TRY(dev_alloc((void**)&T.consts, sizeof(Fq) * (1 + 4 * L)));
+  G753_TRY(dev_alloc((void**)&T.tw_fwd, sizeof(Fq) * half));
+  G753_TRY(dev_alloc((void**)&T.tw_inv, sizeof(Fq) * half));
+  G753_TRY(dev_alloc((void**)&T.coset, sizeof(Fq) * n));
+  G753_TRY(dev_alloc((void**)&T.coset_inv, sizeof(Fq) * n));
+  G753_LAUNCH(k_ntt_setup<FID>, 1, 1, stream, log_n, T.consts);
+  G753_LAUNCH(k_table_init<FID>, 1, 1, stream, T.tw_fwd, (const Fq*)nullptr);
+  G753_LAUNCH(k_table_init<FID>, 1, 1, stream, T.tw_inv, (const Fq*)nullptr);
+  G753_LAUNCH(k_table_init<FID>, 1, 1, stream, T.coset, (const Fq*)nullptr);
+  G753_LAUNCH(k_table_init<FID>, 1, 1, stream, T.coset_inv, (const Fq*)T.consts);
+  if (launches) *launches += 5;
+  for (unsigned l = 0; l < log_n; l++) {
+    unsigned len = 1u << l;
+    if (len < half) {
+      G753_LAUNCH(k_table_double<FID>, div_up(len, 128), 128, stream, T.tw_fwd, T.consts + 1 + l, len,
+                  (unsigned)half);
+      G753_LAUNCH(k_table_double<FID>, div_up(len, 128), 128, stream, T.tw_inv, T.consts + 1 + L + l, len,
+                  (unsigned)half);
+      if (launches) *launches += 2;
+    }
+    G753_LAUNCH(k_table_double<FID>, div_up(len, 128), 128, stream, T.coset, T.consts + 1 + 2 * L + l, len,
+                (unsigned)n);
+    G753_LAUNCH(k_table_double<FID>, div_up(len, 128), 128, stream, T.coset_inv, T.consts + 1 + 3 * L + l, len,
+                (unsigned)n);
+    if (launches) *launches += 2;
+  }
+  return launch_check("ntt_tables_build");
+}
+
+// One Stockham radix-2 pass (stage s, sub-transform length Ns = 2^s -> 2^(s+1)):
+//   out[j0], out[j0 + Ns] = in[j] +- in[j + n/2] * omega^(k n / (2 Ns)),  k = j mod Ns,
+//   j0 = (j div Ns) * 2 Ns + k.
+// pre  (first pass): inputs are multiplied by pre[index]            (coset_fft: g^i)
+// post (last pass):  outputs are multiplied by post[index] or *post_const (ifft: n^-1,
+//                    coset_ifft: g^-i n^-1)
+template <int FID>
+__global__ void __launch_bounds__(256)
+k_ntt_stage(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restrict__ tw, unsigned log_n,
+            unsigned s, const Fq* __restrict__ pre, const Fq* __restrict__ post,
+            const Fq* __restrict__ post_const) {
+  const unsigned half = 1u << (log_n - 1);
+  unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= half) return;
+  const unsigned Ns = 1u << s;
+  const unsigned k = j & (Ns - 1);
+  Fq a = in[j];
+  Fq b = in[j + half];
+  if (pre != nullptr) {
+    a = fq_mul<FID>(a, pre[j]);
+    b = fq_mul<FID>(b, pre[j + half]);
+  }
+  b = fq_mul<FID>(b, tw[(size_t)k << (log_n - 1 - s)]);
+  const unsigned j0 = ((j >> s) << (s + 1)) | k;
+  Fq x = fq_add<FID>(a, b);
+  Fq y = fq_sub<FID>(a, b);
+  if (post != nullptr) {
+    x = fq_mul<FID>(x, post[j0]);
+    y = fq_mul<FID>(y, post[j0 + Ns]);
+  } else if (post_const != nullptr) {
+    Fq cst = *post_const;
+    x = fq_mul<FID>(x, cst);
+    y = fq_mul<FID>(y, cst);
+  }
+  out[j0] = x;
+  out[j0 + Ns] = y;
+}
+
+template <int FID>
+__global__ void __launch_bounds__(256)
+k_vec_op(Fq* __restrict__ a, const Fq* __restrict__ b, int op, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq x = a[i];
+  Fq y = b ? b[i] : x;
+  Fq r;
+  switch (op) {
+    case G753_OP_MUL: r = fq_mul<FID>(x, y); break;
+    case G753_OP_ADD: r = fq_add<FID>(x, y); break;
+    case G753_OP_SUB: r = fq_sub<FID>(x, y); break;
+    case G753_OP_SQR: r = fq_sqr<FID>(x); break;
+    case G753_OP_INV: r = fq_is_zero(x) ? x : fq_inv<FID>(x); break;
+    case G753_OP_TO_MONT: r = fq_to_mont<FID>(x); break;
+    case G753_OP_FROM_MONT: r = fq_from_mont<FID>(x); break;
+    default: r = x;
+  }
+  a[i] = r;
+}
+
+template <int FID>
+__global__ void __launch_bounds__(256) k_vec_scale(Fq* __restrict__ a, const Fq* __restrict__ k, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  a[i] = fq_mul<FID>(a[i], *k);
+}
+
+// In-place transform of d_data (n = 2^log_n elements) using d_tmp (same size) as the
+// ping-pong buffer.
+template <int FID>
+static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tmp, int mode,
+                   uint64_t* launches) {
+  const unsigned log_n = T.log_n;
+  const size_t n = (size_t)1 << log_n;
+  if (log_n == 0) return G753_OK;  // size-1 domain: every transform is the identity
+  const bool inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
+  const Fq* tw = inverse ? T.tw_inv : T.tw_fwd;
+  Fq* src = d_data;
+  Fq* dst = d_tmp;
+  for (unsigned s = 0; s < log_n; s++) {
+    const Fq* pre = (s == 0 && mode == G753_COSET_FFT) ? T.coset : nullptr;
+    const Fq* post = (s == log_n - 1 && mode == G753_COSET_IFFT) ? T.coset_inv : nullptr;
+    const Fq* post_c = (s == log_n - 1 && mode == G753_IFFT) ? T.consts : nullptr;
+    G753_LAUNCH(k_ntt_stage<FID>, div_up(n / 2, 256), 256, stream, src, dst, tw, log_n, s, pre, post, post_c);
+    if (launches) ++*launches;
+    Fq* t = src;
+    src = dst;
+    dst = t;
+  }
+  if (src != d_data) G753_TRY(d2d(d_data, src, sizeof(Fq) * n, stream));
+  return launch_check("ntt_run");
+}
+
+}  // namespace g753

@@ -1,0 +1,156 @@
+/* g753 - C ABI of the B200-native Groth16 prover hot path for MNT4-753 / MNT6-753.
+ *
+ * This is the drop-in boundary: exactly the entry points a thin FFI layer
+ * under ginger-lib's `algebra::msm` / `algebra::fft` would bind (INTEGRATION.md shows the
+ * Rust `-sys` crate).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Data formats (identical to the reference's in-memory forms, so buffers cross unconverted):
+ *   - a base-field element Fq is 12 little-endian uint64 limbs = BigInteger768.0
+ *     (algebra/src/biginteger/mod.rs:20), holding the MONTGOMERY representation
+ *     (value * 2^768 mod p), as Fp768 stores it (algebra/src/fields/models/fp_768.rs:24-30);
+ *   - Fq2 = c0,c1 and Fq3 = c0,c1,c2, consecutive (fields/models/fp2.rs:51-57, fp3.rs:60-67);
+ *   - an affine point is x then y (2*k*12 limbs, k = 1/2/3) plus one byte in a separate
+ *     `infinity` array (GroupAffine{x,y,infinity}, curves/models/short_weierstrass_projective.rs:26-32);
+ *   - an MSM scalar is the CANONICAL integer < r, 12 limbs, i.e. `Fr::into_repr()`
+ *     (proof-systems/src/groth16/prover.rs:241-267);
+ *   - an MSM result is a homogeneous projective point X,Y,Z (3*k*12 limbs, Montgomery form,
+ *     every coordinate fully reduced), any representative - what
+ *     VariableBaseMSM::multi_scalar_mul returns (algebra/src/msm/variable_base.rs:85-90);
+ *     the point at infinity is (0, 1, 0) as GroupProjective::zero().
+ *
+ * Every function returns 0 on success or a G753_ERR_* code; nothing aborts or unwinds across
+ * the boundary.  g753_last_error() gives a thread-local description of the last failure.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef G753_H
+#define G753_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G753_OK 0
+#define G753_ERR_BAD_ARG 1      /* null pointer, unknown id, size out of range            */
+#define G753_ERR_CUDA 2         /* a CUDA runtime call or kernel failed                   */
+#define G753_ERR_OOM 3          /* device memory exhausted                                */
+#define G753_ERR_DOMAIN 4       /* log_n >= two-adicity: EvaluationDomain::new -> None    */
+#define G753_ERR_NO_DEVICE 5    /* no usable CUDA device                                  */
+
+#define G753_LIMBS 12           /* uint64 limbs per Fq element                            */
+
+/* groups: AffineCurve instantiations on the prover path
+ *   curves/mnt4753/mod.rs:105-109, curves/mnt6753/mod.rs:106-110 */
+#define G753_MNT4_G1 0          /* over Fq   (k = 1) */
+#define G753_MNT4_G2 1          /* over Fq2  (k = 2) */
+#define G753_MNT6_G1 2          /* over Fq   (k = 1) */
+#define G753_MNT6_G2 3          /* over Fq3  (k = 3) */
+
+/* prime fields.  mnt4753::Fq == mnt6753::Fr and mnt6753::Fq == mnt4753::Fr
+ *   (fields/mnt4753/fr.rs:1, fields/mnt6753/fr.rs:1) */
+#define G753_FIELD_MNT4_FQ 0
+#define G753_FIELD_MNT6_FQ 1
+#define G753_FIELD_MNT6_FR 0    /* two-adicity 15: domains up to 2^14 */
+#define G753_FIELD_MNT4_FR 1    /* two-adicity 30: domains up to 2^29 */
+
+/* EvaluationDomain transforms (algebra/src/fft/domain.rs:113-179) */
+#define G753_FFT 0              /* fft_in_place        :120-123 */
+#define G753_IFFT 1             /* ifft_in_place       :134-138 */
+#define G753_COSET_FFT 2        /* coset_fft_in_place  :163-166 */
+#define G753_COSET_IFFT 3       /* coset_ifft_in_place :176-179 */
+
+/* element-wise field operations (test / witness_map helpers) */
+#define G753_OP_MUL 0           /* Fp768::mul_assign  fp_768.rs:1009-1185 */
+#define G753_OP_ADD 1           /* add_assign         fp_768.rs:929-937   */
+#define G753_OP_SUB 2           /* sub_assign         fp_768.rs:939-949   */
+#define G753_OP_SQR 3           /* square_in_place    fp_768.rs:339-548   */
+#define G753_OP_INV 5           /* inverse            fp_768.rs:551-605   */
+#define G753_OP_TO_MONT 6       /* from_repr          fp_768.rs:627-635   */
+#define G753_OP_FROM_MONT 7     /* into_repr          fp_768.rs:637-667   */
+
+typedef struct g753_ctx g753_ctx;       /* one CUDA device + stream + scratch + tables */
+typedef struct g753_bases g753_bases;   /* a device-resident slice of proving-key bases */
+
+/* ---- context ------------------------------------------------------------------------- */
+int g753_device_count(int* count);
+int g753_ctx_create(int device, g753_ctx** out);
+int g753_ctx_destroy(g753_ctx* ctx);
+const char* g753_last_error(void);
+const char* g753_version(void);
+
+/* ---- MSM: VariableBaseMSM::multi_scalar_mul (algebra/src/msm/variable_base.rs:85-90) -- */
+/* Upload n affine bases once per proving key (Parameters::{a,b_g1,b_g2,h,l}_query,
+ * proof-systems/src/groth16/mod.rs:313-371); they stay resident in HBM. */
+int g753_bases_upload(g753_ctx* ctx, int group, const uint64_t* coords, const uint8_t* infinity,
+                      size_t n, g753_bases** out);
+int g753_bases_free(g753_ctx* ctx, g753_bases* bases);
+size_t g753_bases_len(const g753_bases* bases);
+
+/* sum_{i<count} scalars[i] * bases[first+i]  ->  out_xyz (host, 3*k*12 limbs).
+ * `first`/`count` give the sub-slice views the prover takes (groth16/mod.rs:318-350); the
+ * reference's zip-truncation (variable_base.rs:36) is `count = min(len(bases)-first, len(scalars))`,
+ * applied by the caller-side shim.  count == 0 returns the point at infinity. */
+int g753_msm(g753_ctx* ctx, const g753_bases* bases, size_t first, size_t count,
+             const uint64_t* scalars, uint64_t* out_xyz);
+/* same, scalars already in device memory (count*12 limbs) and result left in device memory */
+int g753_msm_dev(g753_ctx* ctx, const g753_bases* bases, size_t first, size_t count,
+                 const void* d_scalars, void* d_out_xyz);
+/* one-shot form with host bases: exactly multi_scalar_mul(&bases[..n_bases], &scalars[..n_scalars]) */
+int g753_msm_host(g753_ctx* ctx, int group, const uint64_t* coords, const uint8_t* infinity,
+                  size_t n_bases, const uint64_t* scalars, size_t n_scalars, uint64_t* out_xyz);
+/* sum of `count` projective points (device memory, 3*k*12 limbs each) -> one projective point;
+ * the fold that follows the multi-GPU gather of per-shard partial sums */
+int g753_points_sum_dev(g753_ctx* ctx, int group, const void* d_points_xyz, size_t count,
+                        void* d_out_xyz);
+/* limbs per coordinate element (12 * k) of a group */
+int g753_group_coord_limbs(int group);
+
+/* ---- NTT: EvaluationDomain (algebra/src/fft/domain.rs:65-179) -------------------------- */
+/* 0 if a radix-2 domain of size 2^log_n exists for the field (domain.rs:70-72), else
+ * G753_ERR_DOMAIN - the `None` of EvaluationDomain::new */
+int g753_domain_check(int field, unsigned log_n);
+/* in place on host memory: data = n = 2^log_n elements, already resized by the caller
+ * (domain.rs:121 zero-pads or truncates).  mode is one of G753_FFT..G753_COSET_IFFT */
+int g753_ntt(g753_ctx* ctx, int field, uint64_t* data, unsigned log_n, int mode);
+/* same on a device pointer, for chaining the 7 transforms of R1CStoQAP::witness_map
+ * (proof-systems/src/groth16/r1cs_to_qap.rs:121-161) without host round trips */
+int g753_ntt_dev(g753_ctx* ctx, int field, void* d_data, unsigned log_n, int mode);
+/* element-wise helpers on device vectors for witness_map: a[i] = a[i] op b[i]
+ * (mul_polynomials_in_evaluation_domain domain.rs:289-302; ab - c r1cs_to_qap.rs:156-158) and
+ * a[i] *= k (divide_by_vanishing_poly_on_coset_in_place domain.rs:245-256) */
+int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n);
+int g753_vec_scale_dev(g753_ctx* ctx, int field, void* d_a, const uint64_t* k_mont, size_t n);
+
+/* ---- device memory / stream plumbing (so callers can chain without a CUDA toolchain) --- */
+int g753_dev_alloc(g753_ctx* ctx, size_t bytes, void** d_ptr);
+int g753_dev_free(g753_ctx* ctx, void* d_ptr);
+int g753_h2d(g753_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int g753_d2h(g753_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int g753_sync(g753_ctx* ctx);
+/* the context's cudaStream_t, as an opaque pointer (for event timing by the harness) */
+void* g753_stream(g753_ctx* ctx);
+
+/* ---- introspection / test entry points -------------------------------------------------- */
+/* out[i] = a[i] op b[i] over n host elements (b ignored for unary ops) */
+int g753_field_op(g753_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b,
+                  uint64_t* out, size_t n);
+/* group-law test hook: op 0: out = a + b (affine + affine), 1: 2a, 2: scalar * a;
+ * a, b affine (2*k*12 limbs, (0,0) = infinity), scalar 12 limbs canonical, out projective */
+int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uint64_t* b,
+                  uint64_t* out_xyz);
+/* Run `iters` dependent Montgomery multiplications per thread on `blocks` x `threads`
+ * threads and report the kernel time in ms (CUDA events): the integer-pipe roofline probe
+ * of SURVEY.md 8d.  variant 0 = fq_mul, 1 = fq_sqr, 2 = raw independent IMAD.WIDE stream */
+int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms);
+/* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
+uint64_t g753_launch_count(const g753_ctx* ctx);
+/* per-phase device times (ms) of the last g753_msm* call: digits, sort, accumulate, reduce,
+ * combine - CUDA events on the context stream; returns the number of phases written */
+int g753_last_msm_phases(const g753_ctx* ctx, float* ms, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G753_H */

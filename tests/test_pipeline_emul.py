@@ -1,0 +1,153 @@
+"""CPU-tier check of the kernel/orchestration logic through the C ABI, using the TEST-ONLY
+host-emulation build (tests/host_emul/capi_emul.cpp): digit recoding, counting sort, bucket
+bookkeeping, reduction levels, window fold and Stockham indexing versus the oracle.
+
+The same assertions run against the real library on a B200 in tests/test_gpu_parity.py.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import g753 as O
+from util753 import (FIELDS, G, GROUPS, array_field, field_array, ffi, ints_to_array, points_to_arrays,
+                     projective_to_point, sample_points, sample_scalars)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "capi_emul.cpp")
+LIB = os.path.join(HERE, "host_emul", "libg753_emul.so")
+CSRC = os.path.join(HERE, "..", "ginger-lib_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    deps = [SRC, os.path.join(HERE, "..", "include", "g753.h")] + [
+        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".cu", ".inc"))]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", LIB, SRC])
+    lib = ffi.Library(LIB)
+    c = G.Context(0, library=lib)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_msm_small(ctx, group):
+    C = GROUPS[group]
+    n = 24 if C.F.k == 1 else 10
+    pts = sample_points(C, n, 0xA0 + group)
+    sc = sample_scalars(C, n, 0xB0 + group)
+    # the special cases the reference branches on (variable_base.rs:36-57) plus signed-digit edges
+    pts[1] = None
+    sc[2] = 0
+    sc[3] = 1
+    sc[4] = C.r - 1
+    pts[6] = pts[5]
+    sc[6] = sc[5]
+    pts[7] = C.neg(pts[5])
+    sc[7] = sc[5]
+    sc[8] = (1 << 752) - 1 if (1 << 752) - 1 < C.r else C.r - 2
+    coords, inf = points_to_arrays(C, pts)
+    bases = ctx.upload_bases(group, coords, inf)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    # zip-truncation both ways + slice views (groth16/mod.rs:318-350)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc[:5]))
+    assert projective_to_point(C, got) == O.msm_naive(C, pts[:5], sc[:5])
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc), first=3)
+    assert projective_to_point(C, got) == O.msm_naive(C, pts[3:], sc)
+    # empty -> zero
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array([]))
+    assert projective_to_point(C, got) is None
+    # one-shot host form
+    got = G.VariableBaseMSM.multi_scalar_mul(coords, ints_to_array(sc + [5]), group=group, infinity=inf, ctx=ctx)
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    bases.free()
+
+
+def test_msm_window_sizes(ctx, monkeypatch):
+    """force several window widths through the same input (exercises multi-level reduction)"""
+    C = O.MNT4_G1
+    n = 40
+    pts = sample_points(C, n, 0x77)
+    sc = sample_scalars(C, n, 0x78)
+    coords, inf = points_to_arrays(C, pts)
+    want = O.msm_naive(C, pts, sc)
+    for c in (3, 7, 11):
+        monkeypatch.setenv("G753_MSM_C", str(c))
+        cx = G.Context(0, library=ctx.lib)
+        bases = cx.upload_bases(ffi.MNT4_G1, coords, inf)
+        got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+        assert projective_to_point(C, got) == want, c
+        bases.free()
+        cx.close()
+
+
+@pytest.mark.parametrize("field", sorted(FIELDS))
+def test_ntt_small(ctx, field):
+    F = FIELDS[field]
+    rng = O.SplitMix64(0xD0 + field)
+    for log_n in (0, 1, 2, 5, 7):
+        n = 1 << log_n
+        dom = G.EvaluationDomain.new(field, n, ctx=ctx)
+        ref = O.EvaluationDomain(F, n)
+        a = [O.random_field_element(rng, F) for _ in range(n)]
+        arr = field_array(F, a)
+        assert array_field(F, dom.fft(arr)) == ref.fft(a)
+        assert array_field(F, dom.ifft(arr)) == ref.ifft(a)
+        assert array_field(F, dom.coset_fft(arr)) == ref.coset_fft(a)
+        assert array_field(F, dom.coset_ifft(arr)) == ref.coset_ifft(a)
+    # short input zero-pads, long input truncates (domain.rs:121)
+    dom = G.EvaluationDomain.new(field, 6, ctx=ctx)
+    assert dom.size() == 8
+    ref = O.EvaluationDomain(F, 6)
+    a = [O.random_field_element(rng, F) for _ in range(11)]
+    assert array_field(F, dom.coset_fft(field_array(F, a[:5]))) == ref.coset_fft(a[:5])
+    assert array_field(F, dom.fft(field_array(F, a))) == ref.fft(a)
+
+
+def test_domain_new_none(ctx):
+    assert G.EvaluationDomain.new(ffi.FIELD_MNT6_FR, (1 << 14) + 1, ctx=ctx) is None
+    assert G.EvaluationDomain.new(ffi.FIELD_MNT6_FR, 1 << 14, ctx=ctx) is not None
+    assert G.EvaluationDomain.new(ffi.FIELD_MNT4_FR, (1 << 29) + 1, ctx=ctx) is None
+
+
+def test_device_vector_chain(ctx):
+    """ifft -> coset_fft -> pointwise -> coset_ifft chained on 'device' memory"""
+    F = O.MNT4_FR
+    field = ffi.FIELD_MNT4_FR
+    rng = O.SplitMix64(99)
+    n = 16
+    a = [O.random_field_element(rng, F) for _ in range(n)]
+    b = [O.random_field_element(rng, F) for _ in range(n)]
+    ref = O.EvaluationDomain(F, n)
+    va = G.DeviceVector(ctx, field, n, field_array(F, a))
+    vb = G.DeviceVector(ctx, field, n, field_array(F, b))
+    for v in (va, vb):
+        v.ntt(ffi.IFFT)
+        v.ntt(ffi.COSET_FFT)
+    va.op(ffi.OP_MUL, vb)
+    k = 12345
+    va.scale(ints_to_array([F.to_mont(k)]))
+    va.ntt(ffi.COSET_IFFT)
+    ea = ref.coset_fft(ref.ifft(a))
+    eb = ref.coset_fft(ref.ifft(b))
+    want = ref.coset_ifft([x * y * k % F.p for x, y in zip(ea, eb)])
+    assert array_field(F, va.download()) == want
+    va.free()
+    vb.free()
+
+
+def test_bad_arguments(ctx):
+    lib = ctx.lib
+    assert lib.ntt(ctx.handle, 5, None, 3, 0) != 0
+    assert lib.domain_check(0, 15) == ffi.ERR_DOMAIN
+    assert lib.domain_check(1, 29) == ffi.OK
+    assert lib.domain_check(1, 30) == ffi.ERR_DOMAIN
+    assert lib.group_coord_limbs(ffi.MNT6_G2) == 36
+    import ctypes
+    h = ctypes.c_void_p()
+    z = np.zeros((1, 24), dtype=np.uint64)
+    assert lib.bases_upload(ctx.handle, 9, ffi.ptr(z), None, 1, ctypes.byref(h)) == ffi.ERR_BAD_ARG
+    assert b"unknown group" in lib.last_error()
