@@ -156,6 +156,12 @@ __global__ void k_point_op(int op, const Affine<C>* a, const Affine<C>* b, const
   } else if (op == 1) {
     r = xyzz_from_affine<C>(*a);
     xyzz_dbl<C>(r);
+  } else if (op == 3) {  // 2a + 2b through the full (XYZZ + XYZZ) addition
+    r = xyzz_from_affine<C>(*a);
+    xyzz_dbl<C>(r);
+    Xyzz<C> s = xyzz_from_affine<C>(*b);
+    xyzz_dbl<C>(s);
+    xyzz_add<C>(r, s);
   } else {
     r = xyzz_scalar_mul<C>(*a, scalar);
   }
@@ -177,7 +183,7 @@ static int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_
   uint32_t* ds = cv.take<uint32_t>(NL);
   F* dout = cv.take<F>(3);
   G753_TRY(h2d(da, a, aff, ctx->stream));
-  if (op == 0) G753_TRY(h2d(db, b, aff, ctx->stream));
+  if (op == 0 || op == 3) G753_TRY(h2d(db, b, aff, ctx->stream));
   if (op == 2) G753_TRY(h2d(ds, b, 96, ctx->stream));
   G753_LAUNCH(k_point_op<C>, 1, 1, ctx->stream, op, da, db, ds, dout);
   ctx->launches++;
@@ -250,6 +256,21 @@ int g753_ctx_create(int device, g753_ctx** out) {
   e = cudaSetDevice(device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   G753_TRY(load_constants(device));
+  if (const char* sb = getenv("G753_STACK_BYTES")) {
+    size_t cur = 0;
+    cudaDeviceGetLimit(&cur, cudaLimitStackSize);
+    cudaError_t se = cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atol(sb));
+    size_t now = 0;
+    cudaDeviceGetLimit(&now, cudaLimitStackSize);
+    fprintf(stderr, "[g753] stack limit %zu -> %zu (%s)\n", cur, now, cudaGetErrorString(se));
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, (const void*)k_bucket_acc<CurveM4G2>) == cudaSuccess)
+      fprintf(stderr, "[g753] k_bucket_acc<M4G2> localSizeBytes=%zu regs=%d\n", fa.localSizeBytes, fa.numRegs);
+    if (cudaFuncGetAttributes(&fa, (const void*)k_reduce_level<CurveM4G2>) == cudaSuccess)
+      fprintf(stderr, "[g753] k_reduce_level<M4G2> localSizeBytes=%zu regs=%d\n", fa.localSizeBytes, fa.numRegs);
+    if (cudaFuncGetAttributes(&fa, (const void*)k_bucket_acc<CurveM4G1>) == cudaSuccess)
+      fprintf(stderr, "[g753] k_bucket_acc<M4G1> localSizeBytes=%zu regs=%d\n", fa.localSizeBytes, fa.numRegs);
+  }
 #endif
   g753_ctx* ctx = new (std::nothrow) g753_ctx();
   if (!ctx) return fail(G753_ERR_OOM, "host allocation failed");
@@ -599,6 +620,15 @@ int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iter
   dev_free(d_seed);
   return rc;
 #endif
+}
+
+int g753_debug_scratch(g753_ctx* ctx, void* h_dst, size_t bytes, size_t* cap) {
+  CHECK_CTX(ctx);
+  if (cap) *cap = ctx->scratch.cap;
+  if (!h_dst || bytes == 0) return G753_OK;
+  if (bytes > ctx->scratch.cap) bytes = ctx->scratch.cap;
+  G753_TRY(d2h(h_dst, ctx->scratch.ptr, bytes, ctx->stream));
+  return stream_sync(ctx->stream);
 }
 
 uint64_t g753_launch_count(const g753_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -51,6 +51,7 @@ SYMBOLS = [
     ("g753_field_op", _i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     ("g753_point_op", _i, [_vp, _i, _i, _vp, _vp, _vp]),
     ("g753_mac_probe", _i, [_vp, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float)]),
+    ("g753_debug_scratch", _i, [_vp, _vp, _sz, ctypes.POINTER(_sz)]),
     ("g753_launch_count", ctypes.c_uint64, [_vp]),
     ("g753_last_msm_phases", _i, [_vp, ctypes.POINTER(ctypes.c_float), _i]),
 ]

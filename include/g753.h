@@ -136,7 +136,8 @@ void* g753_stream(g753_ctx* ctx);
 /* out[i] = a[i] op b[i] over n host elements (b ignored for unary ops) */
 int g753_field_op(g753_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b,
                   uint64_t* out, size_t n);
-/* group-law test hook: op 0: out = a + b (affine + affine), 1: 2a, 2: scalar * a;
+/* group-law test hook: op 0: out = a + b (affine + affine), 1: 2a, 2: scalar * a,
+ * 3: 2a + 2b through the full projective addition;
  * a, b affine (2*k*12 limbs, (0,0) = infinity), scalar 12 limbs canonical, out projective */
 int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uint64_t* b,
                   uint64_t* out_xyz);
@@ -144,6 +145,8 @@ int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uin
  * threads and report the kernel time in ms (CUDA events): the integer-pipe roofline probe
  * of SURVEY.md 8d.  variant 0 = fq_mul, 1 = fq_sqr, 2 = raw independent IMAD.WIDE stream */
 int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms);
+/* debugging aid: copy the first `bytes` of the MSM workspace to the host; *cap = its size */
+int g753_debug_scratch(g753_ctx* ctx, void* h_dst, size_t bytes, size_t* cap);
 /* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
 uint64_t g753_launch_count(const g753_ctx* ctx);
 /* per-phase device times (ms) of the last g753_msm* call: digits, sort, accumulate, reduce,

@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI of libg753.so) against the oracle on a real B200.
+
+Small sizes are compared value-for-value with the Python oracle; the reference's own KATs are
+replayed through the device code; larger sizes use size-independent properties (see
+test_gpu_large.py for the 2^16+ cases checked against the C++ oracle).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import g753 as O
+from util753 import (FIELDS, G, GROUPS, array_field, array_to_ints, field_array, ffi, ints_to_array,
+                     points_to_arrays, projective_to_point, sample_points, sample_scalars)
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "reference_kat.json")))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = G.Context(0)           # raises if libg753.so or the GPU is missing: no CPU path
+    yield c
+    c.close()
+
+
+def field_op(ctx, field, op, a, b=None):
+    a = ints_to_array(a)
+    bb = ints_to_array(b) if b is not None else None
+    out = np.zeros_like(a)
+    ctx.lib.check(ctx.lib.field_op(ctx.handle, field, op, ffi.ptr(a), ffi.ptr(bb), ffi.ptr(out), a.shape[0]))
+    return array_to_ints(out)
+
+
+@pytest.mark.parametrize("field,key,F", [(0, "fields_mnt4753_tests", O.MNT4_FQ), (1, "fields_mnt6753_tests", O.MNT6_FQ)])
+def test_reference_field_kats_on_device(ctx, field, key, F):
+    """fields/mnt4753/tests.rs:605-650 (mul), :697-730 (square), :271-600 (add/sub) and the
+    mnt6753 twins, raw Montgomery limbs, through the device multiplier."""
+    t = KAT[key]["tests"]
+    a, b, c = [int(x["value"], 16) for x in t["test_fq_mul_assign"]]
+    assert field_op(ctx, field, ffi.OP_MUL, [a], [b]) == [c]
+    a, c = [int(x["value"], 16) for x in t["test_fq_squaring"]]
+    assert field_op(ctx, field, ffi.OP_SQR, [a]) == [F.to_mont(c)]
+    v = [int(x["value"], 16) for x in t["test_fq_add_assign"]]
+    assert field_op(ctx, field, ffi.OP_ADD, [v[4], v[9]], [v[5], v[10]]) == [v[6], v[11]]
+    v = [int(x["value"], 16) for x in t["test_fq_sub_assign"]]
+    assert field_op(ctx, field, ffi.OP_SUB, [v[0], v[3]], [v[1], v[4]]) == [v[2], v[5]]
+
+
+@pytest.mark.parametrize("field,F", [(0, O.MNT4_FQ), (1, O.MNT6_FQ)])
+def test_field_ops_random(ctx, field, F):
+    rng = O.SplitMix64(0x1234 + field)
+    p = F.p
+    edge = [0, 1, p - 1, p - 2, (p - 1) // 2, F.R, (1 << 752), p - (1 << 32)]
+    a = edge + [O.random_field_element(rng, F) for _ in range(2000)]
+    b = list(reversed(edge)) + [O.random_field_element(rng, F) for _ in range(2000)]
+    assert field_op(ctx, field, ffi.OP_MUL, a, b) == [F.mont_mul(x, y) for x, y in zip(a, b)]
+    assert field_op(ctx, field, ffi.OP_ADD, a, b) == [(x + y) % p for x, y in zip(a, b)]
+    assert field_op(ctx, field, ffi.OP_SUB, a, b) == [(x - y) % p for x, y in zip(a, b)]
+    assert field_op(ctx, field, ffi.OP_SQR, a) == [F.mont_mul(x, x) for x in a]
+    assert field_op(ctx, field, ffi.OP_TO_MONT, a) == [F.to_mont(x) for x in a]
+    assert field_op(ctx, field, ffi.OP_FROM_MONT, a) == [F.from_mont(x) for x in a]
+    inv = field_op(ctx, field, ffi.OP_INV, a[1:40])
+    assert inv == [F.to_mont(F.inv(F.from_mont(x))) for x in a[1:40]]
+
+
+CURVE_KATS = [
+    (ffi.MNT4_G1, "curves_mnt4753_tests", "g1"), (ffi.MNT4_G2, "curves_mnt4753_tests", "g2"),
+    (ffi.MNT6_G1, "curves_mnt6753_tests", "g1"), (ffi.MNT6_G2, "curves_mnt6753_tests", "g2"),
+]
+
+
+def point_op(ctx, group, op, A, B=None, scalar=None):
+    C = GROUPS[group]
+    ca, _ = points_to_arrays(C, [A])
+    if A is None:
+        ca[:] = 0
+    cb = None
+    if op in (0, 3):
+        cb, _ = points_to_arrays(C, [B])
+        if B is None:
+            cb[:] = 0
+    elif op == 2:
+        cb = ints_to_array([scalar])
+    out = np.zeros((3, C.F.k * 12), dtype=np.uint64)
+    ctx.lib.check(ctx.lib.point_op(ctx.handle, group, op, ffi.ptr(ca), ffi.ptr(cb), ffi.ptr(out)))
+    return projective_to_point(C, out)
+
+
+@pytest.mark.parametrize("group,key,g", CURVE_KATS)
+def test_reference_curve_kats_on_device(ctx, group, key, g):
+    """curves/mnt{4,6}753/tests.rs addition / doubling / scalar-multiplication KATs through the
+    device group law."""
+    C = GROUPS[group]
+    k = C.F.k
+    t = KAT[key]["tests"]
+
+    def coords(scope):
+        v = [int(x["value"], 16) for x in t[scope]]
+        return [tuple(v[i:i + k]) for i in range(0, len(v), k)]
+
+    x1, y1, z1, x2, y2, z2, ex, ey = coords("test_%s_addition_correctness" % g)
+    P, Q = C.from_projective(x1, y1, z1), C.from_projective(x2, y2, z2)
+    assert point_op(ctx, group, 0, P, Q) == (ex, ey)
+    x1, y1, z1, ex, ey = coords("test_%s_doubling_correctness" % g)
+    P = C.from_projective(x1, y1, z1)
+    assert point_op(ctx, group, 1, P) == (ex, ey)
+    assert point_op(ctx, group, 0, P, P) == (ex, ey)
+    assert point_op(ctx, group, 0, P, C.neg(P)) is None
+    assert point_op(ctx, group, 0, None, P) == P
+    assert point_op(ctx, group, 0, P, None) == P
+    # full (XYZZ + XYZZ) addition incl. its exceptional cases
+    assert point_op(ctx, group, 3, P, Q) == C.add(C.double(P), C.double(Q))
+    assert point_op(ctx, group, 3, P, P) == C.double(C.double(P))
+    assert point_op(ctx, group, 3, P, C.neg(P)) is None
+    assert point_op(ctx, group, 3, None, Q) == C.double(Q)
+    if g == "g1":
+        x, y, s, ex, ey = [int(v["value"], 16) for v in t["test_g1_scalar_multiplication"]]
+        assert point_op(ctx, group, 2, ((x,), (y,)), scalar=s) == ((ex,), (ey,))
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_msm_small_vs_oracle(ctx, group):
+    C = GROUPS[group]
+    n = 96 if C.F.k == 1 else 40
+    pts = sample_points(C, n, 0xA0 + group)
+    sc = sample_scalars(C, n, 0xB0 + group)
+    pts[1] = None
+    sc[2] = 0
+    sc[3] = 1
+    sc[4] = C.r - 1
+    pts[6], sc[6] = pts[5], sc[5]
+    pts[7], sc[7] = C.neg(pts[5]), sc[5]
+    sc[8] = 3
+    sc[9] = (1 << 752) - 1 if (1 << 752) - 1 < C.r else C.r - 2
+    coords, inf = points_to_arrays(C, pts)
+    bases = ctx.upload_bases(group, coords, inf)
+    arr = ints_to_array(sc)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, arr)
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, arr[:31])       # < 32 scalars (c = 3 in the reference)
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc[:31])
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, arr, first=5)   # bases.len() != scalars.len()
+    assert projective_to_point(C, got) == O.msm_naive(C, pts[5:], sc)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, arr[:0])
+    assert projective_to_point(C, got) is None
+    got = G.VariableBaseMSM.multi_scalar_mul(coords, arr, group=group, infinity=inf, ctx=ctx)
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    bases.free()
+
+
+def test_msm_linearity_2e14(ctx):
+    """size-independent property: msm(B, s) + msm(B, t) == msm(B, s + t mod r); bases are a
+    short list repeated, so the oracle answer is also computable directly."""
+    C = O.MNT4_G1
+    base_pts = sample_points(C, 8, 0x51)
+    n = 1 << 14
+    reps = n // 8
+    coords8, _ = points_to_arrays(C, base_pts)
+    coords = np.tile(coords8, (reps, 1))
+    rng = np.random.default_rng(7)
+    s = [int.from_bytes(rng.bytes(94), "little") % C.r for _ in range(n)]
+    t = [int.from_bytes(rng.bytes(94), "little") % C.r for _ in range(n)]
+    bases = ctx.upload_bases(ffi.MNT4_G1, coords)
+    r1 = projective_to_point(C, G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(s)))
+    r2 = projective_to_point(C, G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(t)))
+    r3 = projective_to_point(C, G.VariableBaseMSM.multi_scalar_mul(
+        bases, ints_to_array([(x + y) % C.r for x, y in zip(s, t)])))
+    assert C.add(r1, r2) == r3
+    # direct: sum over the 8 distinct points of (sum of their scalars mod r)
+    agg = [sum(s[j::8]) % C.r for j in range(8)]
+    assert r1 == O.msm_naive(C, base_pts, agg)
+    bases.free()
+
+
+@pytest.mark.parametrize("field", sorted(FIELDS))
+def test_ntt_vs_oracle(ctx, field):
+    F = FIELDS[field]
+    rng = O.SplitMix64(0xD0 + field)
+    for log_n in (0, 1, 4, 9):
+        n = 1 << log_n
+        dom = G.EvaluationDomain.new(field, n, ctx=ctx)
+        ref = O.EvaluationDomain(F, n)
+        a = [O.random_field_element(rng, F) for _ in range(n)]
+        arr = field_array(F, a)
+        assert array_field(F, dom.fft(arr)) == ref.fft(a)
+        assert array_field(F, dom.ifft(arr)) == ref.ifft(a)
+        assert array_field(F, dom.coset_fft(arr)) == ref.coset_fft(a)
+        assert array_field(F, dom.coset_ifft(arr)) == ref.coset_ifft(a)
+    dom = G.EvaluationDomain.new(field, 100, ctx=ctx)      # ragged: pads to 128
+    ref = O.EvaluationDomain(F, 100)
+    a = [O.random_field_element(rng, F) for _ in range(100)]
+    assert dom.size() == 128
+    assert array_field(F, dom.fft(field_array(F, a))) == ref.fft(a)
+
+
+def test_ntt_max_size_mnt6_fr(ctx):
+    """mnt6753::Fr tops out at 2^14: bit-exact round trip + spot evaluation"""
+    F = O.MNT6_FR
+    field = ffi.FIELD_MNT6_FR
+    n = 1 << 14
+    assert G.EvaluationDomain.new(field, n + 1, ctx=ctx) is None
+    dom = G.EvaluationDomain.new(field, n, ctx=ctx)
+    rng = np.random.default_rng(3)
+    a = [int.from_bytes(rng.bytes(94), "little") % F.p for _ in range(n)]
+    arr = field_array(F, a)
+    ev = dom.fft(arr)
+    assert np.array_equal(dom.ifft(ev), arr)
+    ref = O.EvaluationDomain(F, n)
+    evi = array_field(F, ev)
+    for i in (0, 1, 5, n // 2, n - 1):
+        x = pow(ref.group_gen, i, F.p)
+        acc = 0
+        for c in reversed(a):
+            acc = (acc * x + c) % F.p
+        assert evi[i] == acc
+    cev = dom.coset_fft(arr)
+    assert np.array_equal(dom.coset_ifft(cev), arr)
+
+
+def test_ntt_large_properties(ctx):
+    """2^20 on mnt4753::Fr (BASELINE config 2): round trips, linearity and Horner spot checks"""
+    F = O.MNT4_FR
+    field = ffi.FIELD_MNT4_FR
+    n = 1 << 20
+    dom = G.EvaluationDomain.new(field, n, ctx=ctx)
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 1 << 63, size=(n, 12), dtype=np.uint64)
+    raw[:, 11] &= np.uint64(0xFFFF)             # < 2^752 < p : valid Montgomery representations
+    ev = dom.fft(raw)
+    assert np.array_equal(dom.ifft(ev), raw)
+    cev = dom.coset_fft(raw)
+    assert np.array_equal(dom.coset_ifft(cev), raw)
+    ref = O.EvaluationDomain(F, n)
+    coeffs = array_field(F, raw)
+    evi = array_field(F, ev[:4])
+    cevi = array_field(F, cev[:4])
+    for i in (0, 1, 3):
+        for vals, shift in ((evi, 1), (cevi, ref.generator)):
+            x = shift * pow(ref.group_gen, i, F.p) % F.p
+            acc = 0
+            for c in reversed(coeffs):
+                acc = (acc * x + c) % F.p
+            assert vals[i] == acc
