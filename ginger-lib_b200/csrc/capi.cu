@@ -3,127 +3,46 @@
 // Built two ways: nvcc for sm_100a (the product) and, with G753_HOST_EMUL, by g++ into a
 // test-only library that runs the barrier-free kernels sequentially on the host so that
 // indexing and orchestration can be checked without a GPU (tests/host_emul).
-#include <map>
-#include <mutex>
-#include <new>
-#include <vector>
-
-#include "device.cuh"
-#include "ec.cuh"
-#include "msm.cuh"
-#include "ntt.cuh"
-
-namespace g753 {
-#if !defined(G753_HOST_EMUL)
-thread_local char g_last_error[512] = "";
+#include "ctx.cuh"
+#if defined(G753_HOST_EMUL)
+#include "msm_impl.cuh"  // the test-only host build is a single translation unit
+G753_INSTANTIATE_GROUP(0)
+G753_INSTANTIATE_GROUP(1)
+G753_INSTANTIATE_GROUP(2)
+G753_INSTANTIATE_GROUP(3)
 #else
-static thread_local char g_last_error[512] = "";
-#endif
-static int fail(int code, const char* msg) {
-  snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
-  return code;
+namespace g753 {
+thread_local char g_last_error[512] = "";
 }
-}  // namespace g753
+#endif
 
 using namespace g753;
 
-enum { MSM_PHASES = 5 };
-
-struct g753_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  Scratch scratch;      // MSM workspace
-  Scratch scratch_io;   // host-API staging (scalars / NTT ping-pong)
-  std::map<unsigned, NttTables> tables[2];  // per field, keyed by log_n
-  uint64_t launches = 0;
-  float phase_ms[MSM_PHASES] = {0, 0, 0, 0, 0};
-  int forced_c = 0;
-  std::mutex mu;
-#if !defined(G753_HOST_EMUL)
-  cudaEvent_t ev[MSM_PHASES + 1];
-  bool ev_ok = false;
-#endif
-};
-
-struct g753_bases {
-  int group = 0;
-  size_t n = 0;
-  void* d_points = nullptr;
-  uint8_t* d_inf = nullptr;
-};
-
-static int group_k(int group) {
-  switch (group) {
-    case G753_MNT4_G1: return 1;
-    case G753_MNT4_G2: return 2;
-    case G753_MNT6_G1: return 1;
-    case G753_MNT6_G2: return 3;
-    default: return 0;
+// zero the coordinates of bases flagged infinite so that (0, 0) is the only encoding the
+// accumulation kernels ever see (their digits are dropped in k_msm_digits as well)
+__global__ void k_bases_sanitize(Fq* __restrict__ bases, const uint8_t* __restrict__ inf, unsigned n,
+                                 unsigned fq_per_point) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (inf[i]) {
+    Fq z;
+    for (int k = 0; k < NL; k++) z.l[k] = 0;
+    for (unsigned k = 0; k < fq_per_point; k++) bases[(size_t)i * fq_per_point + k] = z;
   }
 }
-
-#if !defined(G753_HOST_EMUL)
-static int use_device(g753_ctx* ctx) {
-  cudaError_t e = cudaSetDevice(ctx->device);
-  return e == cudaSuccess ? G753_OK : cuda_fail(e, "cudaSetDevice");
-}
-static void phase_mark(void* user, int phase) {
-  g753_ctx* ctx = (g753_ctx*)user;
-  if (ctx->ev_ok && phase <= MSM_PHASES) cudaEventRecord(ctx->ev[phase], ctx->stream);
-}
-static bool g_consts_loaded[64] = {false};
-static int load_constants(int device) {
-  if (device < 64 && g_consts_loaded[device]) return G753_OK;
-  cudaError_t e = cudaMemcpyToSymbol(d_fc, G753_FIELD_CONSTANTS, sizeof(G753_FIELD_CONSTANTS));
-  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyToSymbol(field constants)");
-  if (device < 64) g_consts_loaded[device] = true;
-  return G753_OK;
-}
-#else
-static int use_device(g753_ctx*) { return G753_OK; }
-#endif
-
-#define CHECK_CTX(ctx)                                              \
-  do {                                                              \
-    if (!(ctx)) return fail(G753_ERR_BAD_ARG, "null context");      \
-    G753_TRY(use_device(ctx));                                      \
-  } while (0)
 
 // ------------------------------------------------------------------------------------
 // dispatch helpers
 // ------------------------------------------------------------------------------------
-template <class C>
-static int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
-                        const uint32_t* d_scalars, void* d_out) {
-  MsmHooks hooks;
-  hooks.launches = &ctx->launches;
-#if !defined(G753_HOST_EMUL)
-  hooks.mark = phase_mark;
-  hooks.user = ctx;
-#endif
-  const Affine<C>* pts = (const Affine<C>*)b->d_points + first;
-  const uint8_t* inf = b->d_inf ? b->d_inf + first : nullptr;
-  int rc = msm_run<C>(ctx->scratch, ctx->stream, pts, inf, d_scalars, count, (typename C::F*)d_out,
-                      ctx->forced_c, hooks);
-  return rc;
-}
-
 static int msm_any(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
                    const uint32_t* d_scalars, void* d_out) {
   switch (b->group) {
-    case G753_MNT4_G1: return msm_dispatch<CurveM4G1>(ctx, b, first, count, d_scalars, d_out);
-    case G753_MNT4_G2: return msm_dispatch<CurveM4G2>(ctx, b, first, count, d_scalars, d_out);
-    case G753_MNT6_G1: return msm_dispatch<CurveM6G1>(ctx, b, first, count, d_scalars, d_out);
-    case G753_MNT6_G2: return msm_dispatch<CurveM6G2>(ctx, b, first, count, d_scalars, d_out);
+    case G753_MNT4_G1: return msm_dispatch<0>(ctx, b, first, count, d_scalars, d_out);
+    case G753_MNT4_G2: return msm_dispatch<1>(ctx, b, first, count, d_scalars, d_out);
+    case G753_MNT6_G1: return msm_dispatch<2>(ctx, b, first, count, d_scalars, d_out);
+    case G753_MNT6_G2: return msm_dispatch<3>(ctx, b, first, count, d_scalars, d_out);
   }
   return fail(G753_ERR_BAD_ARG, "unknown group");
-}
-
-template <class C>
-static void sanitize_launch(g753_ctx* ctx, g753_bases* b) {
-  G753_LAUNCH(k_bases_sanitize<C>, div_up(b->n, 256), 256, ctx->stream, (Affine<C>*)b->d_points, b->d_inf,
-              (unsigned)b->n);
-  ctx->launches++;
 }
 
 template <int FID>
@@ -145,53 +64,6 @@ static int ntt_field(g753_ctx* ctx, Fq* d_data, Fq* d_tmp, unsigned log_n, int m
 // ------------------------------------------------------------------------------------
 // test kernels: group law / field ops through the real device code
 // ------------------------------------------------------------------------------------
-template <class C>
-__global__ void k_point_op(int op, const Affine<C>* a, const Affine<C>* b, const uint32_t* scalar,
-                           typename C::F* out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Xyzz<C> r;
-  if (op == 0) {
-    r = xyzz_from_affine<C>(*a);
-    xyzz_madd<C>(r, *b);
-  } else if (op == 1) {
-    r = xyzz_from_affine<C>(*a);
-    xyzz_dbl<C>(r);
-  } else if (op == 3) {  // 2a + 2b through the full (XYZZ + XYZZ) addition
-    r = xyzz_from_affine<C>(*a);
-    xyzz_dbl<C>(r);
-    Xyzz<C> s = xyzz_from_affine<C>(*b);
-    xyzz_dbl<C>(s);
-    xyzz_add<C>(r, s);
-  } else {
-    r = xyzz_scalar_mul<C>(*a, scalar);
-  }
-  typename C::F X, Y, Z;
-  xyzz_to_projective<C>(r, X, Y, Z);
-  out[0] = X;
-  out[1] = Y;
-  out[2] = Z;
-}
-
-template <class C>
-static int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
-  typedef typename C::F F;
-  const size_t aff = sizeof(Affine<C>), prj = 3 * sizeof(F);
-  G753_TRY(ctx->scratch_io.reserve(2 * aff + 96 + prj + 1024));
-  Carver cv(ctx->scratch_io.ptr);
-  Affine<C>* da = cv.take<Affine<C>>(1);
-  Affine<C>* db = cv.take<Affine<C>>(1);
-  uint32_t* ds = cv.take<uint32_t>(NL);
-  F* dout = cv.take<F>(3);
-  G753_TRY(h2d(da, a, aff, ctx->stream));
-  if (op == 0 || op == 3) G753_TRY(h2d(db, b, aff, ctx->stream));
-  if (op == 2) G753_TRY(h2d(ds, b, 96, ctx->stream));
-  G753_LAUNCH(k_point_op<C>, 1, 1, ctx->stream, op, da, db, ds, dout);
-  ctx->launches++;
-  G753_TRY(launch_check("k_point_op"));
-  G753_TRY(d2h(out, dout, prj, ctx->stream));
-  return stream_sync(ctx->stream);
-}
-
 #if !defined(G753_HOST_EMUL)
 // integer-pipe roofline probe: dependent Montgomery products per thread
 template <int VARIANT>
@@ -255,22 +127,6 @@ int g753_ctx_create(int device, g753_ctx** out) {
   if (device < 0 || device >= count) return fail(G753_ERR_BAD_ARG, "device index out of range");
   e = cudaSetDevice(device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-  G753_TRY(load_constants(device));
-  if (const char* sb = getenv("G753_STACK_BYTES")) {
-    size_t cur = 0;
-    cudaDeviceGetLimit(&cur, cudaLimitStackSize);
-    cudaError_t se = cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atol(sb));
-    size_t now = 0;
-    cudaDeviceGetLimit(&now, cudaLimitStackSize);
-    fprintf(stderr, "[g753] stack limit %zu -> %zu (%s)\n", cur, now, cudaGetErrorString(se));
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, (const void*)k_bucket_acc<CurveM4G2>) == cudaSuccess)
-      fprintf(stderr, "[g753] k_bucket_acc<M4G2> localSizeBytes=%zu regs=%d\n", fa.localSizeBytes, fa.numRegs);
-    if (cudaFuncGetAttributes(&fa, (const void*)k_reduce_level<CurveM4G2>) == cudaSuccess)
-      fprintf(stderr, "[g753] k_reduce_level<M4G2> localSizeBytes=%zu regs=%d\n", fa.localSizeBytes, fa.numRegs);
-    if (cudaFuncGetAttributes(&fa, (const void*)k_bucket_acc<CurveM4G1>) == cudaSuccess)
-      fprintf(stderr, "[g753] k_bucket_acc<M4G1> localSizeBytes=%zu regs=%d\n", fa.localSizeBytes, fa.numRegs);
-  }
 #endif
   g753_ctx* ctx = new (std::nothrow) g753_ctx();
   if (!ctx) return fail(G753_ERR_OOM, "host allocation failed");
@@ -331,12 +187,9 @@ int g753_bases_upload(g753_ctx* ctx, int group, const uint64_t* coords, const ui
     rc = dev_alloc((void**)&b->d_inf, n);
     if (rc == G753_OK) rc = h2d(b->d_inf, infinity, n, ctx->stream);
     if (rc == G753_OK) {
-      switch (group) {
-        case G753_MNT4_G1: sanitize_launch<CurveM4G1>(ctx, b); break;
-        case G753_MNT4_G2: sanitize_launch<CurveM4G2>(ctx, b); break;
-        case G753_MNT6_G1: sanitize_launch<CurveM6G1>(ctx, b); break;
-        case G753_MNT6_G2: sanitize_launch<CurveM6G2>(ctx, b); break;
-      }
+      G753_LAUNCH(k_bases_sanitize, div_up(n, 256), 256, ctx->stream, (Fq*)b->d_points, b->d_inf, (unsigned)n,
+                  (unsigned)(2 * k));
+      ctx->launches++;
       rc = launch_check("k_bases_sanitize");
     }
   }
@@ -429,18 +282,10 @@ int g753_points_sum_dev(g753_ctx* ctx, int group, const void* d_points_xyz, size
   if (!d_points_xyz || !d_out_xyz || count > 0xffffffffull) return fail(G753_ERR_BAD_ARG, "bad argument");
   std::lock_guard<std::mutex> lock(ctx->mu);
   switch (group) {
-    case G753_MNT4_G1:
-      G753_LAUNCH(k_points_sum<CurveM4G1>, 1, 1, ctx->stream, (const FqM4*)d_points_xyz, (unsigned)count, (FqM4*)d_out_xyz);
-      break;
-    case G753_MNT4_G2:
-      G753_LAUNCH(k_points_sum<CurveM4G2>, 1, 1, ctx->stream, (const Fq2M4*)d_points_xyz, (unsigned)count, (Fq2M4*)d_out_xyz);
-      break;
-    case G753_MNT6_G1:
-      G753_LAUNCH(k_points_sum<CurveM6G1>, 1, 1, ctx->stream, (const FqM6*)d_points_xyz, (unsigned)count, (FqM6*)d_out_xyz);
-      break;
-    case G753_MNT6_G2:
-      G753_LAUNCH(k_points_sum<CurveM6G2>, 1, 1, ctx->stream, (const Fq3M6*)d_points_xyz, (unsigned)count, (Fq3M6*)d_out_xyz);
-      break;
+    case G753_MNT4_G1: points_sum_launch<0>(ctx, d_points_xyz, count, d_out_xyz); break;
+    case G753_MNT4_G2: points_sum_launch<1>(ctx, d_points_xyz, count, d_out_xyz); break;
+    case G753_MNT6_G1: points_sum_launch<2>(ctx, d_points_xyz, count, d_out_xyz); break;
+    case G753_MNT6_G2: points_sum_launch<3>(ctx, d_points_xyz, count, d_out_xyz); break;
     default: return fail(G753_ERR_BAD_ARG, "unknown group");
   }
   ctx->launches++;
@@ -575,10 +420,10 @@ int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uin
   if (!a || !out_xyz || (op != 1 && !b)) return fail(G753_ERR_BAD_ARG, "null pointer");
   std::lock_guard<std::mutex> lock(ctx->mu);
   switch (group) {
-    case G753_MNT4_G1: return point_op_impl<CurveM4G1>(ctx, op, a, b, out_xyz);
-    case G753_MNT4_G2: return point_op_impl<CurveM4G2>(ctx, op, a, b, out_xyz);
-    case G753_MNT6_G1: return point_op_impl<CurveM6G1>(ctx, op, a, b, out_xyz);
-    case G753_MNT6_G2: return point_op_impl<CurveM6G2>(ctx, op, a, b, out_xyz);
+    case G753_MNT4_G1: return point_op_impl<0>(ctx, op, a, b, out_xyz);
+    case G753_MNT4_G2: return point_op_impl<1>(ctx, op, a, b, out_xyz);
+    case G753_MNT6_G1: return point_op_impl<2>(ctx, op, a, b, out_xyz);
+    case G753_MNT6_G2: return point_op_impl<3>(ctx, op, a, b, out_xyz);
   }
   return fail(G753_ERR_BAD_ARG, "unknown group");
 }

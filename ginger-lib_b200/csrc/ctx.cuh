@@ -1,0 +1,85 @@
+// Context / handle definitions shared by the translation units of libg753.so.
+#pragma once
+#include <map>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "device.cuh"
+#include "ntt.cuh"
+
+namespace g753 {
+#if defined(G753_HOST_EMUL)
+static thread_local char g_last_error[512] = "";
+#endif
+static inline int fail(int code, const char* msg) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
+  return code;
+}
+}  // namespace g753
+
+using namespace g753;
+
+enum { MSM_PHASES = 5 };
+
+struct g753_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Scratch scratch;      // MSM workspace
+  Scratch scratch_io;   // host-API staging (scalars / NTT ping-pong)
+  std::map<unsigned, NttTables> tables[2];  // per field, keyed by log_n
+  uint64_t launches = 0;
+  float phase_ms[MSM_PHASES] = {0, 0, 0, 0, 0};
+  int forced_c = 0;
+  std::mutex mu;
+#if !defined(G753_HOST_EMUL)
+  cudaEvent_t ev[MSM_PHASES + 1];
+  bool ev_ok = false;
+#endif
+};
+
+struct g753_bases {
+  int group = 0;
+  size_t n = 0;
+  void* d_points = nullptr;
+  uint8_t* d_inf = nullptr;
+};
+
+static int group_k(int group) {
+  switch (group) {
+    case G753_MNT4_G1: return 1;
+    case G753_MNT4_G2: return 2;
+    case G753_MNT6_G1: return 1;
+    case G753_MNT6_G2: return 3;
+    default: return 0;
+  }
+}
+
+#if !defined(G753_HOST_EMUL)
+static inline int use_device(g753_ctx* ctx) {
+  cudaError_t e = cudaSetDevice(ctx->device);
+  return e == cudaSuccess ? G753_OK : cuda_fail(e, "cudaSetDevice");
+}
+static inline void phase_mark(void* user, int phase) {
+  g753_ctx* ctx = (g753_ctx*)user;
+  if (ctx->ev_ok && phase <= MSM_PHASES) cudaEventRecord(ctx->ev[phase], ctx->stream);
+}
+#else
+static inline int use_device(g753_ctx*) { return G753_OK; }
+#endif
+
+#define CHECK_CTX(ctx)                                              \
+  do {                                                              \
+    if (!(ctx)) return fail(G753_ERR_BAD_ARG, "null context");      \
+    G753_TRY(use_device(ctx));                                      \
+  } while (0)
+
+
+// per-group entry points (one translation unit per group: msm_g0.cu .. msm_g3.cu)
+template <int GID>
+int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, const uint32_t* d_scalars,
+                 void* d_out);
+template <int GID>
+int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out);
+template <int GID>
+void points_sum_launch(g753_ctx* ctx, const void* d_pts, size_t count, void* d_out);

@@ -29,6 +29,9 @@ static thread_local EmulDim blockIdx, threadIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __restrict__
 typedef void* cudaStream_t;
+struct alignas(16) uint4 {
+  unsigned x, y, z, w;
+};
 template <class T>
 static inline T atomicAdd(T* p, T v) {
   T old = *p;
@@ -51,6 +54,7 @@ static inline unsigned __brev(unsigned x) {
         kernel(__VA_ARGS__);                                                \
       }                                                                     \
   } while (0)
+#define G753_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) G753_LAUNCH(kernel, grid, block, stream, __VA_ARGS__)
 namespace g753 {
 static inline int dev_alloc(void** p, size_t bytes) {
   *p = malloc(bytes ? bytes : 1);
@@ -81,6 +85,12 @@ static inline int launch_check(const char*) { return G753_OK; }
 #include <cuda_runtime.h>
 #define G753_LAUNCH(kernel, grid, block, stream, ...) \
   kernel<<<(unsigned)(grid), (unsigned)(block), 0, (stream)>>>(__VA_ARGS__)
+// launch with `smem` bytes of dynamic shared memory (opt-in above 48 KB)
+#define G753_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                                        \
+  do {                                                                                                  \
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));             \
+    kernel<<<(unsigned)(grid), (unsigned)(block), (size_t)(smem), (stream)>>>(__VA_ARGS__);             \
+  } while (0)
 namespace g753 {
 extern thread_local char g_last_error[512];
 static inline int cuda_fail(cudaError_t e, const char* what) {

@@ -1,0 +1,292 @@
+// Short-Weierstrass group law in XYZZ coordinates on shared-memory slots (see slots.cuh).
+//
+// Replaces (reference, relative to /root/reference/algebra/src):
+//   curves/models/short_weierstrass_projective.rs:481-519  add_assign_mixed -> EcS::madd_g
+//   curves/models/short_weierstrass_projective.rs:444-479  double_in_place  -> EcS::dbl
+//   curves/models/short_weierstrass_projective.rs:574-617  AddAssign        -> EcS::add / add_g
+// The reference's formulas are homogeneous-projective (madd-1998-cmo, dbl-2007-bl,
+// add-1998-cmo-2); XYZZ (x = X/ZZ, y = Y/ZZZ) computes the same group element in 8M+2S /
+// 12M+2S and converts to the reference's (X:Y:Z) layout once at the end.  Unlike the
+// reference's mixed addition, P + (-P) and P + P are both handled explicitly.
+//
+// A point occupies 4 tower elements = 4K slots in the order X, Y, ZZ, ZZZ; infinity <=> ZZ == 0.
+// `W` is the first scratch slot: madd_g / mdbl_g need 4K + NTMP, add / add_g / dbl need
+// 5K + NTMP scratch slots.
+#pragma once
+#include "slots.cuh"
+
+namespace g753 {
+
+// curve descriptors on slots: tower type + multiplication by the curve coefficient a
+template <int T>
+struct SCurveM4G1 {
+  typedef Tw1<0, T> M;
+  static constexpr int ID = 0;
+  static G753_D void mul_by_a(int d, int a) { s_dbl<0, T>(d, a); }  // a = 2 (curves/mnt4753/g1.rs:18-33)
+};
+template <int T>
+struct SCurveM4G2 {
+  typedef Tw2<0, T, 13> M;
+  static constexpr int ID = 1;
+  // twist a' = (26, 0), coefficient-wise (curves/mnt4753/g2.rs:112-118)
+  static G753_D void mul_by_a(int d, int a) {
+    s_mul_small<0, T, 26>(d, a);
+    s_mul_small<0, T, 26>(d + 1, a + 1);
+  }
+};
+template <int T>
+struct SCurveM6G1 {
+  typedef Tw1<1, T> M;
+  static constexpr int ID = 2;
+  static G753_D void mul_by_a(int d, int a) { s_mul_small<1, T, 11>(d, a); }  // a = 11 (curves/mnt6753/g1.rs:18-33)
+};
+template <int T>
+struct SCurveM6G2 {
+  typedef Tw3<1, T, 11> M;
+  static constexpr int ID = 3;
+  // twist a' = 11 u^2: (c0, c1, c2) -> (121 c1, 121 c2, 11 c0) (curves/mnt6753/g2.rs:148-155); d != a
+  static G753_D void mul_by_a(int d, int a) {
+    s_mul_small<1, T, 121>(d, a + 1);
+    s_mul_small<1, T, 121>(d + 1, a + 2);
+    s_mul_small<1, T, 11>(d + 2, a);
+  }
+};
+
+template <class SC>
+struct EcS {
+  typedef typename SC::M M;
+  static constexpr int K = M::K;
+  static constexpr int PT = 4 * K;                      // slots per XYZZ point
+  static constexpr int MADD_SCRATCH = 4 * K + M::NTMP;  // scratch slots of madd_g / mdbl_g
+  static constexpr int ADD_SCRATCH = 5 * K + M::NTMP;   // scratch slots of add / add_g / dbl
+
+  static G753_D bool is_inf(int P) { return M::is_zero(P + 2 * K); }
+  static G753_D void set_inf(int P) {
+    M::set_zero(P);
+    M::set_one(P + K);
+    M::set_zero(P + 2 * K);
+    M::set_zero(P + 3 * K);
+  }
+  static G753_D void copy(int D, int P) {
+    for (int i = 0; i < 4; i++) M::copy(D + i * K, P + i * K);
+  }
+  static G753_D void ldg(int P, const Fq* g) {
+    for (int i = 0; i < 4; i++) M::ldg(P + i * K, g + i * K);
+  }
+  static G753_D void stg(Fq* g, int P) {
+    for (int i = 0; i < 4; i++) M::stg(g + i * K, P + i * K);
+  }
+
+  // P = 2 * (+-q), q affine (x, y) in global memory, finite: mdbl-2008-s-1 with general a
+  static G753_NI void mdbl_g(int P, const Fq* q, bool negq, int W) {
+    const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, tt = W + 4 * K;
+    M::ldg(t0, q + K);
+    if (negq) M::neg(t0, t0);  // y
+    M::dbl(t1, t0);            // U = 2y
+    if (M::is_zero(t1)) {
+      set_inf(P);
+      return;
+    }
+    M::sqr(ZZ, t1, tt);        // V
+    M::mul(ZZZ, t1, ZZ, tt);   // W
+    M::ldg(t1, q);             // x
+    M::mul(t2, t1, ZZ, tt);    // S = x V
+    M::sqr(t1, t1, tt);        // x^2
+    M::dbl(t3, t1);
+    M::add(t1, t3, t1);        // 3 x^2
+    M::set_one(X);
+    SC::mul_by_a(t3, X);       // a
+    M::add(t1, t1, t3);        // M = 3 x^2 + a
+    M::sqr(X, t1, tt);
+    M::dbl(t3, t2);
+    M::sub(X, X, t3);          // X3 = M^2 - 2S
+    M::sub(t2, t2, X);
+    M::mul(t2, t1, t2, tt);    // M (S - X3)
+    M::mul(t3, ZZZ, t0, tt);   // W y
+    M::sub(Y, t2, t3);
+  }
+
+  // P += (+-q), q affine in global memory, finite: madd-2008-s, 8M + 2S
+  static G753_NI void madd_g(int P, const Fq* q, bool negq, int W) {
+    const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, tt = W + 4 * K;
+    if (M::is_zero(ZZ)) {
+      M::ldg(X, q);
+      M::ldg(Y, q + K);
+      if (negq) M::neg(Y, Y);
+      M::set_one(ZZ);
+      M::set_one(ZZZ);
+      return;
+    }
+    M::ldg(t0, q);
+    M::mul(t0, t0, ZZ, tt);
+    M::sub(t0, t0, X);         // P = x2 ZZ1 - X1
+    M::ldg(t1, q + K);
+    M::mul(t1, t1, ZZZ, tt);
+    if (negq) {
+      M::add(t1, t1, Y);
+      M::neg(t1, t1);          // R = -(y2 ZZZ1) - Y1
+    } else {
+      M::sub(t1, t1, Y);       // R = y2 ZZZ1 - Y1
+    }
+    if (M::is_zero(t0)) {
+      if (M::is_zero(t1)) mdbl_g(P, q, negq, W);
+      else set_inf(P);
+      return;
+    }
+    M::sqr(t2, t0, tt);        // PP
+    M::mul(t0, t0, t2, tt);    // PPP
+    M::mul(t3, X, t2, tt);     // Q = X1 PP
+    M::mul(ZZ, ZZ, t2, tt);
+    M::mul(ZZZ, ZZZ, t0, tt);
+    M::sqr(X, t1, tt);
+    M::sub(X, X, t0);
+    M::dbl(t2, t3);
+    M::sub(X, X, t2);          // X3 = R^2 - PPP - 2Q
+    M::mul(t2, Y, t0, tt);     // Y1 PPP
+    M::sub(t3, t3, X);
+    M::mul(Y, t1, t3, tt);
+    M::sub(Y, Y, t2);          // Y3 = R (Q - X3) - Y1 PPP
+  }
+
+  // P = 2P: dbl-2008-s-1
+  static G753_NI void dbl(int P, int W) {
+    const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, t4 = W + 4 * K, tt = W + 5 * K;
+    if (M::is_zero(ZZ)) return;
+    M::dbl(t0, Y);             // U = 2 Y1
+    if (M::is_zero(t0)) {
+      set_inf(P);
+      return;
+    }
+    M::sqr(t1, t0, tt);        // V
+    M::mul(t0, t0, t1, tt);    // W
+    M::mul(t2, X, t1, tt);     // S = X1 V
+    M::sqr(t3, ZZ, tt);
+    SC::mul_by_a(t4, t3);      // a ZZ1^2
+    M::sqr(t3, X, tt);
+    M::add(t4, t4, t3);
+    M::dbl(t3, t3);
+    M::add(t3, t3, t4);        // M = 3 X1^2 + a ZZ1^2
+    M::mul(ZZ, ZZ, t1, tt);
+    M::mul(ZZZ, ZZZ, t0, tt);
+    M::sqr(X, t3, tt);
+    M::dbl(t4, t2);
+    M::sub(X, X, t4);          // X3 = M^2 - 2S
+    M::sub(t2, t2, X);
+    M::mul(t2, t3, t2, tt);    // M (S - X3)
+    M::mul(t4, t0, Y, tt);     // W Y1
+    M::sub(Y, t2, t4);
+  }
+
+  // P += Q (both on slots, Q preserved): add-2008-s, 12M + 2S
+  static G753_NI void add(int P, int Q, int W) {
+    const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, t4 = W + 4 * K, tt = W + 5 * K;
+    if (M::is_zero(Q + 2 * K)) return;
+    if (M::is_zero(ZZ)) {
+      copy(P, Q);
+      return;
+    }
+    M::mul(t0, X, Q + 2 * K, tt);   // U1 = X1 ZZ2
+    M::mul(t1, Y, Q + 3 * K, tt);   // S1 = Y1 ZZZ2
+    M::mul(t2, Q, ZZ, tt);
+    M::sub(t2, t2, t0);             // P = X2 ZZ1 - U1
+    M::mul(t3, Q + K, ZZZ, tt);
+    M::sub(t3, t3, t1);             // R = Y2 ZZZ1 - S1
+    if (M::is_zero(t2)) {
+      if (M::is_zero(t3)) dbl(P, W);
+      else set_inf(P);
+      return;
+    }
+    M::sqr(t4, t2, tt);             // PP
+    M::mul(t2, t2, t4, tt);         // PPP
+    M::mul(t0, t0, t4, tt);         // Q = U1 PP
+    M::mul(ZZ, ZZ, Q + 2 * K, tt);
+    M::mul(ZZ, ZZ, t4, tt);
+    M::mul(ZZZ, ZZZ, Q + 3 * K, tt);
+    M::mul(ZZZ, ZZZ, t2, tt);
+    M::sqr(X, t3, tt);
+    M::sub(X, X, t2);
+    M::dbl(t4, t0);
+    M::sub(X, X, t4);               // X3 = R^2 - PPP - 2Q
+    M::mul(t4, t1, t2, tt);         // S1 PPP
+    M::sub(t0, t0, X);
+    M::mul(Y, t3, t0, tt);
+    M::sub(Y, Y, t4);
+  }
+
+  // P += q, q an XYZZ point in global memory (4K Fq, order X, Y, ZZ, ZZZ)
+  static G753_NI void add_g(int P, const Fq* q, int W) {
+    const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, t4 = W + 4 * K, tt = W + 5 * K;
+    M::ldg(t4, q + 2 * K);          // ZZ2
+    if (M::is_zero(t4)) return;
+    if (M::is_zero(ZZ)) {
+      ldg(P, q);
+      return;
+    }
+    M::mul(t0, X, t4, tt);          // U1 = X1 ZZ2
+    M::ldg(t2, q);
+    M::mul(t2, t2, ZZ, tt);
+    M::sub(t2, t2, t0);             // P = X2 ZZ1 - U1
+    M::ldg(t3, q + 3 * K);          // ZZZ2
+    M::mul(t1, Y, t3, tt);          // S1 = Y1 ZZZ2
+    M::ldg(t3, q + K);
+    M::mul(t3, t3, ZZZ, tt);
+    M::sub(t3, t3, t1);             // R = Y2 ZZZ1 - S1
+    if (M::is_zero(t2)) {
+      if (M::is_zero(t3)) dbl(P, W);
+      else set_inf(P);
+      return;
+    }
+    M::mul(ZZ, ZZ, t4, tt);         // ZZ1 ZZ2
+    M::ldg(t4, q + 3 * K);
+    M::mul(ZZZ, ZZZ, t4, tt);       // ZZZ1 ZZZ2
+    M::sqr(t4, t2, tt);             // PP
+    M::mul(t2, t2, t4, tt);         // PPP
+    M::mul(t0, t0, t4, tt);         // Q = U1 PP
+    M::mul(ZZ, ZZ, t4, tt);
+    M::mul(ZZZ, ZZZ, t2, tt);
+    M::sqr(X, t3, tt);
+    M::sub(X, X, t2);
+    M::dbl(t4, t0);
+    M::sub(X, X, t4);
+    M::mul(t4, t1, t2, tt);
+    M::sub(t0, t0, X);
+    M::mul(Y, t3, t0, tt);
+    M::sub(Y, Y, t4);
+  }
+
+  // XYZZ -> the reference's homogeneous projective (X:Y:Z) = (X ZZZ : Y ZZ : ZZ ZZZ), in place
+  // over the first three elements of P (infinity -> (0 : 1 : 0), GroupProjective::zero())
+  static G753_D void to_projective(int P, int W) {
+    const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
+    if (M::is_zero(ZZ)) {
+      M::set_zero(X);
+      M::set_one(Y);
+      return;
+    }
+    M::mul(X, X, ZZZ, W);
+    M::mul(Y, Y, ZZ, W);
+    M::mul(ZZ, ZZ, ZZZ, W);
+  }
+  // homogeneous projective (X:Y:Z) in global memory -> XYZZ on slots
+  static G753_D void from_projective_g(int P, const Fq* g, int W) {
+    const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
+    M::ldg(ZZZ, g + 2 * K);  // Z
+    if (M::is_zero(ZZZ)) {
+      set_inf(P);
+      return;
+    }
+    M::sqr(ZZ, ZZZ, W);       // Z^2
+    M::ldg(X, g);
+    M::mul(X, X, ZZZ, W);     // X Z
+    M::ldg(Y, g + K);
+    M::mul(Y, Y, ZZ, W);      // Y Z^2
+    M::mul(ZZZ, ZZZ, ZZ, W);  // Z^3
+  }
+};
+
+}  // namespace g753

@@ -57,9 +57,11 @@ struct FieldConstants {
 };
 
 #include "constants.inc"
+static const FieldConstants G753_FIELD_CONSTANTS[2] = G753_FIELD_CONSTANTS_INIT;
 
 #if defined(__CUDACC__)
-__constant__ FieldConstants d_fc[2];
+// statically initialised, one copy per translation unit (no cudaMemcpyToSymbol at start-up)
+static __constant__ FieldConstants d_fc[2] = G753_FIELD_CONSTANTS_INIT;
 #endif
 
 #if defined(__CUDA_ARCH__)

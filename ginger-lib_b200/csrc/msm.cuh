@@ -5,7 +5,7 @@
 //   reference: unsigned c-bit windows, 2^c - 1 buckets, one CPU task per window, serial
 //              running-sum reduction, c from scalars.len() (variable_base.rs:14-18);
 //   here:      signed-digit windows (2^(c-1) buckets), a counting sort of (digit, point)
-//              pairs per window, one accumulation pass over the sorted runs, a multi-level
+//              pairs per window, length-balanced accumulation of the sorted runs, a multi-level
 //              parallel running-sum reduction, Horner window fold.
 // Reference semantics preserved: zero scalars and infinity bases contribute
 // nothing, duplicate bases hit the doubling branch, P + (-P) gives infinity, count == 0
@@ -13,16 +13,20 @@
 // semantic: 1 * P is accumulated through window 0 like any other digit.)
 //
 // Kernels (all barrier-free, so the host-emulation test build can run them):
-//   k_msm_digits     K4  scalar -> signed window digits + per-window histogram
-//   k_scan_*         K4  exclusive scan of the histograms (bucket offsets)
-//   k_msm_scatter    K4  counting-sort scatter of point indices into bucket order
-//   k_bucket_acc     K5  one accumulator per bucket over its sorted run (mixed additions)
-//   k_reduce_level   K6  sum_b b * B_b by segmented running sums, log_s(B) levels
-//   k_window_combine K6  Horner fold of the window sums, XYZZ -> homogeneous projective
-//   k_points_sum     K6  fold of per-shard partial results (multi-GPU)
+//   k_msm_digits      K4  scalar -> signed window digits + per-window histogram
+//   k_scan_*          K4  exclusive scan of the histograms (bucket offsets)
+//   k_msm_scatter     K4  counting-sort scatter of point indices into bucket order
+//   k_item_*          K5  cut every bucket's run into work items of <= ITEM_LEN points and order
+//                         the items by length (longest first), so the 32 lanes of a warp run
+//                         the same number of mixed additions
+//   k_bucket_acc      K5  one thread per item: XYZZ accumulator in shared-memory slots
+//   k_bucket_fixup    K5  buckets cut into several items: sum the partial results
+//   k_reduce_level    K6  sum_b b * B_b by segmented running sums, log_s(B) levels
+//   k_window_combine  K6  Horner fold of the window sums, XYZZ -> homogeneous projective
+//   k_points_sum      K6  fold of per-shard partial results (multi-GPU)
 #pragma once
 #include "device.cuh"
-#include "ec.cuh"
+#include "ec_slots.cuh"
 
 namespace g753 {
 
@@ -31,6 +35,16 @@ constexpr unsigned SCAN_CHUNK = 256;
 constexpr unsigned REDUCE_SEG_LOG = 5;     // running-sum segment = 32 buckets
 constexpr unsigned REDUCE_SEG = 1u << REDUCE_SEG_LOG;
 constexpr unsigned MSM_MAX_C = 20;
+constexpr unsigned ITEM_LEN = 64;          // longest run one thread accumulates
+constexpr unsigned ITEM_REP = 16;          // replicated length counters (spreads the atomics)
+
+// per-group launch shapes: threads per block chosen so the slot footprint fits 227 KB of
+// shared memory (accumulate: 8K + NTMP slots, reduce: 13K + NTMP slots of 96 B per thread)
+template <int GID> struct MsmCfg;
+template <> struct MsmCfg<0> { static constexpr int K = 1, T_ACC = 128, T_RED = 128; template <int T> using SC = SCurveM4G1<T>; };
+template <> struct MsmCfg<1> { static constexpr int K = 2, T_ACC = 96, T_RED = 64; template <int T> using SC = SCurveM4G2<T>; };
+template <> struct MsmCfg<2> { static constexpr int K = 1, T_ACC = 128, T_RED = 128; template <int T> using SC = SCurveM6G1<T>; };
+template <> struct MsmCfg<3> { static constexpr int K = 3, T_ACC = 64, T_RED = 32; template <int T> using SC = SCurveM6G2<T>; };
 
 struct MsmPlan {
   unsigned c;  // window bits
@@ -58,7 +72,7 @@ static inline MsmPlan msm_plan(size_t n, int forced_c = 0) {
 // ------------------------------------------------------------------------------------
 // K4: digits + histogram
 // ------------------------------------------------------------------------------------
-__global__ void k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
+static __global__ void k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
                              unsigned n, unsigned c, unsigned W, unsigned B,
                              uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,8 +105,8 @@ __global__ void k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t
   }
 }
 
-// exclusive scan of each window's histogram, in three barrier-free steps
-__global__ void k_scan_chunks(const uint32_t* __restrict__ hist, unsigned len, unsigned n_chunks,
+// exclusive scan of each row (`W` rows of `len` counters), in three barrier-free steps
+static __global__ void k_scan_chunks(const uint32_t* __restrict__ hist, unsigned len, unsigned n_chunks,
                               unsigned W, uint32_t* __restrict__ chunk_sums) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= W * n_chunks) return;
@@ -102,7 +116,9 @@ __global__ void k_scan_chunks(const uint32_t* __restrict__ hist, unsigned len, u
   for (unsigned k = lo; k < hi; k++) sum += hist[(size_t)w * len + k];
   chunk_sums[t] = sum;
 }
-__global__ void k_scan_tops(uint32_t* __restrict__ chunk_sums, unsigned n_chunks, unsigned W) {
+// row totals go to totals[w] when given
+static __global__ void k_scan_tops(uint32_t* __restrict__ chunk_sums, unsigned n_chunks, unsigned W,
+                            uint32_t* __restrict__ totals) {
   unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   uint32_t run = 0;
@@ -111,8 +127,9 @@ __global__ void k_scan_tops(uint32_t* __restrict__ chunk_sums, unsigned n_chunks
     chunk_sums[(size_t)w * n_chunks + k] = run;
     run += v;
   }
+  if (totals) totals[w] = run;
 }
-__global__ void k_scan_apply(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_sums,
+static __global__ void k_scan_apply(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_sums,
                              unsigned len, unsigned n_chunks, unsigned W,
                              uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,12 +141,12 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ hist, const uint32_t* 
     size_t idx = (size_t)w * len + k;
     uint32_t v = hist[idx];
     offsets[idx] = run;
-    cursor[idx] = run;
+    if (cursor) cursor[idx] = run;
     run += v;
   }
 }
 
-__global__ void k_msm_scatter(const uint32_t* __restrict__ digits, unsigned n, unsigned W, unsigned B,
+static __global__ void k_msm_scatter(const uint32_t* __restrict__ digits, unsigned n, unsigned W, unsigned B,
                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)W * n) return;
@@ -142,26 +159,107 @@ __global__ void k_msm_scatter(const uint32_t* __restrict__ digits, unsigned n, u
 }
 
 // ------------------------------------------------------------------------------------
-// K5: bucket accumulation
+// K5a: work items.  Bucket t = w * (B+1) + b owns sorted[w*n + offsets[t] .. w*n + ends[t]).
+// It is cut into ceil(count / ITEM_LEN) items; item ids are item_off[t] + j.  The result of an
+// item goes to points[t] when the bucket has a single item, else to points[NB + item id]
+// (summed into points[t] by k_bucket_fixup).  len_hist[key * ITEM_REP + r] counts items of
+// length ITEM_LEN - key.
 // ------------------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(128)
-k_bucket_acc(const Affine<C>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-             const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ends, unsigned n,
-             unsigned W, unsigned B, Xyzz<C>* __restrict__ buckets) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (size_t)W * (B + 1)) return;
-  unsigned w = (unsigned)(t / (B + 1));
-  Xyzz<C> acc = xyzz_inf<C>();
-  uint32_t lo = offsets[t], hi = ends[t];
-  if (t % (B + 1) == 0) hi = lo;  // bucket 0 is the discard bucket
-  for (uint32_t k = lo; k < hi; k++) {
-    uint32_t e = sorted[(size_t)w * n + k];
-    Affine<C> q = bases[e & 0x7fffffffu];
-    if (e & 0x80000000u) q.y = C::F::neg(q.y);
-    xyzz_madd<C>(acc, q);
+static __global__ void k_item_count(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ends,
+                             unsigned NB, unsigned B, uint32_t* __restrict__ item_cnt,
+                             uint32_t* __restrict__ len_hist) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NB) return;
+  uint32_t cnt = (t % (B + 1) == 0) ? 0u : ends[t] - offsets[t];  // bucket 0 is the discard bucket
+  uint32_t items = (cnt + ITEM_LEN - 1) / ITEM_LEN;
+  item_cnt[t] = items;
+  if (!items) return;
+  const unsigned r = t % ITEM_REP;
+  if (items > 1) atomicAdd(&len_hist[0 * ITEM_REP + r], items - 1);  // full-length items
+  uint32_t last = cnt - (items - 1) * ITEM_LEN;
+  atomicAdd(&len_hist[(ITEM_LEN - last) * ITEM_REP + r], 1u);
+}
+
+// single-thread exclusive scan of the ITEM_LEN * ITEM_REP length counters
+static __global__ void k_item_len_scan(const uint32_t* __restrict__ len_hist, uint32_t* __restrict__ len_cursor,
+                                uint32_t* __restrict__ item_total) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t run = 0;
+  for (unsigned k = 0; k < ITEM_LEN * ITEM_REP; k++) {
+    len_cursor[k] = run;
+    run += len_hist[k];
   }
-  buckets[t] = acc;
+  *item_total = run;
+}
+
+struct MsmItem {  // 16 bytes
+  uint32_t start;  // first entry, as a flat index into sorted[]
+  uint32_t len;    // entries to accumulate (1..ITEM_LEN)
+  uint32_t dest;   // index into points[]
+  uint32_t pad;
+};
+
+static __global__ void k_item_emit(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ends,
+                            const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict__ item_off,
+                            unsigned NB, unsigned B, unsigned n, uint32_t* __restrict__ len_cursor,
+                            MsmItem* __restrict__ items) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NB) return;
+  const uint32_t cnt_items = item_cnt[t];
+  if (!cnt_items) return;
+  const unsigned w = t / (B + 1);
+  const unsigned r = t % ITEM_REP;
+  const uint32_t lo = offsets[t], hi = ends[t];
+  const uint32_t first_id = item_off[t];
+  for (uint32_t j = 0; j < cnt_items; j++) {
+    uint32_t s = lo + j * ITEM_LEN;
+    uint32_t len = hi - s < ITEM_LEN ? hi - s : ITEM_LEN;
+    uint32_t pos = atomicAdd(&len_cursor[(ITEM_LEN - len) * ITEM_REP + r], 1u);
+    MsmItem it;
+    it.start = (uint32_t)((size_t)w * n + s);
+    it.len = len;
+    it.dest = cnt_items == 1 ? t : NB + first_id + j;
+    it.pad = 0;
+    items[pos] = it;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K5b: bucket accumulation.  One thread per item; the accumulator and the formula temporaries
+// live in shared-memory slots (ec_slots.cuh), bases are gathered straight from HBM.
+// ------------------------------------------------------------------------------------
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T)
+k_bucket_acc(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
+             const MsmItem* __restrict__ items, const uint32_t* __restrict__ item_total,
+             Fq* __restrict__ points) {
+  typedef EcS<SC> E;
+  unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= *item_total) return;
+  const MsmItem it = items[pos];
+  E::set_inf(0);
+  for (uint32_t k = 0; k < it.len; k++) {
+    uint32_t e = sorted[it.start + k];
+    const Fq* q = bases + (size_t)(e & 0x7fffffffu) * (2 * E::K);
+    E::madd_g(0, q, (e >> 31) != 0, E::PT);
+  }
+  E::stg(points + (size_t)it.dest * E::PT, 0);
+}
+
+// buckets that were cut into several items: points[t] = sum of their partial results
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T)
+k_bucket_fixup(const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict__ item_off,
+               unsigned NB, Fq* __restrict__ points) {
+  typedef EcS<SC> E;
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NB) return;
+  const uint32_t cnt = item_cnt[t];
+  if (cnt < 2) return;
+  const uint32_t first = NB + item_off[t];
+  E::set_inf(0);
+  for (uint32_t j = 0; j < cnt; j++) E::add_g(0, points + (size_t)(first + j) * E::PT, E::PT);
+  E::stg(points + (size_t)t * E::PT, 0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -170,127 +268,95 @@ k_bucket_acc(const Affine<C>* __restrict__ bases, const uint32_t* __restrict__ s
 // problem over n_out = ceil(n_in / s) entries with f' = f * s:
 //   R_j  = sum_{i in seg j} X_i
 //   Y'_j = sum_{i in seg j} Y_i + f * sum_{i in seg j} (i - j s) X_i        (running sums)
+// Row w of X / Y starts at w * x_stride / w * y_stride (in points).
 // ------------------------------------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(128)
-k_reduce_level(const Xyzz<C>* __restrict__ X, const Xyzz<C>* __restrict__ Y, unsigned n_in,
-               unsigned log2f, unsigned W, unsigned n_out, Xyzz<C>* __restrict__ R,
-               Xyzz<C>* __restrict__ Yout) {
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T)
+k_reduce_level(const Fq* __restrict__ X, size_t x_stride, const Fq* __restrict__ Y, size_t y_stride,
+               unsigned n_in, unsigned log2f, unsigned W, unsigned n_out, Fq* __restrict__ R,
+               Fq* __restrict__ Yout) {
+  typedef EcS<SC> E;
+  constexpr int RUN = 0, ACC = E::PT, SCR = 2 * E::PT;
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= W * n_out) return;
   unsigned w = t / n_out, j = t % n_out;
   unsigned lo = j * REDUCE_SEG;
   unsigned hi = lo + REDUCE_SEG < n_in ? lo + REDUCE_SEG : n_in;
-  const Xyzz<C>* x = X + (size_t)w * n_in;
-  Xyzz<C> running = xyzz_inf<C>();
-  Xyzz<C> acc = xyzz_inf<C>();
+  const Fq* x = X + (size_t)w * x_stride * E::PT;
+  E::set_inf(RUN);
+  E::set_inf(ACC);
   for (unsigned i = hi - 1; i > lo; i--) {
-    xyzz_add<C>(running, x[i]);
-    xyzz_add<C>(acc, running);
+    E::add_g(RUN, x + (size_t)i * E::PT, SCR);
+    E::add(ACC, RUN, SCR);
   }
-  xyzz_add<C>(running, x[lo]);
-  for (unsigned k = 0; k < log2f; k++) xyzz_dbl<C>(acc);
+  E::add_g(RUN, x + (size_t)lo * E::PT, SCR);
+  for (unsigned k = 0; k < log2f; k++) E::dbl(ACC, SCR);
   if (Y != nullptr) {
-    const Xyzz<C>* y = Y + (size_t)w * n_in;
-    for (unsigned i = lo; i < hi; i++) xyzz_add<C>(acc, y[i]);
+    const Fq* y = Y + (size_t)w * y_stride * E::PT;
+    for (unsigned i = lo; i < hi; i++) E::add_g(ACC, y + (size_t)i * E::PT, SCR);
   }
-  R[t] = running;
-  Yout[t] = acc;
+  E::stg(R + (size_t)t * E::PT, RUN);
+  E::stg(Yout + (size_t)t * E::PT, ACC);
 }
 
-// Horner fold over the W window sums (stride between windows given), then convert to the
-// reference's homogeneous projective layout.  One thread: W*c doublings are a serial chain.
-template <class C>
-__global__ void k_window_combine(const Xyzz<C>* __restrict__ sums, unsigned stride, unsigned W,
-                                 unsigned c, typename C::F* __restrict__ out_xyz) {
+// Horner fold over the W window sums (stride between windows given, in points), then convert
+// to the reference's homogeneous projective layout.  One thread: W*c doublings are a serial chain.
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T)
+k_window_combine(const Fq* __restrict__ sums, unsigned stride, unsigned W, unsigned c,
+                 Fq* __restrict__ out_xyz) {
+  typedef EcS<SC> E;
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Xyzz<C> total = xyzz_inf<C>();
+  E::set_inf(0);
   for (int w = (int)W - 1; w >= 0; w--) {
     if (w != (int)W - 1)
-      for (unsigned k = 0; k < c; k++) xyzz_dbl<C>(total);
-    xyzz_add<C>(total, sums[(size_t)w * stride]);
+      for (unsigned k = 0; k < c; k++) E::dbl(0, E::PT);
+    E::add_g(0, sums + (size_t)w * stride * E::PT, E::PT);
   }
-  typename C::F X, Y, Z;
-  xyzz_to_projective<C>(total, X, Y, Z);
-  out_xyz[0] = X;
-  out_xyz[1] = Y;
-  out_xyz[2] = Z;
+  E::to_projective(0, E::PT);
+  for (int i = 0; i < 3; i++) E::M::stg(out_xyz + i * E::K, i * E::K);
 }
 
-template <class C>
-__global__ void k_write_infinity(typename C::F* __restrict__ out_xyz) {
+template <class SC>
+__global__ void k_write_infinity(Fq* __restrict__ out_xyz) {
+  typedef EcS<SC> E;
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  typedef typename C::F F;
-  out_xyz[0] = F::zero();
-  out_xyz[1] = F::one();
-  out_xyz[2] = F::zero();
-}
-
-// homogeneous projective (X:Y:Z) -> XYZZ
-template <class C>
-G753_HD Xyzz<C> xyzz_from_projective(const typename C::F& X, const typename C::F& Y, const typename C::F& Z) {
-  typedef typename C::F F;
-  if (F::is_zero(Z)) return xyzz_inf<C>();
-  Xyzz<C> r;
-  r.zz = F::sqr(Z);
-  r.zzz = F::mul(r.zz, Z);
-  r.x = F::mul(X, Z);
-  r.y = F::mul(Y, r.zz);
-  return r;
+  for (int i = 0; i < 3 * E::K; i++) g_st(out_xyz + i, i == E::K ? fq_one<E::M::FIELD>() : fq_zero<E::M::FIELD>());
 }
 
 // sum of `count` projective points (the multi-GPU fold; count is the number of ranks)
-template <class C>
-__global__ void k_points_sum(const typename C::F* __restrict__ pts, unsigned count,
-                             typename C::F* __restrict__ out_xyz) {
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T)
+k_points_sum(const Fq* __restrict__ pts, unsigned count, Fq* __restrict__ out_xyz) {
+  typedef EcS<SC> E;
+  constexpr int TOT = 0, CUR = E::PT, SCR = 2 * E::PT;
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Xyzz<C> total = xyzz_inf<C>();
+  E::set_inf(TOT);
   for (unsigned k = 0; k < count; k++) {
-    Xyzz<C> p = xyzz_from_projective<C>(pts[3 * k], pts[3 * k + 1], pts[3 * k + 2]);
-    xyzz_add<C>(total, p);
+    E::from_projective_g(CUR, pts + (size_t)k * 3 * E::K, SCR);
+    E::add(TOT, CUR, SCR);
   }
-  typename C::F X, Y, Z;
-  xyzz_to_projective<C>(total, X, Y, Z);
-  out_xyz[0] = X;
-  out_xyz[1] = Y;
-  out_xyz[2] = Z;
-}
-
-// zero the coordinates of bases flagged infinite so that (0, 0) is the only encoding the
-// accumulation kernels ever see
-template <class C>
-__global__ void k_bases_sanitize(Affine<C>* __restrict__ bases, const uint8_t* __restrict__ inf, unsigned n) {
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (inf[i]) {
-    bases[i].x = C::F::zero();
-    bases[i].y = C::F::zero();
-  }
+  E::to_projective(TOT, SCR);
+  for (int i = 0; i < 3; i++) E::M::stg(out_xyz + i * E::K, TOT + i * E::K);
 }
 
 // ------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------
-struct MsmPhaseTimer;  // defined by the product build (CUDA events); a no-op in emulation
-
-struct MsmWorkspaceSizes {
-  size_t digits, hist, offsets, cursor, chunk_sums, sorted, buckets, level, total;
-  unsigned n_chunks, level_entries;
+struct MsmWorkspace {
+  unsigned n_chunks, nb_chunks, level_entries, max_items;
+  size_t total;
 };
 
-template <class C>
-static inline MsmWorkspaceSizes msm_workspace(const MsmPlan& pl, size_t n) {
-  MsmWorkspaceSizes s;
-  size_t len = (size_t)pl.B + 1;
+template <int GID>
+static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n) {
+  constexpr size_t PT_BYTES = sizeof(Fq) * 4 * MsmCfg<GID>::K;
+  MsmWorkspace s;
+  const size_t len = (size_t)pl.B + 1;
+  const size_t NB = pl.W * len;
   s.n_chunks = div_up(len, SCAN_CHUNK);
-  s.digits = Carver::pad(sizeof(uint32_t) * pl.W * n);
-  s.sorted = Carver::pad(sizeof(uint32_t) * pl.W * n);
-  s.hist = Carver::pad(sizeof(uint32_t) * pl.W * len);
-  s.offsets = s.hist;
-  s.cursor = s.hist;
-  s.chunk_sums = Carver::pad(sizeof(uint32_t) * pl.W * s.n_chunks);
-  s.buckets = Carver::pad(sizeof(Xyzz<C>) * pl.W * len);
-  // reduction levels: n_out entries per window per level, two arrays (R, Y') per level
+  s.nb_chunks = div_up(NB, SCAN_CHUNK);
+  s.max_items = (unsigned)(NB + (size_t)pl.W * n / ITEM_LEN);
   unsigned entries = 0;
   for (size_t m = len; m > 1;) {
     m = div_up(m, REDUCE_SEG);
@@ -298,8 +364,16 @@ static inline MsmWorkspaceSizes msm_workspace(const MsmPlan& pl, size_t n) {
   }
   if (entries == 0) entries = 1;
   s.level_entries = entries;
-  s.level = Carver::pad(sizeof(Xyzz<C>) * pl.W * entries) * 2;
-  s.total = s.digits + s.sorted + s.hist * 3 + s.chunk_sums + s.buckets + s.level + 4096;
+  size_t t = 0;
+  t += Carver::pad(sizeof(uint32_t) * pl.W * n) * 2;                    // digits, sorted
+  t += Carver::pad(sizeof(uint32_t) * NB) * 5;                          // hist, offsets, cursor, item_cnt, item_off
+  t += Carver::pad(sizeof(uint32_t) * pl.W * s.n_chunks);               // chunk sums
+  t += Carver::pad(sizeof(uint32_t) * s.nb_chunks);                     // item-count chunk sums
+  t += Carver::pad(sizeof(uint32_t) * ITEM_LEN * ITEM_REP) * 2 + 512;   // length counters + total
+  t += Carver::pad(sizeof(MsmItem) * s.max_items);
+  t += Carver::pad(PT_BYTES * (NB + s.max_items));                      // buckets + item partials
+  t += Carver::pad(PT_BYTES * pl.W * entries) * 2;                      // reduction levels
+  s.total = t + 8192;
   return s;
 }
 
@@ -314,66 +388,114 @@ struct MsmHooks {  // phase timing hooks; the emulation build leaves them null
     G753_LAUNCH(__VA_ARGS__);                  \
     if ((hooks).launches) ++*(hooks).launches; \
   } while (0)
+#define G753_MSM_LAUNCH_SMEM(hooks, ...)       \
+  do {                                         \
+    G753_LAUNCH_SMEM(__VA_ARGS__);             \
+    if ((hooks).launches) ++*(hooks).launches; \
+  } while (0)
 
-// d_bases: `count` affine points (device); d_inf: their infinity flags (device, may be null);
-// d_scalars: count x 24 u32 canonical (device); d_out: 3 field elements (device)
-template <class C>
-static int msm_run(Scratch& scratch, cudaStream_t stream, const Affine<C>* d_bases, const uint8_t* d_inf,
-                   const uint32_t* d_scalars, size_t count, typename C::F* d_out, int forced_c,
-                   MsmHooks hooks) {
-  typedef Xyzz<C> P;
+template <class E, int T>
+constexpr size_t slot_bytes(int slots) {
+  return (size_t)slots * sizeof(Fq) * T;
+}
+
+// d_bases: `count` affine points (device, 2K Fq each); d_inf: their infinity flags (device, may
+// be null); d_scalars: count x 24 u32 canonical (device); d_out: 3K Fq (device)
+template <int GID>
+static int msm_run(Scratch& scratch, cudaStream_t stream, const Fq* d_bases, const uint8_t* d_inf,
+                   const uint32_t* d_scalars, size_t count, Fq* d_out, int forced_c, MsmHooks hooks) {
+  typedef MsmCfg<GID> Cfg;
+  constexpr int TA = Cfg::T_ACC, TR = Cfg::T_RED;
+  typedef typename Cfg::template SC<TA> SCA;
+  typedef typename Cfg::template SC<TR> SCR;
+  typedef EcS<SCA> EA;
+  typedef EcS<SCR> ER;
+  constexpr size_t PT = 4 * Cfg::K;  // Fq per XYZZ point
+  constexpr size_t SMEM_ACC = slot_bytes<EA, TA>(EA::PT + EA::MADD_SCRATCH);
+  constexpr size_t SMEM_FIX = slot_bytes<EA, TA>(EA::PT + EA::ADD_SCRATCH);
+  constexpr size_t SMEM_RED = slot_bytes<ER, TR>(2 * ER::PT + ER::ADD_SCRATCH);
+  static_assert(SMEM_ACC <= 232448 && SMEM_FIX <= 232448 && SMEM_RED <= 232448, "slot footprint exceeds 227 KB");
   if (count == 0) {
-    G753_MSM_LAUNCH(hooks, k_write_infinity<C>, 1, 1, stream, d_out);
+    G753_MSM_LAUNCH(hooks, k_write_infinity<SCR>, 1, 1, stream, d_out);
     return launch_check("k_write_infinity");
   }
   if (count > 0x7fffffffull) return G753_ERR_BAD_ARG;
   const unsigned n = (unsigned)count;
   const MsmPlan pl = msm_plan(n, forced_c);
-  const MsmWorkspaceSizes ws = msm_workspace<C>(pl, n);
+  if ((uint64_t)pl.W * n >= 0xffffffffull) return G753_ERR_BAD_ARG;
+  const MsmWorkspace ws = msm_workspace<GID>(pl, n);
   G753_TRY(scratch.reserve(ws.total));
   Carver cv(scratch.ptr);
   const size_t len = (size_t)pl.B + 1;
+  const unsigned NB = (unsigned)(pl.W * len);
   uint32_t* digits = cv.take<uint32_t>((size_t)pl.W * n);
   uint32_t* sorted = cv.take<uint32_t>((size_t)pl.W * n);
-  uint32_t* hist = cv.take<uint32_t>(pl.W * len);
-  uint32_t* offsets = cv.take<uint32_t>(pl.W * len);
-  uint32_t* cursor = cv.take<uint32_t>(pl.W * len);
+  uint32_t* hist = cv.take<uint32_t>(NB);
+  uint32_t* offsets = cv.take<uint32_t>(NB);
+  uint32_t* cursor = cv.take<uint32_t>(NB);
+  uint32_t* item_cnt = cv.take<uint32_t>(NB);
+  uint32_t* item_off = cv.take<uint32_t>(NB);
   uint32_t* chunk_sums = cv.take<uint32_t>((size_t)pl.W * ws.n_chunks);
-  P* buckets = cv.take<P>(pl.W * len);
-  P* lvl_r = cv.take<P>((size_t)pl.W * ws.level_entries);
-  P* lvl_y = cv.take<P>((size_t)pl.W * ws.level_entries);
+  uint32_t* item_chunk_sums = cv.take<uint32_t>(ws.nb_chunks);
+  uint32_t* len_hist = cv.take<uint32_t>(ITEM_LEN * ITEM_REP);
+  uint32_t* len_cursor = cv.take<uint32_t>(ITEM_LEN * ITEM_REP);
+  uint32_t* item_total = cv.take<uint32_t>(64);
+  MsmItem* items = cv.take<MsmItem>(ws.max_items);
+  Fq* points = cv.take<Fq>(PT * ((size_t)NB + ws.max_items));
+  Fq* lvl_r = cv.take<Fq>(PT * pl.W * ws.level_entries);
+  Fq* lvl_y = cv.take<Fq>(PT * pl.W * ws.level_entries);
 
   if (hooks.mark) hooks.mark(hooks.user, 0);
-  G753_TRY(dev_memset(hist, 0, sizeof(uint32_t) * pl.W * len, stream));
+  G753_TRY(dev_memset(hist, 0, sizeof(uint32_t) * NB, stream));
+  G753_TRY(dev_memset(len_hist, 0, sizeof(uint32_t) * ITEM_LEN * ITEM_REP, stream));
+  // empty buckets are never written by the accumulation: all-zero limbs = ZZ == 0 = infinity
+  G753_TRY(dev_memset(points, 0, sizeof(Fq) * PT * NB, stream));
   G753_MSM_LAUNCH(hooks, k_msm_digits, div_up(n, 256), 256, stream, d_scalars, d_inf, n, pl.c, pl.W, pl.B,
                   digits, hist);
   if (hooks.mark) hooks.mark(hooks.user, 1);
   G753_MSM_LAUNCH(hooks, k_scan_chunks, div_up((size_t)pl.W * ws.n_chunks, 128), 128, stream, hist,
                   (unsigned)len, ws.n_chunks, pl.W, chunk_sums);
-  G753_MSM_LAUNCH(hooks, k_scan_tops, div_up(pl.W, 64), 64, stream, chunk_sums, ws.n_chunks, pl.W);
+  G753_MSM_LAUNCH(hooks, k_scan_tops, div_up(pl.W, 64), 64, stream, chunk_sums, ws.n_chunks, pl.W,
+                  (uint32_t*)nullptr);
   G753_MSM_LAUNCH(hooks, k_scan_apply, div_up((size_t)pl.W * ws.n_chunks, 128), 128, stream, hist,
                   chunk_sums, (unsigned)len, ws.n_chunks, pl.W, offsets, cursor);
   G753_MSM_LAUNCH(hooks, k_msm_scatter, div_up((size_t)pl.W * n, 256), 256, stream, digits, n, pl.W, pl.B,
                   cursor, sorted);
+  // work items (after the scatter, cursor[t] is the end of bucket t's run)
+  G753_MSM_LAUNCH(hooks, k_item_count, div_up(NB, 256), 256, stream, offsets, cursor, NB, pl.B, item_cnt,
+                  len_hist);
+  G753_MSM_LAUNCH(hooks, k_scan_chunks, div_up(ws.nb_chunks, 128), 128, stream, item_cnt, NB, ws.nb_chunks,
+                  1u, item_chunk_sums);
+  G753_MSM_LAUNCH(hooks, k_scan_tops, 1, 64, stream, item_chunk_sums, ws.nb_chunks, 1u, (uint32_t*)nullptr);
+  G753_MSM_LAUNCH(hooks, k_scan_apply, div_up(ws.nb_chunks, 128), 128, stream, item_cnt, item_chunk_sums,
+                  NB, ws.nb_chunks, 1u, item_off, (uint32_t*)nullptr);
+  G753_MSM_LAUNCH(hooks, k_item_len_scan, 1, 32, stream, len_hist, len_cursor, item_total);
+  G753_MSM_LAUNCH(hooks, k_item_emit, div_up(NB, 256), 256, stream, offsets, cursor, item_cnt, item_off, NB,
+                  pl.B, n, len_cursor, items);
   if (hooks.mark) hooks.mark(hooks.user, 2);
-  G753_MSM_LAUNCH(hooks, k_bucket_acc<C>, div_up(pl.W * len, 128), 128, stream, d_bases, sorted, offsets,
-                  cursor, n, pl.W, pl.B, buckets);
+  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc<SCA>, div_up(ws.max_items, TA), TA, SMEM_ACC, stream, d_bases,
+                       sorted, items, item_total, points);
+  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup<SCA>, div_up(NB, TA), TA, SMEM_FIX, stream, item_cnt, item_off,
+                       NB, points);
   if (hooks.mark) hooks.mark(hooks.user, 3);
   // reduction levels
-  const P* X = buckets;
-  const P* Y = nullptr;
+  const Fq* X = points;
+  size_t x_stride = len;
+  const Fq* Y = nullptr;
+  size_t y_stride = 0;
   unsigned n_in = (unsigned)len, log2f = 0;
   size_t lvl_off = 0;
-  const P* window_sums = nullptr;
+  const Fq* window_sums = nullptr;
   for (;;) {
     unsigned n_out = div_up(n_in, REDUCE_SEG);
-    P* R = lvl_r + lvl_off;
-    P* Yo = lvl_y + lvl_off;
-    G753_MSM_LAUNCH(hooks, k_reduce_level<C>, div_up((size_t)pl.W * n_out, 128), 128, stream, X, Y, n_in,
-                    log2f, pl.W, n_out, R, Yo);
+    Fq* R = lvl_r + lvl_off * PT;
+    Fq* Yo = lvl_y + lvl_off * PT;
+    G753_MSM_LAUNCH_SMEM(hooks, k_reduce_level<SCR>, div_up((size_t)pl.W * n_out, TR), TR, SMEM_RED, stream, X,
+                         x_stride, Y, y_stride, n_in, log2f, pl.W, n_out, R, Yo);
     lvl_off += (size_t)pl.W * n_out;
     X = R;
     Y = Yo;
+    x_stride = y_stride = n_out;
     n_in = n_out;
     log2f += REDUCE_SEG_LOG;
     if (n_out == 1) {
@@ -382,7 +504,8 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const Affine<C>* d_bas
     }
   }
   if (hooks.mark) hooks.mark(hooks.user, 4);
-  G753_MSM_LAUNCH(hooks, k_window_combine<C>, 1, 32, stream, window_sums, 1u, pl.W, pl.c, d_out);
+  G753_MSM_LAUNCH_SMEM(hooks, k_window_combine<SCR>, 1, TR, SMEM_RED, stream, window_sums, 1u, pl.W, pl.c,
+                       d_out);
   if (hooks.mark) hooks.mark(hooks.user, 5);
   return launch_check("msm_run");
 }

@@ -1,0 +1,3 @@
+// group 0 of include/g753.h (see msm_impl.cuh)
+#include "msm_impl.cuh"
+G753_INSTANTIATE_GROUP(0)

@@ -15,7 +15,7 @@
 // into the first / last butterfly pass.
 #pragma once
 #include "device.cuh"
-#include "fqk.cuh"
+#include "fq.cuh"
 
 namespace g753 {
 

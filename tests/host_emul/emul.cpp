@@ -1,13 +1,14 @@
 // Host-emulation build of the device limb arithmetic (TEST ONLY - never linked into the
 // product library).  The PTX carry-chain primitives of csrc/fq.cuh are replaced by their
-// thread-local-carry emulation so the limb logic can be checked against the oracle
-// without a GPU.
-#include "../../ginger-lib_b200/csrc/fq.cuh"
-#include "../../ginger-lib_b200/csrc/fqk.cuh"
-#include "../../ginger-lib_b200/csrc/ec.cuh"
+// thread-local-carry emulation and the shared-memory slots of csrc/slots.cuh by a static
+// buffer, so the limb logic, the tower formulas and the group law can be checked against the
+// oracle without a GPU.
+#define G753_HOST_EMUL 1
+#include "../../ginger-lib_b200/csrc/ec_slots.cuh"
 #include <cstring>
 
 using namespace g753;
+static const int T = 32;  // emulated block size (thread 0 is the one that runs)
 
 template <int FID>
 static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
@@ -33,55 +34,72 @@ static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out
   memcpy(out, r.l, 96);
 }
 
-template <class F>
-static void ext_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
-  F x, y, r;
-  memcpy(&x, a, sizeof(F));
-  memcpy(&y, b, sizeof(F));
-  switch (op) {
-    case 0: r = F::mul(x, y); break;
-    case 1: r = F::add(x, y); break;
-    case 2: r = F::sub(x, y); break;
-    case 3: r = F::sqr(x); break;
-    case 4: r = F::neg(x); break;
-    case 5: r = F::inv(x); break;
-    case 12: r = F::dbl(x); break;
-    default: r = F::zero();
+static void put(int slot, const uint32_t* src, int count) {
+  for (int i = 0; i < count; i++) {
+    Fq v;
+    memcpy(v.l, src + i * NL, 96);
+    s_st<T>(slot + i, v);
   }
-  memcpy(out, &r, sizeof(F));
+}
+static void get(uint32_t* dst, int slot, int count) {
+  for (int i = 0; i < count; i++) {
+    Fq v = s_ld<T>(slot + i);
+    memcpy(dst + i * NL, v.l, 96);
+  }
+}
+
+// tower ops on slots; `alias` makes the destination alias the first operand (the in-place use
+// the curve formulas rely on)
+template <class M>
+static void ext_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  const int K = M::K, A = 0, B = K, D = 2 * K, TMP = 3 * K;
+  threadIdx.x = 0;
+  put(A, a, K);
+  put(B, b, K);
+  int res = D;
+  switch (op) {
+    case 0: M::mul(D, A, B, TMP); break;
+    case 1: M::add(D, A, B); break;
+    case 2: M::sub(D, A, B); break;
+    case 3: M::sqr(D, A, TMP); break;
+    case 4: M::neg(D, A); break;
+    case 12: M::dbl(D, A); break;
+    case 20: M::mul(A, A, B, TMP); res = A; break;  // d aliases a
+    case 21: M::mul(B, A, B, TMP); res = B; break;  // d aliases b
+    case 23: M::sqr(A, A, TMP); res = A; break;
+    default: M::set_zero(D);
+  }
+  get(out, res, K);
 }
 
 // curve ops on XYZZ accumulators: op 0 = madd(acc, affine), 1 = add(acc, acc2), 2 = dbl(acc),
-// 3 = to homogeneous projective (X, Y, Z)
-template <class C>
+// 3 = to homogeneous projective (X, Y, Z), 5 = add_g(acc, acc2 in "global" memory),
+// 6 = madd(acc, -affine)
+template <class SC>
 static void curve_op(int op, const uint32_t* acc_in, const uint32_t* other, uint32_t* out) {
-  typedef typename C::F F;
-  Xyzz<C> p;
-  memcpy(&p, acc_in, sizeof(p));
-  if (op == 0) {
-    Affine<C> q;
-    memcpy(&q, other, sizeof(q));
-    xyzz_madd<C>(p, q);
-    memcpy(out, &p, sizeof(p));
+  typedef EcS<SC> E;
+  const int K = E::K, P = 0, Q = E::PT, S = 2 * E::PT;
+  threadIdx.x = 0;
+  put(P, acc_in, 4 * K);
+  static Fq gbuf[16];
+  if (op == 0 || op == 6) {
+    memcpy(gbuf, other, 96 * 2 * K);
+    E::madd_g(P, gbuf, op == 6, S);
+    get(out, P, 4 * K);
   } else if (op == 1) {
-    Xyzz<C> q;
-    memcpy(&q, other, sizeof(q));
-    xyzz_add<C>(p, q);
-    memcpy(out, &p, sizeof(p));
+    put(Q, other, 4 * K);
+    E::add(P, Q, S);
+    get(out, P, 4 * K);
+  } else if (op == 5) {
+    memcpy(gbuf, other, 96 * 4 * K);
+    E::add_g(P, gbuf, S);
+    get(out, P, 4 * K);
   } else if (op == 2) {
-    xyzz_dbl<C>(p);
-    memcpy(out, &p, sizeof(p));
+    E::dbl(P, S);
+    get(out, P, 4 * K);
   } else if (op == 3) {
-    F X, Y, Z;
-    xyzz_to_projective<C>(p, X, Y, Z);
-    memcpy(out, &X, sizeof(F));
-    memcpy((char*)out + sizeof(F), &Y, sizeof(F));
-    memcpy((char*)out + 2 * sizeof(F), &Z, sizeof(F));
-  } else if (op == 4) {  // scalar multiplication by a 768-bit scalar in `other` of an affine point in acc_in.x/.y
-    Affine<C> q;
-    memcpy(&q, acc_in, sizeof(q));
-    Xyzz<C> r = xyzz_scalar_mul<C>(q, other);
-    memcpy(out, &r, sizeof(r));
+    E::to_projective(P, S);
+    get(out, P, 3 * K);
   }
 }
 
@@ -92,16 +110,16 @@ void emul_field_op(int fid, int op, const uint32_t* a, const uint32_t* b, uint32
 }
 // ext 2 = Fq2 over field 0 (MNT4 G2 base field); ext 3 = Fq3 over field 1 (MNT6 G2 base field)
 void emul_ext_op(int ext, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
-  if (ext == 2) ext_op<Fq2M4>(op, a, b, out);
-  else ext_op<Fq3M6>(op, a, b, out);
+  if (ext == 2) ext_op<Tw2<0, T, 13>>(op, a, b, out);
+  else ext_op<Tw3<1, T, 11>>(op, a, b, out);
 }
 // curve ids as in include/g753.h: 0 = MNT4 G1, 1 = MNT4 G2, 2 = MNT6 G1, 3 = MNT6 G2
 void emul_curve_op(int curve, int op, const uint32_t* acc, const uint32_t* other, uint32_t* out) {
   switch (curve) {
-    case 0: curve_op<CurveM4G1>(op, acc, other, out); break;
-    case 1: curve_op<CurveM4G2>(op, acc, other, out); break;
-    case 2: curve_op<CurveM6G1>(op, acc, other, out); break;
-    case 3: curve_op<CurveM6G2>(op, acc, other, out); break;
+    case 0: curve_op<SCurveM4G1<T>>(op, acc, other, out); break;
+    case 1: curve_op<SCurveM4G2<T>>(op, acc, other, out); break;
+    case 2: curve_op<SCurveM6G1<T>>(op, acc, other, out); break;
+    case 3: curve_op<SCurveM6G2<T>>(op, acc, other, out); break;
   }
 }
 }

@@ -84,6 +84,22 @@ def test_msm_window_sizes(ctx, monkeypatch):
         cx.close()
 
 
+@pytest.mark.parametrize("group", [ffi.MNT4_G1, ffi.MNT4_G2])
+def test_msm_heavy_buckets(ctx, group):
+    """skewed scalars (many equal / tiny ones, as boolean witnesses give): buckets longer than
+    one work item are cut into several items and re-joined by k_bucket_fixup"""
+    C = GROUPS[group]
+    base = sample_points(C, 3, 0x91 + group)
+    n = 150
+    pts = [base[i % 3] for i in range(n)]
+    sc = [5] * 140 + [1, 0, 2, 7, C.r - 5, 5, 5, 3, 1, 1]
+    coords, inf = points_to_arrays(C, pts)
+    bases = ctx.upload_bases(group, coords, inf)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    bases.free()
+
+
 @pytest.mark.parametrize("field", sorted(FIELDS))
 def test_ntt_small(ctx, field):
     F = FIELDS[field]
