@@ -22,12 +22,16 @@ LIMBS = 12
 class Context:
     """One GPU (device index) with its stream, scratch memory and twiddle tables."""
 
-    def __init__(self, device=0, library=None):
+    def __init__(self, device=0, library=None, stream=None):
+        """`stream`: optional raw cudaStream_t (int), e.g. `torch.cuda.Stream().cuda_stream`, so that
+        the library's kernels are ordered with the caller's own work (NCCL collectives, events)."""
         self.lib = library or ffi.default_library()
         h = ctypes.c_void_p()
         self.lib.check(self.lib.ctx_create(int(device), ctypes.byref(h)))
         self.handle = h
         self.device = device
+        if stream is not None:
+            self.lib.check(self.lib.ctx_set_stream(self.handle, ctypes.c_void_p(int(stream))))
 
     def close(self):
         if getattr(self, "handle", None):
@@ -43,6 +47,10 @@ class Context:
     # -- proving-key bases ------------------------------------------------------------
     def upload_bases(self, group, coords, infinity=None):
         return Bases(self, group, coords, infinity)
+
+    def generate_bases(self, group, n, seed):
+        """synthetic resident key: bases[i] = a_i * G (see Bases.generated_logs)"""
+        return Bases.generate(self, group, n, seed)
 
     def sync(self):
         self.lib.check(self.lib.sync(self.handle))
@@ -86,6 +94,35 @@ class Bases:
 
     def __len__(self):
         return self.n
+
+    @classmethod
+    def generate(cls, ctx, group, n, seed):
+        from . import params
+        self = cls.__new__(cls)
+        self.ctx, self.group, self.k, self.n = ctx, group, ffi.GROUP_K[group], int(n)
+        gen = np.array([[(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(LIMBS)]
+                        for v in params.GENERATOR_MONT[group]], dtype=np.uint64)
+        h = ctypes.c_void_p()
+        ctx.lib.check(ctx.lib.bases_generate(ctx.handle, group, ffi.ptr(gen), ctypes.c_uint64(seed), self.n,
+                                             ctypes.byref(h)))
+        self.handle = h
+        return self
+
+    @staticmethod
+    def generated_logs(n, seed, first=0):
+        """a_i of `generate`: splitmix64(seed + (i+1) * golden) | 1, as a numpy uint64 array"""
+        with np.errstate(over="ignore"):
+            i = np.arange(first + 1, first + n + 1, dtype=np.uint64)
+            z = np.uint64(seed) + i * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return (z ^ (z >> np.uint64(31))) | np.uint64(1)
+
+    def download(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.zeros((count, 2 * self.k * LIMBS), dtype=np.uint64)
+        self.ctx.lib.check(self.ctx.lib.bases_download(self.ctx.handle, self.handle, first, count, ffi.ptr(out)))
+        return out
 
     def free(self):
         if getattr(self, "handle", None):

@@ -158,7 +158,7 @@ int g753_ctx_destroy(g753_ctx* ctx) {
 #if !defined(G753_HOST_EMUL)
   if (ctx->ev_ok)
     for (int i = 0; i <= MSM_PHASES; i++) cudaEventDestroy(ctx->ev[i]);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
 #endif
   delete ctx;
   return G753_OK;
@@ -218,6 +218,58 @@ int g753_bases_free(g753_ctx* ctx, g753_bases* b) {
 
 size_t g753_bases_len(const g753_bases* b) { return b ? b->n : 0; }
 
+int g753_ctx_set_stream(g753_ctx* ctx, void* cuda_stream) {
+  CHECK_CTX(ctx);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  G753_TRY(stream_sync(ctx->stream));
+#if !defined(G753_HOST_EMUL)
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+#endif
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return G753_OK;
+}
+
+int g753_bases_generate(g753_ctx* ctx, int group, const uint64_t* gen_xy, uint64_t seed, size_t n,
+                        g753_bases** out) {
+  CHECK_CTX(ctx);
+  if (!out || !gen_xy) return fail(G753_ERR_BAD_ARG, "null pointer");
+  *out = nullptr;
+  const int k = group_k(group);
+  if (k == 0) return fail(G753_ERR_BAD_ARG, "unknown group");
+  if (n > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "too many bases");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  g753_bases* b = new (std::nothrow) g753_bases();
+  if (!b) return fail(G753_ERR_OOM, "host allocation failed");
+  b->group = group;
+  b->n = n;
+  int rc = dev_alloc(&b->d_points, (size_t)2 * k * 96 * n);
+  if (rc == G753_OK) {
+    switch (group) {
+      case G753_MNT4_G1: rc = bases_generate_impl<0>(ctx, gen_xy, seed, n, b->d_points); break;
+      case G753_MNT4_G2: rc = bases_generate_impl<1>(ctx, gen_xy, seed, n, b->d_points); break;
+      case G753_MNT6_G1: rc = bases_generate_impl<2>(ctx, gen_xy, seed, n, b->d_points); break;
+      case G753_MNT6_G2: rc = bases_generate_impl<3>(ctx, gen_xy, seed, n, b->d_points); break;
+    }
+  }
+  if (rc != G753_OK) {
+    dev_free(b->d_points);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return G753_OK;
+}
+
+int g753_bases_download(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, uint64_t* coords) {
+  CHECK_CTX(ctx);
+  if (!b || (count && !coords)) return fail(G753_ERR_BAD_ARG, "null pointer");
+  if (first > b->n || count > b->n - first) return fail(G753_ERR_BAD_ARG, "bases slice out of range");
+  const size_t pt_bytes = (size_t)2 * group_k(b->group) * 96;
+  G753_TRY(d2h(coords, (const char*)b->d_points + first * pt_bytes, count * pt_bytes, ctx->stream));
+  return stream_sync(ctx->stream);
+}
+
 static int msm_check(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count) {
   if (!b) return fail(G753_ERR_BAD_ARG, "null bases");
   if (first > b->n || count > b->n - first) return fail(G753_ERR_BAD_ARG, "bases slice out of range");
@@ -259,9 +311,6 @@ int g753_msm(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, con
   G753_TRY(msm_any(ctx, b, first, count, d_scalars, d_out));
   G753_TRY(d2h(out_xyz, d_out, out_bytes, ctx->stream));
   G753_TRY(stream_sync(ctx->stream));
-#if !defined(G753_HOST_EMUL)
-  if (count) collect_phases(ctx);
-#endif
   return G753_OK;
 }
 
@@ -478,8 +527,11 @@ int g753_debug_scratch(g753_ctx* ctx, void* h_dst, size_t bytes, size_t* cap) {
 
 uint64_t g753_launch_count(const g753_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int g753_last_msm_phases(const g753_ctx* ctx, float* ms, int cap) {
+int g753_last_msm_phases(g753_ctx* ctx, float* ms, int cap) {
   if (!ctx || !ms) return 0;
+#if !defined(G753_HOST_EMUL)
+  if (use_device(ctx) == G753_OK && stream_sync(ctx->stream) == G753_OK) collect_phases(ctx);
+#endif
   int k = cap < MSM_PHASES ? cap : MSM_PHASES;
   for (int i = 0; i < k; i++) ms[i] = ctx->phase_ms[i];
   return k;

@@ -25,6 +25,7 @@ enum { MSM_PHASES = 5 };
 struct g753_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   Scratch scratch;      // MSM workspace
   Scratch scratch_io;   // host-API staging (scalars / NTT ping-pong)
   std::map<unsigned, NttTables> tables[2];  // per field, keyed by log_n
@@ -83,3 +84,5 @@ template <int GID>
 int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out);
 template <int GID>
 void points_sum_launch(g753_ctx* ctx, const void* d_pts, size_t count, void* d_out);
+template <int GID>
+int bases_generate_impl(g753_ctx* ctx, const uint64_t* gen_xy, uint64_t seed, size_t n, void* d_points);

@@ -272,6 +272,19 @@ struct EcS {
     M::mul(Y, Y, ZZ, W);
     M::mul(ZZ, ZZ, ZZZ, W);
   }
+  // XYZZ -> affine (x, y) in the X, Y elements (ZZ, ZZZ become 1); P finite.  2K + NTMP scratch.
+  static G753_D void to_affine(int P, int W) {
+    const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
+    const int t0 = W, t1 = W + K, tt = W + 2 * K;
+    M::mul(t0, ZZ, ZZZ, tt);
+    M::inv(t0, t0, tt);
+    M::mul(t1, t0, ZZZ, tt);  // 1 / ZZ
+    M::mul(X, X, t1, tt);
+    M::mul(t1, t0, ZZ, tt);   // 1 / ZZZ
+    M::mul(Y, Y, t1, tt);
+    M::set_one(ZZ);
+    M::set_one(ZZZ);
+  }
   // homogeneous projective (X:Y:Z) in global memory -> XYZZ on slots
   static G753_D void from_projective_g(int P, const Fq* g, int W) {
     const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;

@@ -32,7 +32,7 @@ namespace g753 {
 
 constexpr unsigned SCALAR_BITS = 753;      // FpParameters::MODULUS_BITS of both scalar fields
 constexpr unsigned SCAN_CHUNK = 256;
-constexpr unsigned REDUCE_SEG_LOG = 5;     // running-sum segment = 32 buckets
+constexpr unsigned REDUCE_SEG_LOG = 3;     // running-sum segment = 8 buckets: short serial chains, more levels
 constexpr unsigned REDUCE_SEG = 1u << REDUCE_SEG_LOG;
 constexpr unsigned MSM_MAX_C = 20;
 constexpr unsigned ITEM_LEN = 64;          // longest run one thread accumulates

@@ -100,7 +100,62 @@ void points_sum_launch(g753_ctx* ctx, const void* d_pts, size_t count, void* d_o
 }
 
 
+// Synthetic proving-key bases for benchmarks and full-size parity checks:
+// P_i = a_i * G with a_i = splitmix64(seed, i) | 1, normalised to affine.  The discrete logs a_i
+// are reproducible on the host, so sum_i s_i P_i can be checked at any size as
+// (sum_i s_i a_i mod r) * G.
+G753_HD uint64_t splitmix64_at(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T)
+k_bases_generate(const Fq* __restrict__ gen, uint64_t seed, unsigned n, Fq* __restrict__ out) {
+  typedef EcS<SC> E;
+  typedef typename E::M M;
+  constexpr int K = E::K, P = 0, S = E::PT;
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t a = splitmix64_at(seed, i) | 1ull;
+  E::set_inf(P);
+  bool started = false;
+  for (int b = 63; b >= 0; b--) {
+    if (started) E::dbl(P, S);
+    if ((a >> b) & 1) {
+      E::madd_g(P, gen, false, S);
+      started = true;
+    }
+  }
+  // a_i < 2^64 << r and G has prime order r: the result is never the point at infinity
+  E::to_affine(P, S);
+  M::stg(out + (size_t)i * 2 * K, P);
+  M::stg(out + (size_t)i * 2 * K + K, P + K);
+}
+
+template <int GID>
+int bases_generate_impl(g753_ctx* ctx, const uint64_t* gen_xy, uint64_t seed, size_t n, void* d_points) {
+  constexpr int K = MsmCfg<GID>::K, T = 64;
+  typedef typename MsmCfg<GID>::template SC<T> SC;
+  typedef EcS<SC> E;
+  if (n == 0) return G753_OK;
+  Fq* d_gen = nullptr;
+  G753_TRY(dev_alloc((void**)&d_gen, sizeof(Fq) * 2 * K));
+  int rc = h2d(d_gen, gen_xy, sizeof(Fq) * 2 * K, ctx->stream);
+  if (rc == G753_OK) {
+    G753_LAUNCH_SMEM(k_bases_generate<SC>, div_up(n, T), T, (slot_bytes<E, T>(E::PT + E::ADD_SCRATCH)), ctx->stream,
+                     d_gen, seed, (unsigned)n, (Fq*)d_points);
+    ctx->launches++;
+    rc = launch_check("k_bases_generate");
+  }
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d_gen);
+  return rc;
+}
+
 #define G753_INSTANTIATE_GROUP(GID)                                                                        \
   template int msm_dispatch<GID>(g753_ctx*, const g753_bases*, size_t, size_t, const uint32_t*, void*);   \
   template int point_op_impl<GID>(g753_ctx*, int, const uint64_t*, const uint64_t*, uint64_t*);            \
-  template void points_sum_launch<GID>(g753_ctx*, const void*, size_t, void*);
+  template void points_sum_launch<GID>(g753_ctx*, const void*, size_t, void*);                               \
+  template int bases_generate_impl<GID>(g753_ctx*, const uint64_t*, uint64_t, size_t, void*);

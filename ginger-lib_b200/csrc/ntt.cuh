@@ -129,7 +129,7 @@ static int ntt_tables_build(NttTables& T, unsigned log_n, cudaStream_t stream, u
 // post (last pass):  outputs are multiplied by post[index] or *post_const (ifft: n^-1,
 //                    coset_ifft: g^-i n^-1)
 template <int FID>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_ntt_stage(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restrict__ tw, unsigned log_n,
             unsigned s, const Fq* __restrict__ pre, const Fq* __restrict__ post,
             const Fq* __restrict__ post_const) {
@@ -144,7 +144,7 @@ k_ntt_stage(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restric
     a = fq_mul<FID>(a, pre[j]);
     b = fq_mul<FID>(b, pre[j + half]);
   }
-  b = fq_mul<FID>(b, tw[(size_t)k << (log_n - 1 - s)]);
+  if (s != 0) b = fq_mul<FID>(b, tw[(size_t)k << (log_n - 1 - s)]);  // stage 0: every twiddle is omega^0 = 1
   const unsigned j0 = ((j >> s) << (s + 1)) | k;
   Fq x = fq_add<FID>(a, b);
   Fq y = fq_sub<FID>(a, b);

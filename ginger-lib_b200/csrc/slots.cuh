@@ -119,6 +119,10 @@ template <int FID, int T, unsigned KK>
 G753_NI void s_mul_small(int d, int a) {
   s_st<T>(d, fq_mul_small<FID, KK>(s_ld<T>(a)));
 }
+template <int FID, int T>
+G753_NI void s_inv(int d, int a) {  // Fermat; the inverse is unique, so the limbs equal fp_768.rs:551-605's
+  s_st<T>(d, fq_inv<FID>(s_ld<T>(a)));
+}
 template <int T>
 G753_D void s_copy(int d, int a) {
   if (d == a) return;
@@ -171,6 +175,7 @@ struct Tw1 {
   static constexpr int K = 1, NTMP = 0, FIELD = FID, T = T_;
   static G753_D void mul(int d, int a, int b, int) { s_mul<FID, T>(d, a, b); }
   static G753_D void sqr(int d, int a, int) { s_sqr<FID, T>(d, a); }
+  static G753_D void inv(int d, int a, int) { s_inv<FID, T>(d, a); }
   static G753_D void add(int d, int a, int b) { s_add<FID, T>(d, a, b); }
   static G753_D void sub(int d, int a, int b) { s_sub<FID, T>(d, a, b); }
   static G753_D void dbl(int d, int a) { s_dbl<FID, T>(d, a); }
@@ -209,6 +214,17 @@ struct Tw2 {
     s_dbl<FID, T>(d + 1, t);
     s_sub<FID, T>(d, t + 1, t);
     s_sub<FID, T>(d, d, t + 2);
+  }
+  // fp2.rs:83-127: (a0 - a1 u) / (a0^2 - NR a1^2)
+  static G753_NI void inv(int d, int a, int t) {
+    s_sqr<FID, T>(t, a);
+    s_sqr<FID, T>(t + 1, a + 1);
+    s_mul_small<FID, T, NR>(t + 1, t + 1);
+    s_sub<FID, T>(t, t, t + 1);
+    s_inv<FID, T>(t, t);
+    s_mul<FID, T>(d, a, t);
+    s_mul<FID, T>(d + 1, a + 1, t);
+    s_neg<FID, T>(d + 1, d + 1);
   }
   static G753_D void add(int d, int a, int b) {
     s_add<FID, T>(d, a, b);
@@ -298,6 +314,30 @@ struct Tw3 {
     s_add<FID, T>(d, t, t + 5);              // c0
     s_mul_small<FID, T, NR>(t + 5, t + 4);
     s_add<FID, T>(d + 1, t + 1, t + 5);      // c1
+  }
+  // fp3.rs:107-164
+  static G753_NI void inv(int d, int a, int t) {
+    s_sqr<FID, T>(t, a);
+    s_mul<FID, T>(t + 3, a + 1, a + 2);
+    s_mul_small<FID, T, NR>(t + 3, t + 3);
+    s_sub<FID, T>(t, t, t + 3);              // t0 = a0^2 - NR a1 a2
+    s_sqr<FID, T>(t + 1, a + 2);
+    s_mul_small<FID, T, NR>(t + 1, t + 1);
+    s_mul<FID, T>(t + 3, a, a + 1);
+    s_sub<FID, T>(t + 1, t + 1, t + 3);      // t1 = NR a2^2 - a0 a1
+    s_sqr<FID, T>(t + 2, a + 1);
+    s_mul<FID, T>(t + 3, a, a + 2);
+    s_sub<FID, T>(t + 2, t + 2, t + 3);      // t2 = a1^2 - a0 a2
+    s_mul<FID, T>(t + 3, a + 2, t + 1);
+    s_mul<FID, T>(t + 4, a + 1, t + 2);
+    s_add<FID, T>(t + 3, t + 3, t + 4);
+    s_mul_small<FID, T, NR>(t + 3, t + 3);
+    s_mul<FID, T>(t + 4, a, t);
+    s_add<FID, T>(t + 3, t + 3, t + 4);      // norm
+    s_inv<FID, T>(t + 3, t + 3);
+    s_mul<FID, T>(d, t, t + 3);
+    s_mul<FID, T>(d + 1, t + 1, t + 3);
+    s_mul<FID, T>(d + 2, t + 2, t + 3);
   }
   static G753_D void add(int d, int a, int b) {
     for (int i = 0; i < 3; i++) s_add<FID, T>(d + i, a + i, b + i);

@@ -27,11 +27,14 @@ SYMBOLS = [
     ("g753_device_count", _i, [ctypes.POINTER(_i)]),
     ("g753_ctx_create", _i, [_i, _pvp]),
     ("g753_ctx_destroy", _i, [_vp]),
+    ("g753_ctx_set_stream", _i, [_vp, _vp]),
     ("g753_last_error", ctypes.c_char_p, []),
     ("g753_version", ctypes.c_char_p, []),
     ("g753_bases_upload", _i, [_vp, _i, _vp, _vp, _sz, _pvp]),
     ("g753_bases_free", _i, [_vp, _vp]),
     ("g753_bases_len", _sz, [_vp]),
+    ("g753_bases_generate", _i, [_vp, _i, _vp, ctypes.c_uint64, _sz, _pvp]),
+    ("g753_bases_download", _i, [_vp, _vp, _sz, _sz, _vp]),
     ("g753_msm", _i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     ("g753_msm_dev", _i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     ("g753_msm_host", _i, [_vp, _i, _vp, _vp, _sz, _vp, _sz, _vp]),

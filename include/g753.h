@@ -77,6 +77,9 @@ typedef struct g753_bases g753_bases;   /* a device-resident slice of proving-ke
 int g753_device_count(int* count);
 int g753_ctx_create(int device, g753_ctx** out);
 int g753_ctx_destroy(g753_ctx* ctx);
+/* run every later call of this context on the caller's CUDA stream (a cudaStream_t, e.g. the
+ * one torch.distributed's NCCL collectives are ordered on); the context stops owning a stream */
+int g753_ctx_set_stream(g753_ctx* ctx, void* cuda_stream);
 const char* g753_last_error(void);
 const char* g753_version(void);
 
@@ -86,6 +89,15 @@ const char* g753_version(void);
 int g753_bases_upload(g753_ctx* ctx, int group, const uint64_t* coords, const uint8_t* infinity,
                       size_t n, g753_bases** out);
 int g753_bases_free(g753_ctx* ctx, g753_bases* bases);
+/* synthetic key for benchmarks / full-size parity checks: bases[i] = a_i * G on the
+ * device, a_i = splitmix64(seed + (i+1) * 0x9E3779B97F4A7C15) | 1 (64 bits), G = gen_xy (affine,
+ * Montgomery limbs, e.g. AffineCurve::prime_subgroup_generator(), curves/mnt4753/g1.rs:79-109),
+ * normalised to affine.  sum_i s_i bases[i] = (sum_i s_i a_i mod r) * G at any size. */
+int g753_bases_generate(g753_ctx* ctx, int group, const uint64_t* gen_xy, uint64_t seed, size_t n,
+                        g753_bases** out);
+/* copy `count` resident bases starting at `first` back to the host (2*k*12 limbs each) */
+int g753_bases_download(g753_ctx* ctx, const g753_bases* bases, size_t first, size_t count,
+                        uint64_t* coords);
 size_t g753_bases_len(const g753_bases* bases);
 
 /* sum_{i<count} scalars[i] * bases[first+i]  ->  out_xyz (host, 3*k*12 limbs).
@@ -151,7 +163,7 @@ int g753_debug_scratch(g753_ctx* ctx, void* h_dst, size_t bytes, size_t* cap);
 uint64_t g753_launch_count(const g753_ctx* ctx);
 /* per-phase device times (ms) of the last g753_msm* call: digits, sort, accumulate, reduce,
  * combine - CUDA events on the context stream; returns the number of phases written */
-int g753_last_msm_phases(const g753_ctx* ctx, float* ms, int cap);
+int g753_last_msm_phases(g753_ctx* ctx, float* ms, int cap);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,60 @@
+"""N > 1 path on CPU: two gloo ranks, each with its own point-range shard, run the sharded MSM
+(local MSM -> all-gather of partial points -> fold) and must agree with the single-rank result and
+the oracle.  The compute inside each rank is the TEST-ONLY host-emulation build of the C ABI
+(tests/host_emul), standing in for the GPU; the sharding / exchange / fold logic under test is the
+product's ginger-lib_b200/distributed.py."""
+import importlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+WORKER = r'''
+import importlib, os, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {here!r})
+import torch.distributed as dist
+from oracle import g753 as O
+from util753 import G, GROUPS, ffi, ints_to_array, points_to_arrays, projective_to_point, sample_points, sample_scalars
+D = importlib.import_module("ginger-lib_b200.distributed")
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size={world})
+rank, world = dist.get_rank(), dist.get_world_size()
+lib = ffi.Library(os.path.join({here!r}, "host_emul", "libg753_emul.so"))
+ctx = G.Context(0, library=lib)
+for group, n in ((ffi.MNT4_G1, 23), (ffi.MNT4_G2, 7)):
+    C = GROUPS[group]
+    pts = sample_points(C, n, 0x600 + group)          # same seeded inputs on every rank
+    sc = sample_scalars(C, n, 0x700 + group)
+    pts[2] = None
+    sc[4] = 0
+    lo, hi = D.shard_range(n, rank, world)
+    coords, inf = points_to_arrays(C, pts[lo:hi])
+    bases = ctx.upload_bases(group, coords, inf)
+    got = D.ShardedMSM(ctx, bases).multi_scalar_mul(ints_to_array(sc[lo:hi]))
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc), (rank, group)
+    bases.free()
+assert [D.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharded_msm_two_ranks_gloo(tmp_path):
+    lib = os.path.join(HERE, "host_emul", "libg753_emul.so")
+    if not os.path.exists(lib):
+        pytest.skip("host-emulation library not built yet (tests/test_pipeline_emul.py builds it)")
+    script = tmp_path / "worker.py"
+    port = 29500 + (os.getpid() % 2000)
+    script.write_text(WORKER.format(root=ROOT, here=HERE, port=port, world=2))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, o[-3000:])
+        assert "rank %d ok" % r in o

@@ -244,3 +244,79 @@ def test_ntt_large_properties(ctx):
             for c in reversed(coeffs):
                 acc = (acc * x + c) % F.p
             assert vals[i] == acc
+
+
+# ---- synthetic key generator + full-size properties -------------------------------------------
+def _dot_mod(scalars, logs, r):
+    return sum(int(s) * int(a) for s, a in zip(array_to_ints(scalars), logs)) % r
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_generated_bases_vs_oracle(ctx, group):
+    """g753_bases_generate: bases[i] = a_i * G, affine, for the documented a_i"""
+    from util753 import g2_generator
+    C = GROUPS[group]
+    n = 5
+    bases = ctx.generate_bases(group, n, 0xABC + group)
+    logs = G.Bases.generated_logs(n, 0xABC + group)
+    got = bases.download()
+    k = C.F.k
+    F = C.F.base
+    params = __import__("importlib").import_module("ginger-lib_b200.params")
+    gen_m = params.GENERATOR_MONT[group]
+    gen = (tuple(F.from_mont(v) for v in gen_m[:k]), tuple(F.from_mont(v) for v in gen_m[k:]))
+    if k > 1:
+        assert gen == g2_generator(C)
+    for i in range(n):
+        vals = [F.from_mont(v) for v in array_to_ints(got[i].reshape(-1, 12))]
+        assert (tuple(vals[:k]), tuple(vals[k:])) == C.mul(gen, int(logs[i]))
+    # MSM over the generated key == (sum s_i a_i) * G
+    sc = sample_scalars(C, n, 0x77)
+    out = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+    assert projective_to_point(C, out) == C.mul(gen, _dot_mod(ints_to_array(sc), logs, C.r))
+    bases.free()
+
+
+@pytest.mark.parametrize("group,log_n", [(ffi.MNT4_G1, 20), (ffi.MNT6_G1, 16), (ffi.MNT4_G2, 15), (ffi.MNT6_G2, 14)])
+def test_msm_large_discrete_log_property(ctx, group, log_n):
+    """size-independent check at sizes no CPU oracle reaches: sum_i s_i (a_i G) == (sum_i s_i a_i mod r) G"""
+    import bench
+    C = GROUPS[group]
+    n = 1 << log_n
+    params = __import__("importlib").import_module("ginger-lib_b200.params")
+    bases = ctx.generate_bases(group, n, 0x5EED + group)
+    logs = G.Bases.generated_logs(n, 0x5EED + group)
+    sc = bench.random_scalars(n, 0xF00 + group)
+    sc[1] = 0                                     # zero scalar
+    sc[2] = 0
+    sc[2, 0] = 1                                  # scalar one
+    sc[3] = ints_to_array([C.r - 1])[0]
+    out = G.VariableBaseMSM.multi_scalar_mul(bases, sc)
+    k = bench.dot_mod(sc, logs, C.r)
+    F = C.F.base
+    kk = C.F.k
+    gen_m = params.GENERATOR_MONT[group]
+    gen = (tuple(F.from_mont(v) for v in gen_m[:kk]), tuple(F.from_mont(v) for v in gen_m[kk:]))
+    assert projective_to_point(C, out) == C.mul(gen, k)
+    # zip truncation on a slice view of the resident key (groth16/mod.rs:318-350)
+    out = G.VariableBaseMSM.multi_scalar_mul(bases, sc[:1000], first=n - 1500)
+    k = bench.dot_mod(sc[:1000], logs[n - 1500:n - 500], C.r)
+    assert projective_to_point(C, out) == C.mul(gen, k)
+    bases.free()
+
+
+@pytest.mark.parametrize("group,log_n", [(ffi.MNT4_G1, 14), (ffi.MNT6_G2, 10)])
+def test_msm_vs_cpp_restatement(ctx, group, log_n):
+    """CUDA MSM == the C++ restatement of the reference's Pippenger (oracle/ref753.cpp) on the same
+    bases and scalars, after normalisation (BASELINE config 1 shape, smaller n)"""
+    import bench
+    from oracle import ref753
+    C = GROUPS[group]
+    n = 1 << log_n
+    bases = ctx.generate_bases(group, n, 0xC0FFEE + group)
+    coords = bases.download()
+    sc = bench.random_scalars(n, 0xBEEF + group)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, sc)
+    want = ref753.msm(group, coords, None, sc)
+    assert projective_to_point(C, got) == projective_to_point(C, want)
+    bases.free()
