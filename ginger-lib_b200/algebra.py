@@ -118,6 +118,11 @@ class Bases:
             z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
             return (z ^ (z >> np.uint64(31))) | np.uint64(1)
 
+    def precompute(self, copies=0):
+        """build the shifted key copies (g753_bases_precompute); MSM results are unchanged"""
+        self.ctx.lib.check(self.ctx.lib.bases_precompute(self.ctx.handle, self.handle, int(copies)))
+        return self
+
     def download(self, first=0, count=None):
         count = self.n - first if count is None else count
         out = np.zeros((count, 2 * self.k * LIMBS), dtype=np.uint64)

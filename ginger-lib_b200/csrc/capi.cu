@@ -261,6 +261,22 @@ int g753_bases_generate(g753_ctx* ctx, int group, const uint64_t* gen_xy, uint64
   return G753_OK;
 }
 
+int g753_bases_precompute(g753_ctx* ctx, g753_bases* b, unsigned copies) {
+  CHECK_CTX(ctx);
+  if (!b) return fail(G753_ERR_BAD_ARG, "null bases");
+  if (copies == 0) copies = 8;
+  if (copies > 64) return fail(G753_ERR_BAD_ARG, "too many copies");
+  if (b->copies > 1 || copies == 1) return G753_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  switch (b->group) {
+    case G753_MNT4_G1: return bases_precompute_impl<0>(ctx, b, copies);
+    case G753_MNT4_G2: return bases_precompute_impl<1>(ctx, b, copies);
+    case G753_MNT6_G1: return bases_precompute_impl<2>(ctx, b, copies);
+    case G753_MNT6_G2: return bases_precompute_impl<3>(ctx, b, copies);
+  }
+  return fail(G753_ERR_BAD_ARG, "unknown group");
+}
+
 int g753_bases_download(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, uint64_t* coords) {
   CHECK_CTX(ctx);
   if (!b || (count && !coords)) return fail(G753_ERR_BAD_ARG, "null pointer");

@@ -42,8 +42,10 @@ struct g753_ctx {
 struct g753_bases {
   int group = 0;
   size_t n = 0;
-  void* d_points = nullptr;
-  uint8_t* d_inf = nullptr;
+  void* d_points = nullptr;   // copies x n affine points; copy j = 2^(j * rows * c) * P_i
+  uint8_t* d_inf = nullptr;   // infinity flags, copies x n (null: no base is infinite)
+  unsigned copies = 1;        // > 1 after g753_bases_precompute
+  unsigned c = 0, rows = 0;   // window bits / bucket rows the copies were built for
 };
 
 static int group_k(int group) {
@@ -86,3 +88,5 @@ template <int GID>
 void points_sum_launch(g753_ctx* ctx, const void* d_pts, size_t count, void* d_out);
 template <int GID>
 int bases_generate_impl(g753_ctx* ctx, const uint64_t* gen_xy, uint64_t seed, size_t n, void* d_points);
+template <int GID>
+int bases_precompute_impl(g753_ctx* ctx, g753_bases* b, unsigned copies);

@@ -47,22 +47,30 @@ template <> struct MsmCfg<2> { static constexpr int K = 1, T_ACC = 128, T_RED = 
 template <> struct MsmCfg<3> { static constexpr int K = 3, T_ACC = 64, T_RED = 32; template <int T> using SC = SCurveM6G2<T>; };
 
 struct MsmPlan {
-  unsigned c;  // window bits
-  unsigned W;  // windows: W * c >= SCALAR_BITS + 1 so the signed recoding never carries out
-  unsigned B;  // buckets per window = 2^(c-1); bucket b holds digit magnitude b, 0 = discard
+  unsigned c;       // window bits
+  unsigned W;       // windows: W * c >= SCALAR_BITS + 1 so the signed recoding never carries out
+  unsigned B;       // buckets per window = 2^(c-1); bucket b holds digit magnitude b, 0 = discard
+  unsigned rows;    // bucket rows = ceil(W / copies): window w = j * rows + r lands in row r and
+                    // uses copy j of the key (copy j holds 2^(j * rows * c) * P_i); copies = 1: rows = W
+  unsigned copies;  // key copies actually used = ceil(W / rows)
 };
 
-// field multiplications: mixed add 10, full add 14 (XYZZ); reduction does 2 full adds / bucket
-static inline MsmPlan msm_plan(size_t n, int forced_c = 0) {
-  MsmPlan best{0, 0, 0};
+// Cost model in field multiplications: mixed add 10, full add 14 (XYZZ); the reduction does 2 full
+// adds per bucket; the final Horner fold is a serial chain of rows * c doublings on ONE thread, each
+// field multiplication of which costs as much wall time as ~20 000 multiplications of the
+// saturated bucket kernels (2.8 us vs 7.7 G/s, measured).
+static inline MsmPlan msm_plan(size_t n, unsigned copies = 1, int forced_c = 0, unsigned forced_rows = 0) {
+  MsmPlan best{0, 0, 0, 0, 0};
   double best_cost = 0;
+  if (copies == 0) copies = 1;
   for (unsigned c = 3; c <= MSM_MAX_C; c++) {
     if (forced_c && (int)c != forced_c) continue;
     unsigned W = (SCALAR_BITS + 1 + c - 1) / c;
+    unsigned rows = forced_rows ? forced_rows : (W + copies - 1) / copies;
     double B = (double)(1u << (c - 1));
-    double cost = (double)W * (10.0 * (double)n + 28.0 * B);
+    double cost = (double)W * 10.0 * (double)n + (double)rows * 28.0 * B + (double)rows * c * 10.0 * 20000.0;
     if (best.c == 0 || cost < best_cost) {
-      best = MsmPlan{c, W, 1u << (c - 1)};
+      best = MsmPlan{c, W, 1u << (c - 1), rows, (W + rows - 1) / rows};
       best_cost = cost;
     }
   }
@@ -72,13 +80,14 @@ static inline MsmPlan msm_plan(size_t n, int forced_c = 0) {
 // ------------------------------------------------------------------------------------
 // K4: digits + histogram
 // ------------------------------------------------------------------------------------
+// window w = j * rows + r: histogram row r; inf (may be null) holds one flag per (copy, point):
+// inf[j * inf_stride + i]
 static __global__ void k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
-                             unsigned n, unsigned c, unsigned W, unsigned B,
+                             size_t inf_stride, unsigned n, unsigned c, unsigned W, unsigned B, unsigned rows,
                              uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t* s = scalars + (size_t)i * NL;
-  bool skip = inf != nullptr && inf[i] != 0;
   const uint32_t half = 1u << (c - 1);
   const uint32_t mask = (1u << c) - 1;
   uint32_t carry = 0;
@@ -99,9 +108,9 @@ static __global__ void k_msm_digits(const uint32_t* __restrict__ scalars, const 
       neg = 0;
       carry = 0;
     }
-    if (skip) mag = 0;
+    if (inf != nullptr && inf[(size_t)(w / rows) * inf_stride + i] != 0) mag = 0;
     digits[(size_t)w * n + i] = mag ? (mag | neg) : 0u;
-    if (mag) atomicAdd(&hist[(size_t)w * (B + 1) + mag], 1u);
+    if (mag) atomicAdd(&hist[(size_t)(w % rows) * (B + 1) + mag], 1u);
   }
 }
 
@@ -146,7 +155,9 @@ static __global__ void k_scan_apply(const uint32_t* __restrict__ hist, const uin
   }
 }
 
+// row r of `sorted` holds row_cap = copies * n entries: base index (j * copy_stride + i) | sign
 static __global__ void k_msm_scatter(const uint32_t* __restrict__ digits, unsigned n, unsigned W, unsigned B,
+                              unsigned rows, size_t copy_stride, size_t row_cap,
                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)W * n) return;
@@ -154,12 +165,13 @@ static __global__ void k_msm_scatter(const uint32_t* __restrict__ digits, unsign
   uint32_t d = digits[t];
   uint32_t mag = d & 0x7fffffffu;
   if (!mag) return;
-  uint32_t pos = atomicAdd(&cursor[(size_t)w * (B + 1) + mag], 1u);
-  sorted[(size_t)w * n + pos] = i | (d & 0x80000000u);
+  const unsigned r = w % rows, j = w / rows;
+  uint32_t pos = atomicAdd(&cursor[(size_t)r * (B + 1) + mag], 1u);
+  sorted[(size_t)r * row_cap + pos] = (uint32_t)(j * copy_stride + i) | (d & 0x80000000u);
 }
 
 // ------------------------------------------------------------------------------------
-// K5a: work items.  Bucket t = w * (B+1) + b owns sorted[w*n + offsets[t] .. w*n + ends[t]).
+// K5a: work items.  Bucket t = r * (B+1) + b owns sorted[r*row_cap + offsets[t] .. r*row_cap + ends[t]).
 // It is cut into ceil(count / ITEM_LEN) items; item ids are item_off[t] + j.  The result of an
 // item goes to points[t] when the bucket has a single item, else to points[NB + item id]
 // (summed into points[t] by k_bucket_fixup).  len_hist[key * ITEM_REP + r] counts items of
@@ -201,7 +213,7 @@ struct MsmItem {  // 16 bytes
 
 static __global__ void k_item_emit(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ends,
                             const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict__ item_off,
-                            unsigned NB, unsigned B, unsigned n, uint32_t* __restrict__ len_cursor,
+                            unsigned NB, unsigned B, size_t row_cap, uint32_t* __restrict__ len_cursor,
                             MsmItem* __restrict__ items) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= NB) return;
@@ -216,7 +228,7 @@ static __global__ void k_item_emit(const uint32_t* __restrict__ offsets, const u
     uint32_t len = hi - s < ITEM_LEN ? hi - s : ITEM_LEN;
     uint32_t pos = atomicAdd(&len_cursor[(ITEM_LEN - len) * ITEM_REP + r], 1u);
     MsmItem it;
-    it.start = (uint32_t)((size_t)w * n + s);
+    it.start = (uint32_t)((size_t)w * row_cap + s);
     it.len = len;
     it.dest = cnt_items == 1 ? t : NB + first_id + j;
     it.pad = 0;
@@ -345,6 +357,7 @@ k_points_sum(const Fq* __restrict__ pts, unsigned count, Fq* __restrict__ out_xy
 // ------------------------------------------------------------------------------------
 struct MsmWorkspace {
   unsigned n_chunks, nb_chunks, level_entries, max_items;
+  size_t row_cap;  // entries per row of sorted[]
   size_t total;
 };
 
@@ -353,10 +366,11 @@ static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n) {
   constexpr size_t PT_BYTES = sizeof(Fq) * 4 * MsmCfg<GID>::K;
   MsmWorkspace s;
   const size_t len = (size_t)pl.B + 1;
-  const size_t NB = pl.W * len;
+  const size_t NB = pl.rows * len;
+  s.row_cap = (size_t)pl.copies * n;
   s.n_chunks = div_up(len, SCAN_CHUNK);
   s.nb_chunks = div_up(NB, SCAN_CHUNK);
-  s.max_items = (unsigned)(NB + (size_t)pl.W * n / ITEM_LEN);
+  s.max_items = (unsigned)(NB + (size_t)pl.rows * s.row_cap / ITEM_LEN);
   unsigned entries = 0;
   for (size_t m = len; m > 1;) {
     m = div_up(m, REDUCE_SEG);
@@ -365,14 +379,15 @@ static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n) {
   if (entries == 0) entries = 1;
   s.level_entries = entries;
   size_t t = 0;
-  t += Carver::pad(sizeof(uint32_t) * pl.W * n) * 2;                    // digits, sorted
+  t += Carver::pad(sizeof(uint32_t) * pl.W * n);                        // digits
+  t += Carver::pad(sizeof(uint32_t) * pl.rows * s.row_cap);             // sorted
   t += Carver::pad(sizeof(uint32_t) * NB) * 5;                          // hist, offsets, cursor, item_cnt, item_off
-  t += Carver::pad(sizeof(uint32_t) * pl.W * s.n_chunks);               // chunk sums
+  t += Carver::pad(sizeof(uint32_t) * pl.rows * s.n_chunks);            // chunk sums
   t += Carver::pad(sizeof(uint32_t) * s.nb_chunks);                     // item-count chunk sums
   t += Carver::pad(sizeof(uint32_t) * ITEM_LEN * ITEM_REP) * 2 + 512;   // length counters + total
   t += Carver::pad(sizeof(MsmItem) * s.max_items);
   t += Carver::pad(PT_BYTES * (NB + s.max_items));                      // buckets + item partials
-  t += Carver::pad(PT_BYTES * pl.W * entries) * 2;                      // reduction levels
+  t += Carver::pad(PT_BYTES * pl.rows * entries) * 2;                   // reduction levels
   s.total = t + 8192;
   return s;
 }
@@ -399,11 +414,23 @@ constexpr size_t slot_bytes(int slots) {
   return (size_t)slots * sizeof(Fq) * T;
 }
 
-// d_bases: `count` affine points (device, 2K Fq each); d_inf: their infinity flags (device, may
-// be null); d_scalars: count x 24 u32 canonical (device); d_out: 3K Fq (device)
+// The bases of one MSM call: `copies` tables of affine points (device, 2K Fq each), table j at
+// bases + j * copy_stride points holding 2^(j * rows * c) * P_i (see g753_bases_precompute);
+// copies == 1 is a plain key.  inf: infinity flags, one per (copy, point), may be null.
+struct MsmKey {
+  const Fq* bases = nullptr;
+  const uint8_t* inf = nullptr;
+  size_t copy_stride = 0;
+  size_t inf_stride = 0;
+  unsigned copies = 1;
+  int c = 0;          // window bits the tables were built for (0 = choose per call)
+  unsigned rows = 0;  // bucket rows the tables were built for (0 = derive)
+};
+
+// d_scalars: count x 24 u32 canonical (device); d_out: 3K Fq (device)
 template <int GID>
-static int msm_run(Scratch& scratch, cudaStream_t stream, const Fq* d_bases, const uint8_t* d_inf,
-                   const uint32_t* d_scalars, size_t count, Fq* d_out, int forced_c, MsmHooks hooks) {
+static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, const uint32_t* d_scalars,
+                   size_t count, Fq* d_out, MsmHooks hooks) {
   typedef MsmCfg<GID> Cfg;
   constexpr int TA = Cfg::T_ACC, TR = Cfg::T_RED;
   typedef typename Cfg::template SC<TA> SCA;
@@ -421,46 +448,50 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const Fq* d_bases, con
   }
   if (count > 0x7fffffffull) return G753_ERR_BAD_ARG;
   const unsigned n = (unsigned)count;
-  const MsmPlan pl = msm_plan(n, forced_c);
-  if ((uint64_t)pl.W * n >= 0xffffffffull) return G753_ERR_BAD_ARG;
+  const MsmPlan pl = msm_plan(n, key.copies, key.c, key.rows);
+  if (pl.c == 0) return G753_ERR_BAD_ARG;
   const MsmWorkspace ws = msm_workspace<GID>(pl, n);
+  if ((uint64_t)pl.W * n >= 0xffffffffull || (uint64_t)pl.rows * ws.row_cap >= 0xffffffffull ||
+      (uint64_t)(pl.copies - 1) * key.copy_stride + n > 0x7fffffffull)
+    return G753_ERR_BAD_ARG;
   G753_TRY(scratch.reserve(ws.total));
   Carver cv(scratch.ptr);
   const size_t len = (size_t)pl.B + 1;
-  const unsigned NB = (unsigned)(pl.W * len);
+  const unsigned R = pl.rows;
+  const unsigned NB = (unsigned)(R * len);
   uint32_t* digits = cv.take<uint32_t>((size_t)pl.W * n);
-  uint32_t* sorted = cv.take<uint32_t>((size_t)pl.W * n);
+  uint32_t* sorted = cv.take<uint32_t>((size_t)R * ws.row_cap);
   uint32_t* hist = cv.take<uint32_t>(NB);
   uint32_t* offsets = cv.take<uint32_t>(NB);
   uint32_t* cursor = cv.take<uint32_t>(NB);
   uint32_t* item_cnt = cv.take<uint32_t>(NB);
   uint32_t* item_off = cv.take<uint32_t>(NB);
-  uint32_t* chunk_sums = cv.take<uint32_t>((size_t)pl.W * ws.n_chunks);
+  uint32_t* chunk_sums = cv.take<uint32_t>((size_t)R * ws.n_chunks);
   uint32_t* item_chunk_sums = cv.take<uint32_t>(ws.nb_chunks);
   uint32_t* len_hist = cv.take<uint32_t>(ITEM_LEN * ITEM_REP);
   uint32_t* len_cursor = cv.take<uint32_t>(ITEM_LEN * ITEM_REP);
   uint32_t* item_total = cv.take<uint32_t>(64);
   MsmItem* items = cv.take<MsmItem>(ws.max_items);
   Fq* points = cv.take<Fq>(PT * ((size_t)NB + ws.max_items));
-  Fq* lvl_r = cv.take<Fq>(PT * pl.W * ws.level_entries);
-  Fq* lvl_y = cv.take<Fq>(PT * pl.W * ws.level_entries);
+  Fq* lvl_r = cv.take<Fq>(PT * R * ws.level_entries);
+  Fq* lvl_y = cv.take<Fq>(PT * R * ws.level_entries);
 
   if (hooks.mark) hooks.mark(hooks.user, 0);
   G753_TRY(dev_memset(hist, 0, sizeof(uint32_t) * NB, stream));
   G753_TRY(dev_memset(len_hist, 0, sizeof(uint32_t) * ITEM_LEN * ITEM_REP, stream));
   // empty buckets are never written by the accumulation: all-zero limbs = ZZ == 0 = infinity
   G753_TRY(dev_memset(points, 0, sizeof(Fq) * PT * NB, stream));
-  G753_MSM_LAUNCH(hooks, k_msm_digits, div_up(n, 256), 256, stream, d_scalars, d_inf, n, pl.c, pl.W, pl.B,
-                  digits, hist);
+  G753_MSM_LAUNCH(hooks, k_msm_digits, div_up(n, 256), 256, stream, d_scalars, key.inf, key.inf_stride, n, pl.c,
+                  pl.W, pl.B, R, digits, hist);
   if (hooks.mark) hooks.mark(hooks.user, 1);
-  G753_MSM_LAUNCH(hooks, k_scan_chunks, div_up((size_t)pl.W * ws.n_chunks, 128), 128, stream, hist,
-                  (unsigned)len, ws.n_chunks, pl.W, chunk_sums);
-  G753_MSM_LAUNCH(hooks, k_scan_tops, div_up(pl.W, 64), 64, stream, chunk_sums, ws.n_chunks, pl.W,
+  G753_MSM_LAUNCH(hooks, k_scan_chunks, div_up((size_t)R * ws.n_chunks, 128), 128, stream, hist,
+                  (unsigned)len, ws.n_chunks, R, chunk_sums);
+  G753_MSM_LAUNCH(hooks, k_scan_tops, div_up(R, 64), 64, stream, chunk_sums, ws.n_chunks, R,
                   (uint32_t*)nullptr);
-  G753_MSM_LAUNCH(hooks, k_scan_apply, div_up((size_t)pl.W * ws.n_chunks, 128), 128, stream, hist,
-                  chunk_sums, (unsigned)len, ws.n_chunks, pl.W, offsets, cursor);
-  G753_MSM_LAUNCH(hooks, k_msm_scatter, div_up((size_t)pl.W * n, 256), 256, stream, digits, n, pl.W, pl.B,
-                  cursor, sorted);
+  G753_MSM_LAUNCH(hooks, k_scan_apply, div_up((size_t)R * ws.n_chunks, 128), 128, stream, hist,
+                  chunk_sums, (unsigned)len, ws.n_chunks, R, offsets, cursor);
+  G753_MSM_LAUNCH(hooks, k_msm_scatter, div_up((size_t)pl.W * n, 256), 256, stream, digits, n, pl.W, pl.B, R,
+                  key.copy_stride, ws.row_cap, cursor, sorted);
   // work items (after the scatter, cursor[t] is the end of bucket t's run)
   G753_MSM_LAUNCH(hooks, k_item_count, div_up(NB, 256), 256, stream, offsets, cursor, NB, pl.B, item_cnt,
                   len_hist);
@@ -471,9 +502,9 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const Fq* d_bases, con
                   NB, ws.nb_chunks, 1u, item_off, (uint32_t*)nullptr);
   G753_MSM_LAUNCH(hooks, k_item_len_scan, 1, 32, stream, len_hist, len_cursor, item_total);
   G753_MSM_LAUNCH(hooks, k_item_emit, div_up(NB, 256), 256, stream, offsets, cursor, item_cnt, item_off, NB,
-                  pl.B, n, len_cursor, items);
+                  pl.B, ws.row_cap, len_cursor, items);
   if (hooks.mark) hooks.mark(hooks.user, 2);
-  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc<SCA>, div_up(ws.max_items, TA), TA, SMEM_ACC, stream, d_bases,
+  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc<SCA>, div_up(ws.max_items, TA), TA, SMEM_ACC, stream, key.bases,
                        sorted, items, item_total, points);
   G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup<SCA>, div_up(NB, TA), TA, SMEM_FIX, stream, item_cnt, item_off,
                        NB, points);
@@ -488,12 +519,12 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const Fq* d_bases, con
   const Fq* window_sums = nullptr;
   for (;;) {
     unsigned n_out = div_up(n_in, REDUCE_SEG);
-    Fq* R = lvl_r + lvl_off * PT;
+    Fq* Rr = lvl_r + lvl_off * PT;
     Fq* Yo = lvl_y + lvl_off * PT;
-    G753_MSM_LAUNCH_SMEM(hooks, k_reduce_level<SCR>, div_up((size_t)pl.W * n_out, TR), TR, SMEM_RED, stream, X,
-                         x_stride, Y, y_stride, n_in, log2f, pl.W, n_out, R, Yo);
-    lvl_off += (size_t)pl.W * n_out;
-    X = R;
+    G753_MSM_LAUNCH_SMEM(hooks, k_reduce_level<SCR>, div_up((size_t)R * n_out, TR), TR, SMEM_RED, stream, X,
+                         x_stride, Y, y_stride, n_in, log2f, R, n_out, Rr, Yo);
+    lvl_off += (size_t)R * n_out;
+    X = Rr;
     Y = Yo;
     x_stride = y_stride = n_out;
     n_in = n_out;
@@ -504,7 +535,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const Fq* d_bases, con
     }
   }
   if (hooks.mark) hooks.mark(hooks.user, 4);
-  G753_MSM_LAUNCH_SMEM(hooks, k_window_combine<SCR>, 1, TR, SMEM_RED, stream, window_sums, 1u, pl.W, pl.c,
+  G753_MSM_LAUNCH_SMEM(hooks, k_window_combine<SCR>, 1, TR, SMEM_RED, stream, window_sums, 1u, R, pl.c,
                        d_out);
   if (hooks.mark) hooks.mark(hooks.user, 5);
   return launch_check("msm_run");

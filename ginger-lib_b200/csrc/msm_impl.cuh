@@ -16,9 +16,21 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
   hooks.mark = phase_mark;
   hooks.user = ctx;
 #endif
-  const Fq* pts = (const Fq*)b->d_points + first * 2 * MsmCfg<GID>::K;
-  const uint8_t* inf = b->d_inf ? b->d_inf + first : nullptr;
-  return msm_run<GID>(ctx->scratch, ctx->stream, pts, inf, d_scalars, count, (Fq*)d_out, ctx->forced_c, hooks);
+  MsmKey key;
+  key.bases = (const Fq*)b->d_points + first * 2 * MsmCfg<GID>::K;
+  key.inf = b->d_inf ? b->d_inf + first : nullptr;
+  key.copy_stride = key.inf_stride = b->n;
+  // the precomputed copies pay off when the slice is a sizeable part of the key they were sized
+  // for; short slices (the prover's input-query views) run the plain pipeline on copy 0
+  if (b->copies > 1 && count * 4 >= b->n) {
+    key.copies = b->copies;
+    key.c = (int)b->c;
+    key.rows = b->rows;
+  } else {
+    key.copies = 1;
+    key.c = ctx->forced_c;
+  }
+  return msm_run<GID>(ctx->scratch, ctx->stream, key, d_scalars, count, (Fq*)d_out, hooks);
 }
 
 // group-law test hook on the product's own slot code (ec_slots.cuh); affine (0, 0) = infinity
@@ -154,8 +166,86 @@ int bases_generate_impl(g753_ctx* ctx, const uint64_t* gen_xy, uint64_t seed, si
   return rc;
 }
 
+// Precomputed key copies (g753_bases_precompute): copy j of point i is 2^(j * shift) * P_i in
+// affine form, shift = rows * c.  Window w = j * rows + r of a scalar then selects a bucket of
+// row r with the base taken from copy j, so the MSM has `rows` bucket rows instead of W: the
+// bucket reduction and the serial Horner fold shrink by W / rows.
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T)
+k_bases_precompute(Fq* __restrict__ pts, uint8_t* __restrict__ inf, unsigned n, unsigned copies, unsigned shift) {
+  typedef EcS<SC> E;
+  typedef typename E::M M;
+  constexpr int K = E::K, P = 0, S = E::PT;
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool is_inf = inf[i] != 0;
+  if (!is_inf) {
+    M::ldg(P, pts + (size_t)i * 2 * K);
+    M::ldg(P + K, pts + (size_t)i * 2 * K + K);
+    M::set_one(P + 2 * K);
+    M::set_one(P + 3 * K);
+  }
+  for (unsigned j = 1; j < copies; j++) {
+    Fq* out = pts + ((size_t)j * n + i) * 2 * K;
+    if (!is_inf) {
+      for (unsigned k = 0; k < shift; k++) E::dbl(P, S);
+      is_inf = E::is_inf(P);
+    }
+    if (is_inf) {
+      M::set_zero(S);
+      M::stg(out, S);
+      M::stg(out + K, S);
+      inf[(size_t)j * n + i] = 1;
+    } else {
+      E::to_affine(P, S);
+      M::stg(out, P);
+      M::stg(out + K, P + K);
+      inf[(size_t)j * n + i] = 0;
+    }
+  }
+}
+
+template <int GID>
+int bases_precompute_impl(g753_ctx* ctx, g753_bases* b, unsigned copies) {
+  constexpr int K = MsmCfg<GID>::K, T = 64;
+  typedef typename MsmCfg<GID>::template SC<T> SC;
+  typedef EcS<SC> E;
+  const size_t n = b->n;
+  const MsmPlan pl = msm_plan(n, copies, ctx->forced_c);
+  if (pl.copies <= 1 || n == 0) return G753_OK;
+  if ((uint64_t)pl.copies * n > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "copies * n exceeds the 31-bit base index");
+  const size_t pt_bytes = sizeof(Fq) * 2 * K;
+  void* d_new = nullptr;
+  uint8_t* d_inf = nullptr;
+  G753_TRY(dev_alloc(&d_new, pt_bytes * n * pl.copies));
+  int rc = dev_alloc((void**)&d_inf, n * pl.copies);
+  if (rc == G753_OK) rc = d2d(d_new, b->d_points, pt_bytes * n, ctx->stream);
+  if (rc == G753_OK) rc = b->d_inf ? d2d(d_inf, b->d_inf, n, ctx->stream) : dev_memset(d_inf, 0, n, ctx->stream);
+  if (rc == G753_OK) {
+    G753_LAUNCH_SMEM(k_bases_precompute<SC>, div_up(n, T), T, (slot_bytes<E, T>(E::PT + E::ADD_SCRATCH)), ctx->stream,
+                     (Fq*)d_new, d_inf, (unsigned)n, pl.copies, pl.rows * pl.c);
+    ctx->launches++;
+    rc = launch_check("k_bases_precompute");
+  }
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  if (rc != G753_OK) {
+    dev_free(d_new);
+    dev_free(d_inf);
+    return rc;
+  }
+  dev_free(b->d_points);
+  dev_free(b->d_inf);
+  b->d_points = d_new;
+  b->d_inf = d_inf;
+  b->copies = pl.copies;
+  b->c = pl.c;
+  b->rows = pl.rows;
+  return G753_OK;
+}
+
 #define G753_INSTANTIATE_GROUP(GID)                                                                        \
   template int msm_dispatch<GID>(g753_ctx*, const g753_bases*, size_t, size_t, const uint32_t*, void*);   \
   template int point_op_impl<GID>(g753_ctx*, int, const uint64_t*, const uint64_t*, uint64_t*);            \
   template void points_sum_launch<GID>(g753_ctx*, const void*, size_t, void*);                               \
-  template int bases_generate_impl<GID>(g753_ctx*, const uint64_t*, uint64_t, size_t, void*);
+  template int bases_generate_impl<GID>(g753_ctx*, const uint64_t*, uint64_t, size_t, void*);                \
+  template int bases_precompute_impl<GID>(g753_ctx*, g753_bases*, unsigned);

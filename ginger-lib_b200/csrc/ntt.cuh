@@ -122,12 +122,145 @@ static int ntt_tables_build(NttTables& T, unsigned log_n, cudaStream_t stream, u
   return launch_check("ntt_tables_build");
 }
 
-// One Stockham radix-2 pass (stage s, sub-transform length Ns = 2^s -> 2^(s+1)):
+// Stockham radix-2 stage s (sub-transform length Ns = 2^s -> 2^(s+1)) on the whole vector:
 //   out[j0], out[j0 + Ns] = in[j] +- in[j + n/2] * omega^(k n / (2 Ns)),  k = j mod Ns,
 //   j0 = (j div Ns) * 2 Ns + k.
+// In index bits (n = 2^L): the input index is [h | u | k] (h = top bit, k = low s bits) and the
+// output index [u | b | k]: every stage consumes the top bit and re-inserts the butterflied bit at
+// position s.  q consecutive stages s .. s+q-1 therefore close over the 2^q elements
+//   in:  (t << (L - q)) | m,                   t < 2^q,   column m = (u' << s) | k  fixed
+//   out: (u' << (s + q)) | (P << s) | k,       P < 2^q,
+// which is what one pass of k_ntt_pass keeps in shared memory: q stages for one trip through HBM.
+// Local stage d of a pass is a Stockham stage of the 2^q-point column with the GLOBAL twiddle
+//   omega^(((kl << s) | k) * 2^(L-1-s-d)),  kl = low d bits of the local butterfly index.
 // pre  (first pass): inputs are multiplied by pre[index]            (coset_fft: g^i)
 // post (last pass):  outputs are multiplied by post[index] or *post_const (ifft: n^-1,
 //                    coset_ifft: g^-i n^-1)
+constexpr int NTT_T = 128;            // threads per block = butterflies per stage per block
+constexpr int NTT_E = 2 * NTT_T;      // elements per block (columns x 2^q)
+constexpr unsigned NTT_MAX_Q = 8;     // 2^q <= NTT_E
+constexpr size_t NTT_SMEM = 2 * (size_t)NTT_E * sizeof(Fq);  // ping-pong buffers, 48 KB
+
+#if !defined(G753_HOST_EMUL)
+// shared-memory layout: buffer b, 16-byte chunk c, element e -> sm[(b * 6 + c) * NTT_E + e]
+G753_D Fq ntt_lds(const uint4* sm, unsigned buf, unsigned e) {
+  const uint4* p = sm + buf * (6 * NTT_E) + e;
+  Fq r;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    uint4 v = p[c * NTT_E];
+    r.l[4 * c] = v.x;
+    r.l[4 * c + 1] = v.y;
+    r.l[4 * c + 2] = v.z;
+    r.l[4 * c + 3] = v.w;
+  }
+  return r;
+}
+G753_D void ntt_sts(uint4* sm, unsigned buf, unsigned e, const Fq& a) {
+  uint4* p = sm + buf * (6 * NTT_E) + e;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    uint4 v;
+    v.x = a.l[4 * c];
+    v.y = a.l[4 * c + 1];
+    v.z = a.l[4 * c + 2];
+    v.w = a.l[4 * c + 3];
+    p[c * NTT_E] = v;
+  }
+}
+G753_D Fq ntt_ldg(const Fq* g) {
+  const uint4* p = (const uint4*)g;
+  Fq r;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    uint4 v = p[c];
+    r.l[4 * c] = v.x;
+    r.l[4 * c + 1] = v.y;
+    r.l[4 * c + 2] = v.z;
+    r.l[4 * c + 3] = v.w;
+  }
+  return r;
+}
+G753_D void ntt_stg(Fq* g, const Fq& a) {
+  uint4* p = (uint4*)g;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    uint4 v;
+    v.x = a.l[4 * c];
+    v.y = a.l[4 * c + 1];
+    v.z = a.l[4 * c + 2];
+    v.w = a.l[4 * c + 3];
+    p[c] = v;
+  }
+}
+
+template <int FID>
+__global__ void __launch_bounds__(NTT_T, 4)
+k_ntt_pass(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restrict__ tw, unsigned L, unsigned s,
+           unsigned q, const Fq* __restrict__ pre, const Fq* __restrict__ post,
+           const Fq* __restrict__ post_const) {
+  extern __shared__ uint4 ntt_sm[];
+  const unsigned tid = threadIdx.x;
+  const unsigned half_q = 1u << (q - 1);
+  const unsigned cidx = tid >> (q - 1);           // column within the block
+  const unsigned jl = tid & (half_q - 1);         // local butterfly index
+  const unsigned cols_per_block = NTT_E >> q;
+  const size_t n_cols = (size_t)1 << (L - q);
+  const size_t m = (size_t)blockIdx.x * cols_per_block + cidx;
+  const bool active = m < n_cols;
+  const size_t k = m & (((size_t)1 << s) - 1), u = m >> s;
+  const unsigned ebase = cidx << q;
+  const size_t i0 = ((size_t)jl << (L - q)) | m, i1 = i0 + ((size_t)1 << (L - 1));
+  for (unsigned d = 0; d < q; d++) {
+    const unsigned kl = jl & ((1u << d) - 1);
+    const unsigned jl0 = ((jl >> d) << (d + 1)) | kl;
+    if (active) {
+      // b (and its twiddle product) first, a afterwards: keeps the multiplier's live set small
+      Fq b;
+      if (d == 0) {
+        b = ntt_ldg(in + i1);
+        if (pre != nullptr) b = fq_mul<FID>(b, ntt_ldg(pre + i1));
+      } else {
+        b = ntt_lds(ntt_sm, (d - 1) & 1, ebase + jl + half_q);
+      }
+      if (s + d != 0) {  // global stage 0: every twiddle is omega^0 = 1
+        const size_t ti = (((size_t)kl << s) | k) << (L - 1 - s - d);
+        b = fq_mul<FID>(b, ntt_ldg(tw + ti));
+      }
+      Fq a;
+      if (d == 0) {
+        a = ntt_ldg(in + i0);
+        if (pre != nullptr) a = fq_mul<FID>(a, ntt_ldg(pre + i0));
+      } else {
+        a = ntt_lds(ntt_sm, (d - 1) & 1, ebase + jl);
+      }
+      Fq x = fq_add<FID>(a, b);
+      Fq y = fq_sub<FID>(a, b);
+      if (d + 1 < q) {
+        ntt_sts(ntt_sm, d & 1, ebase + jl0, x);
+        ntt_sts(ntt_sm, d & 1, ebase + jl0 + (1u << d), y);
+      } else {
+        const size_t o0 = (u << (s + q)) | ((size_t)jl0 << s) | k, o1 = o0 + ((size_t)1 << (d + s));
+        if (post != nullptr) {
+          x = fq_mul<FID>(x, ntt_ldg(post + o0));
+          y = fq_mul<FID>(y, ntt_ldg(post + o1));
+        } else if (post_const != nullptr) {
+          Fq cst = ntt_ldg(post_const);
+          x = fq_mul<FID>(x, cst);
+          y = fq_mul<FID>(y, cst);
+        }
+        ntt_stg(out + o0, x);
+        ntt_stg(out + o1, y);
+      }
+    }
+    if (d + 1 < q) __syncthreads();
+  }
+}
+#endif
+
+// single-stage form of the same recurrence (q = 1 per launch): the TEST-ONLY host-emulation
+// build runs kernels thread by thread and cannot execute block barriers, so it checks the
+// stage indexing through this kernel; the product library launches k_ntt_pass.
 template <int FID>
 __global__ void __launch_bounds__(256, 2)
 k_ntt_stage(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restrict__ tw, unsigned log_n,
@@ -189,7 +322,7 @@ __global__ void __launch_bounds__(256) k_vec_scale(Fq* __restrict__ a, const Fq*
 }
 
 // In-place transform of d_data (n = 2^log_n elements) using d_tmp (same size) as the
-// ping-pong buffer.
+// ping-pong buffer.  The log_n stages are split into ceil(log_n / 8) passes of near-equal depth.
 template <int FID>
 static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tmp, int mode,
                    uint64_t* launches) {
@@ -200,6 +333,7 @@ static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tm
   const Fq* tw = inverse ? T.tw_inv : T.tw_fwd;
   Fq* src = d_data;
   Fq* dst = d_tmp;
+#if defined(G753_HOST_EMUL)
   for (unsigned s = 0; s < log_n; s++) {
     const Fq* pre = (s == 0 && mode == G753_COSET_FFT) ? T.coset : nullptr;
     const Fq* post = (s == log_n - 1 && mode == G753_COSET_IFFT) ? T.coset_inv : nullptr;
@@ -210,6 +344,26 @@ static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tm
     src = dst;
     dst = t;
   }
+#else
+  const unsigned passes = (log_n + NTT_MAX_Q - 1) / NTT_MAX_Q;
+  unsigned s = 0;
+  for (unsigned pi = 0; pi < passes; pi++) {
+    const unsigned q = (log_n - s + (passes - pi) - 1) / (passes - pi);
+    const bool first = (pi == 0), last = (pi + 1 == passes);
+    const Fq* pre = (first && mode == G753_COSET_FFT) ? T.coset : nullptr;
+    const Fq* post = (last && mode == G753_COSET_IFFT) ? T.coset_inv : nullptr;
+    const Fq* post_c = (last && mode == G753_IFFT) ? T.consts : nullptr;
+    const size_t n_cols = n >> q;
+    const unsigned cols_per_block = NTT_E >> q;
+    G753_LAUNCH_SMEM(k_ntt_pass<FID>, div_up(n_cols, cols_per_block), NTT_T, NTT_SMEM, stream, src, dst, tw, log_n, s,
+                     q, pre, post, post_c);
+    if (launches) ++*launches;
+    s += q;
+    Fq* t = src;
+    src = dst;
+    dst = t;
+  }
+#endif
   if (src != d_data) G753_TRY(d2d(d_data, src, sizeof(Fq) * n, stream));
   return launch_check("ntt_run");
 }

@@ -34,6 +34,7 @@ SYMBOLS = [
     ("g753_bases_free", _i, [_vp, _vp]),
     ("g753_bases_len", _sz, [_vp]),
     ("g753_bases_generate", _i, [_vp, _i, _vp, ctypes.c_uint64, _sz, _pvp]),
+    ("g753_bases_precompute", _i, [_vp, _vp, _u]),
     ("g753_bases_download", _i, [_vp, _vp, _sz, _sz, _vp]),
     ("g753_msm", _i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     ("g753_msm_dev", _i, [_vp, _vp, _sz, _sz, _vp, _vp]),

@@ -95,6 +95,13 @@ int g753_bases_free(g753_ctx* ctx, g753_bases* bases);
  * normalised to affine.  sum_i s_i bases[i] = (sum_i s_i a_i mod r) * G at any size. */
 int g753_bases_generate(g753_ctx* ctx, int group, const uint64_t* gen_xy, uint64_t seed, size_t n,
                         g753_bases** out);
+/* Optional, once per resident key: build `copies` (0 = default 8) tables 2^(j*shift) * P_i next to
+ * the key so that an MSM over (most of) it needs W/copies bucket rows instead of W: the bucket
+ * reduction and the serial window fold of variable_base.rs:60-82 shrink accordingly.  Costs
+ * copies x the key's memory and ~(copies-1) * 760 doublings per point, once; results of later
+ * g753_msm* calls are unchanged (same group element).  Calls over short slices (count < n/4)
+ * keep using the plain pipeline. */
+int g753_bases_precompute(g753_ctx* ctx, g753_bases* bases, unsigned copies);
 /* copy `count` resident bases starting at `first` back to the host (2*k*12 limbs each) */
 int g753_bases_download(g753_ctx* ctx, const g753_bases* bases, size_t first, size_t count,
                         uint64_t* coords);

@@ -300,8 +300,19 @@ def test_msm_large_discrete_log_property(ctx, group, log_n):
     assert projective_to_point(C, out) == C.mul(gen, k)
     # zip truncation on a slice view of the resident key (groth16/mod.rs:318-350)
     out = G.VariableBaseMSM.multi_scalar_mul(bases, sc[:1000], first=n - 1500)
-    k = bench.dot_mod(sc[:1000], logs[n - 1500:n - 500], C.r)
+    k_slice = bench.dot_mod(sc[:1000], logs[n - 1500:n - 500], C.r)
+    assert projective_to_point(C, out) == C.mul(gen, k_slice)
+    # same key with the precomputed shifted copies (g753_bases_precompute): same group element,
+    # for the whole key, a long slice (on the copies) and a short slice (plain pipeline)
+    plain = out
+    bases.precompute(8 if kk == 1 else 4)
+    out = G.VariableBaseMSM.multi_scalar_mul(bases, sc)
     assert projective_to_point(C, out) == C.mul(gen, k)
+    out = G.VariableBaseMSM.multi_scalar_mul(bases, sc[:1000], first=n - 1500)
+    assert projective_to_point(C, out) == projective_to_point(C, plain)
+    m = n // 2 + 3
+    out = G.VariableBaseMSM.multi_scalar_mul(bases, sc[:m], first=5)
+    assert projective_to_point(C, out) == C.mul(gen, bench.dot_mod(sc[:m], logs[5:5 + m], C.r))
     bases.free()
 
 

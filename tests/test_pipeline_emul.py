@@ -167,3 +167,35 @@ def test_bad_arguments(ctx):
     z = np.zeros((1, 24), dtype=np.uint64)
     assert lib.bases_upload(ctx.handle, 9, ffi.ptr(z), None, 1, ctypes.byref(h)) == ffi.ERR_BAD_ARG
     assert b"unknown group" in lib.last_error()
+
+
+@pytest.mark.parametrize("group,c,copies", [(ffi.MNT4_G1, 7, 4), (ffi.MNT4_G1, 0, 8), (ffi.MNT6_G2, 9, 3)])
+def test_msm_precomputed_key_copies(ctx, monkeypatch, group, c, copies):
+    """g753_bases_precompute: copy j holds 2^(j*rows*c) * P_i; the MSM over the key (and over
+    slices of it) must give the same group element as the plain pipeline / the naive sum"""
+    C = GROUPS[group]
+    n = 24 if C.F.k == 1 else 8
+    pts = sample_points(C, n, 0x1A0 + group)
+    sc = sample_scalars(C, n, 0x1B0 + group)
+    pts[1] = None
+    sc[2] = 0
+    sc[3] = 1
+    sc[4] = C.r - 1
+    pts[6] = pts[5]
+    pts[7] = C.neg(pts[5])
+    sc[7] = sc[5]
+    coords, inf = points_to_arrays(C, pts)
+    if c:
+        monkeypatch.setenv("G753_MSM_C", str(c))
+    cx = G.Context(0, library=ctx.lib)
+    bases = cx.upload_bases(group, coords, inf).precompute(copies)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc), first=2)      # slice, still on the copies
+    assert projective_to_point(C, got) == O.msm_naive(C, pts[2:], sc)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc[:3]), first=4)  # short slice: plain pipeline
+    assert projective_to_point(C, got) == O.msm_naive(C, pts[4:7], sc[:3])
+    keep = inf == 0                                        # infinite bases are zeroed on upload
+    assert (bases.download(0, n)[keep] == coords[keep]).all()
+    bases.free()
+    cx.close()
