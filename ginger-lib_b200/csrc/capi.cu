@@ -61,6 +61,29 @@ static int ntt_field(g753_ctx* ctx, Fq* d_data, Fq* d_tmp, unsigned log_n, int m
   return ntt_run<FID>(it->second, ctx->stream, d_data, d_tmp, mode, &ctx->launches);
 }
 
+// R1CStoQAP::witness_map after the constraint evaluation (r1cs_to_qap.rs:121-166), chained on
+// the device: 7 transforms + the element-wise steps, no host round trips.
+template <int FID>
+static int witness_map_field(g753_ctx* ctx, Fq* a, Fq* b, Fq* c, unsigned log_n, const Fq* d_d, Fq* h) {
+  const size_t n = (size_t)1 << log_n;
+  G753_TRY(ctx->scratch_io.reserve(sizeof(Fq) * n + 1024));
+  Fq* tmp = (Fq*)ctx->scratch_io.ptr;
+  G753_TRY(ntt_field<FID>(ctx, a, tmp, log_n, G753_IFFT));
+  G753_TRY(ntt_field<FID>(ctx, b, tmp, log_n, G753_IFFT));
+  G753_TRY(ntt_field<FID>(ctx, a, tmp, log_n, G753_COSET_FFT));
+  G753_TRY(ntt_field<FID>(ctx, b, tmp, log_n, G753_COSET_FFT));
+  G753_TRY(ntt_field<FID>(ctx, c, tmp, log_n, G753_IFFT));
+  G753_TRY(ntt_field<FID>(ctx, c, tmp, log_n, G753_COSET_FFT));
+  const NttTables& T = ctx->tables[FID].find(log_n)->second;
+  const unsigned L = log_n ? log_n : 1;
+  G753_LAUNCH(k_witness_combine<FID>, div_up(n, 256), 256, ctx->stream, a, b, c, T.consts + 1 + 4 * L, n);
+  ctx->launches++;
+  G753_TRY(ntt_field<FID>(ctx, a, tmp, log_n, G753_COSET_IFFT));
+  G753_LAUNCH(k_witness_finish<FID>, div_up(n + 1, 256), 256, ctx->stream, a, d_d, h, n);
+  ctx->launches++;
+  return launch_check("witness_map");
+}
+
 // ------------------------------------------------------------------------------------
 // test kernels: group law / field ops through the real device code
 // ------------------------------------------------------------------------------------
@@ -357,6 +380,22 @@ int g753_points_sum_dev(g753_ctx* ctx, int group, const void* d_points_xyz, size
   return launch_check("k_points_sum");
 }
 
+int g753_batch_normalize(g753_ctx* ctx, int group, const uint64_t* xyz, size_t count, uint64_t* xy,
+                         uint8_t* infinity) {
+  CHECK_CTX(ctx);
+  if (count && (!xyz || !xy || !infinity)) return fail(G753_ERR_BAD_ARG, "null pointer");
+  if (count > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "too many points");
+  if (count == 0) return G753_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  switch (group) {
+    case G753_MNT4_G1: return batch_normalize_impl<0>(ctx, xyz, count, xy, infinity);
+    case G753_MNT4_G2: return batch_normalize_impl<1>(ctx, xyz, count, xy, infinity);
+    case G753_MNT6_G1: return batch_normalize_impl<2>(ctx, xyz, count, xy, infinity);
+    case G753_MNT6_G2: return batch_normalize_impl<3>(ctx, xyz, count, xy, infinity);
+  }
+  return fail(G753_ERR_BAD_ARG, "unknown group");
+}
+
 // ---- NTT ---------------------------------------------------------------------------------
 int g753_domain_check(int field, unsigned log_n) {
   if (field != 0 && field != 1) return fail(G753_ERR_BAD_ARG, "unknown field");
@@ -395,6 +434,48 @@ int g753_ntt(g753_ctx* ctx, int field, uint64_t* data, unsigned log_n, int mode)
   G753_TRY(ntt_any(ctx, field, d_data, d_tmp, log_n, mode));
   G753_TRY(d2h(data, d_data, bytes, ctx->stream));
   return stream_sync(ctx->stream);
+}
+
+int g753_witness_map_dev(g753_ctx* ctx, int field, void* d_a, void* d_b, void* d_c, unsigned log_n,
+                         const uint64_t* d123_mont, void* d_h) {
+  CHECK_CTX(ctx);
+  if (!d_a || !d_b || !d_c || !d123_mont || !d_h) return fail(G753_ERR_BAD_ARG, "null pointer");
+  G753_TRY(g753_domain_check(field, log_n));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  // d1, d2, d3 travel through a small dedicated device slot
+  Fq* d_d = nullptr;
+  G753_TRY(dev_alloc((void**)&d_d, sizeof(Fq) * 3));
+  int rc = h2d(d_d, d123_mont, sizeof(Fq) * 3, ctx->stream);
+  if (rc == G753_OK)
+    rc = field == 0 ? witness_map_field<0>(ctx, (Fq*)d_a, (Fq*)d_b, (Fq*)d_c, log_n, d_d, (Fq*)d_h)
+                    : witness_map_field<1>(ctx, (Fq*)d_a, (Fq*)d_b, (Fq*)d_c, log_n, d_d, (Fq*)d_h);
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d_d);
+  return rc;
+}
+
+int g753_witness_map(g753_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                     unsigned log_n, const uint64_t* d123_mont, uint64_t* h) {
+  CHECK_CTX(ctx);
+  if (!a || !b || !c || !d123_mont || !h) return fail(G753_ERR_BAD_ARG, "null pointer");
+  G753_TRY(g753_domain_check(field, log_n));
+  const size_t n = (size_t)1 << log_n, bytes = sizeof(Fq) * n;
+  void *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_h = nullptr;
+  int rc = dev_alloc(&d_a, bytes);
+  if (rc == G753_OK) rc = dev_alloc(&d_b, bytes);
+  if (rc == G753_OK) rc = dev_alloc(&d_c, bytes);
+  if (rc == G753_OK) rc = dev_alloc(&d_h, bytes + sizeof(Fq));
+  if (rc == G753_OK) rc = h2d(d_a, a, bytes, ctx->stream);
+  if (rc == G753_OK) rc = h2d(d_b, b, bytes, ctx->stream);
+  if (rc == G753_OK) rc = h2d(d_c, c, bytes, ctx->stream);
+  if (rc == G753_OK) rc = g753_witness_map_dev(ctx, field, d_a, d_b, d_c, log_n, d123_mont, d_h);
+  if (rc == G753_OK) rc = d2h(h, d_h, bytes + sizeof(Fq), ctx->stream);
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d_a);
+  dev_free(d_b);
+  dev_free(d_c);
+  dev_free(d_h);
+  return rc;
 }
 
 int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n) {
@@ -454,6 +535,10 @@ int g753_d2h(g753_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
   CHECK_CTX(ctx);
   G753_TRY(d2h(h_dst, d_src, bytes, ctx->stream));
   return stream_sync(ctx->stream);
+}
+int g753_d2d(g753_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+  CHECK_CTX(ctx);
+  return d2d(d_dst, d_src, bytes, ctx->stream);
 }
 int g753_sync(g753_ctx* ctx) {
   CHECK_CTX(ctx);

@@ -90,3 +90,5 @@ template <int GID>
 int bases_generate_impl(g753_ctx* ctx, const uint64_t* gen_xy, uint64_t seed, size_t n, void* d_points);
 template <int GID>
 int bases_precompute_impl(g753_ctx* ctx, g753_bases* b, unsigned copies);
+template <int GID>
+int batch_normalize_impl(g753_ctx* ctx, const uint64_t* xyz, size_t count, uint64_t* xy, uint8_t* infinity);

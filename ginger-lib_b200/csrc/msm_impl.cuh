@@ -243,9 +243,67 @@ int bases_precompute_impl(g753_ctx* ctx, g753_bases* b, unsigned copies) {
   return G753_OK;
 }
 
+// GroupProjective::batch_normalization / into_affine (short_weierstrass_projective.rs:402-442,
+// 663-678): homogeneous (X:Y:Z) -> affine (X/Z, Y/Z); Z == 0 -> GroupAffine::zero() = (0, 1, true).  One thread
+// per point with its own inversion: the prover normalises 3 points per proof.
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T)
+k_batch_normalize(const Fq* __restrict__ xyz, unsigned n, Fq* __restrict__ xy, uint8_t* __restrict__ inf) {
+  typedef EcS<SC> E;
+  typedef typename E::M M;
+  constexpr int K = E::K, X = 0, Y = K, Z = 2 * K, ZI = 3 * K, S = 4 * K;
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  M::ldg(Z, xyz + (size_t)i * 3 * K + 2 * K);
+  if (M::is_zero(Z)) {
+    M::set_zero(X);
+    M::stg(xy + (size_t)i * 2 * K, X);
+    M::set_one(Y);  // GroupAffine::zero() = (0, 1, infinity) (short_weierstrass_projective.rs:130-132)
+    M::stg(xy + (size_t)i * 2 * K + K, Y);
+    inf[i] = 1;
+    return;
+  }
+  M::ldg(X, xyz + (size_t)i * 3 * K);
+  M::ldg(Y, xyz + (size_t)i * 3 * K + K);
+  M::inv(ZI, Z, S);
+  M::mul(X, X, ZI, S);
+  M::mul(Y, Y, ZI, S);
+  M::stg(xy + (size_t)i * 2 * K, X);
+  M::stg(xy + (size_t)i * 2 * K + K, Y);
+  inf[i] = 0;
+}
+
+template <int GID>
+int batch_normalize_impl(g753_ctx* ctx, const uint64_t* xyz, size_t count, uint64_t* xy, uint8_t* infinity) {
+  constexpr int K = MsmCfg<GID>::K, T = 32;
+  typedef typename MsmCfg<GID>::template SC<T> SC;
+  typedef EcS<SC> E;
+  const size_t prj = sizeof(Fq) * 3 * K, aff = sizeof(Fq) * 2 * K;
+  Fq *d_in = nullptr, *d_out = nullptr;
+  uint8_t* d_inf = nullptr;
+  int rc = dev_alloc((void**)&d_in, prj * count);
+  if (rc == G753_OK) rc = dev_alloc((void**)&d_out, aff * count);
+  if (rc == G753_OK) rc = dev_alloc((void**)&d_inf, count);
+  if (rc == G753_OK) rc = h2d(d_in, xyz, prj * count, ctx->stream);
+  if (rc == G753_OK) {
+    G753_LAUNCH_SMEM(k_batch_normalize<SC>, div_up(count, T), T, (slot_bytes<E, T>(4 * K + E::M::NTMP + 1)), ctx->stream,
+                     d_in, (unsigned)count, d_out, d_inf);
+    ctx->launches++;
+    rc = launch_check("k_batch_normalize");
+  }
+  if (rc == G753_OK) rc = d2h(xy, d_out, aff * count, ctx->stream);
+  if (rc == G753_OK) rc = d2h(infinity, d_inf, count, ctx->stream);
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d_in);
+  dev_free(d_out);
+  dev_free(d_inf);
+  return rc;
+}
+
 #define G753_INSTANTIATE_GROUP(GID)                                                                        \
   template int msm_dispatch<GID>(g753_ctx*, const g753_bases*, size_t, size_t, const uint32_t*, void*);   \
   template int point_op_impl<GID>(g753_ctx*, int, const uint64_t*, const uint64_t*, uint64_t*);            \
   template void points_sum_launch<GID>(g753_ctx*, const void*, size_t, void*);                               \
   template int bases_generate_impl<GID>(g753_ctx*, const uint64_t*, uint64_t, size_t, void*);                \
-  template int bases_precompute_impl<GID>(g753_ctx*, g753_bases*, unsigned);
+  template int bases_precompute_impl<GID>(g753_ctx*, g753_bases*, unsigned);                                 \
+  template int batch_normalize_impl<GID>(g753_ctx*, const uint64_t*, size_t, uint64_t*, uint8_t*);

@@ -27,7 +27,7 @@ struct NttTables {
   Fq* tw_inv = nullptr;     // omega^-j
   Fq* coset = nullptr;      // g^i,            i < n       (g = 17)
   Fq* coset_inv = nullptr;  // g^-i * n^-1
-  Fq* consts = nullptr;     // [0] = n^-1, then the four squaring chains
+  Fq* consts = nullptr;     // [0] = n^-1, the four squaring chains, then (g^n - 1)^-1
   void release() {
     dev_free(tw_fwd);
     dev_free(tw_inv);
@@ -39,7 +39,8 @@ struct NttTables {
 };
 
 // consts layout: [0] n^-1 ; [1 + l] omega^(2^l) ; [1 + L + l] omega^-(2^l) ; [1 + 2L + l] g^(2^l) ;
-// [1 + 3L + l] g^-(2^l), L = max(log_n, 1), l < L
+// [1 + 3L + l] g^-(2^l), L = max(log_n, 1), l < L ; [1 + 4L] (g^n - 1)^-1, the inverse of the
+// vanishing polynomial on the coset (divide_by_vanishing_poly_on_coset_in_place, domain.rs:245-256)
 template <int FID>
 __global__ void k_ntt_setup(unsigned log_n, Fq* consts) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -71,6 +72,9 @@ __global__ void k_ntt_setup(unsigned log_n, Fq* consts) {
     g = fq_sqr<FID>(g);
     gi = fq_sqr<FID>(gi);
   }
+  // after the loop g = 17^(2^L); for log_n = 0 the domain has one element and g^n = 17
+  Fq gn = log_n ? g : consts[1 + 2 * L];
+  consts[1 + 4 * L] = fq_inv<FID>(fq_sub<FID>(gn, fq_one<FID>()));
 }
 
 // tab[0] = *first (or one)
@@ -93,7 +97,7 @@ static int ntt_tables_build(NttTables& T, unsigned log_n, cudaStream_t stream, u
   const size_t n = (size_t)1 << log_n;
   const size_t half = n > 1 ? n / 2 : 1;
   const unsigned L = log_n ? log_n : 1;
-  G753_TRY(dev_alloc((void**)&T.consts, sizeof(Fq) * (1 + 4 * L)));
+  G753_TRY(dev_alloc((void**)&T.consts, sizeof(Fq) * (2 + 4 * L)));
   G753_TRY(dev_alloc((void**)&T.tw_fwd, sizeof(Fq) * half));
   G753_TRY(dev_alloc((void**)&T.tw_inv, sizeof(Fq) * half));
   G753_TRY(dev_alloc((void**)&T.coset, sizeof(Fq) * n));
@@ -319,6 +323,42 @@ __global__ void __launch_bounds__(256) k_vec_scale(Fq* __restrict__ a, const Fq*
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   a[i] = fq_mul<FID>(a[i], *k);
+}
+
+// R1CStoQAP::witness_map element-wise steps (proof-systems/src/groth16/r1cs_to_qap.rs:137-166):
+//   ab[i] = (a[i] * b[i] - c[i]) * (g^n - 1)^-1        mul_polynomials_in_evaluation_domain,
+//                                                       ab -= c, divide_by_vanishing_poly_on_coset
+template <int FID>
+__global__ void __launch_bounds__(256)
+k_witness_combine(Fq* __restrict__ a, const Fq* __restrict__ b, const Fq* __restrict__ c,
+                  const Fq* __restrict__ zinv, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq t = fq_mul<FID>(a[i], b[i]);
+  t = fq_sub<FID>(t, c[i]);
+  a[i] = fq_mul<FID>(t, *zinv);
+}
+// h has n + 1 entries (r1cs_to_qap.rs:125-132, 163-166).  The reference builds h as
+// `vec![zero; n]` and then MULTIPLIES each h_i by (d2 a_i + d1 b_i) (:127-130), which leaves the
+// zeros in place; so h = [-d3 - d1 d2, 0, ..., 0, d1 d2] before the quotient is added to
+// h[..n-1].  Reproduced as is: d[0] = d1, d[1] = d2, d[2] = d3 (device, Montgomery form).
+template <int FID>
+__global__ void __launch_bounds__(256)
+k_witness_finish(const Fq* __restrict__ ab, const Fq* __restrict__ d, Fq* __restrict__ h, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  Fq v = fq_zero<FID>();
+  if (i + 1 < n) v = ab[i];
+  if (i == 0 || i == n) {
+    Fq d1d2 = fq_mul<FID>(d[0], d[1]);
+    if (i == n) {
+      v = d1d2;
+    } else {
+      Fq base = fq_sub<FID>(fq_sub<FID>(fq_zero<FID>(), d[2]), d1d2);  // h[0] -= d3; h[0] -= d1 d2
+      v = fq_add<FID>(base, v);
+    }
+  }
+  h[i] = v;
 }
 
 // In-place transform of d_data (n = 2^log_n elements) using d_tmp (same size) as the

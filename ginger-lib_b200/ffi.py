@@ -40,16 +40,20 @@ SYMBOLS = [
     ("g753_msm_dev", _i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     ("g753_msm_host", _i, [_vp, _i, _vp, _vp, _sz, _vp, _sz, _vp]),
     ("g753_points_sum_dev", _i, [_vp, _i, _vp, _sz, _vp]),
+    ("g753_batch_normalize", _i, [_vp, _i, _vp, _sz, _vp, _vp]),
     ("g753_group_coord_limbs", _i, [_i]),
     ("g753_domain_check", _i, [_i, _u]),
     ("g753_ntt", _i, [_vp, _i, _vp, _u, _i]),
     ("g753_ntt_dev", _i, [_vp, _i, _vp, _u, _i]),
     ("g753_vec_op_dev", _i, [_vp, _i, _i, _vp, _vp, _sz]),
     ("g753_vec_scale_dev", _i, [_vp, _i, _vp, _vp, _sz]),
+    ("g753_witness_map", _i, [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp]),
+    ("g753_witness_map_dev", _i, [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp]),
     ("g753_dev_alloc", _i, [_vp, _sz, _pvp]),
     ("g753_dev_free", _i, [_vp, _vp]),
     ("g753_h2d", _i, [_vp, _vp, _vp, _sz]),
     ("g753_d2h", _i, [_vp, _vp, _vp, _sz]),
+    ("g753_d2d", _i, [_vp, _vp, _vp, _sz]),
     ("g753_sync", _i, [_vp]),
     ("g753_stream", _vp, [_vp]),
     ("g753_field_op", _i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),

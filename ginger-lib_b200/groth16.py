@@ -1,0 +1,236 @@
+"""Host-side mirror of the Groth16 prover's hot path: `R1CStoQAP::witness_map` from the evaluated
+constraints onwards (proof-systems/src/groth16/r1cs_to_qap.rs:121-166) and `create_proof` from the
+witness map onwards (proof-systems/src/groth16/prover.rs:241-345).
+
+Same inputs, outputs and semantics as the reference:
+  * `Parameters` holds what `groth16::Parameters<E>` holds for the prover (mod.rs:313-371): the five
+    queries (resident on the GPU as `Bases`) and the vk points alpha_g1, beta_g1, beta_g2, delta_g1,
+    delta_g2;
+  * `create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s)` returns the affine
+    proof (A in G1, B in G2, C in G1), every coordinate fully reduced - the bits the reference's
+    `Proof { a: g_a.into_affine(), b: g2_b.into_affine(), c: g_c.into_affine() }` holds.
+Constraint synthesis / evaluation (prover.rs:215-237, r1cs_to_qap.rs:84-119) is R1CS code outside the
+hot path: the caller passes the evaluation vectors a, b, c and the assignment.
+
+All arithmetic runs in libg753.so on the GPU: the witness map is chained on the device
+(g753_witness_map_dev), `into_repr` (prover.rs:241-267) is a device pass, the scalars of the nine
+MSMs never visit the host, and the fixed small terms (delta * r, query[0], alpha, ...) ride along in
+the input-query MSMs.  This file only shapes buffers and sequences C-ABI calls.
+"""
+import ctypes
+
+import numpy as np
+
+from . import ffi
+from .algebra import Bases
+
+LIMBS = 12
+ONE = np.array([[1] + [0] * 11], dtype=np.uint64)
+
+
+def _limbs(v):
+    return np.array([[(int(v) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(LIMBS)]], dtype=np.uint64)
+
+
+class Parameters:
+    """`groth16::Parameters<E>` as the prover reads it.  Queries: (coords (n, 2*k*12) Montgomery
+    uint64, infinity (n,) uint8 or None), or an already resident `Bases` (no infinite entries among
+    its first num_inputs).  vk points: (2*k*12,) Montgomery affine limbs."""
+
+    def __init__(self, ctx, g1, g2, field, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, a_query, b_g1_query,
+                 b_g2_query, h_query, l_query, num_inputs, precompute=0):
+        self.ctx, self.g1, self.g2, self.field, self.num_inputs = ctx, g1, g2, field, num_inputs
+        k2 = ffi.GROUP_K[g2]
+        ni = num_inputs
+
+        def up(group, q):
+            b = q if isinstance(q, Bases) else Bases(ctx, group, q[0], q[1])
+            if precompute and len(b) >= 1 << 12:
+                b.precompute(precompute)
+            return b
+
+
+        # small resident keys: query[0..ni] followed by the vk points their proof element adds
+        # (prover.rs:274-283, 290-299, 306-315), so one short MSM covers all fixed small terms
+        def small(group, q, extra, k):
+            coords, inf = (q.download(0, ni), None) if isinstance(q, Bases) else q
+            c = np.concatenate([ffi.as_u64(coords).reshape(-1, 2 * k * LIMBS)[:ni]] +
+                               [ffi.as_u64(e).reshape(1, 2 * k * LIMBS) for e in extra])
+            i = np.zeros(c.shape[0], dtype=np.uint8)
+            if inf is not None:
+                i[:ni] = np.asarray(inf, dtype=np.uint8)[:ni]
+            return Bases(ctx, group, c, i)
+
+        self.a_small = small(g1, a_query, [delta_g1, alpha_g1], 1)
+        self.b1_small = small(g1, b_g1_query, [delta_g1, beta_g1], 1)
+        self.b2_small = small(g2, b_g2_query, [delta_g2, beta_g2], k2)
+        self.a_query, self.b_g1_query, self.h_query, self.l_query = (up(g1, q) for q in (a_query, b_g1_query, h_query, l_query))
+        self.b_g2_query = up(g2, b_g2_query)
+        self.delta_g1 = ffi.as_u64(delta_g1).reshape(1, 2 * LIMBS)
+
+    def free(self):
+        for b in (self.a_query, self.b_g1_query, self.b_g2_query, self.h_query, self.l_query, self.a_small,
+                  self.b1_small, self.b2_small):
+            b.free()
+
+
+class Proof:
+    def __init__(self, a, b, c, inf):
+        self.a, self.b, self.c, self.infinity = a, b, c, inf
+
+
+class _Dev:
+    """a device buffer of `n` field elements / scalars"""
+
+    def __init__(self, ctx, n):
+        self.ctx, self.n = ctx, n
+        self.p = ctypes.c_void_p()
+        ctx.lib.check(ctx.lib.dev_alloc(ctx.handle, max(n, 1) * 96, ctypes.byref(self.p)))
+
+    def at(self, i):
+        return ctypes.c_void_p(self.p.value + 96 * i)
+
+    def put(self, host, first=0):
+        host = ffi.as_u64(host).reshape(-1, LIMBS)
+        self.ctx.lib.check(self.ctx.lib.h2d(self.ctx.handle, self.at(first), ffi.ptr(host), host.shape[0] * 96))
+
+    def get(self, first=0, count=None):
+        count = self.n - first if count is None else count
+        out = np.empty((count, LIMBS), dtype=np.uint64)
+        self.ctx.lib.check(self.ctx.lib.d2h(self.ctx.handle, ffi.ptr(out), self.at(first), count * 96))
+        return out
+
+    def free(self):
+        if self.p:
+            self.ctx.lib.dev_free(self.ctx.handle, self.p)
+            self.p = None
+
+
+def witness_map(ctx, field, a, b, c, d1, d2, d3):
+    """host-buffer form: a, b, c (n, 12) Montgomery evaluations, d1..d3 canonical ints -> h (n+1, 12)
+    Montgomery (r1cs_to_qap.rs:121-166)"""
+    lib = ctx.lib
+    a, b, c = (ffi.as_u64(v).reshape(-1, LIMBS) for v in (a, b, c))
+    n = a.shape[0]
+    log_n = n.bit_length() - 1
+    if 1 << log_n != n or b.shape[0] != n or c.shape[0] != n:
+        raise ValueError("a, b, c must have the domain's size (a power of two)")
+    d = np.concatenate([_limbs(d1), _limbs(d2), _limbs(d3)])
+    dm = np.zeros_like(d)
+    lib.check(lib.field_op(ctx.handle, field, ffi.OP_TO_MONT, ffi.ptr(d), None, ffi.ptr(dm), 3))
+    h = np.zeros((n + 1, LIMBS), dtype=np.uint64)
+    lib.check(lib.witness_map(ctx.handle, field, ffi.ptr(a), ffi.ptr(b), ffi.ptr(c), log_n, ffi.ptr(dm), ffi.ptr(h)))
+    return h
+
+
+def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=None):
+    """prover.rs:201-345 after constraint synthesis.
+
+    full_assignment: (num_inputs + num_aux, 12) Montgomery, inputs first, index 0 = the constant one;
+    a, b, c: (domain_size, 12) Montgomery evaluation vectors; d1, d2, d3, r, s: canonical ints (E::Fr).
+    Returns Proof with affine Montgomery limbs: a (2, 12), b (2, k2*12), c (2, 12)."""
+    import time
+    ctx, lib, field = params.ctx, params.ctx.lib, params.field
+    g1, g2, ni = params.g1, params.g2, params.num_inputs
+    k2 = ffi.GROUP_K[g2]
+    t0 = time.perf_counter()
+    a, b, c = (ffi.as_u64(v).reshape(-1, LIMBS) for v in (a, b, c))
+    z = ffi.as_u64(full_assignment).reshape(-1, LIMBS)
+    n = a.shape[0]
+    log_n = n.bit_length() - 1
+    n_vars = z.shape[0]
+    n_aux = n_vars - ni
+
+    # ---- witness map on the device, then into_repr of h and the assignment (prover.rs:241-267) ----
+    dev = [_Dev(ctx, n) for _ in range(3)]
+    d_h = _Dev(ctx, n + 1)
+    d_z = _Dev(ctx, n_vars + 1)
+    consts = _Dev(ctx, 8)
+    try:
+        for dv, host in zip(dev, (a, b, c)):
+            dv.put(host)
+        dd = np.concatenate([_limbs(d1), _limbs(d2), _limbs(d3), _limbs(r), _limbs(s)])
+        dm = np.zeros_like(dd)
+        lib.check(lib.field_op(ctx.handle, field, ffi.OP_TO_MONT, ffi.ptr(dd), None, ffi.ptr(dm), 5))
+        lib.check(lib.witness_map_dev(ctx.handle, field, dev[0].p, dev[1].p, dev[2].p, log_n, ffi.ptr(dm), d_h.p))
+        lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_h.p, None, n + 1))
+        d_z.put(z)
+        lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_z.p, None, n_vars))
+        if timings is not None:
+            ctx.sync()
+            timings["witness_map"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+
+        # -rs for the C term (prover.rs:327): field arithmetic on the device, canonical result
+        rs = np.zeros((1, LIMBS), dtype=np.uint64)
+        lib.check(lib.field_op(ctx.handle, field, ffi.OP_MUL, ffi.ptr(dm[3:4]), ffi.ptr(dm[4:5]), ffi.ptr(rs), 1))
+        zero = np.zeros((1, LIMBS), dtype=np.uint64)
+        lib.check(lib.field_op(ctx.handle, field, ffi.OP_SUB, ffi.ptr(zero), ffi.ptr(rs), ffi.ptr(rs), 1))
+        lib.check(lib.field_op(ctx.handle, field, ffi.OP_FROM_MONT, ffi.ptr(rs), None, ffi.ptr(rs), 1))
+
+        # small scalar vectors [1, inputs..., r|s, 1]: the constant-one slot of the assignment is
+        # replaced by a literal 1 (the reference adds query[0] unconditionally, prover.rs:277)
+        def small_scalars(blind):
+            dv = _Dev(ctx, ni + 2)
+            dv.put(ONE, 0)
+            if ni > 1:
+                lib.check(lib.d2d(ctx.handle, dv.at(1), d_z.at(1), (ni - 1) * 96))
+            dv.put(_limbs(blind), ni)
+            dv.put(ONE, ni + 1)
+            return dv
+
+        out1 = _Dev(ctx, 3 * 16)        # G1 partial results, 3 Fq each
+        out2 = _Dev(ctx, 3 * k2 * 4)    # G2 partial results
+
+        def msm(bases, first, count, d_scalars, d_out):
+            count = max(0, min(count, len(bases) - first))
+            lib.check(lib.msm_dev(ctx.handle, bases.handle, first, count, d_scalars, d_out))
+
+        sr, ss = small_scalars(r), small_scalars(s)
+        slot = lambda o, i, k=1: o.at(3 * k * i)
+        # A (prover.rs:270-283): slots 0, 1
+        msm(params.a_small, 0, ni + 2, sr.p, slot(out1, 0))
+        msm(params.a_query, ni, n_aux, d_z.at(ni), slot(out1, 1))
+        # B in G1 (:286-299): slots 2, 3
+        msm(params.b1_small, 0, ni + 2, ss.p, slot(out1, 2))
+        msm(params.b_g1_query, ni, n_aux, d_z.at(ni), slot(out1, 3))
+        # B in G2 (:302-315)
+        msm(params.b2_small, 0, ni + 2, ss.p, slot(out2, 0, k2))
+        msm(params.b_g2_query, ni, n_aux, d_z.at(ni), slot(out2, 1, k2))
+        # C (:318-337): H (zip-truncated against h, n + 1 scalars vs n - 1 bases), L; slots 4..6
+        msm(params.h_query, 0, min(ni, n + 1), d_h.at(0), slot(out1, 4))
+        msm(params.h_query, ni, n + 1 - ni, d_h.at(ni), slot(out1, 5))
+        msm(params.l_query, 0, n_aux, d_z.at(ni), slot(out1, 6))
+        # g_a, g1_b
+        lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 0), 2, slot(out1, 8)))
+        lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 2), 2, slot(out1, 9)))
+        lib.check(lib.points_sum_dev(ctx.handle, g2, slot(out2, 0, k2), 2, slot(out2, 2, k2)))
+        ga_b1 = out1.get(3 * 8, 6).reshape(2, 3 * LIMBS)
+        xy = np.zeros((2, 2 * LIMBS), dtype=np.uint64)
+        inf = np.zeros(2, dtype=np.uint8)
+        lib.check(lib.batch_normalize(ctx.handle, g1, ffi.ptr(ga_b1), 2, ffi.ptr(xy), ffi.ptr(inf)))
+        # s * g_a + r * g1_b - rs * delta_g1 (:322-329) as one 3-point MSM over fresh bases
+        fresh = Bases(ctx, g1, np.concatenate([xy, params.delta_g1]), np.array([inf[0], inf[1], 0], dtype=np.uint8))
+        sc3 = _Dev(ctx, 3)
+        sc3.put(np.concatenate([_limbs(s), _limbs(r), rs]))
+        msm(fresh, 0, 3, sc3.p, slot(out1, 7))
+        lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 4), 4, slot(out1, 10)))
+        gc = out1.get(3 * 10, 3).reshape(1, 3 * LIMBS)
+        gb2 = out2.get(3 * k2 * 2, 3 * k2).reshape(1, 3 * k2 * LIMBS)
+        xyc = np.zeros((1, 2 * LIMBS), dtype=np.uint64)
+        infc = np.zeros(1, dtype=np.uint8)
+        lib.check(lib.batch_normalize(ctx.handle, g1, ffi.ptr(gc), 1, ffi.ptr(xyc), ffi.ptr(infc)))
+        xyb = np.zeros((1, 2 * k2 * LIMBS), dtype=np.uint64)
+        infb = np.zeros(1, dtype=np.uint8)
+        lib.check(lib.batch_normalize(ctx.handle, g2, ffi.ptr(gb2), 1, ffi.ptr(xyb), ffi.ptr(infb)))
+        if timings is not None:
+            ctx.sync()
+            timings["msm_and_assembly"] = time.perf_counter() - t0
+        for dv in (sr, ss, out1, out2, sc3):
+            dv.free()
+        fresh.free()
+        return Proof(xy[0].reshape(2, LIMBS), xyb[0].reshape(2, k2 * LIMBS), xyc[0].reshape(2, LIMBS),
+                     (bool(inf[0]), bool(infb[0]), bool(infc[0])))
+    finally:
+        for dv in dev + [d_h, d_z, consts]:
+            dv.free()

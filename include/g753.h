@@ -123,6 +123,12 @@ int g753_msm_host(g753_ctx* ctx, int group, const uint64_t* coords, const uint8_
  * the fold that follows the multi-GPU gather of per-shard partial sums */
 int g753_points_sum_dev(g753_ctx* ctx, int group, const void* d_points_xyz, size_t count,
                         void* d_out_xyz);
+/* GroupProjective::batch_normalization / into_affine (curves/models/short_weierstrass_projective.rs:
+ * 402-442, 663-678): `count` homogeneous points (host, 3*k*12 limbs each) -> affine x,y (2*k*12
+ * limbs each, fully reduced) + infinity flags; Z == 0 gives GroupAffine::zero() = (0, 1, true).
+ * This is the normalisation that defines bit-exactness of a proof (prover.rs:340-345). */
+int g753_batch_normalize(g753_ctx* ctx, int group, const uint64_t* xyz, size_t count, uint64_t* xy,
+                         uint8_t* infinity);
 /* limbs per coordinate element (12 * k) of a group */
 int g753_group_coord_limbs(int group);
 
@@ -142,11 +148,22 @@ int g753_ntt_dev(g753_ctx* ctx, int field, void* d_data, unsigned log_n, int mod
 int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n);
 int g753_vec_scale_dev(g753_ctx* ctx, int field, void* d_a, const uint64_t* k_mont, size_t n);
 
+/* R1CStoQAP::witness_map from the evaluated constraints onwards (proof-systems/src/groth16/
+ * r1cs_to_qap.rs:121-166): a, b, c = the n = 2^log_n evaluations <A_i,z>, <B_i,z>, <C_i,z> padded as
+ * :111-119 does (Montgomery form); d123 = d1, d2, d3 (3 x 12 limbs, Montgomery form); h receives
+ * n + 1 coefficients (Montgomery form).  Seven transforms and the element-wise steps run chained
+ * on the device.  The _dev form takes device pointers (a, b, c are clobbered; h holds n + 1). */
+int g753_witness_map(g753_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                     unsigned log_n, const uint64_t* d123_mont, uint64_t* h);
+int g753_witness_map_dev(g753_ctx* ctx, int field, void* d_a, void* d_b, void* d_c, unsigned log_n,
+                         const uint64_t* d123_mont, void* d_h);
+
 /* ---- device memory / stream plumbing (so callers can chain without a CUDA toolchain) --- */
 int g753_dev_alloc(g753_ctx* ctx, size_t bytes, void** d_ptr);
 int g753_dev_free(g753_ctx* ctx, void* d_ptr);
 int g753_h2d(g753_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int g753_d2h(g753_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int g753_d2d(g753_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);  /* ordered on the context's stream */
 int g753_sync(g753_ctx* ctx);
 /* the context's cudaStream_t, as an opaque pointer (for event timing by the harness) */
 void* g753_stream(g753_ctx* ctx);

@@ -513,3 +513,79 @@ def random_g1_point(rng, curve):
         if y & 1:
             y = fld.p - y
         return ((x,), (y,))
+
+
+# --------------------------------------------------------------------------------------
+# Groth16 prover algebra  (proof-systems/src/groth16/{r1cs_to_qap.rs, prover.rs, mod.rs})
+# --------------------------------------------------------------------------------------
+
+def witness_map(field, a_evals, b_evals, c_evals, d1, d2, d3):
+    """R1CStoQAP::witness_map from the evaluated constraints onwards (r1cs_to_qap.rs:121-166), in
+    canonical integers.  a_evals / b_evals / c_evals are the domain_size evaluation vectors the
+    reference fills at :111-119 and :141-152 (padding included).  Returns h, domain_size + 1 values.
+
+    The reference initialises h to zeros and then MULTIPLIES h_i by (d2 a_i + d1 b_i) (:125-130), so
+    those entries stay zero; restated literally."""
+    p = field.p
+    n = len(a_evals)
+    assert len(b_evals) == n and len(c_evals) == n
+    dom = EvaluationDomain(field, n)
+    assert dom.size == n
+    a = dom.ifft(a_evals)                                    # :121
+    b = dom.ifft(b_evals)                                    # :122
+    h = [0 * ((d2 * ai + d1 * bi) % p) % p for ai, bi in zip(a, b)]   # :124-130  (0 *= ...)
+    d1d2 = d1 * d2 % p
+    h[0] = (h[0] - d3) % p                                   # :131
+    h[0] = (h[0] - d1d2) % p                                 # :133
+    h.append(d1d2)                                           # :134
+    a = dom.coset_fft(a)                                     # :136
+    b = dom.coset_fft(b)                                     # :137
+    ab = [x * y % p for x, y in zip(a, b)]                   # :139  mul_polynomials_in_evaluation_domain
+    c = dom.coset_fft(dom.ifft(c_evals))                     # :154-155
+    ab = [(x - y) % p for x, y in zip(ab, c)]                # :157-159
+    z_inv = pow((pow(dom.generator, n, p) - 1) % p, -1, p)   # domain.rs:245-256
+    ab = [x * z_inv % p for x in ab]
+    ab = dom.coset_ifft(ab)                                  # :162
+    for i in range(n - 1):                                   # :164-167
+        h[i] = (h[i] + ab[i]) % p
+    return h
+
+
+class Groth16Key:
+    """The fields of groth16::Parameters the prover reads (mod.rs:313-371), as affine oracle points
+    (None = infinity).  g1 / g2 are the curves of E::G1Affine / E::G2Affine."""
+
+    def __init__(self, g1, g2, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, a_query, b_g1_query,
+                 b_g2_query, h_query, l_query):
+        self.g1, self.g2 = g1, g2
+        self.alpha_g1, self.beta_g1, self.beta_g2 = alpha_g1, beta_g1, beta_g2
+        self.delta_g1, self.delta_g2 = delta_g1, delta_g2
+        self.a_query, self.b_g1_query, self.b_g2_query = a_query, b_g1_query, b_g2_query
+        self.h_query, self.l_query = h_query, l_query
+
+
+def groth16_create_proof(key, num_inputs, full_assignment, h, r, s, msm=msm_naive):
+    """prover.rs:241-345 from the witness map's outputs onwards: the nine MSMs (zip-truncating, as
+    variable_base.rs:36) and the assembly of (A, B, C), normalised to affine.
+    full_assignment: canonical ints, inputs first (index 0 is the constant one); h: canonical ints."""
+    g1, g2 = key.g1, key.g2
+    inp = full_assignment[1:num_inputs]                       # :241-246
+    aux = full_assignment[num_inputs:]                        # :248-253
+    h_in, h_aux = h[:num_inputs], h[num_inputs:]              # :256-267
+
+    def acc(curve, *pts):
+        t = None
+        for q in pts:
+            t = curve.add(t, q)
+        return t
+
+    g_a = acc(g1, g1.mul(key.delta_g1, r), key.a_query[0], msm(g1, key.a_query[1:num_inputs], inp),
+              msm(g1, key.a_query[num_inputs:], aux), key.alpha_g1)                      # :270-283
+    g1_b = acc(g1, g1.mul(key.delta_g1, s), key.b_g1_query[0], msm(g1, key.b_g1_query[1:num_inputs], inp),
+               msm(g1, key.b_g1_query[num_inputs:], aux), key.beta_g1)                   # :286-299
+    g2_b = acc(g2, g2.mul(key.delta_g2, s), key.b_g2_query[0], msm(g2, key.b_g2_query[1:num_inputs], inp),
+               msm(g2, key.b_g2_query[num_inputs:], aux), key.beta_g2)                   # :302-315
+    rs_delta = g1.mul(g1.mul(key.delta_g1, r), s)
+    g_c = acc(g1, g1.mul(g_a, s), g1.mul(g1_b, r), g1.neg(rs_delta), msm(g1, key.l_query, aux),
+              msm(g1, key.h_query[:num_inputs], h_in), msm(g1, key.h_query[num_inputs:], h_aux))  # :318-337
+    return g_a, g2_b, g_c
