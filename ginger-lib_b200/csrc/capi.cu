@@ -300,6 +300,32 @@ int g753_bases_precompute(g753_ctx* ctx, g753_bases* b, unsigned copies) {
   return fail(G753_ERR_BAD_ARG, "unknown group");
 }
 
+int g753_bases_update(g753_ctx* ctx, g753_bases* b, size_t first, size_t count, const uint64_t* coords,
+                      const uint8_t* infinity) {
+  CHECK_CTX(ctx);
+  if (!b || (count && !coords)) return fail(G753_ERR_BAD_ARG, "null pointer");
+  if (first > b->n || count > b->n - first) return fail(G753_ERR_BAD_ARG, "bases slice out of range");
+  if (b->copies > 1) return fail(G753_ERR_BAD_ARG, "key has precomputed copies");
+  if (count == 0) return G753_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const int k = group_k(b->group);
+  const size_t pt_bytes = (size_t)2 * k * 96;
+  if (!b->d_inf) {
+    G753_TRY(dev_alloc((void**)&b->d_inf, b->n));
+    G753_TRY(dev_memset(b->d_inf, 0, b->n, ctx->stream));
+  }
+  G753_TRY(h2d((char*)b->d_points + first * pt_bytes, coords, count * pt_bytes, ctx->stream));
+  if (infinity)
+    G753_TRY(h2d(b->d_inf + first, infinity, count, ctx->stream));
+  else
+    G753_TRY(dev_memset(b->d_inf + first, 0, count, ctx->stream));
+  G753_LAUNCH(k_bases_sanitize, div_up(count, 256), 256, ctx->stream, (Fq*)b->d_points + first * 2 * k,
+              b->d_inf + first, (unsigned)count, (unsigned)(2 * k));
+  ctx->launches++;
+  G753_TRY(launch_check("k_bases_sanitize"));
+  return stream_sync(ctx->stream);  // the host buffers may be reused as soon as this returns
+}
+
 int g753_bases_download(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, uint64_t* coords) {
   CHECK_CTX(ctx);
   if (!b || (count && !coords)) return fail(G753_ERR_BAD_ARG, "null pointer");
@@ -543,6 +569,21 @@ int g753_d2d(g753_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
 int g753_sync(g753_ctx* ctx) {
   CHECK_CTX(ctx);
   return stream_sync(ctx->stream);
+}
+int g753_ctx_wait(g753_ctx* ctx, g753_ctx* other) {
+  CHECK_CTX(ctx);
+  if (!other) return fail(G753_ERR_BAD_ARG, "null context");
+#if !defined(G753_HOST_EMUL)
+  if (other->device != ctx->device) return fail(G753_ERR_BAD_ARG, "contexts live on different devices");
+  cudaEvent_t ev;
+  cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+  e = cudaEventRecord(ev, other->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ev, 0);
+  cudaEventDestroy(ev);  // released once the wait has been satisfied
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+#endif
+  return G753_OK;
 }
 void* g753_stream(g753_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 

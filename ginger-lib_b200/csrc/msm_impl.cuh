@@ -279,25 +279,21 @@ int batch_normalize_impl(g753_ctx* ctx, const uint64_t* xyz, size_t count, uint6
   typedef typename MsmCfg<GID>::template SC<T> SC;
   typedef EcS<SC> E;
   const size_t prj = sizeof(Fq) * 3 * K, aff = sizeof(Fq) * 2 * K;
-  Fq *d_in = nullptr, *d_out = nullptr;
-  uint8_t* d_inf = nullptr;
-  int rc = dev_alloc((void**)&d_in, prj * count);
-  if (rc == G753_OK) rc = dev_alloc((void**)&d_out, aff * count);
-  if (rc == G753_OK) rc = dev_alloc((void**)&d_inf, count);
-  if (rc == G753_OK) rc = h2d(d_in, xyz, prj * count, ctx->stream);
-  if (rc == G753_OK) {
-    G753_LAUNCH_SMEM(k_batch_normalize<SC>, div_up(count, T), T, (slot_bytes<E, T>(4 * K + E::M::NTMP + 1)), ctx->stream,
-                     d_in, (unsigned)count, d_out, d_inf);
-    ctx->launches++;
-    rc = launch_check("k_batch_normalize");
-  }
-  if (rc == G753_OK) rc = d2h(xy, d_out, aff * count, ctx->stream);
-  if (rc == G753_OK) rc = d2h(infinity, d_inf, count, ctx->stream);
-  if (rc == G753_OK) rc = stream_sync(ctx->stream);
-  dev_free(d_in);
-  dev_free(d_out);
-  dev_free(d_inf);
-  return rc;
+  // staged through the context's grow-only I/O scratch: no cudaMalloc / cudaFree (a device-wide
+  // synchronisation) on the prover's critical path
+  G753_TRY(ctx->scratch_io.reserve((prj + aff + 1) * count + 1024));
+  Carver cv(ctx->scratch_io.ptr);
+  Fq* d_in = cv.take<Fq>(3 * K * count);
+  Fq* d_out = cv.take<Fq>(2 * K * count);
+  uint8_t* d_inf = cv.take<uint8_t>(count);
+  G753_TRY(h2d(d_in, xyz, prj * count, ctx->stream));
+  G753_LAUNCH_SMEM(k_batch_normalize<SC>, div_up(count, T), T, (slot_bytes<E, T>(4 * K + E::M::NTMP + 1)), ctx->stream,
+                   d_in, (unsigned)count, d_out, d_inf);
+  ctx->launches++;
+  G753_TRY(launch_check("k_batch_normalize"));
+  G753_TRY(d2h(xy, d_out, aff * count, ctx->stream));
+  G753_TRY(d2h(infinity, d_inf, count, ctx->stream));
+  return stream_sync(ctx->stream);
 }
 
 #define G753_INSTANTIATE_GROUP(GID)                                                                        \

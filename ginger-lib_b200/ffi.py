@@ -35,6 +35,7 @@ SYMBOLS = [
     ("g753_bases_len", _sz, [_vp]),
     ("g753_bases_generate", _i, [_vp, _i, _vp, ctypes.c_uint64, _sz, _pvp]),
     ("g753_bases_precompute", _i, [_vp, _vp, _u]),
+    ("g753_bases_update", _i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     ("g753_bases_download", _i, [_vp, _vp, _sz, _sz, _vp]),
     ("g753_msm", _i, [_vp, _vp, _sz, _sz, _vp, _vp]),
     ("g753_msm_dev", _i, [_vp, _vp, _sz, _sz, _vp, _vp]),
@@ -55,6 +56,7 @@ SYMBOLS = [
     ("g753_d2h", _i, [_vp, _vp, _vp, _sz]),
     ("g753_d2d", _i, [_vp, _vp, _vp, _sz]),
     ("g753_sync", _i, [_vp]),
+    ("g753_ctx_wait", _i, [_vp, _vp]),
     ("g753_stream", _vp, [_vp]),
     ("g753_field_op", _i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     ("g753_point_op", _i, [_vp, _i, _i, _vp, _vp, _vp]),

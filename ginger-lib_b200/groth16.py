@@ -66,12 +66,20 @@ class Parameters:
         self.b2_small = small(g2, b_g2_query, [delta_g2, beta_g2], k2)
         self.a_query, self.b_g1_query, self.h_query, self.l_query = (up(g1, q) for q in (a_query, b_g1_query, h_query, l_query))
         self.b_g2_query = up(g2, b_g2_query)
+        for b in (self.a_small, self.b1_small, self.b2_small):
+            b.precompute(64)        # fixed tiny keys: ~12 doublings left in the serial window fold
         self.delta_g1 = ffi.as_u64(delta_g1).reshape(1, 2 * LIMBS)
+        # second context of the same device for the per-proof latency chain, with its pre-allocated
+        # 3-point key [g_a, g1_b, delta_g1] (the first two are overwritten every proof)
+        from .algebra import Context
+        self.ctx2 = Context(ctx.device, library=ctx.lib)
+        self.fresh = Bases(self.ctx2, g1, np.concatenate([self.delta_g1] * 3), np.zeros(3, dtype=np.uint8))
 
     def free(self):
         for b in (self.a_query, self.b_g1_query, self.b_g2_query, self.h_query, self.l_query, self.a_small,
-                  self.b1_small, self.b2_small):
+                  self.b1_small, self.b2_small, self.fresh):
             b.free()
+        self.ctx2.close()
 
 
 class Proof:
@@ -128,9 +136,13 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
 
     full_assignment: (num_inputs + num_aux, 12) Montgomery, inputs first, index 0 = the constant one;
     a, b, c: (domain_size, 12) Montgomery evaluation vectors; d1, d2, d3, r, s: canonical ints (E::Fr).
-    Returns Proof with affine Montgomery limbs: a (2, 12), b (2, k2*12), c (2, 12)."""
+    Returns Proof with affine Montgomery limbs: a (2, 12), b (2, k2*12), c (2, 12).
+
+    Scheduling: the large (throughput-bound) MSMs are queued on the main context's stream; the one MSM
+    over per-proof bases (s*g_a + r*g1_b - rs*delta, a 753-doubling latency chain) runs on a second
+    context of the same device as soon as g_a and g1_b exist, overlapping the remaining large MSMs."""
     import time
-    ctx, lib, field = params.ctx, params.ctx.lib, params.field
+    ctx, ctx2, lib, field = params.ctx, params.ctx2, params.ctx.lib, params.field
     g1, g2, ni = params.g1, params.g2, params.num_inputs
     k2 = ffi.GROUP_K[g2]
     t0 = time.perf_counter()
@@ -141,79 +153,76 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
     n_vars = z.shape[0]
     n_aux = n_vars - ni
 
-    # ---- witness map on the device, then into_repr of h and the assignment (prover.rs:241-267) ----
+    # every device buffer of the proof is allocated before anything is queued (cudaFree synchronises)
     dev = [_Dev(ctx, n) for _ in range(3)]
     d_h = _Dev(ctx, n + 1)
     d_z = _Dev(ctx, n_vars + 1)
-    consts = _Dev(ctx, 8)
+    sr, ss = _Dev(ctx, ni + 2), _Dev(ctx, ni + 2)
+    sc3 = _Dev(ctx, 3)
+    out1 = _Dev(ctx, 3 * 16)        # G1 partial results, 3 Fq each
+    out2 = _Dev(ctx, 3 * k2 * 4)    # G2 partial results
+    slot = lambda o, i, k=1: o.at(3 * k * i)
     try:
+        # ---- witness map on the device, then into_repr of h and the assignment (prover.rs:241-267) ----
         for dv, host in zip(dev, (a, b, c)):
             dv.put(host)
         dd = np.concatenate([_limbs(d1), _limbs(d2), _limbs(d3), _limbs(r), _limbs(s)])
         dm = np.zeros_like(dd)
         lib.check(lib.field_op(ctx.handle, field, ffi.OP_TO_MONT, ffi.ptr(dd), None, ffi.ptr(dm), 5))
-        lib.check(lib.witness_map_dev(ctx.handle, field, dev[0].p, dev[1].p, dev[2].p, log_n, ffi.ptr(dm), d_h.p))
-        lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_h.p, None, n + 1))
-        d_z.put(z)
-        lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_z.p, None, n_vars))
-        if timings is not None:
-            ctx.sync()
-            timings["witness_map"] = time.perf_counter() - t0
-            t0 = time.perf_counter()
-
         # -rs for the C term (prover.rs:327): field arithmetic on the device, canonical result
         rs = np.zeros((1, LIMBS), dtype=np.uint64)
         lib.check(lib.field_op(ctx.handle, field, ffi.OP_MUL, ffi.ptr(dm[3:4]), ffi.ptr(dm[4:5]), ffi.ptr(rs), 1))
         zero = np.zeros((1, LIMBS), dtype=np.uint64)
         lib.check(lib.field_op(ctx.handle, field, ffi.OP_SUB, ffi.ptr(zero), ffi.ptr(rs), ffi.ptr(rs), 1))
         lib.check(lib.field_op(ctx.handle, field, ffi.OP_FROM_MONT, ffi.ptr(rs), None, ffi.ptr(rs), 1))
-
+        sc3.put(np.concatenate([_limbs(s), _limbs(r), rs]))
+        lib.check(lib.witness_map_dev(ctx.handle, field, dev[0].p, dev[1].p, dev[2].p, log_n, ffi.ptr(dm), d_h.p))
+        lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_h.p, None, n + 1))
+        d_z.put(z)
+        lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_z.p, None, n_vars))
         # small scalar vectors [1, inputs..., r|s, 1]: the constant-one slot of the assignment is
         # replaced by a literal 1 (the reference adds query[0] unconditionally, prover.rs:277)
-        def small_scalars(blind):
-            dv = _Dev(ctx, ni + 2)
+        for dv, blind in ((sr, r), (ss, s)):
             dv.put(ONE, 0)
             if ni > 1:
                 lib.check(lib.d2d(ctx.handle, dv.at(1), d_z.at(1), (ni - 1) * 96))
             dv.put(_limbs(blind), ni)
             dv.put(ONE, ni + 1)
-            return dv
+        if timings is not None:
+            ctx.sync()
+            timings["witness_map"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
 
-        out1 = _Dev(ctx, 3 * 16)        # G1 partial results, 3 Fq each
-        out2 = _Dev(ctx, 3 * k2 * 4)    # G2 partial results
-
-        def msm(bases, first, count, d_scalars, d_out):
+        def msm(cx, bases, first, count, d_scalars, d_out):
             count = max(0, min(count, len(bases) - first))
-            lib.check(lib.msm_dev(ctx.handle, bases.handle, first, count, d_scalars, d_out))
+            lib.check(lib.msm_dev(cx.handle, bases.handle, first, count, d_scalars, d_out))
 
-        sr, ss = small_scalars(r), small_scalars(s)
-        slot = lambda o, i, k=1: o.at(3 * k * i)
-        # A (prover.rs:270-283): slots 0, 1
-        msm(params.a_small, 0, ni + 2, sr.p, slot(out1, 0))
-        msm(params.a_query, ni, n_aux, d_z.at(ni), slot(out1, 1))
-        # B in G1 (:286-299): slots 2, 3
-        msm(params.b1_small, 0, ni + 2, ss.p, slot(out1, 2))
-        msm(params.b_g1_query, ni, n_aux, d_z.at(ni), slot(out1, 3))
-        # B in G2 (:302-315)
-        msm(params.b2_small, 0, ni + 2, ss.p, slot(out2, 0, k2))
-        msm(params.b_g2_query, ni, n_aux, d_z.at(ni), slot(out2, 1, k2))
-        # C (:318-337): H (zip-truncated against h, n + 1 scalars vs n - 1 bases), L; slots 4..6
-        msm(params.h_query, 0, min(ni, n + 1), d_h.at(0), slot(out1, 4))
-        msm(params.h_query, ni, n + 1 - ni, d_h.at(ni), slot(out1, 5))
-        msm(params.l_query, 0, n_aux, d_z.at(ni), slot(out1, 6))
-        # g_a, g1_b
+        # A (prover.rs:270-283) -> slots 0, 1; B in G1 (:286-299) -> slots 2, 3; g_a, g1_b -> slots 8, 9
+        msm(ctx, params.a_query, ni, n_aux, d_z.at(ni), slot(out1, 1))
+        msm(ctx, params.b_g1_query, ni, n_aux, d_z.at(ni), slot(out1, 3))
+        msm(ctx, params.a_small, 0, ni + 2, sr.p, slot(out1, 0))
+        msm(ctx, params.b1_small, 0, ni + 2, ss.p, slot(out1, 2))
         lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 0), 2, slot(out1, 8)))
         lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 2), 2, slot(out1, 9)))
+        lib.check(lib.ctx_wait(ctx2.handle, ctx.handle))
+        # C (:318-337): L, H (zip-truncated against h: n + 1 scalars vs n - 1 bases) -> slots 4..6
+        msm(ctx, params.l_query, 0, n_aux, d_z.at(ni), slot(out1, 6))
+        msm(ctx, params.h_query, ni, n + 1 - ni, d_h.at(ni), slot(out1, 5))
+        msm(ctx, params.h_query, 0, min(ni, n + 1), d_h.at(0), slot(out1, 4))
+        # B in G2 (:302-315)
+        msm(ctx, params.b2_small, 0, ni + 2, ss.p, slot(out2, 0, k2))
+        msm(ctx, params.b_g2_query, ni, n_aux, d_z.at(ni), slot(out2, 1, k2))
         lib.check(lib.points_sum_dev(ctx.handle, g2, slot(out2, 0, k2), 2, slot(out2, 2, k2)))
-        ga_b1 = out1.get(3 * 8, 6).reshape(2, 3 * LIMBS)
+
+        # second context: s * g_a + r * g1_b - rs * delta_g1 (:322-329) as one MSM over fresh bases
+        ga_b1 = np.empty((2, 3 * LIMBS), dtype=np.uint64)
+        lib.check(lib.d2h(ctx2.handle, ffi.ptr(ga_b1), slot(out1, 8), 2 * 3 * 96))
         xy = np.zeros((2, 2 * LIMBS), dtype=np.uint64)
         inf = np.zeros(2, dtype=np.uint8)
-        lib.check(lib.batch_normalize(ctx.handle, g1, ffi.ptr(ga_b1), 2, ffi.ptr(xy), ffi.ptr(inf)))
-        # s * g_a + r * g1_b - rs * delta_g1 (:322-329) as one 3-point MSM over fresh bases
-        fresh = Bases(ctx, g1, np.concatenate([xy, params.delta_g1]), np.array([inf[0], inf[1], 0], dtype=np.uint8))
-        sc3 = _Dev(ctx, 3)
-        sc3.put(np.concatenate([_limbs(s), _limbs(r), rs]))
-        msm(fresh, 0, 3, sc3.p, slot(out1, 7))
+        lib.check(lib.batch_normalize(ctx2.handle, g1, ffi.ptr(ga_b1), 2, ffi.ptr(xy), ffi.ptr(inf)))
+        lib.check(lib.bases_update(ctx2.handle, params.fresh.handle, 0, 2, ffi.ptr(xy), ffi.ptr(inf)))
+        msm(ctx2, params.fresh, 0, 3, sc3.p, slot(out1, 7))
+        lib.check(lib.ctx_wait(ctx.handle, ctx2.handle))
         lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 4), 4, slot(out1, 10)))
         gc = out1.get(3 * 10, 3).reshape(1, 3 * LIMBS)
         gb2 = out2.get(3 * k2 * 2, 3 * k2).reshape(1, 3 * k2 * LIMBS)
@@ -226,11 +235,9 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
         if timings is not None:
             ctx.sync()
             timings["msm_and_assembly"] = time.perf_counter() - t0
-        for dv in (sr, ss, out1, out2, sc3):
-            dv.free()
-        fresh.free()
         return Proof(xy[0].reshape(2, LIMBS), xyb[0].reshape(2, k2 * LIMBS), xyc[0].reshape(2, LIMBS),
                      (bool(inf[0]), bool(infb[0]), bool(infc[0])))
     finally:
-        for dv in dev + [d_h, d_z, consts]:
+        ctx2.sync()
+        for dv in dev + [d_h, d_z, sr, ss, sc3, out1, out2]:
             dv.free()

@@ -102,6 +102,11 @@ int g753_bases_generate(g753_ctx* ctx, int group, const uint64_t* gen_xy, uint64
  * g753_msm* calls are unchanged (same group element).  Calls over short slices (count < n/4)
  * keep using the plain pipeline. */
 int g753_bases_precompute(g753_ctx* ctx, g753_bases* bases, unsigned copies);
+/* overwrite `count` bases of a resident key (not one with precomputed copies) starting at `first`:
+ * lets a caller keep one small pre-allocated key for per-proof points (prover.rs:322-329:
+ * s*g_a + r*g1_b - rs*delta_g1 is an MSM over fresh bases) without allocating in the hot path */
+int g753_bases_update(g753_ctx* ctx, g753_bases* bases, size_t first, size_t count, const uint64_t* coords,
+                      const uint8_t* infinity);
 /* copy `count` resident bases starting at `first` back to the host (2*k*12 limbs each) */
 int g753_bases_download(g753_ctx* ctx, const g753_bases* bases, size_t first, size_t count,
                         uint64_t* coords);
@@ -165,6 +170,10 @@ int g753_h2d(g753_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int g753_d2h(g753_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 int g753_d2d(g753_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);  /* ordered on the context's stream */
 int g753_sync(g753_ctx* ctx);
+/* make every later call on `ctx` wait (on the device, not the host) for all work queued so far on
+ * `other` - two contexts of one device overlap independent chains of calls, e.g. the latency-bound
+ * small MSMs of a proof with its throughput-bound large ones */
+int g753_ctx_wait(g753_ctx* ctx, g753_ctx* other);
 /* the context's cudaStream_t, as an opaque pointer (for event timing by the harness) */
 void* g753_stream(g753_ctx* ctx);
 
