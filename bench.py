@@ -386,6 +386,13 @@ def run_ours(args):
                          "variable_base.rs:10-83, 1 run of %.1f s; result equal to the CUDA path's" %
                          (args.cpu_log_n, times[0])}
 
+    # ---- config 5: end-to-end Groth16 proof (rank 0, N = 1) ----------------------------------
+    g16 = None
+    if rank == 0 and world == 1 and not args.no_groth16:
+        import bench_groth16
+        bases.free()
+        g16 = bench_groth16.run(ctx, args.groth16_log_n, steps=max(2, min(args.steps, 3)), warmup=1, copies=args.copies)
+
     if rank == 0:
         canon_all, canon_acc = canonical_field_muls(n_local)
         acc_ms = phases.get("accumulate", 0.0)
@@ -429,7 +436,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 288,
                     "path": "g753_msm: pinned host scalars -> H2D -> MSM -> D2H result; bases resident (proving key)"},
             "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "fft": fft,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "fft": fft, "groth16": g16,
             "setup_s": setup_s, "key_precompute_s": precompute_s,
         }
         print(json.dumps(line), flush=True)
@@ -453,6 +460,8 @@ def main():
                     help="precomputed shifted copies of the resident key (1 = plain key)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fft", action="store_true")
+    ap.add_argument("--no-groth16", action="store_true")
+    ap.add_argument("--groth16-log-n", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -4,6 +4,7 @@
 // test-only library that runs the barrier-free kernels sequentially on the host so that
 // indexing and orchestration can be checked without a GPU (tests/host_emul).
 #include "ctx.cuh"
+#include "ntt_dist.cuh"
 #if defined(G753_HOST_EMUL)
 #include "msm_impl.cuh"  // the test-only host build is a single translation unit
 G753_INSTANTIATE_GROUP(0)
@@ -46,19 +47,12 @@ static int msm_any(g753_ctx* ctx, const g753_bases* b, size_t first, size_t coun
 }
 
 template <int FID>
+static int ntt_tables_get(g753_ctx* ctx, unsigned log_n, const NttTables** out);
+template <int FID>
 static int ntt_field(g753_ctx* ctx, Fq* d_data, Fq* d_tmp, unsigned log_n, int mode) {
-  std::map<unsigned, NttTables>& m = ctx->tables[FID];
-  auto it = m.find(log_n);
-  if (it == m.end()) {
-    NttTables T;
-    int rc = ntt_tables_build<FID>(T, log_n, ctx->stream, &ctx->launches);
-    if (rc != G753_OK) {
-      T.release();
-      return rc;
-    }
-    it = m.emplace(log_n, T).first;
-  }
-  return ntt_run<FID>(it->second, ctx->stream, d_data, d_tmp, mode, &ctx->launches);
+  const NttTables* T = nullptr;
+  G753_TRY(ntt_tables_get<FID>(ctx, log_n, &T));
+  return ntt_run<FID>(*T, ctx->stream, d_data, d_tmp, mode, &ctx->launches);
 }
 
 // R1CStoQAP::witness_map after the constraint evaluation (r1cs_to_qap.rs:121-166), chained on
@@ -82,6 +76,98 @@ static int witness_map_field(g753_ctx* ctx, Fq* a, Fq* b, Fq* c, unsigned log_n,
   G753_LAUNCH(k_witness_finish<FID>, div_up(n + 1, 256), 256, ctx->stream, a, d_d, h, n);
   ctx->launches++;
   return launch_check("witness_map");
+}
+
+// ---- sharded four-step NTT (ntt_dist.cuh) ----------------------------------------------------
+template <int FID>
+static int ntt_tables_get(g753_ctx* ctx, unsigned log_n, const NttTables** out) {
+  std::map<unsigned, NttTables>& m = ctx->tables[FID];
+  auto it = m.find(log_n);
+  if (it == m.end()) {
+    NttTables T;
+    int rc = ntt_tables_build<FID>(T, log_n, ctx->stream, &ctx->launches);
+    if (rc != G753_OK) {
+      T.release();
+      return rc;
+    }
+    it = m.emplace(log_n, T).first;
+  }
+  *out = &it->second;
+  return G753_OK;
+}
+
+template <int FID>
+static int shard_build(g753_ctx* ctx, g753_ntt_shard* p) {
+  const unsigned L = p->log_n ? p->log_n : 1;
+  G753_TRY(ntt_consts_build<FID>(&p->consts, p->log_n, ctx->stream, &ctx->launches));
+  const Fq* K = p->consts;
+  const Fq *ninv = K, *w = K + 1, *wi = K + 1 + L, *g = K + 1 + 2 * L, *gi = K + 1 + 3 * L;
+  // g^n2 = g^(2^log_n2), g^-n1 = g^-(2^log_n1); for log_n == 0 both exponents are 1
+  const Fq* g_n2 = p->log_n ? K + 1 + 2 * L + p->log_n2 : g;
+  const Fq* gi_n1 = p->log_n ? K + 1 + 3 * L + p->log_n1 : gi;
+  // when log_n2 == log_n (n1 == 1) the chain stops one short of g^n: not needed, the table has len 1
+  const size_t bytes1 = sizeof(Fq) * p->cols * p->n1, bytes2 = sizeof(Fq) * p->rows * p->n2;
+  G753_TRY(dev_alloc((void**)&p->t1f, bytes1));
+  G753_TRY(dev_alloc((void**)&p->t1i, bytes1));
+  G753_TRY(dev_alloc((void**)&p->cp, bytes1));
+  G753_TRY(dev_alloc((void**)&p->cq, bytes2));
+  const Fq* none = nullptr;
+  const uint64_t c0 = (uint64_t)p->rank * p->cols, r0 = (uint64_t)p->rank * p->rows;
+  G753_LAUNCH(k_pow_table<FID>, div_up(p->cols, 64), 64, ctx->stream, p->t1f, (unsigned)p->cols, (unsigned)p->n1, c0,
+              none, w, none, none);
+  G753_LAUNCH(k_pow_table<FID>, div_up(p->cols, 64), 64, ctx->stream, p->t1i, (unsigned)p->cols, (unsigned)p->n1, c0,
+              none, wi, ninv, none);
+  G753_LAUNCH(k_pow_table<FID>, div_up(p->cols, 64), 64, ctx->stream, p->cp, (unsigned)p->cols, (unsigned)p->n1, c0,
+              p->log_n1 ? g_n2 : none, none, none, g);
+  G753_LAUNCH(k_pow_table<FID>, div_up(p->rows, 64), 64, ctx->stream, p->cq, (unsigned)p->rows, (unsigned)p->n2, r0,
+              p->log_n2 ? gi_n1 : none, none, none, gi);
+  ctx->launches += 4;
+  G753_TRY(launch_check("k_pow_table"));
+  return stream_sync(ctx->stream);
+}
+
+template <int FID>
+static int shard_step1(g753_ctx* ctx, const g753_ntt_shard* p, Fq* data, Fq* send, int mode) {
+  const NttTables* T = nullptr;
+  G753_TRY(ntt_tables_get<FID>(ctx, p->log_n1, &T));
+  NttCall c;
+  c.inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
+  c.batch = (unsigned)p->cols;
+  if (mode == G753_COSET_FFT) {
+    c.pre = p->cp;
+    c.pre_stride = p->n1;
+  }
+  c.post = c.inverse ? p->t1i : p->t1f;
+  c.post_stride = p->n1;
+  G753_TRY(ctx->scratch_io.reserve(sizeof(Fq) * p->cols * p->n1 + 1024));
+  G753_TRY(ntt_run<FID>(*T, ctx->stream, data, (Fq*)ctx->scratch_io.ptr, c, &ctx->launches));
+  // Y[i2l][h][k1l] -> send[h][k1l][i2l]
+  const size_t total = p->cols * p->n1;
+  G753_LAUNCH(k_permute3, div_up(total, 256), 256, ctx->stream, data, send, (unsigned)p->cols, p->world,
+              (unsigned)p->rows, (size_t)1, p->rows * p->cols, p->cols);
+  ctx->launches++;
+  return launch_check("shard_step1");
+}
+
+template <int FID>
+static int shard_step2(g753_ctx* ctx, const g753_ntt_shard* p, const Fq* recv, Fq* data, int mode) {
+  const NttTables* T = nullptr;
+  G753_TRY(ntt_tables_get<FID>(ctx, p->log_n2, &T));
+  // recv[g][k1l][i2l] -> Z[k1l][g cols + i2l]
+  const size_t total = p->rows * p->n2;
+  G753_LAUNCH(k_permute3, div_up(total, 256), 256, ctx->stream, recv, data, p->world, (unsigned)p->rows,
+              (unsigned)p->cols, p->cols, p->n2, (size_t)1);
+  ctx->launches++;
+  NttCall c;
+  c.inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
+  c.batch = (unsigned)p->rows;
+  if (mode == G753_COSET_IFFT) {
+    c.post = p->cq;
+    c.post_stride = p->n2;
+  }
+  G753_TRY(ctx->scratch_io.reserve(sizeof(Fq) * total + 1024));
+  G753_TRY(ntt_run<FID>(*T, ctx->stream, data, (Fq*)ctx->scratch_io.ptr, c, &ctx->launches));
+  return launch_check("shard_step2");
 }
 
 // ------------------------------------------------------------------------------------
@@ -502,6 +588,78 @@ int g753_witness_map(g753_ctx* ctx, int field, const uint64_t* a, const uint64_t
   dev_free(d_c);
   dev_free(d_h);
   return rc;
+}
+
+int g753_ntt_shard_create(g753_ctx* ctx, int field, unsigned log_n, unsigned world, unsigned rank,
+                          g753_ntt_shard** out) {
+  CHECK_CTX(ctx);
+  if (!out) return fail(G753_ERR_BAD_ARG, "null out");
+  *out = nullptr;
+  G753_TRY(g753_domain_check(field, log_n));
+  if (world == 0 || (world & (world - 1)) || rank >= world) return fail(G753_ERR_BAD_ARG, "world must be a power of two");
+  unsigned log_w = 0;
+  while ((1u << log_w) < world) log_w++;
+  const unsigned log_n2 = log_n / 2, log_n1 = log_n - log_n2;   // n1 >= n2
+  if (log_n2 < log_w) return fail(G753_ERR_BAD_ARG, "domain too small to shard over this many ranks");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  g753_ntt_shard* p = new (std::nothrow) g753_ntt_shard();
+  if (!p) return fail(G753_ERR_OOM, "host allocation failed");
+  p->field = field;
+  p->log_n = log_n;
+  p->log_n1 = log_n1;
+  p->log_n2 = log_n2;
+  p->world = world;
+  p->rank = rank;
+  p->n1 = (size_t)1 << log_n1;
+  p->n2 = (size_t)1 << log_n2;
+  p->cols = p->n2 / world;
+  p->rows = p->n1 / world;
+  int rc = field == 0 ? shard_build<0>(ctx, p) : shard_build<1>(ctx, p);
+  if (rc != G753_OK) {
+    p->release();
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return G753_OK;
+}
+
+int g753_ntt_shard_destroy(g753_ctx* ctx, g753_ntt_shard* plan) {
+  if (!plan) return G753_OK;
+  if (ctx) {
+    use_device(ctx);
+    stream_sync(ctx->stream);
+  }
+  plan->release();
+  delete plan;
+  return G753_OK;
+}
+
+int g753_ntt_shard_shape(const g753_ntt_shard* plan, size_t* n1, size_t* n2, size_t* cols, size_t* rows) {
+  if (!plan) return fail(G753_ERR_BAD_ARG, "null plan");
+  if (n1) *n1 = plan->n1;
+  if (n2) *n2 = plan->n2;
+  if (cols) *cols = plan->cols;
+  if (rows) *rows = plan->rows;
+  return G753_OK;
+}
+
+int g753_ntt_shard_step1(g753_ctx* ctx, const g753_ntt_shard* plan, void* d_data, void* d_send, int mode) {
+  CHECK_CTX(ctx);
+  if (!plan || !d_data || !d_send) return fail(G753_ERR_BAD_ARG, "null pointer");
+  if (mode < G753_FFT || mode > G753_COSET_IFFT) return fail(G753_ERR_BAD_ARG, "unknown transform");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return plan->field == 0 ? shard_step1<0>(ctx, plan, (Fq*)d_data, (Fq*)d_send, mode)
+                          : shard_step1<1>(ctx, plan, (Fq*)d_data, (Fq*)d_send, mode);
+}
+
+int g753_ntt_shard_step2(g753_ctx* ctx, const g753_ntt_shard* plan, const void* d_recv, void* d_data, int mode) {
+  CHECK_CTX(ctx);
+  if (!plan || !d_data || !d_recv) return fail(G753_ERR_BAD_ARG, "null pointer");
+  if (mode < G753_FFT || mode > G753_COSET_IFFT) return fail(G753_ERR_BAD_ARG, "unknown transform");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return plan->field == 0 ? shard_step2<0>(ctx, plan, (const Fq*)d_recv, (Fq*)d_data, mode)
+                          : shard_step2<1>(ctx, plan, (const Fq*)d_recv, (Fq*)d_data, mode);
 }
 
 int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n) {

@@ -91,6 +91,16 @@ __global__ void k_table_double(Fq* tab, const Fq* step, unsigned len, unsigned c
   tab[len + t] = fq_mul<FID>(tab[t], *step);
 }
 
+// the constants of a size-2^log_n domain alone (no O(n) tables): consts layout as k_ntt_setup's
+template <int FID>
+static int ntt_consts_build(Fq** consts, unsigned log_n, cudaStream_t stream, uint64_t* launches) {
+  const unsigned L = log_n ? log_n : 1;
+  G753_TRY(dev_alloc((void**)consts, sizeof(Fq) * (2 + 4 * L)));
+  G753_LAUNCH(k_ntt_setup<FID>, 1, 1, stream, log_n, *consts);
+  if (launches) ++*launches;
+  return launch_check("k_ntt_setup");
+}
+
 template <int FID>
 static int ntt_tables_build(NttTables& T, unsigned log_n, cudaStream_t stream, uint64_t* launches) {
   T.log_n = log_n;
@@ -201,10 +211,17 @@ G753_D void ntt_stg(Fq* g, const Fq& a) {
 template <int FID>
 __global__ void __launch_bounds__(NTT_T, 4)
 k_ntt_pass(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restrict__ tw, unsigned L, unsigned s,
-           unsigned q, const Fq* __restrict__ pre, const Fq* __restrict__ post,
-           const Fq* __restrict__ post_const) {
+           unsigned q, const Fq* __restrict__ pre, size_t pre_stride, const Fq* __restrict__ post,
+           size_t post_stride, const Fq* __restrict__ post_const) {
   extern __shared__ uint4 ntt_sm[];
   const unsigned tid = threadIdx.x;
+  {  // blockIdx.y = index of the vector within a batch of equal-length transforms
+    const size_t bi = blockIdx.y;
+    in += bi << L;
+    out += bi << L;
+    if (pre != nullptr) pre += bi * pre_stride;
+    if (post != nullptr) post += bi * post_stride;
+  }
   const unsigned half_q = 1u << (q - 1);
   const unsigned cidx = tid >> (q - 1);           // column within the block
   const unsigned jl = tid & (half_q - 1);         // local butterfly index
@@ -259,6 +276,29 @@ k_ntt_pass(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restrict
     }
     if (d + 1 < q) __syncthreads();
   }
+}
+#endif
+
+// length-1 "transforms" of a batch: out[b] = in[b] * pre * post (each optional)
+#if defined(G753_HOST_EMUL)
+template <int FID>
+__global__ void k_ntt_scale1(const Fq* in, Fq* out, const Fq* pre, const Fq* post, const Fq* post_const) {
+  Fq v = *in;
+  if (pre) v = fq_mul<FID>(v, *pre);
+  if (post) v = fq_mul<FID>(v, *post);
+  else if (post_const) v = fq_mul<FID>(v, *post_const);
+  *out = v;
+}
+#else
+template <int FID>
+__global__ void k_ntt_scale1(const Fq* in, Fq* out, const Fq* pre, size_t pre_stride, const Fq* post,
+                             size_t post_stride, const Fq* post_const) {
+  const size_t b = blockIdx.x;
+  Fq v = in[b];
+  if (pre) v = fq_mul<FID>(v, pre[b * pre_stride]);
+  if (post) v = fq_mul<FID>(v, post[b * post_stride]);
+  else if (post_const) v = fq_mul<FID>(v, *post_const);
+  out[b] = v;
 }
 #endif
 
@@ -361,42 +401,81 @@ k_witness_finish(const Fq* __restrict__ ab, const Fq* __restrict__ d, Fq* __rest
   h[i] = v;
 }
 
-// In-place transform of d_data (n = 2^log_n elements) using d_tmp (same size) as the
+// What one transform (or a batch of equal-length ones) does around the butterflies.
+struct NttCall {
+  bool inverse = false;             // twiddles omega^-j instead of omega^j
+  const Fq* pre = nullptr;          // inputs  *= pre[batch * pre_stride + index]   (first pass)
+  size_t pre_stride = 0;
+  const Fq* post = nullptr;         // outputs *= post[batch * post_stride + index] (last pass)
+  size_t post_stride = 0;
+  const Fq* post_const = nullptr;   // outputs *= *post_const (when post == nullptr)
+  unsigned batch = 1;               // contiguous vectors of n elements each
+};
+
+static inline NttCall ntt_call_for_mode(const NttTables& T, int mode) {
+  NttCall c;
+  c.inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
+  if (mode == G753_COSET_FFT) c.pre = T.coset;
+  if (mode == G753_COSET_IFFT) c.post = T.coset_inv;
+  if (mode == G753_IFFT) c.post_const = T.consts;
+  return c;
+}
+
+// In-place transform of d_data (batch x n elements, n = 2^log_n) using d_tmp (same size) as the
 // ping-pong buffer.  The log_n stages are split into ceil(log_n / 8) passes of near-equal depth.
 template <int FID>
-static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tmp, int mode,
+static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tmp, const NttCall& call,
                    uint64_t* launches) {
   const unsigned log_n = T.log_n;
   const size_t n = (size_t)1 << log_n;
-  if (log_n == 0) return G753_OK;  // size-1 domain: every transform is the identity
-  const bool inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
-  const Fq* tw = inverse ? T.tw_inv : T.tw_fwd;
+  if (call.batch == 0) return G753_OK;
+  if (call.batch > 65535) return G753_ERR_BAD_ARG;
+  const Fq* tw = call.inverse ? T.tw_inv : T.tw_fwd;
   Fq* src = d_data;
   Fq* dst = d_tmp;
+  if (log_n == 0) {
+    // size-1 transforms are the identity up to the pre / post factors
+    if (call.pre == nullptr && call.post == nullptr && call.post_const == nullptr) return G753_OK;
+  }
 #if defined(G753_HOST_EMUL)
-  for (unsigned s = 0; s < log_n; s++) {
-    const Fq* pre = (s == 0 && mode == G753_COSET_FFT) ? T.coset : nullptr;
-    const Fq* post = (s == log_n - 1 && mode == G753_COSET_IFFT) ? T.coset_inv : nullptr;
-    const Fq* post_c = (s == log_n - 1 && mode == G753_IFFT) ? T.consts : nullptr;
-    G753_LAUNCH(k_ntt_stage<FID>, div_up(n / 2, 256), 256, stream, src, dst, tw, log_n, s, pre, post, post_c);
+  const unsigned stages = log_n ? log_n : 1;
+  for (unsigned s = 0; s < stages; s++) {
+    for (unsigned bi = 0; bi < call.batch; bi++) {
+      const Fq* pre = (s == 0 && call.pre) ? call.pre + bi * call.pre_stride : nullptr;
+      const Fq* post = (s == stages - 1 && call.post) ? call.post + bi * call.post_stride : nullptr;
+      const Fq* post_c = (s == stages - 1) ? call.post_const : nullptr;
+      if (log_n == 0)
+        G753_LAUNCH(k_ntt_scale1<FID>, 1, 1, stream, src + bi, dst + bi, pre, post, post_c);
+      else
+        G753_LAUNCH(k_ntt_stage<FID>, div_up(n / 2, 256), 256, stream, src + bi * n, dst + bi * n, tw, log_n, s, pre,
+                    post, post_c);
+    }
     if (launches) ++*launches;
     Fq* t = src;
     src = dst;
     dst = t;
   }
 #else
+  if (log_n == 0) {
+    k_ntt_scale1<FID><<<call.batch, 1, 0, stream>>>(src, dst, call.pre, call.pre_stride, call.post, call.post_stride,
+                                                    call.post_const);
+    if (launches) ++*launches;
+    Fq* t = src;
+    src = dst;
+    dst = t;
+  }
   const unsigned passes = (log_n + NTT_MAX_Q - 1) / NTT_MAX_Q;
   unsigned s = 0;
+  cudaFuncSetAttribute(k_ntt_pass<FID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT_SMEM);
   for (unsigned pi = 0; pi < passes; pi++) {
     const unsigned q = (log_n - s + (passes - pi) - 1) / (passes - pi);
     const bool first = (pi == 0), last = (pi + 1 == passes);
-    const Fq* pre = (first && mode == G753_COSET_FFT) ? T.coset : nullptr;
-    const Fq* post = (last && mode == G753_COSET_IFFT) ? T.coset_inv : nullptr;
-    const Fq* post_c = (last && mode == G753_IFFT) ? T.consts : nullptr;
     const size_t n_cols = n >> q;
     const unsigned cols_per_block = NTT_E >> q;
-    G753_LAUNCH_SMEM(k_ntt_pass<FID>, div_up(n_cols, cols_per_block), NTT_T, NTT_SMEM, stream, src, dst, tw, log_n, s,
-                     q, pre, post, post_c);
+    dim3 grid(div_up(n_cols, cols_per_block), call.batch);
+    k_ntt_pass<FID><<<grid, NTT_T, NTT_SMEM, stream>>>(src, dst, tw, log_n, s, q, first ? call.pre : nullptr,
+                                                       call.pre_stride, last ? call.post : nullptr, call.post_stride,
+                                                       last ? call.post_const : nullptr);
     if (launches) ++*launches;
     s += q;
     Fq* t = src;
@@ -404,8 +483,13 @@ static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tm
     dst = t;
   }
 #endif
-  if (src != d_data) G753_TRY(d2d(d_data, src, sizeof(Fq) * n, stream));
+  if (src != d_data) G753_TRY(d2d(d_data, src, sizeof(Fq) * n * call.batch, stream));
   return launch_check("ntt_run");
+}
+
+template <int FID>
+static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tmp, int mode, uint64_t* launches) {
+  return ntt_run<FID>(T, stream, d_data, d_tmp, ntt_call_for_mode(T, mode), launches);
 }
 
 }  // namespace g753

@@ -93,3 +93,125 @@ def fold_points(ctx, group, points_xyz, count):
         lib.dev_free(ctx.handle, d_in)
         lib.dev_free(ctx.handle, d_out)
     return out
+
+
+class ShardedEvaluationDomain:
+    """`EvaluationDomain` transforms over a vector sharded across the ranks of a process group
+    (four-step NTT).  Rank g holds the `cols x n1` input shard
+    local[i2l][i1] = x[i1*n2 + g*cols + i2l]; a transform leaves the `rows x n2` output shard
+    local[k1l][k2] = X[(g*rows + k1l) + n1*k2].  The only collective is one all-to-all per transform
+    (`all_to_all_single` on device tensors with NCCL; host-staged with gloo in the CPU tests)."""
+
+    def __init__(self, ctx, field, log_n, process_group=None):
+        import torch.distributed as dist
+        self.dist, self.ctx, self.field, self.log_n, self.pg = dist, ctx, field, log_n, process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self.backend = dist.get_backend(process_group) if dist.is_initialized() else None
+        h = ctypes.c_void_p()
+        ctx.lib.check(ctx.lib.ntt_shard_create(ctx.handle, field, log_n, self.world, self.rank, ctypes.byref(h)))
+        self.plan = h
+        v = [ctypes.c_size_t() for _ in range(4)]
+        ctx.lib.check(ctx.lib.ntt_shard_shape(h, *[ctypes.byref(x) for x in v]))
+        self.n1, self.n2, self.cols, self.rows = (int(x.value) for x in v)
+        self.local = (1 << log_n) // self.world
+
+    # ---- layout helpers (host side, for tests / callers that start from a whole vector) ----------
+    def scatter(self, full):
+        """whole natural-order vector (n, 12) -> this rank's input shard (local, 12)"""
+        x = ffi.as_u64(full).reshape(self.n1, self.n2, LIMBS)            # x[i1][i2]
+        lo = self.rank * self.cols
+        return np.ascontiguousarray(x[:, lo:lo + self.cols].transpose(1, 0, 2)).reshape(-1, LIMBS)
+
+    def gather(self, shard):
+        """output shards of all ranks -> whole natural-order vector (n, 12), on every rank"""
+        import torch
+        mine = torch.from_numpy(np.ascontiguousarray(shard).view(np.int64).reshape(-1).copy())
+        if self.world == 1:
+            parts = [mine]
+        elif self.backend == "nccl":
+            dev = torch.device("cuda", self.ctx.device)
+            buf = [torch.empty_like(mine, device=dev) for _ in range(self.world)]
+            self.dist.all_gather(buf, mine.to(dev), group=self.pg)
+            parts = [b.cpu() for b in buf]
+        else:
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(parts, mine, group=self.pg)
+        out = np.empty((self.n2, self.n1, LIMBS), dtype=np.uint64)          # X[k2][k1], k = k1 + n1*k2
+        for g, p in enumerate(parts):
+            blk = p.numpy().view(np.uint64).reshape(self.rows, self.n2, LIMBS)   # [k1l][k2]
+            out[:, g * self.rows:(g + 1) * self.rows] = blk.transpose(1, 0, 2)
+        return out.reshape(-1, LIMBS)
+
+    # ---- the transform -----------------------------------------------------------------------------
+    def transform_dev(self, d_data, d_send, d_recv, mode, exchange):
+        """d_data / d_send / d_recv: device pointers to `local` elements each; `exchange(d_send, d_recv)`
+        performs the all-to-all of world blocks of rows*cols elements"""
+        lib, ctx = self.ctx.lib, self.ctx
+        lib.check(lib.ntt_shard_step1(ctx.handle, self.plan, d_data, d_send, mode))
+        exchange()
+        lib.check(lib.ntt_shard_step2(ctx.handle, self.plan, d_recv, d_data, mode))
+
+    def transform(self, shard, mode):
+        """host shard in, host shard out (any backend)"""
+        import torch
+        lib, ctx = self.ctx.lib, self.ctx
+        shard = ffi.as_u64(shard).reshape(self.local, LIMBS)
+        nbytes = self.local * 96
+        if self.backend == "nccl":
+            dev = torch.device("cuda", ctx.device)
+            t_data = torch.from_numpy(shard.view(np.int64).reshape(-1).copy()).to(dev)
+            t_send, t_recv = torch.empty_like(t_data), torch.empty_like(t_data)
+            torch.cuda.synchronize(dev)
+
+            def exchange():
+                lib.check(lib.sync(ctx.handle))
+                self.dist.all_to_all_single(t_recv, t_send, group=self.pg)
+                torch.cuda.synchronize(dev)
+            self.transform_dev(ctypes.c_void_p(t_data.data_ptr()), ctypes.c_void_p(t_send.data_ptr()),
+                               ctypes.c_void_p(t_recv.data_ptr()), mode, exchange)
+            lib.check(lib.sync(ctx.handle))
+            return t_data.cpu().numpy().view(np.uint64).reshape(self.local, LIMBS)
+        bufs = [ctypes.c_void_p() for _ in range(3)]
+        for b in bufs:
+            lib.check(lib.dev_alloc(ctx.handle, nbytes, ctypes.byref(b)))
+        try:
+            lib.check(lib.h2d(ctx.handle, bufs[0], ffi.ptr(shard), nbytes))
+
+            def exchange():
+                send = np.empty((self.local, LIMBS), dtype=np.uint64)
+                lib.check(lib.d2h(ctx.handle, ffi.ptr(send), bufs[1], nbytes))
+                if self.world > 1:
+                    t_send = torch.from_numpy(send.view(np.int64).reshape(-1))
+                    t_recv = torch.empty_like(t_send)
+                    if self.backend == "gloo":   # gloo has no all_to_all_single on CPU tensors in every build
+                        ins = list(t_send.chunk(self.world))
+                        outs = [torch.empty_like(c) for c in ins]
+                        reqs = []
+                        for peer in range(self.world):
+                            if peer == self.rank:
+                                outs[peer].copy_(ins[peer])
+                                continue
+                            reqs.append(self.dist.isend(ins[peer].contiguous(), peer, group=self.pg))
+                            reqs.append(self.dist.irecv(outs[peer], peer, group=self.pg))
+                        for q in reqs:
+                            q.wait()
+                        t_recv = torch.cat(outs)
+                    else:
+                        self.dist.all_to_all_single(t_recv, t_send, group=self.pg)
+                    recv = t_recv.numpy().view(np.uint64).reshape(self.local, LIMBS)
+                else:
+                    recv = send
+                lib.check(lib.h2d(ctx.handle, bufs[2], ffi.ptr(np.ascontiguousarray(recv)), nbytes))
+            self.transform_dev(bufs[0], bufs[1], bufs[2], mode, exchange)
+            out = np.empty((self.local, LIMBS), dtype=np.uint64)
+            lib.check(lib.d2h(ctx.handle, ffi.ptr(out), bufs[0], nbytes))
+            return out
+        finally:
+            for b in bufs:
+                lib.dev_free(ctx.handle, b)
+
+    def close(self):
+        if getattr(self, "plan", None):
+            self.ctx.lib.ntt_shard_destroy(self.ctx.handle, self.plan)
+            self.plan = None

@@ -46,6 +46,11 @@ SYMBOLS = [
     ("g753_domain_check", _i, [_i, _u]),
     ("g753_ntt", _i, [_vp, _i, _vp, _u, _i]),
     ("g753_ntt_dev", _i, [_vp, _i, _vp, _u, _i]),
+    ("g753_ntt_shard_create", _i, [_vp, _i, _u, _u, _u, _pvp]),
+    ("g753_ntt_shard_destroy", _i, [_vp, _vp]),
+    ("g753_ntt_shard_shape", _i, [_vp, ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
+    ("g753_ntt_shard_step1", _i, [_vp, _vp, _vp, _vp, _i]),
+    ("g753_ntt_shard_step2", _i, [_vp, _vp, _vp, _vp, _i]),
     ("g753_vec_op_dev", _i, [_vp, _i, _i, _vp, _vp, _sz]),
     ("g753_vec_scale_dev", _i, [_vp, _i, _vp, _vp, _sz]),
     ("g753_witness_map", _i, [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp]),

@@ -72,6 +72,7 @@ extern "C" {
 
 typedef struct g753_ctx g753_ctx;       /* one CUDA device + stream + scratch + tables */
 typedef struct g753_bases g753_bases;   /* a device-resident slice of proving-key bases */
+typedef struct g753_ntt_shard g753_ntt_shard; /* one rank's plan of a transform sharded over several GPUs */
 
 /* ---- context ------------------------------------------------------------------------- */
 int g753_device_count(int* count);
@@ -152,6 +153,22 @@ int g753_ntt_dev(g753_ctx* ctx, int field, void* d_data, unsigned log_n, int mod
  * a[i] *= k (divide_by_vanishing_poly_on_coset_in_place domain.rs:245-256) */
 int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n);
 int g753_vec_scale_dev(g753_ctx* ctx, int field, void* d_a, const uint64_t* k_mont, size_t n);
+
+/* ---- NTT sharded over `world` GPUs (one process per GPU), four-step ------------
+ * n = n1 * n2 (n1 = 2^ceil(log_n/2) >= n2); rank g owns cols = n2/world columns of the n1 x n2 view:
+ *   input  shard  local[i2l][i1] = x[i1*n2 + g*cols + i2l]            (cols x n1 elements)
+ *   output shard  local[k1l][k2] = X[(g*rows + k1l) + n1*k2]          (rows x n2 elements, rows = n1/world)
+ * One transform = step1 (local column transforms + twiddles, packed into d_send as `world` blocks of
+ * rows*cols elements, block h for rank h), an all-to-all of those blocks done by the caller
+ * (NCCL over NVLink: the transpose IS the exchange), step2 (unpack d_recv + local row transforms
+ * into d_data).  When n1 == n2 an output shard is directly the input shard of the next transform.
+ * Results equal g753_ntt's on the gathered vector, for all four modes. */
+int g753_ntt_shard_create(g753_ctx* ctx, int field, unsigned log_n, unsigned world, unsigned rank,
+                          g753_ntt_shard** out);
+int g753_ntt_shard_destroy(g753_ctx* ctx, g753_ntt_shard* plan);
+int g753_ntt_shard_shape(const g753_ntt_shard* plan, size_t* n1, size_t* n2, size_t* cols, size_t* rows);
+int g753_ntt_shard_step1(g753_ctx* ctx, const g753_ntt_shard* plan, void* d_data, void* d_send, int mode);
+int g753_ntt_shard_step2(g753_ctx* ctx, const g753_ntt_shard* plan, const void* d_recv, void* d_data, int mode);
 
 /* R1CStoQAP::witness_map from the evaluated constraints onwards (proof-systems/src/groth16/
  * r1cs_to_qap.rs:121-166): a, b, c = the n = 2^log_n evaluations <A_i,z>, <B_i,z>, <C_i,z> padded as

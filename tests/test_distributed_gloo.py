@@ -39,6 +39,23 @@ for group, n in ((ffi.MNT4_G1, 23), (ffi.MNT4_G2, 7)):
     assert projective_to_point(C, got) == O.msm_naive(C, pts, sc), (rank, group)
     bases.free()
 assert [D.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+# sharded four-step NTT: scatter -> step1 -> all-to-all -> step2 -> gather == the oracle's transform
+from util753 import FIELDS, array_field, field_array
+for field, log_n in ((ffi.FIELD_MNT4_FR, 4), (ffi.FIELD_MNT6_FR, 5), (ffi.FIELD_MNT4_FR, 2)):
+    F = FIELDS[field]
+    n = 1 << log_n
+    rng = O.SplitMix64(0x800 + log_n)
+    a = [O.random_field_element(rng, F) for _ in range(n)]
+    ref = O.EvaluationDomain(F, n)
+    dom = D.ShardedEvaluationDomain(ctx, field, log_n)
+    for mode, want in ((ffi.FFT, ref.fft(a)), (ffi.IFFT, ref.ifft(a)), (ffi.COSET_FFT, ref.coset_fft(a)),
+                       (ffi.COSET_IFFT, ref.coset_ifft(a))):
+        out = dom.gather(dom.transform(dom.scatter(field_array(F, a)), mode))
+        assert array_field(F, out) == want, (rank, field, log_n, mode)
+    if log_n % 2 == 0:   # n1 == n2: shards chain without re-layout (ifft then coset_fft, as the witness map does)
+        sh = dom.transform(dom.transform(dom.scatter(field_array(F, a)), ffi.IFFT), ffi.COSET_FFT)
+        assert array_field(F, dom.gather(sh)) == ref.coset_fft(ref.ifft(a)), (rank, "chain")
+    dom.close()
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
@@ -46,9 +63,9 @@ print("rank", rank, "ok")
 
 
 def test_sharded_msm_two_ranks_gloo(tmp_path):
-    lib = os.path.join(HERE, "host_emul", "libg753_emul.so")
-    if not os.path.exists(lib):
-        pytest.skip("host-emulation library not built yet (tests/test_pipeline_emul.py builds it)")
+    sys.path.insert(0, HERE)
+    from util753 import build_emul
+    build_emul()
     script = tmp_path / "worker.py"
     port = 29500 + (os.getpid() % 2000)
     script.write_text(WORKER.format(root=ROOT, here=HERE, port=port, world=2))

@@ -22,11 +22,8 @@ CSRC = os.path.join(HERE, "..", "ginger-lib_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def ctx():
-    deps = [SRC, os.path.join(HERE, "..", "include", "g753.h")] + [
-        os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".cu", ".inc"))]
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", LIB, SRC])
-    lib = ffi.Library(LIB)
+    from util753 import build_emul
+    lib = ffi.Library(build_emul())
     c = G.Context(0, library=lib)
     yield c
     c.close()
@@ -199,3 +196,21 @@ def test_msm_precomputed_key_copies(ctx, monkeypatch, group, c, copies):
     assert (bases.download(0, n)[keep] == coords[keep]).all()
     bases.free()
     cx.close()
+
+
+@pytest.mark.parametrize("field,log_n", [(ffi.FIELD_MNT4_FR, 4), (ffi.FIELD_MNT6_FR, 5), (ffi.FIELD_MNT4_FR, 1), (ffi.FIELD_MNT4_FR, 0)])
+def test_sharded_ntt_single_rank(ctx, field, log_n):
+    """four-step decomposition (ntt_dist.cuh) with world = 1: column transforms + twiddles, the
+    (identity) exchange, row transforms == the oracle's transform, all four modes"""
+    D = __import__("importlib").import_module("ginger-lib_b200.distributed")
+    F = FIELDS[field]
+    n = 1 << log_n
+    rng = O.SplitMix64(0x4D + log_n)
+    a = [O.random_field_element(rng, F) for _ in range(n)]
+    ref = O.EvaluationDomain(F, n)
+    dom = D.ShardedEvaluationDomain(ctx, field, log_n)
+    for mode, want in ((ffi.FFT, ref.fft(a)), (ffi.IFFT, ref.ifft(a)), (ffi.COSET_FFT, ref.coset_fft(a)),
+                       (ffi.COSET_IFFT, ref.coset_ifft(a))):
+        out = dom.gather(dom.transform(dom.scatter(field_array(F, a)), mode))
+        assert array_field(F, out) == want, mode
+    dom.close()
