@@ -17,40 +17,69 @@
 
 namespace g753 {
 
-// curve descriptors on slots: tower type + multiplication by the curve coefficient a
-template <int T>
+// curve descriptors on slots: tower type + multiplication by the curve coefficient a.
+// L is the block layout (slots.cuh): Lay<columns, 1> for the prime-field curves and the test-only
+// host build, Lay<columns, 4> / Lay<columns, 8> (cooperative towers) for G2 on the device.
+template <bool COND, class A, class B>
+struct SelectT { typedef A type; };
+template <class A, class B>
+struct SelectT<false, A, B> { typedef B type; };
+
+template <class L>
 struct SCurveM4G1 {
-  typedef Tw1<0, T> M;
+  typedef Tw1<0, L> M;
   static constexpr int ID = 0;
-  static G753_D void mul_by_a(int d, int a) { s_dbl<0, T>(d, a); }  // a = 2 (curves/mnt4753/g1.rs:18-33)
+  static G753_D void mul_by_a(int d, int a) { s_dbl<0, L>(d, a); }  // a = 2 (curves/mnt4753/g1.rs:18-33)
 };
-template <int T>
+template <class L>
+struct SCurveM6G1 {
+  typedef Tw1<1, L> M;
+  static constexpr int ID = 2;
+  static G753_D void mul_by_a(int d, int a) { s_mul_small<1, L, 11>(d, a); }  // a = 11 (curves/mnt6753/g1.rs:18-33)
+};
+#if defined(G753_HOST_EMUL)
+template <class L>
 struct SCurveM4G2 {
-  typedef Tw2<0, T, 13> M;
+  typedef Tw2<0, L, 13> M;
   static constexpr int ID = 1;
   // twist a' = (26, 0), coefficient-wise (curves/mnt4753/g2.rs:112-118)
   static G753_D void mul_by_a(int d, int a) {
-    s_mul_small<0, T, 26>(d, a);
-    s_mul_small<0, T, 26>(d + 1, a + 1);
+    s_mul_small<0, L, 26>(d, a);
+    s_mul_small<0, L, 26>(d + 1, a + 1);
   }
 };
-template <int T>
-struct SCurveM6G1 {
-  typedef Tw1<1, T> M;
-  static constexpr int ID = 2;
-  static G753_D void mul_by_a(int d, int a) { s_mul_small<1, T, 11>(d, a); }  // a = 11 (curves/mnt6753/g1.rs:18-33)
-};
-template <int T>
+template <class L>
 struct SCurveM6G2 {
-  typedef Tw3<1, T, 11> M;
+  typedef Tw3<1, L, 11> M;
   static constexpr int ID = 3;
   // twist a' = 11 u^2: (c0, c1, c2) -> (121 c1, 121 c2, 11 c0) (curves/mnt6753/g2.rs:148-155); d != a
   static G753_D void mul_by_a(int d, int a) {
-    s_mul_small<1, T, 121>(d, a + 1);
-    s_mul_small<1, T, 121>(d + 1, a + 2);
-    s_mul_small<1, T, 11>(d + 2, a);
+    s_mul_small<1, L, 121>(d, a + 1);
+    s_mul_small<1, L, 121>(d + 1, a + 2);
+    s_mul_small<1, L, 11>(d + 2, a);
   }
 };
+#else
+template <class L>
+struct SCurveM4G2 {
+  typedef Tw2C<0, L, 13> M;
+  static constexpr int ID = 1;
+  // twist a' = (26, 0), coefficient-wise (curves/mnt4753/g2.rs:112-118)
+  static G753_D void mul_by_a(int d, int a) { M::template mul_small2<26, 26>(d, a); }
+};
+template <class L>
+struct SCurveM6G2 {
+  typedef Tw3C<1, L, 11> M;
+  static constexpr int ID = 3;
+  // twist a' = 11 u^2: (c0, c1, c2) -> (121 c1, 121 c2, 11 c0) (curves/mnt6753/g2.rs:148-155); d != a
+  static G753_D void mul_by_a(int d, int a) {
+    const int r = L::role();
+    if (r < 2) s_mul_small<1, L, 121>(d + r, a + 1 + r);
+    if (r == 2) s_mul_small<1, L, 11>(d + 2, a);
+    L::sync();
+  }
+};
+#endif
 
 template <class SC>
 struct EcS {

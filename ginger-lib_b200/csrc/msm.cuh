@@ -38,13 +38,21 @@ constexpr unsigned MSM_MAX_C = 20;
 constexpr unsigned ITEM_LEN = 64;          // longest run one thread accumulates
 constexpr unsigned ITEM_REP = 16;          // replicated length counters (spreads the atomics)
 
-// per-group launch shapes: threads per block chosen so the slot footprint fits 227 KB of
-// shared memory (accumulate: 8K + NTMP slots, reduce: 13K + NTMP slots of 96 B per thread)
+// per-group launch shapes: NC_* columns (curve operations) per block, TP lanes per column; chosen so
+// that the slot footprint (accumulate: 8K + NTMP slots, reduce: 13K + NTMP slots of 96 B per column)
+// leaves >= 8 warps per SM inside the 227 KB of shared memory
 template <int GID> struct MsmCfg;
-template <> struct MsmCfg<0> { static constexpr int K = 1, T_ACC = 128, T_RED = 128; template <int T> using SC = SCurveM4G1<T>; };
-template <> struct MsmCfg<1> { static constexpr int K = 2, T_ACC = 96, T_RED = 64; template <int T> using SC = SCurveM4G2<T>; };
-template <> struct MsmCfg<2> { static constexpr int K = 1, T_ACC = 128, T_RED = 128; template <int T> using SC = SCurveM6G1<T>; };
-template <> struct MsmCfg<3> { static constexpr int K = 3, T_ACC = 64, T_RED = 32; template <int T> using SC = SCurveM6G2<T>; };
+#if defined(G753_HOST_EMUL)
+#define G753_TP2 1
+#define G753_TP3 1
+#else
+#define G753_TP2 4
+#define G753_TP3 8
+#endif
+template <> struct MsmCfg<0> { static constexpr int K = 1, TP = 1, NC_ACC = 128, NC_RED = 128; template <int NC> using SC = SCurveM4G1<Lay<NC, 1>>; };
+template <> struct MsmCfg<1> { static constexpr int K = 2, TP = G753_TP2, NC_ACC = 48, NC_RED = 32; template <int NC> using SC = SCurveM4G2<Lay<NC, G753_TP2>>; };
+template <> struct MsmCfg<2> { static constexpr int K = 1, TP = 1, NC_ACC = 128, NC_RED = 128; template <int NC> using SC = SCurveM6G1<Lay<NC, 1>>; };
+template <> struct MsmCfg<3> { static constexpr int K = 3, TP = G753_TP3, NC_ACC = 32, NC_RED = 16; template <int NC> using SC = SCurveM6G2<Lay<NC, G753_TP3>>; };
 
 struct MsmPlan {
   unsigned c;       // window bits
@@ -215,7 +223,7 @@ struct MsmItem {  // 16 bytes
 static __global__ void k_item_emit(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ends,
                             const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict__ item_off,
                             unsigned NB, unsigned B, size_t row_cap, uint32_t* __restrict__ len_cursor,
-                            MsmItem* __restrict__ items) {
+                            MsmItem* __restrict__ items, uint32_t* __restrict__ part_bucket) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= NB) return;
   const uint32_t cnt_items = item_cnt[t];
@@ -234,6 +242,7 @@ static __global__ void k_item_emit(const uint32_t* __restrict__ offsets, const u
     it.dest = cnt_items == 1 ? t : NB + first_id + j;
     it.pad = 0;
     items[pos] = it;
+    part_bucket[first_id + j] = t;
   }
 }
 
@@ -242,12 +251,12 @@ static __global__ void k_item_emit(const uint32_t* __restrict__ offsets, const u
 // live in shared-memory slots (ec_slots.cuh), bases are gathered straight from HBM.
 // ------------------------------------------------------------------------------------
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_bucket_acc(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const MsmItem* __restrict__ items, const uint32_t* __restrict__ item_total,
              Fq* __restrict__ points) {
   typedef EcS<SC> E;
-  unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned pos = E::M::T::item();
   if (pos >= *item_total) return;
   const MsmItem it = items[pos];
   E::set_inf(0);
@@ -259,19 +268,45 @@ k_bucket_acc(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
   E::stg(points + (size_t)it.dest * E::PT, 0);
 }
 
-// buckets that were cut into several items: points[t] = sum of their partial results
+// Buckets that were cut into several items: points[t] = sum of their partial results
+// points[NB + item_off[t] + j], j < item_cnt[t].  A bucket can hold a large share of all points
+// (the top window of a 753-bit scalar has only a few significant bits; real witnesses are full of
+// 0 / 1 / small values), so the partials are summed by an in-place tree: at level l (stride
+// s = FIX_FAN^l) the thread of partial j, j % (FIX_FAN s) == 0, adds partials j + s, j + 2s, ...
+// into its own - every thread writes only inside its own segment - and after the last level
+// partial 0 holds the bucket's sum.  One thread per item id; part_bucket[] maps ids to buckets.
+constexpr unsigned FIX_FAN = 8;
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_bucket_fixup_level(const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict__ item_off,
+                     const uint32_t* __restrict__ part_bucket, const uint32_t* __restrict__ item_total, unsigned NB,
+                     unsigned stride, Fq* __restrict__ points) {
+  typedef EcS<SC> E;
+  unsigned q = E::M::T::item();
+  if (q >= *item_total) return;
+  const uint32_t t = part_bucket[q];
+  const uint32_t cnt = item_cnt[t], first = item_off[t];
+  const uint32_t j = q - first;
+  if (cnt < 2 || j % (FIX_FAN * stride) != 0 || j + stride >= cnt) return;
+  Fq* mine = points + (size_t)(NB + q) * E::PT;
+  E::ldg(0, mine);
+  for (unsigned k = 1; k < FIX_FAN; k++) {
+    const uint32_t jj = j + k * stride;
+    if (jj >= cnt) break;
+    E::add_g(0, points + (size_t)(NB + first + jj) * E::PT, E::PT);
+  }
+  E::stg(mine, 0);
+}
+// points[t] = partial 0 of every multi-item bucket
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_bucket_fixup(const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict__ item_off,
                unsigned NB, Fq* __restrict__ points) {
   typedef EcS<SC> E;
-  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned t = E::M::T::item();
   if (t >= NB) return;
-  const uint32_t cnt = item_cnt[t];
-  if (cnt < 2) return;
-  const uint32_t first = NB + item_off[t];
-  E::set_inf(0);
-  for (uint32_t j = 0; j < cnt; j++) E::add_g(0, points + (size_t)(first + j) * E::PT, E::PT);
+  if (item_cnt[t] < 2) return;
+  E::ldg(0, points + (size_t)(NB + item_off[t]) * E::PT);
   E::stg(points + (size_t)t * E::PT, 0);
 }
 
@@ -284,13 +319,13 @@ k_bucket_fixup(const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict
 // Row w of X / Y starts at w * x_stride / w * y_stride (in points).
 // ------------------------------------------------------------------------------------
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_reduce_level(const Fq* __restrict__ X, size_t x_stride, const Fq* __restrict__ Y, size_t y_stride,
                unsigned n_in, unsigned log2f, unsigned W, unsigned n_out, Fq* __restrict__ R,
                Fq* __restrict__ Yout) {
   typedef EcS<SC> E;
   constexpr int RUN = 0, ACC = E::PT, SCR = 2 * E::PT;
-  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned t = E::M::T::item();
   if (t >= W * n_out) return;
   unsigned w = t / n_out, j = t % n_out;
   unsigned lo = j * REDUCE_SEG;
@@ -315,11 +350,11 @@ k_reduce_level(const Fq* __restrict__ X, size_t x_stride, const Fq* __restrict__
 // Horner fold over the W window sums (stride between windows given, in points), then convert
 // to the reference's homogeneous projective layout.  One thread: W*c doublings are a serial chain.
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_window_combine(const Fq* __restrict__ sums, unsigned stride, unsigned W, unsigned c,
                  Fq* __restrict__ out_xyz) {
   typedef EcS<SC> E;
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (E::M::T::item() != 0) return;
   E::set_inf(0);
   for (int w = (int)W - 1; w >= 0; w--) {
     if (w != (int)W - 1)
@@ -339,11 +374,11 @@ __global__ void k_write_infinity(Fq* __restrict__ out_xyz) {
 
 // sum of `count` projective points (the multi-GPU fold; count is the number of ranks)
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_points_sum(const Fq* __restrict__ pts, unsigned count, Fq* __restrict__ out_xyz) {
   typedef EcS<SC> E;
   constexpr int TOT = 0, CUR = E::PT, SCR = 2 * E::PT;
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (E::M::T::item() != 0) return;
   E::set_inf(TOT);
   for (unsigned k = 0; k < count; k++) {
     E::from_projective_g(CUR, pts + (size_t)k * 3 * E::K, SCR);
@@ -387,6 +422,7 @@ static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n) {
   t += Carver::pad(sizeof(uint32_t) * s.nb_chunks);                     // item-count chunk sums
   t += Carver::pad(sizeof(uint32_t) * ITEM_LEN * ITEM_REP) * 2 + 512;   // length counters + total
   t += Carver::pad(sizeof(MsmItem) * s.max_items);
+  t += Carver::pad(sizeof(uint32_t) * s.max_items);                     // item id -> bucket
   t += Carver::pad(PT_BYTES * (NB + s.max_items));                      // buckets + item partials
   t += Carver::pad(PT_BYTES * pl.rows * entries) * 2;                   // reduction levels
   s.total = t + 8192;
@@ -433,15 +469,16 @@ template <int GID>
 static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, const uint32_t* d_scalars,
                    size_t count, Fq* d_out, MsmHooks hooks) {
   typedef MsmCfg<GID> Cfg;
-  constexpr int TA = Cfg::T_ACC, TR = Cfg::T_RED;
-  typedef typename Cfg::template SC<TA> SCA;
-  typedef typename Cfg::template SC<TR> SCR;
+  constexpr int CA = Cfg::NC_ACC, CR = Cfg::NC_RED;        // columns (curve operations) per block
+  constexpr int TA = CA * Cfg::TP, TR = CR * Cfg::TP;      // threads per block
+  typedef typename Cfg::template SC<CA> SCA;
+  typedef typename Cfg::template SC<CR> SCR;
   typedef EcS<SCA> EA;
   typedef EcS<SCR> ER;
   constexpr size_t PT = 4 * Cfg::K;  // Fq per XYZZ point
-  constexpr size_t SMEM_ACC = slot_bytes<EA, TA>(EA::PT + EA::MADD_SCRATCH);
-  constexpr size_t SMEM_FIX = slot_bytes<EA, TA>(EA::PT + EA::ADD_SCRATCH);
-  constexpr size_t SMEM_RED = slot_bytes<ER, TR>(2 * ER::PT + ER::ADD_SCRATCH);
+  constexpr size_t SMEM_ACC = slot_bytes<EA, CA>(EA::PT + EA::MADD_SCRATCH);
+  constexpr size_t SMEM_FIX = slot_bytes<EA, CA>(EA::PT + EA::ADD_SCRATCH);
+  constexpr size_t SMEM_RED = slot_bytes<ER, CR>(2 * ER::PT + ER::ADD_SCRATCH);
   static_assert(SMEM_ACC <= 232448 && SMEM_FIX <= 232448 && SMEM_RED <= 232448, "slot footprint exceeds 227 KB");
   if (count == 0) {
     G753_MSM_LAUNCH(hooks, k_write_infinity<SCR>, 1, 1, stream, d_out);
@@ -473,6 +510,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   uint32_t* len_cursor = cv.take<uint32_t>(ITEM_LEN * ITEM_REP);
   uint32_t* item_total = cv.take<uint32_t>(64);
   MsmItem* items = cv.take<MsmItem>(ws.max_items);
+  uint32_t* part_bucket = cv.take<uint32_t>(ws.max_items);
   Fq* points = cv.take<Fq>(PT * ((size_t)NB + ws.max_items));
   Fq* lvl_r = cv.take<Fq>(PT * R * ws.level_entries);
   Fq* lvl_y = cv.take<Fq>(PT * R * ws.level_entries);
@@ -503,11 +541,15 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
                   NB, ws.nb_chunks, 1u, item_off, (uint32_t*)nullptr);
   G753_MSM_LAUNCH(hooks, k_item_len_scan, 1, 32, stream, len_hist, len_cursor, item_total);
   G753_MSM_LAUNCH(hooks, k_item_emit, div_up(NB, 256), 256, stream, offsets, cursor, item_cnt, item_off, NB,
-                  pl.B, ws.row_cap, len_cursor, items);
+                  pl.B, ws.row_cap, len_cursor, items, part_bucket);
   if (hooks.mark) hooks.mark(hooks.user, 2);
-  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc<SCA>, div_up(ws.max_items, TA), TA, SMEM_ACC, stream, key.bases,
+  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc<SCA>, div_up(ws.max_items, CA), TA, SMEM_ACC, stream, key.bases,
                        sorted, items, item_total, points);
-  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup<SCA>, div_up(NB, TA), TA, SMEM_FIX, stream, item_cnt, item_off,
+  // a bucket holds at most row_cap points = row_cap / ITEM_LEN + 1 partials
+  for (size_t stride = 1; stride <= ws.row_cap / ITEM_LEN; stride *= FIX_FAN)
+    G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup_level<SCA>, div_up(ws.max_items, CA), TA, SMEM_FIX, stream, item_cnt,
+                         item_off, part_bucket, item_total, NB, (unsigned)stride, points);
+  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup<SCA>, div_up(NB, CA), TA, SMEM_FIX, stream, item_cnt, item_off,
                        NB, points);
   if (hooks.mark) hooks.mark(hooks.user, 3);
   // reduction levels
@@ -522,7 +564,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
     unsigned n_out = div_up(n_in, REDUCE_SEG);
     Fq* Rr = lvl_r + lvl_off * PT;
     Fq* Yo = lvl_y + lvl_off * PT;
-    G753_MSM_LAUNCH_SMEM(hooks, k_reduce_level<SCR>, div_up((size_t)R * n_out, TR), TR, SMEM_RED, stream, X,
+    G753_MSM_LAUNCH_SMEM(hooks, k_reduce_level<SCR>, div_up((size_t)R * n_out, CR), TR, SMEM_RED, stream, X,
                          x_stride, Y, y_stride, n_in, log2f, R, n_out, Rr, Yo);
     lvl_off += (size_t)R * n_out;
     X = Rr;

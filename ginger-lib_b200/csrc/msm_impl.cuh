@@ -35,12 +35,12 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
 
 // group-law test hook on the product's own slot code (ec_slots.cuh); affine (0, 0) = infinity
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_point_op(int op, const Fq* a, const Fq* b, const uint32_t* scalar, Fq* out) {
   typedef EcS<SC> E;
   typedef typename E::M M;
   constexpr int K = E::K, P = 0, Q = E::PT, S = 2 * E::PT;
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (E::M::T::item() != 0) return;
   auto load_affine = [&](int D, const Fq* q) {
     E::set_inf(D);
     M::ldg(S, q);
@@ -94,7 +94,7 @@ int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, u
   G753_TRY(h2d(da, a, aff, ctx->stream));
   if (op == 0 || op == 3) G753_TRY(h2d(db, b, aff, ctx->stream));
   if (op == 2) G753_TRY(h2d(ds, b, 96, ctx->stream));
-  G753_LAUNCH_SMEM(k_point_op<SC>, 1, T, (slot_bytes<E, T>(2 * E::PT + E::ADD_SCRATCH)), ctx->stream, op, da, db,
+  G753_LAUNCH_SMEM(k_point_op<SC>, 1, T * MsmCfg<GID>::TP, (slot_bytes<E, T>(2 * E::PT + E::ADD_SCRATCH)), ctx->stream, op, da, db,
                    ds, dout);
   ctx->launches++;
   G753_TRY(launch_check("k_point_op"));
@@ -104,10 +104,10 @@ int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, u
 
 template <int GID>
 void points_sum_launch(g753_ctx* ctx, const void* d_pts, size_t count, void* d_out) {
-  constexpr int T = 32;
+  constexpr int T = 32;  // columns; only column 0 works
   typedef typename MsmCfg<GID>::template SC<T> SC;
   typedef EcS<SC> E;
-  G753_LAUNCH_SMEM(k_points_sum<SC>, 1, T, (slot_bytes<E, T>(2 * E::PT + E::ADD_SCRATCH)), ctx->stream,
+  G753_LAUNCH_SMEM(k_points_sum<SC>, 1, T * MsmCfg<GID>::TP, (slot_bytes<E, T>(2 * E::PT + E::ADD_SCRATCH)), ctx->stream,
                    (const Fq*)d_pts, (unsigned)count, (Fq*)d_out);
 }
 
@@ -123,12 +123,12 @@ G753_HD uint64_t splitmix64_at(uint64_t seed, uint64_t i) {
   return z ^ (z >> 31);
 }
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_bases_generate(const Fq* __restrict__ gen, uint64_t seed, unsigned n, Fq* __restrict__ out) {
   typedef EcS<SC> E;
   typedef typename E::M M;
   constexpr int K = E::K, P = 0, S = E::PT;
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned i = E::M::T::item();
   if (i >= n) return;
   const uint64_t a = splitmix64_at(seed, i) | 1ull;
   E::set_inf(P);
@@ -156,7 +156,7 @@ int bases_generate_impl(g753_ctx* ctx, const uint64_t* gen_xy, uint64_t seed, si
   G753_TRY(dev_alloc((void**)&d_gen, sizeof(Fq) * 2 * K));
   int rc = h2d(d_gen, gen_xy, sizeof(Fq) * 2 * K, ctx->stream);
   if (rc == G753_OK) {
-    G753_LAUNCH_SMEM(k_bases_generate<SC>, div_up(n, T), T, (slot_bytes<E, T>(E::PT + E::ADD_SCRATCH)), ctx->stream,
+    G753_LAUNCH_SMEM(k_bases_generate<SC>, div_up(n, T), T * MsmCfg<GID>::TP, (slot_bytes<E, T>(E::PT + E::ADD_SCRATCH)), ctx->stream,
                      d_gen, seed, (unsigned)n, (Fq*)d_points);
     ctx->launches++;
     rc = launch_check("k_bases_generate");
@@ -171,12 +171,12 @@ int bases_generate_impl(g753_ctx* ctx, const uint64_t* gen_xy, uint64_t seed, si
 // row r with the base taken from copy j, so the MSM has `rows` bucket rows instead of W: the
 // bucket reduction and the serial Horner fold shrink by W / rows.
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_bases_precompute(Fq* __restrict__ pts, uint8_t* __restrict__ inf, unsigned n, unsigned copies, unsigned shift) {
   typedef EcS<SC> E;
   typedef typename E::M M;
   constexpr int K = E::K, P = 0, S = E::PT;
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned i = E::M::T::item();
   if (i >= n) return;
   bool is_inf = inf[i] != 0;
   if (!is_inf) {
@@ -222,7 +222,7 @@ int bases_precompute_impl(g753_ctx* ctx, g753_bases* b, unsigned copies) {
   if (rc == G753_OK) rc = d2d(d_new, b->d_points, pt_bytes * n, ctx->stream);
   if (rc == G753_OK) rc = b->d_inf ? d2d(d_inf, b->d_inf, n, ctx->stream) : dev_memset(d_inf, 0, n, ctx->stream);
   if (rc == G753_OK) {
-    G753_LAUNCH_SMEM(k_bases_precompute<SC>, div_up(n, T), T, (slot_bytes<E, T>(E::PT + E::ADD_SCRATCH)), ctx->stream,
+    G753_LAUNCH_SMEM(k_bases_precompute<SC>, div_up(n, T), T * MsmCfg<GID>::TP, (slot_bytes<E, T>(E::PT + E::ADD_SCRATCH)), ctx->stream,
                      (Fq*)d_new, d_inf, (unsigned)n, pl.copies, pl.rows * pl.c);
     ctx->launches++;
     rc = launch_check("k_bases_precompute");
@@ -247,12 +247,12 @@ int bases_precompute_impl(g753_ctx* ctx, g753_bases* b, unsigned copies) {
 // 663-678): homogeneous (X:Y:Z) -> affine (X/Z, Y/Z); Z == 0 -> GroupAffine::zero() = (0, 1, true).  One thread
 // per point with its own inversion: the prover normalises 3 points per proof.
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T)
+__global__ void __launch_bounds__(SC::M::T::THREADS)
 k_batch_normalize(const Fq* __restrict__ xyz, unsigned n, Fq* __restrict__ xy, uint8_t* __restrict__ inf) {
   typedef EcS<SC> E;
   typedef typename E::M M;
   constexpr int K = E::K, X = 0, Y = K, Z = 2 * K, ZI = 3 * K, S = 4 * K;
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned i = E::M::T::item();
   if (i >= n) return;
   M::ldg(Z, xyz + (size_t)i * 3 * K + 2 * K);
   if (M::is_zero(Z)) {
@@ -287,7 +287,7 @@ int batch_normalize_impl(g753_ctx* ctx, const uint64_t* xyz, size_t count, uint6
   Fq* d_out = cv.take<Fq>(2 * K * count);
   uint8_t* d_inf = cv.take<uint8_t>(count);
   G753_TRY(h2d(d_in, xyz, prj * count, ctx->stream));
-  G753_LAUNCH_SMEM(k_batch_normalize<SC>, div_up(count, T), T, (slot_bytes<E, T>(4 * K + E::M::NTMP + 1)), ctx->stream,
+  G753_LAUNCH_SMEM(k_batch_normalize<SC>, div_up(count, T), T * MsmCfg<GID>::TP, (slot_bytes<E, T>(4 * K + E::M::NTMP + 1)), ctx->stream,
                    d_in, (unsigned)count, d_out, d_inf);
   ctx->launches++;
   G753_TRY(launch_check("k_batch_normalize"));

@@ -32,17 +32,51 @@ extern __shared__ uint4 g_slots[];
 
 constexpr int SLOT_CHUNKS = NL / 4;  // 6 x 16 bytes per Fq
 
-template <int T>
+// Thread <-> slot-column layout of a block.  NC columns (one curve operation each) of TP lanes:
+//   TP = 1: one thread per column (prime-field curves);
+//   TP = 4 / 8: the lanes of a column share its slots and split the independent base-field
+//   products of an Fq2 / Fq3 operation between them (roles), so the extension-field curves put
+//   4x / 8x more warps on an SM for the same shared-memory footprint.  Within a warp the role is
+//   the slow index (lane = role * (32 / TP) + column-in-warp): a quarter-warp touches
+//   consecutive columns of one slot, keeping LDS.128 / STS.128 conflict-free.
+// A "slot type" T below is either a plain int-like column count (legacy spelling Lay<T, 1>) or Lay.
+template <int NC_, int TP_>
+struct Lay {
+  static constexpr int NC = NC_, TP = TP_, THREADS = NC_ * TP_, CPW = 32 / TP_;  // CPW: columns per warp
+  static G753_D int col() {
+    if (TP == 1) return (int)threadIdx.x;
+    return (int)(threadIdx.x >> 5) * CPW + (int)(threadIdx.x & (CPW - 1));
+  }
+  static G753_D int role() {
+    if (TP == 1) return 0;
+    return (int)((threadIdx.x & 31) / CPW);
+  }
+  // reconverge the lanes of this column and order their slot accesses
+  static G753_D void sync() {
+#if defined(__CUDA_ARCH__)
+    if (TP > 1) {
+      unsigned m = 0;
+#pragma unroll
+      for (int r = 0; r < TP; r++) m |= 1u << (r * CPW);
+      __syncwarp(m << (threadIdx.x & (CPW - 1)));
+    }
+#endif
+  }
+  // index of the column over the whole grid: the work item of this lane's column
+  static G753_D unsigned item() { return blockIdx.x * NC + (unsigned)col(); }
+};
+
+template <class L>
 G753_D uint4* slot_ptr(int s) {
-  return g_slots + s * (SLOT_CHUNKS * T) + threadIdx.x;
+  return g_slots + s * (SLOT_CHUNKS * L::NC) + L::col();
 }
-template <int T>
+template <class T>
 G753_D Fq s_ld(int s) {
   const uint4* p = slot_ptr<T>(s);
   Fq r;
 #pragma unroll
   for (int k = 0; k < SLOT_CHUNKS; k++) {
-    uint4 v = p[k * T];
+    uint4 v = p[k * T::NC];
     r.l[4 * k] = v.x;
     r.l[4 * k + 1] = v.y;
     r.l[4 * k + 2] = v.z;
@@ -50,7 +84,7 @@ G753_D Fq s_ld(int s) {
   }
   return r;
 }
-template <int T>
+template <class T>
 G753_D void s_st(int s, const Fq& a) {
   uint4* p = slot_ptr<T>(s);
 #pragma unroll
@@ -60,7 +94,7 @@ G753_D void s_st(int s, const Fq& a) {
     v.y = a.l[4 * k + 1];
     v.z = a.l[4 * k + 2];
     v.w = a.l[4 * k + 3];
-    p[k * T] = v;
+    p[k * T::NC] = v;
   }
 }
 // global <-> register, 16-byte vector accesses (Fq is 16-byte aligned)
@@ -91,88 +125,89 @@ G753_D void g_st(Fq* g, const Fq& a) {
 }
 
 // ---- Fq on slots (d may alias a or b everywhere: operands are read before d is written) ----
-template <int FID, int T>
+template <int FID, class T>
 G753_NI void s_mul(int d, int a, int b) {
   s_st<T>(d, fq_mul<FID>(s_ld<T>(a), s_ld<T>(b)));
 }
-template <int FID, int T>
+template <int FID, class T>
 G753_NI void s_sqr(int d, int a) {
   s_st<T>(d, fq_sqr<FID>(s_ld<T>(a)));
 }
-template <int FID, int T>
+template <int FID, class T>
 G753_NI void s_add(int d, int a, int b) {
   s_st<T>(d, fq_add<FID>(s_ld<T>(a), s_ld<T>(b)));
 }
-template <int FID, int T>
+template <int FID, class T>
 G753_NI void s_sub(int d, int a, int b) {
   s_st<T>(d, fq_sub<FID>(s_ld<T>(a), s_ld<T>(b)));
 }
-template <int FID, int T>
+template <int FID, class T>
 G753_NI void s_dbl(int d, int a) {
   s_st<T>(d, fq_dbl<FID>(s_ld<T>(a)));
 }
-template <int FID, int T>
+template <int FID, class T>
 G753_NI void s_neg(int d, int a) {
   s_st<T>(d, fq_neg<FID>(s_ld<T>(a)));
 }
-template <int FID, int T, unsigned KK>
+template <int FID, class T, unsigned KK>
 G753_NI void s_mul_small(int d, int a) {
   s_st<T>(d, fq_mul_small<FID, KK>(s_ld<T>(a)));
 }
-template <int FID, int T>
+template <int FID, class T>
 G753_NI void s_inv(int d, int a) {  // Fermat; the inverse is unique, so the limbs equal fp_768.rs:551-605's
   s_st<T>(d, fq_inv<FID>(s_ld<T>(a)));
 }
-template <int T>
+template <class T>
 G753_D void s_copy(int d, int a) {
   if (d == a) return;
   const uint4* p = slot_ptr<T>(a);
   uint4* q = slot_ptr<T>(d);
 #pragma unroll
-  for (int k = 0; k < SLOT_CHUNKS; k++) q[k * T] = p[k * T];
+  for (int k = 0; k < SLOT_CHUNKS; k++) q[k * T::NC] = p[k * T::NC];
 }
-template <int T>
+template <class T>
 G753_D bool s_is_zero(int a) {
   const uint4* p = slot_ptr<T>(a);
   uint32_t t = 0;
 #pragma unroll
   for (int k = 0; k < SLOT_CHUNKS; k++) {
-    uint4 v = p[k * T];
+    uint4 v = p[k * T::NC];
     t |= v.x | v.y | v.z | v.w;
   }
   return t == 0;
 }
-template <int T>
+template <class T>
 G753_D void s_set_zero(int d) {
   uint4* q = slot_ptr<T>(d);
   uint4 z;
   z.x = z.y = z.z = z.w = 0;
 #pragma unroll
-  for (int k = 0; k < SLOT_CHUNKS; k++) q[k * T] = z;
+  for (int k = 0; k < SLOT_CHUNKS; k++) q[k * T::NC] = z;
 }
-template <int FID, int T>
+template <int FID, class T>
 G753_D void s_set_one(int d) {
   s_st<T>(d, fq_one<FID>());
 }
-template <int T>
+template <class T>
 G753_D void s_ldg(int d, const Fq* g) {
   const uint4* p = (const uint4*)g;
   uint4* q = slot_ptr<T>(d);
 #pragma unroll
-  for (int k = 0; k < SLOT_CHUNKS; k++) q[k * T] = p[k];
+  for (int k = 0; k < SLOT_CHUNKS; k++) q[k * T::NC] = p[k];
 }
-template <int T>
+template <class T>
 G753_D void s_stg(Fq* g, int a) {
   uint4* p = (uint4*)g;
   const uint4* q = slot_ptr<T>(a);
 #pragma unroll
-  for (int k = 0; k < SLOT_CHUNKS; k++) p[k] = q[k * T];
+  for (int k = 0; k < SLOT_CHUNKS; k++) p[k] = q[k * T::NC];
 }
 
 // ---- towers: an element is K consecutive slots; `t` is the first of NTMP scratch slots ----
-template <int FID, int T_>
+template <int FID, class T_>
 struct Tw1 {
-  static constexpr int K = 1, NTMP = 0, FIELD = FID, T = T_;
+  typedef T_ T;
+  static constexpr int K = 1, NTMP = 0, FIELD = FID;
   static G753_D void mul(int d, int a, int b, int) { s_mul<FID, T>(d, a, b); }
   static G753_D void sqr(int d, int a, int) { s_sqr<FID, T>(d, a); }
   static G753_D void inv(int d, int a, int) { s_inv<FID, T>(d, a); }
@@ -188,9 +223,10 @@ struct Tw1 {
   static G753_D void stg(Fq* g, int a) { s_stg<T>(g, a); }
 };
 
-template <int FID, int T_, unsigned NR>
+template <int FID, class T_, unsigned NR>
 struct Tw2 {
-  static constexpr int K = 2, NTMP = 3, FIELD = FID, T = T_;
+  typedef T_ T;
+  static constexpr int K = 2, NTMP = 3, FIELD = FID;
   // Karatsuba (fp2.rs:387-401), 3 products
   static G753_NI void mul(int d, int a, int b, int t) {
     s_mul<FID, T>(t, a, b);
@@ -265,9 +301,10 @@ struct Tw2 {
   }
 };
 
-template <int FID, int T_, unsigned NR>
+template <int FID, class T_, unsigned NR>
 struct Tw3 {
-  static constexpr int K = 3, NTMP = 6, FIELD = FID, T = T_;
+  typedef T_ T;
+  static constexpr int K = 3, NTMP = 6, FIELD = FID;
   // Karatsuba (fp3.rs:451-478), 6 products
   static G753_NI void mul(int d, int a, int b, int t) {
     s_mul<FID, T>(t, a, b);                  // v0
@@ -370,5 +407,226 @@ struct Tw3 {
     for (int i = 0; i < 3; i++) s_stg<T>(g + i, a + i);
   }
 };
+
+
+#if !defined(G753_HOST_EMUL)
+// ---- cooperative towers (device only): the TP lanes of a column split the independent base-field
+// products of one extension-field operation.  Lanes that run the SAME function on different
+// slots proceed in lockstep; role-specific steps are serialised by the SIMT hardware, so every
+// phase below is written as "one call, role-dependent slot numbers" wherever it matters
+// (the products).  Every operation ends with L::sync(): its result is visible to all lanes of the
+// column before the next one starts.  d may alias a or b: d is written only after the last read
+// of the operands.  The TEST-ONLY host build keeps the one-thread towers above.
+template <int FID, class L, unsigned NR>
+struct Tw2C {
+  typedef L T;
+  static constexpr int K = 2, NTMP = 4, FIELD = FID;
+  static_assert(L::TP >= 3, "Fq2 needs three product lanes");
+  // Karatsuba (fp2.rs:387-401): products a0 b0, a1 b1, (a0 + a1)(b0 + b1) on lanes 0, 1, 2
+  static G753_NI void mul(int d, int a, int b, int t) {
+    const int r = L::role();
+    if (r == 2 || r == 3) s_add<FID, L>(t + r, r == 2 ? a : b, r == 2 ? a + 1 : b + 1);
+    L::sync();
+    if (r < 3) s_mul<FID, L>(t + r, r == 0 ? a : r == 1 ? a + 1 : t + 2, r == 0 ? b : r == 1 ? b + 1 : t + 3);
+    L::sync();
+    if (r == 1) {
+      s_sub<FID, L>(d + 1, t + 2, t);
+      s_sub<FID, L>(d + 1, d + 1, t + 1);
+    } else if (r == 0) {
+      s_mul_small<FID, L, NR>(t + 3, t + 1);
+      s_add<FID, L>(d, t, t + 3);
+    }
+    L::sync();
+  }
+  // complex squaring (fp2.rs:128-144): a0 a1 and (a0 + a1)(a0 + NR a1) on lanes 0, 1
+  static G753_NI void sqr(int d, int a, int t) {
+    const int r = L::role();
+    if (r == 1) s_add<FID, L>(t + 1, a, a + 1);
+    if (r == 2) {
+      s_mul_small<FID, L, NR>(t + 2, a + 1);
+      s_add<FID, L>(t + 2, a, t + 2);
+    }
+    L::sync();
+    if (r < 2) s_mul<FID, L>(t + r, r == 0 ? a : t + 1, r == 0 ? a + 1 : t + 2);
+    L::sync();
+    if (r == 0) {
+      s_dbl<FID, L>(d + 1, t);
+    } else if (r == 1) {
+      s_mul_small<FID, L, NR>(t + 2, t);
+      s_sub<FID, L>(t + 1, t + 1, t);
+      s_sub<FID, L>(d, t + 1, t + 2);
+    }
+    L::sync();
+  }
+  static G753_NI void inv(int d, int a, int t) {
+    if (L::role() == 0) Tw2<FID, L, NR>::inv(d, a, t);
+    L::sync();
+  }
+  static G753_D void add(int d, int a, int b) {
+    const int r = L::role();
+    if (r < K) s_add<FID, L>(d + r, a + r, b + r);
+    L::sync();
+  }
+  static G753_D void sub(int d, int a, int b) {
+    const int r = L::role();
+    if (r < K) s_sub<FID, L>(d + r, a + r, b + r);
+    L::sync();
+  }
+  static G753_D void dbl(int d, int a) {
+    const int r = L::role();
+    if (r < K) s_dbl<FID, L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D void neg(int d, int a) {
+    const int r = L::role();
+    if (r < K) s_neg<FID, L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D void copy(int d, int a) {
+    const int r = L::role();
+    if (r < K) s_copy<L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D bool is_zero(int a) { return s_is_zero<L>(a) && s_is_zero<L>(a + 1); }
+  static G753_D void set_zero(int d) {
+    const int r = L::role();
+    if (r < K) s_set_zero<L>(d + r);
+    L::sync();
+  }
+  static G753_D void set_one(int d) {
+    const int r = L::role();
+    if (r == 0) s_set_one<FID, L>(d);
+    if (r == 1) s_set_zero<L>(d + 1);
+    L::sync();
+  }
+  static G753_D void ldg(int d, const Fq* g) {
+    const int r = L::role();
+    if (r < K) s_ldg<L>(d + r, g + r);
+    L::sync();
+  }
+  static G753_D void stg(Fq* g, int a) {
+    const int r = L::role();
+    if (r < K) s_stg<L>(g + r, a + r);
+  }
+  // coefficient-wise multiplication by small constants (curve coefficient a of the twists)
+  template <unsigned C0, unsigned C1>
+  static G753_D void mul_small2(int d, int a) {
+    const int r = L::role();
+    if (r == 0) s_mul_small<FID, L, C0>(d, a);
+    if (r == 1) s_mul_small<FID, L, C1>(d + 1, a + 1);
+    L::sync();
+  }
+};
+
+template <int FID, class L, unsigned NR>
+struct Tw3C {
+  typedef L T;
+  static constexpr int K = 3, NTMP = 9, FIELD = FID;
+  static_assert(L::TP >= 6, "Fq3 needs six product lanes");
+  // Karatsuba (fp3.rs:451-478): v0, v1, v2 on lanes 0..2, the three cross products on lanes 3..5.
+  // scratch: t+0..2 = v0, v1, v2; t+3.. = (a1+a2, b1+b2), (a0+a1, b0+b1), (a0+a2, b0+b2)
+  static G753_NI void mul(int d, int a, int b, int t) {
+    const int r = L::role();
+    if (r >= 3 && r < 6) {
+      const int j = r - 3;                                    // 0: (1,2)  1: (0,1)  2: (0,2)
+      const int x = j == 0 ? 1 : 0, y = j == 1 ? 1 : 2;
+      s_add<FID, L>(t + 3 + 2 * j, a + x, a + y);
+      s_add<FID, L>(t + 4 + 2 * j, b + x, b + y);
+    }
+    L::sync();
+    if (r < 6) {
+      const int j = r - 3;
+      s_mul<FID, L>(r < 3 ? t + r : t + 3 + 2 * j, r < 3 ? a + r : t + 3 + 2 * j, r < 3 ? b + r : t + 4 + 2 * j);
+    }
+    L::sync();
+    // m12 = t+3, m01 = t+5, m02 = t+7; one output coordinate per lane 0..2
+    if (r < 3) {
+      const int m = t + 3 + 2 * r;
+      s_sub<FID, L>(m, m, r == 0 ? t + 1 : t);                // m12 - v1 | m01 - v0 | m02 - v0
+      s_sub<FID, L>(m, m, r == 1 ? t + 1 : t + 2);            // ... - v2 | ... - v1 | ... - v2
+      if (r < 2) s_mul_small<FID, L, NR>(r == 0 ? m : m + 1, r == 0 ? m : t + 2);   // NR m12 | NR v2 -> t+6
+      s_add<FID, L>(d + r, r == 0 ? t : m, r == 0 ? m : r == 1 ? m + 1 : t + 1);
+    }
+    L::sync();
+  }
+  // Chung-Hasan SQR2 (fp3.rs:165-185): a0^2, a0 a1, (a0 - a1 + a2)^2, a1 a2, a2^2 on lanes 0..4
+  static G753_NI void sqr(int d, int a, int t) {
+    const int r = L::role();
+    if (r == 2) {
+      s_sub<FID, L>(t + 5, a, a + 1);
+      s_add<FID, L>(t + 5, t + 5, a + 2);
+    }
+    L::sync();
+    if (r < 5) {
+      const int x = r == 0 ? a : r == 1 ? a : r == 2 ? t + 5 : r == 3 ? a + 1 : a + 2;
+      const int y = r == 0 ? a : r == 1 ? a + 1 : r == 2 ? t + 5 : r == 3 ? a + 2 : a + 2;
+      s_mul<FID, L>(t + r, x, y);
+    }
+    L::sync();
+    if (r == 1 || r == 3) s_dbl<FID, L>(t + r, t + r);        // s1 = 2 a0 a1, s3 = 2 a1 a2
+    L::sync();
+    if (r < 2) {
+      s_mul_small<FID, L, NR>(t + 6 + r, r == 0 ? t + 3 : t + 4);   // NR s3 | NR s4
+      s_add<FID, L>(d + r, r == 0 ? t : t + 1, t + 6 + r);          // c0 = s0 + NR s3 | c1 = s1 + NR s4
+    } else if (r == 2) {
+      s_add<FID, L>(t + 5, t + 1, t + 2);
+      s_add<FID, L>(t + 5, t + 5, t + 3);
+      s_sub<FID, L>(t + 5, t + 5, t);
+      s_sub<FID, L>(d + 2, t + 5, t + 4);                           // c2 = s1 + s2 + s3 - s0 - s4
+    }
+    L::sync();
+  }
+  static G753_NI void inv(int d, int a, int t) {
+    if (L::role() == 0) Tw3<FID, L, NR>::inv(d, a, t);
+    L::sync();
+  }
+  static G753_D void add(int d, int a, int b) {
+    const int r = L::role();
+    if (r < K) s_add<FID, L>(d + r, a + r, b + r);
+    L::sync();
+  }
+  static G753_D void sub(int d, int a, int b) {
+    const int r = L::role();
+    if (r < K) s_sub<FID, L>(d + r, a + r, b + r);
+    L::sync();
+  }
+  static G753_D void dbl(int d, int a) {
+    const int r = L::role();
+    if (r < K) s_dbl<FID, L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D void neg(int d, int a) {
+    const int r = L::role();
+    if (r < K) s_neg<FID, L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D void copy(int d, int a) {
+    const int r = L::role();
+    if (r < K) s_copy<L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D bool is_zero(int a) { return s_is_zero<L>(a) && s_is_zero<L>(a + 1) && s_is_zero<L>(a + 2); }
+  static G753_D void set_zero(int d) {
+    const int r = L::role();
+    if (r < K) s_set_zero<L>(d + r);
+    L::sync();
+  }
+  static G753_D void set_one(int d) {
+    const int r = L::role();
+    if (r == 0) s_set_one<FID, L>(d);
+    if (r == 1 || r == 2) s_set_zero<L>(d + r);
+    L::sync();
+  }
+  static G753_D void ldg(int d, const Fq* g) {
+    const int r = L::role();
+    if (r < K) s_ldg<L>(d + r, g + r);
+    L::sync();
+  }
+  static G753_D void stg(Fq* g, int a) {
+    const int r = L::role();
+    if (r < K) s_stg<L>(g + r, a + r);
+  }
+};
+#endif
 
 }  // namespace g753

@@ -8,7 +8,7 @@
 #include <cstring>
 
 using namespace g753;
-static const int T = 32;  // emulated block size (thread 0 is the one that runs)
+typedef Lay<32, 1> T;  // emulated block: 32 columns, one lane each (thread 0 is the one that runs)
 
 template <int FID>
 static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {

@@ -97,6 +97,28 @@ def test_msm_heavy_buckets(ctx, group):
     bases.free()
 
 
+def test_msm_very_heavy_bucket_tree_fixup(ctx):
+    """one bucket holding 700 points (11 work items): the partial sums are joined by the in-place
+    tree of k_bucket_fixup_level over two levels"""
+    C = O.MNT4_G1
+    base = sample_points(C, 5, 0x99)
+    n = 700
+    pts = [base[i % 5] for i in range(n)]
+    sc = [3] * n
+    sc[10] = C.r - 3
+    sc[11] = 0
+    coords, inf = points_to_arrays(C, pts)
+    bases = ctx.upload_bases(ffi.MNT4_G1, coords, inf)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+    cnt = [sum(1 for i in range(n) if i % 5 == j and i not in (10, 11)) for j in range(5)]
+    want = None
+    for j in range(5):
+        want = C.add(want, C.mul(base[j], 3 * cnt[j] % C.r))
+    want = C.add(want, C.mul(base[0], C.r - 3))
+    assert projective_to_point(C, got) == want
+    bases.free()
+
+
 @pytest.mark.parametrize("field", sorted(FIELDS))
 def test_ntt_small(ctx, field):
     F = FIELDS[field]
