@@ -386,12 +386,13 @@ def run_ours(args):
                          "variable_base.rs:10-83, 1 run of %.1f s; result equal to the CUDA path's" %
                          (args.cpu_log_n, times[0])}
 
-    # ---- config 5: end-to-end Groth16 proof (rank 0, N = 1) ----------------------------------
+    # ---- config 5: end-to-end Groth16 proof; N > 1: the long MSMs sharded by point range -------
     g16 = None
-    if rank == 0 and world == 1 and not args.no_groth16:
+    if not args.no_groth16:
         import bench_groth16
         bases.free()
-        g16 = bench_groth16.run(ctx, args.groth16_log_n, steps=max(2, min(args.steps, 3)), warmup=1, copies=args.copies)
+        g16 = bench_groth16.run(ctx, args.groth16_log_n, steps=max(2, min(args.steps, 3)), warmup=1, copies=args.copies,
+                                rank=rank, world=world, barrier=barrier if world > 1 else None)
 
     if rank == 0:
         canon_all, canon_acc = canonical_field_muls(n_local)

@@ -29,7 +29,16 @@ def mont_random(n, seed):
     return v
 
 
-def run(ctx, log_n=20, steps=3, warmup=1, copies=8, verify=True):
+GOLDEN = 0x9E3779B97F4A7C15
+
+
+def gen_range(ctx, group, seed, first, count):
+    """bases[first .. first+count) of the synthetic key `seed` (g753_bases_generate indexes from 0, so
+    the offset goes into the seed: a_i = splitmix64(seed + (i + 1) * GOLDEN))"""
+    return ctx.generate_bases(group, count, (seed + first * GOLDEN) & 0xFFFFFFFFFFFFFFFF)
+
+
+def run(ctx, log_n=20, steps=3, warmup=1, copies=8, verify=True, rank=0, world=1, barrier=None):
     import torch
     G = importlib.import_module("ginger-lib_b200")
     groth16 = importlib.import_module("ginger-lib_b200.groth16")
@@ -43,15 +52,27 @@ def run(ctx, log_n=20, steps=3, warmup=1, copies=8, verify=True):
     n_vars = ni + n_aux
     t0 = time.perf_counter()
     seeds = {"a": 0x6A, "b1": 0x6B, "b2": 0x6C, "h": 0x6D, "l": 0x6E}
-    Ba = ctx.generate_bases(g1, n_vars, seeds["a"])
-    Bb1 = ctx.generate_bases(g1, n_vars, seeds["b1"])
-    Bb2 = ctx.generate_bases(g2, n_vars, seeds["b2"])
-    Bh = ctx.generate_bases(g1, n - 1, seeds["h"])
-    Bl = ctx.generate_bases(g1, n_aux, seeds["l"])
     vk = ctx.generate_bases(g1, 3, 0x71).download()
     vk2 = ctx.generate_bases(g2, 2, 0x72).download()
-    P = groth16.Parameters(ctx, g1, g2, field, vk[0], vk[1], vk2[0], vk[2], vk2[1], Ba, Bb1, Bb2, Bh, Bl, ni,
-                           precompute=copies)
+    if world == 1:
+        Ba = ctx.generate_bases(g1, n_vars, seeds["a"])
+        Bb1 = ctx.generate_bases(g1, n_vars, seeds["b1"])
+        Bb2 = ctx.generate_bases(g2, n_vars, seeds["b2"])
+        Bh = ctx.generate_bases(g1, n - 1, seeds["h"])
+        Bl = ctx.generate_bases(g1, n_aux, seeds["l"])
+        P = groth16.Parameters(ctx, g1, g2, field, vk[0], vk[1], vk2[0], vk[2], vk2[1], Ba, Bb1, Bb2, Bh, Bl, ni,
+                               precompute=copies)
+    else:
+        # every long query split by point range over the ranks, heads replicated
+        heads = {k: (ctx.generate_bases(g2 if k == "b2" else g1, ni, seeds[k]).download(), None)
+                 for k in ("a", "b1", "b2", "h")}
+        shards = {}
+        for k, grp, start, total in (("a", g1, ni, n_aux), ("b1", g1, ni, n_aux), ("b2", g2, ni, n_aux),
+                                     ("h", g1, ni, n - 1 - ni), ("l", g1, 0, n_aux)):
+            lo, hi = groth16.shard_range(total, rank, world)
+            shards[k] = (gen_range(ctx, grp, seeds[k], start + lo, hi - lo), lo)
+        P = groth16.ShardedParameters(ctx, g1, g2, field, vk[0], vk[1], vk2[0], vk[2], vk2[1], heads, shards, ni,
+                                      precompute=copies)
     ctx.sync()
     key_s = time.perf_counter() - t0
     pin = lambda arr: torch.from_numpy(arr.view(np.int64)).pin_memory().numpy().view(np.uint64)
@@ -64,8 +85,12 @@ def run(ctx, log_n=20, steps=3, warmup=1, copies=8, verify=True):
     launches0 = ctx.launches + P.ctx2.launches
     for it in range(warmup + steps):
         t = {}
+        if barrier:
+            barrier()
         t1 = time.perf_counter()
         proof = groth16.create_proof(P, z, a, b, c, 0, 0, 0, r, s, timings=t if it == warmup + steps - 1 else None)
+        if barrier:
+            barrier()                      # the proof is done when the slowest rank is
         dt = time.perf_counter() - t1
         if it >= warmup:
             times.append(dt)
@@ -73,7 +98,7 @@ def run(ctx, log_n=20, steps=3, warmup=1, copies=8, verify=True):
             phases = t
     launches = (ctx.launches + P.ctx2.launches - launches0) // (warmup + steps)
     ok = None
-    if verify:
+    if verify and rank == 0:
         ok = verify_proof(ctx, G, groth16, bench, params_mod, proof, z, a, b, c, r, s, seeds, ni, n, r_mod)
         if not ok:
             raise SystemExit("Groth16 proof differs from the discrete-log prediction - refusing to report a number")
@@ -81,6 +106,7 @@ def run(ctx, log_n=20, steps=3, warmup=1, copies=8, verify=True):
     mean = float(np.mean(times))
     return {
         "metric": "groth16_create_proof_time", "value": mean * 1e3, "unit": "ms", "higher_is_better": False,
+        "n_gpus": world,
         "best_ms": min(times) * 1e3, "steps": steps, "warmup": warmup,
         "config": {"workload": "MNT4-753 Groth16 create_proof after constraint synthesis, domain 2^%d "
                                "(%d constraints, 3 inputs, num_aux = num_constraints; BASELINE config 5)" % (log_n, n - ni),
@@ -152,9 +178,27 @@ def main():
     ap.add_argument("--copies", type=int, default=8)
     args = ap.parse_args()
     G = importlib.import_module("ginger-lib_b200")
-    ctx = G.Context(0)
-    print(json.dumps(run(ctx, args.log_n, args.steps, args.warmup, args.copies)), flush=True)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    barrier = None
+    if world > 1:   # torchrun: one rank per GPU, long MSMs sharded by point range
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+        def barrier():
+            dist.barrier()
+            torch.cuda.synchronize()
+    ctx = G.Context(local_rank)
+    res = run(ctx, args.log_n, args.steps, args.warmup, args.copies, rank=rank, world=world, barrier=barrier)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
     ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

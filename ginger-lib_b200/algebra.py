@@ -249,6 +249,48 @@ class EvaluationDomain:
     coset_ifft_in_place = coset_ifft
 
 
+class MixedRadixDomain:
+    """A multiplicative subgroup of size n = 2^a * m (m odd) - the mixed-radix domain of BASELINE
+    config 4.  The reference snapshot implements radix-2 domains only; the interface mirrors
+    EvaluationDomain (new -> None when no such subgroup exists, fft / ifft / coset_fft / coset_ifft
+    on exactly `size` elements, natural order, omega = GENERATOR^((p-1)/n))."""
+
+    def __init__(self, field, size, ctx):
+        self.field, self.size_, self.ctx = field, size, ctx
+
+    @staticmethod
+    def new(field, size, ctx=None):
+        lib = (ctx.lib if ctx else ffi.default_library())
+        rc = lib.domain_check_mixed(field, size)
+        if rc == ffi.ERR_DOMAIN:
+            return None
+        lib.check(rc)
+        return MixedRadixDomain(field, size, ctx or default_context())
+
+    def size(self):
+        return self.size_
+
+    def _run(self, v, mode):
+        buf = np.zeros((self.size_, LIMBS), dtype=np.uint64)
+        v = ffi.as_u64(v).reshape(-1, LIMBS)
+        m = min(self.size_, v.shape[0])
+        buf[:m] = v[:m]
+        self.ctx.lib.check(self.ctx.lib.ntt_mixed(self.ctx.handle, self.field, ffi.ptr(buf), self.size_, mode))
+        return buf
+
+    def fft(self, coeffs):
+        return self._run(coeffs, ffi.FFT)
+
+    def ifft(self, evals):
+        return self._run(evals, ffi.IFFT)
+
+    def coset_fft(self, coeffs):
+        return self._run(coeffs, ffi.COSET_FFT)
+
+    def coset_ifft(self, evals):
+        return self._run(evals, ffi.COSET_IFFT)
+
+
 class DeviceVector:
     """A vector of field elements resident in HBM, for chaining transforms the way
     R1CStoQAP::witness_map does (r1cs_to_qap.rs:121-161) without host round trips."""

@@ -5,6 +5,7 @@
 // indexing and orchestration can be checked without a GPU (tests/host_emul).
 #include "ctx.cuh"
 #include "ntt_dist.cuh"
+#include "ntt_mixed.cuh"
 #if defined(G753_HOST_EMUL)
 #include "msm_impl.cuh"  // the test-only host build is a single translation unit
 G753_INSTANTIATE_GROUP(0)
@@ -170,6 +171,103 @@ static int shard_step2(g753_ctx* ctx, const g753_ntt_shard* p, const Fq* recv, F
   return launch_check("shard_step2");
 }
 
+// ---- mixed-radix transform (ntt_mixed.cuh) -----------------------------------------------------
+template <int FID>
+static int mixed_tables_get(g753_ctx* ctx, uint64_t N, const MixedTables** out) {
+  std::map<uint64_t, MixedTables>& mm = ctx->mixed[FID];
+  auto it = mm.find(N);
+  if (it != mm.end()) {
+    *out = &it->second;
+    return G753_OK;
+  }
+  MixedTables T;
+  uint32_t exp[NL];
+  if (!mixed_split(FID, N, &T.a, &T.m, exp)) return fail(G753_ERR_DOMAIN, "no mixed-radix domain of this size");
+  T.N = N;
+  const size_t n2 = (size_t)1 << T.a;
+  uint32_t* d_exp = nullptr;
+  int rc = dev_alloc((void**)&d_exp, sizeof(exp));
+  if (rc == G753_OK) rc = dev_alloc((void**)&T.consts, sizeof(Fq) * 8);
+  if (rc == G753_OK) rc = dev_alloc((void**)&T.zeta, sizeof(Fq) * 2 * T.m);
+  if (rc == G753_OK) rc = dev_alloc((void**)&T.tw, sizeof(Fq) * 2 * N);
+  if (rc == G753_OK) rc = dev_alloc((void**)&T.coset, sizeof(Fq) * N);
+  if (rc == G753_OK) rc = dev_alloc((void**)&T.coset_inv, sizeof(Fq) * N);
+  if (rc == G753_OK) rc = h2d(d_exp, exp, sizeof(exp), ctx->stream);
+  if (rc == G753_OK) {
+    const Fq* K = T.consts;
+    const Fq* none = nullptr;
+    G753_LAUNCH(k_mixed_setup<FID>, 1, 1, ctx->stream, d_exp, (uint64_t)N, (uint64_t)n2, T.consts);
+    // zeta^j and zeta^-j: one row of m powers each
+    G753_LAUNCH(k_pow_table<FID>, 1, 1, ctx->stream, T.zeta, 1u, T.m, (uint64_t)0, K + 3, none, none, none);
+    G753_LAUNCH(k_pow_table<FID>, 1, 1, ctx->stream, T.zeta + T.m, 1u, T.m, (uint64_t)0, K + 4, none, none, none);
+    // omega^(+-i2 k1): row k1, base omega^(+-k1)
+    G753_LAUNCH(k_pow_table<FID>, div_up(T.m, 64), 64, ctx->stream, T.tw, T.m, (unsigned)n2, (uint64_t)0, none, K,
+                none, none);
+    G753_LAUNCH(k_pow_table<FID>, div_up(T.m, 64), 64, ctx->stream, T.tw + N, T.m, (unsigned)n2, (uint64_t)0, none,
+                K + 1, none, none);
+    // g^i and g^-i / N, by doubling tables
+    G753_LAUNCH(k_table_init<FID>, 1, 1, ctx->stream, T.coset, (const Fq*)nullptr);
+    G753_LAUNCH(k_table_init<FID>, 1, 1, ctx->stream, T.coset_inv, K + 2);
+    ctx->launches += 7;
+    rc = launch_check("mixed tables");
+  }
+  Fq* steps = nullptr;  // g^(2^l), g^-(2^l)
+  if (rc == G753_OK) rc = dev_alloc((void**)&steps, sizeof(Fq) * 2 * 32);
+  if (rc == G753_OK) {
+    G753_LAUNCH(k_square_chain<FID>, 1, 1, ctx->stream, T.consts + 5, steps, 32u);
+    G753_LAUNCH(k_square_chain<FID>, 1, 1, ctx->stream, T.consts + 6, steps + 32, 32u);
+    for (unsigned l = 0; ((size_t)1 << l) < N; l++) {
+      unsigned len = 1u << l;
+      G753_LAUNCH(k_table_double<FID>, div_up(len, 128), 128, ctx->stream, T.coset, steps + l, len, (unsigned)N);
+      G753_LAUNCH(k_table_double<FID>, div_up(len, 128), 128, ctx->stream, T.coset_inv, steps + 32 + l, len,
+                  (unsigned)N);
+      ctx->launches += 2;
+    }
+    rc = launch_check("mixed coset tables");
+  }
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d_exp);
+  dev_free(steps);
+  if (rc != G753_OK) {
+    T.release();
+    return rc;
+  }
+  *out = &mm.emplace(N, T).first->second;
+  return G753_OK;
+}
+
+// d_data: N elements, in place; d_tmp: N elements
+template <int FID>
+static int mixed_run(g753_ctx* ctx, Fq* d_data, Fq* d_tmp, uint64_t N, int mode) {
+  const MixedTables* T = nullptr;
+  G753_TRY(mixed_tables_get<FID>(ctx, N, &T));
+  const NttTables* T2 = nullptr;
+  G753_TRY(ntt_tables_get<FID>(ctx, T->a, &T2));
+  const bool inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
+  const size_t n2 = (size_t)1 << T->a;
+  // step 1: column DFTs (coset_fft: inputs scaled by g^i on the fly)
+  G753_LAUNCH(k_small_dft<FID>, div_up(N, 128), 128, ctx->stream, d_data, d_tmp, T->zeta + (inverse ? T->m : 0), T->m, n2,
+              mode == G753_COSET_FFT ? T->coset : (const Fq*)nullptr);
+  ctx->launches++;
+  // steps 2 + 3: twiddles as the pre table of the m batched radix-2 transforms
+  NttCall c;
+  c.inverse = inverse;
+  c.batch = T->m;
+  c.pre = T->tw + (inverse ? N : 0);
+  c.pre_stride = n2;
+  G753_TRY(ntt_run<FID>(*T2, ctx->stream, d_tmp, d_data, c, &ctx->launches));
+  // step 4: Z[k1][k2] -> out[k1 + m k2]
+  G753_LAUNCH(k_permute3, div_up(N, 256), 256, ctx->stream, d_tmp, d_data, T->m, (unsigned)n2, 1u, (size_t)1,
+              (size_t)T->m, (size_t)0);
+  ctx->launches++;
+  if (mode == G753_IFFT)
+    G753_LAUNCH(k_vec_scale<FID>, div_up(N, 256), 256, ctx->stream, d_data, T->consts + 2, (size_t)N);
+  else if (mode == G753_COSET_IFFT)
+    G753_LAUNCH(k_vec_op<FID>, div_up(N, 256), 256, ctx->stream, d_data, T->coset_inv, G753_OP_MUL, (size_t)N);
+  if (inverse) ctx->launches++;
+  return launch_check("mixed_run");
+}
+
 // ------------------------------------------------------------------------------------
 // test kernels: group law / field ops through the real device code
 // ------------------------------------------------------------------------------------
@@ -262,8 +360,10 @@ int g753_ctx_destroy(g753_ctx* ctx) {
   stream_sync(ctx->stream);
   ctx->scratch.release();
   ctx->scratch_io.release();
-  for (int f = 0; f < 2; f++)
+  for (int f = 0; f < 2; f++) {
     for (auto& kv : ctx->tables[f]) kv.second.release();
+    for (auto& kv : ctx->mixed[f]) kv.second.release();
+  }
 #if !defined(G753_HOST_EMUL)
   if (ctx->ev_ok)
     for (int i = 0; i <= MSM_PHASES; i++) cudaEventDestroy(ctx->ev[i]);
@@ -660,6 +760,38 @@ int g753_ntt_shard_step2(g753_ctx* ctx, const g753_ntt_shard* plan, const void* 
   std::lock_guard<std::mutex> lock(ctx->mu);
   return plan->field == 0 ? shard_step2<0>(ctx, plan, (const Fq*)d_recv, (Fq*)d_data, mode)
                           : shard_step2<1>(ctx, plan, (const Fq*)d_recv, (Fq*)d_data, mode);
+}
+
+int g753_domain_check_mixed(int field, uint64_t n) {
+  if (field != 0 && field != 1) return fail(G753_ERR_BAD_ARG, "unknown field");
+  if (!mixed_split(field, n, nullptr, nullptr, nullptr))
+    return fail(G753_ERR_DOMAIN, "no mixed-radix domain of this size (needs n = 2^a * m | p - 1, m odd <= 1024)");
+  return G753_OK;
+}
+
+int g753_ntt_mixed_dev(g753_ctx* ctx, int field, void* d_data, uint64_t n, int mode) {
+  CHECK_CTX(ctx);
+  if (!d_data) return fail(G753_ERR_BAD_ARG, "null data");
+  if (mode < G753_FFT || mode > G753_COSET_IFFT) return fail(G753_ERR_BAD_ARG, "unknown transform");
+  G753_TRY(g753_domain_check_mixed(field, n));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  G753_TRY(ctx->scratch_io.reserve(sizeof(Fq) * n + 1024));
+  return field == 0 ? mixed_run<0>(ctx, (Fq*)d_data, (Fq*)ctx->scratch_io.ptr, n, mode)
+                    : mixed_run<1>(ctx, (Fq*)d_data, (Fq*)ctx->scratch_io.ptr, n, mode);
+}
+
+int g753_ntt_mixed(g753_ctx* ctx, int field, uint64_t* data, uint64_t n, int mode) {
+  CHECK_CTX(ctx);
+  if (!data) return fail(G753_ERR_BAD_ARG, "null data");
+  G753_TRY(g753_domain_check_mixed(field, n));
+  void* d = nullptr;
+  G753_TRY(dev_alloc(&d, sizeof(Fq) * n));
+  int rc = h2d(d, data, sizeof(Fq) * n, ctx->stream);
+  if (rc == G753_OK) rc = g753_ntt_mixed_dev(ctx, field, d, n, mode);
+  if (rc == G753_OK) rc = d2h(data, d, sizeof(Fq) * n, ctx->stream);
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d);
+  return rc;
 }
 
 int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n) {

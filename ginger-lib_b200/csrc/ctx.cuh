@@ -7,6 +7,7 @@
 
 #include "device.cuh"
 #include "ntt.cuh"
+#include "ntt_mixed.cuh"
 
 namespace g753 {
 #if defined(G753_HOST_EMUL)
@@ -29,6 +30,7 @@ struct g753_ctx {
   Scratch scratch;      // MSM workspace
   Scratch scratch_io;   // host-API staging (scalars / NTT ping-pong)
   std::map<unsigned, NttTables> tables[2];  // per field, keyed by log_n
+  std::map<uint64_t, MixedTables> mixed[2]; // per field, keyed by the mixed-radix size N
   uint64_t launches = 0;
   float phase_ms[MSM_PHASES] = {0, 0, 0, 0, 0};
   int forced_c = 0;

@@ -64,10 +64,11 @@ struct MsmPlan {
 };
 
 // Cost model in units of one field multiplication of the saturated accumulation kernel (7 G/s
-// measured): a mixed add is 10 (XYZZ); the reduction does 2 full adds (28) per bucket but its
-// 13-slot footprint caps it at ~5 warps per SM, measured 24 ms for 5 x 2^19 buckets = ~70 per
-// bucket; the final Horner fold is a serial chain of rows * c doublings on ONE thread, each field
-// multiplication of which takes ~2.8 us = ~20 000 units.
+// measured): a mixed add is 10 (XYZZ); the reduction does 2 full adds (28) per bucket (its 13-slot
+// footprint caps it at ~5 warps per SM, so it runs at about half rate, but larger windows also
+// shorten the per-addition cost of the accumulation: 30 reproduces the measured optimum, c = 20 at
+// 2^21..2^22 with 8 copies); the final Horner fold is a serial chain of rows * c doublings on ONE
+// thread, each field multiplication of which takes ~2.8 us = ~20 000 units.
 static inline MsmPlan msm_plan(size_t n, unsigned copies = 1, int forced_c = 0, unsigned forced_rows = 0) {
   MsmPlan best{0, 0, 0, 0, 0};
   double best_cost = 0;
@@ -77,7 +78,7 @@ static inline MsmPlan msm_plan(size_t n, unsigned copies = 1, int forced_c = 0, 
     unsigned W = (SCALAR_BITS + 1 + c - 1) / c;
     unsigned rows = forced_rows ? forced_rows : (W + copies - 1) / copies;
     double B = (double)(1u << (c - 1));
-    double cost = (double)W * 10.0 * (double)n + (double)rows * 70.0 * B + (double)rows * c * 10.0 * 20000.0;
+    double cost = (double)W * 10.0 * (double)n + (double)rows * 30.0 * B + (double)rows * c * 10.0 * 20000.0;
     if (best.c == 0 || cost < best_cost) {
       best = MsmPlan{c, W, 1u << (c - 1), rows, (W + rows - 1) / rows};
       best_cost = cost;

@@ -83,6 +83,16 @@ __global__ void k_table_init(Fq* tab, const Fq* first) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   tab[0] = first ? *first : fq_one<FID>();
 }
+// out[l] = x^(2^l), l < count
+template <int FID>
+__global__ void k_square_chain(const Fq* x, Fq* out, unsigned count) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Fq v = *x;
+  for (unsigned l = 0; l < count; l++) {
+    out[l] = v;
+    v = fq_sqr<FID>(v);
+  }
+}
 // tab[len + t] = tab[t] * (*step) for t < len  (doubles the table: step = base^len)
 template <int FID>
 __global__ void k_table_double(Fq* tab, const Fq* step, unsigned len, unsigned cap) {

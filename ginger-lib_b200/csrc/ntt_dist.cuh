@@ -17,7 +17,7 @@
 // The reference has no counterpart (its parallel_fft, domain.rs:360-416, is the same
 // decomposition over CPU threads); the contract is "sharded result == single-GPU result".
 #pragma once
-#include "ctx.cuh"
+#include "ntt.cuh"
 
 namespace g753 {
 
@@ -60,6 +60,8 @@ static __global__ void k_permute3(const Fq* __restrict__ in, Fq* __restrict__ ou
 }
 
 }  // namespace g753
+
+using namespace g753;
 
 struct g753_ntt_shard {
   int field = 0;

@@ -46,6 +46,9 @@ SYMBOLS = [
     ("g753_domain_check", _i, [_i, _u]),
     ("g753_ntt", _i, [_vp, _i, _vp, _u, _i]),
     ("g753_ntt_dev", _i, [_vp, _i, _vp, _u, _i]),
+    ("g753_domain_check_mixed", _i, [_i, ctypes.c_uint64]),
+    ("g753_ntt_mixed", _i, [_vp, _i, _vp, ctypes.c_uint64, _i]),
+    ("g753_ntt_mixed_dev", _i, [_vp, _i, _vp, ctypes.c_uint64, _i]),
     ("g753_ntt_shard_create", _i, [_vp, _i, _u, _u, _u, _pvp]),
     ("g753_ntt_shard_destroy", _i, [_vp, _vp]),
     ("g753_ntt_shard_shape", _i, [_vp, ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),

@@ -66,6 +66,11 @@ class Parameters:
         self.b2_small = small(g2, b_g2_query, [delta_g2, beta_g2], k2)
         self.a_query, self.b_g1_query, self.h_query, self.l_query = (up(g1, q) for q in (a_query, b_g1_query, h_query, l_query))
         self.b_g2_query = up(g2, b_g2_query)
+        # the five long MSMs: name -> (bases, first base, offset of the first scalar inside its vector)
+        self.aux = {"a": (self.a_query, ni, 0), "b1": (self.b_g1_query, ni, 0), "b2": (self.b_g2_query, ni, 0),
+                    "h": (self.h_query, ni, 0), "l": (self.l_query, 0, 0)}
+        self.h_head = self.h_query          # h_query[0..ni] (prover.rs:320)
+        self.sharder = None
         for b in (self.a_small, self.b1_small, self.b2_small):
             b.precompute(64)        # fixed tiny keys: ~12 doublings left in the serial window fold
         self.delta_g1 = ffi.as_u64(delta_g1).reshape(1, 2 * LIMBS)
@@ -80,6 +85,104 @@ class Parameters:
                   self.b1_small, self.b2_small, self.fresh):
             b.free()
         self.ctx2.close()
+
+
+def shard_range(n, rank, world):
+    """contiguous range of `rank` among `world` (sizes differ by at most one)"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedParameters(Parameters):
+    """A proving key sharded over the ranks of a process group: every rank keeps the
+    short head of each query (query[0..num_inputs] and the vk points) and one contiguous point range
+    of each long query.  All ranks run the witness map on the same inputs, the five long MSMs run on
+    the local ranges, their partial sums are all-gathered (N x 288 / 576 bytes over NCCL) and folded
+    on every rank, and every rank finishes the same proof.
+
+    heads: {"a", "b1", "b2", "h"} -> (coords of the first num_inputs bases, infinity or None);
+    shards: {"a", "b1", "b2", "h", "l"} -> (Bases over this rank's range, lo), lo = index of the range's
+    first base counted from the start of the long part (query[num_inputs + lo], l_query[lo])."""
+
+    def __init__(self, ctx, g1, g2, field, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, heads, shards, num_inputs,
+                 process_group=None, precompute=0):
+        import torch.distributed as dist
+        self.ctx, self.g1, self.g2, self.field, self.num_inputs = ctx, g1, g2, field, num_inputs
+        k2 = ffi.GROUP_K[g2]
+        ni = num_inputs
+
+        def small(group, q, extra, k):
+            coords, inf = q
+            c = np.concatenate([ffi.as_u64(coords).reshape(-1, 2 * k * LIMBS)[:ni]] +
+                               [ffi.as_u64(e).reshape(1, 2 * k * LIMBS) for e in extra])
+            i = np.zeros(c.shape[0], dtype=np.uint8)
+            if inf is not None:
+                i[:ni] = np.asarray(inf, dtype=np.uint8)[:ni]
+            return Bases(ctx, group, c, i)
+
+        self.a_small = small(g1, heads["a"], [delta_g1, alpha_g1], 1)
+        self.b1_small = small(g1, heads["b1"], [delta_g1, beta_g1], 1)
+        self.b2_small = small(g2, heads["b2"], [delta_g2, beta_g2], k2)
+        self.h_head = small(g1, heads["h"], [], 1)
+        for b in (self.a_small, self.b1_small, self.b2_small):
+            b.precompute(64)
+        self.aux = {}
+        for name, (bases, lo) in shards.items():
+            if precompute and len(bases) >= 1 << 12:
+                bases.precompute(precompute)
+            self.aux[name] = (bases, 0, lo)
+        self.delta_g1 = ffi.as_u64(delta_g1).reshape(1, 2 * LIMBS)
+        from .algebra import Context
+        self.ctx2 = Context(ctx.device, library=ctx.lib)
+        self.fresh = Bases(self.ctx2, g1, np.concatenate([self.delta_g1] * 3), np.zeros(3, dtype=np.uint8))
+        self.sharder = _Sharder(ctx, dist, process_group)
+
+    def free(self):
+        for b in [v[0] for v in self.aux.values()] + [self.a_small, self.b1_small, self.b2_small, self.h_head, self.fresh]:
+            b.free()
+        self.ctx2.close()
+
+
+class _Sharder:
+    """all-gather + fold of per-rank partial points, in place, on the context's stream"""
+
+    def __init__(self, ctx, dist, pg):
+        self.ctx, self.dist, self.pg = ctx, dist, pg
+        self.world = dist.get_world_size(pg) if dist.is_initialized() else 1
+        self.backend = dist.get_backend(pg) if dist.is_initialized() else None
+
+    def reduce(self, group, d_slots):
+        if self.world == 1:
+            return
+        import torch
+        lib, ctx = self.ctx.lib, self.ctx
+        k = ffi.GROUP_K[group]
+        nb = 3 * k * 96
+        for d in d_slots:
+            if self.backend == "nccl":
+                dev = torch.device("cuda", ctx.device)
+                mine = torch.empty(nb // 8, dtype=torch.int64, device=dev)
+                allp = torch.empty(self.world * nb // 8, dtype=torch.int64, device=dev)
+                lib.check(lib.d2d(ctx.handle, ctypes.c_void_p(mine.data_ptr()), d, nb))
+                lib.check(lib.sync(ctx.handle))
+                self.dist.all_gather_into_tensor(allp, mine, group=self.pg)
+                torch.cuda.synchronize(dev)
+                lib.check(lib.points_sum_dev(ctx.handle, group, ctypes.c_void_p(allp.data_ptr()), self.world, d))
+                lib.check(lib.sync(ctx.handle))
+            else:
+                host = np.empty(nb // 8, dtype=np.uint64)
+                lib.check(lib.d2h(ctx.handle, ffi.ptr(host), d, nb))
+                mine = torch.from_numpy(host.view(np.int64))
+                parts = [torch.empty_like(mine) for _ in range(self.world)]
+                self.dist.all_gather(parts, mine, group=self.pg)
+                allp = np.ascontiguousarray(np.concatenate([p.numpy().view(np.uint64) for p in parts]))
+                tmp = ctypes.c_void_p()
+                lib.check(lib.dev_alloc(ctx.handle, allp.nbytes, ctypes.byref(tmp)))
+                lib.check(lib.h2d(ctx.handle, tmp, ffi.ptr(allp), allp.nbytes))
+                lib.check(lib.points_sum_dev(ctx.handle, group, tmp, self.world, d))
+                lib.check(lib.sync(ctx.handle))
+                lib.dev_free(ctx.handle, tmp)
 
 
 class Proof:
@@ -197,21 +300,32 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
             count = max(0, min(count, len(bases) - first))
             lib.check(lib.msm_dev(cx.handle, bases.handle, first, count, d_scalars, d_out))
 
+        def aux_msm(name, d_vec, base_index, total, d_out):
+            """one of the five long MSMs (or this rank's shard of it, see ShardedParameters)"""
+            bases, first, off = params.aux[name]
+            msm(ctx, bases, first, max(0, total - off), d_vec.at(base_index + off), d_out)
+
+        sharder = params.sharder
         # A (prover.rs:270-283) -> slots 0, 1; B in G1 (:286-299) -> slots 2, 3; g_a, g1_b -> slots 8, 9
-        msm(ctx, params.a_query, ni, n_aux, d_z.at(ni), slot(out1, 1))
-        msm(ctx, params.b_g1_query, ni, n_aux, d_z.at(ni), slot(out1, 3))
+        aux_msm("a", d_z, ni, n_aux, slot(out1, 1))
+        aux_msm("b1", d_z, ni, n_aux, slot(out1, 3))
+        if sharder is not None:
+            sharder.reduce(g1, [slot(out1, 1), slot(out1, 3)])
         msm(ctx, params.a_small, 0, ni + 2, sr.p, slot(out1, 0))
         msm(ctx, params.b1_small, 0, ni + 2, ss.p, slot(out1, 2))
         lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 0), 2, slot(out1, 8)))
         lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 2), 2, slot(out1, 9)))
         lib.check(lib.ctx_wait(ctx2.handle, ctx.handle))
         # C (:318-337): L, H (zip-truncated against h: n + 1 scalars vs n - 1 bases) -> slots 4..6
-        msm(ctx, params.l_query, 0, n_aux, d_z.at(ni), slot(out1, 6))
-        msm(ctx, params.h_query, ni, n + 1 - ni, d_h.at(ni), slot(out1, 5))
-        msm(ctx, params.h_query, 0, min(ni, n + 1), d_h.at(0), slot(out1, 4))
+        aux_msm("l", d_z, ni, n_aux, slot(out1, 6))
+        aux_msm("h", d_h, ni, n + 1 - ni, slot(out1, 5))
+        msm(ctx, params.h_head, 0, min(ni, n + 1), d_h.at(0), slot(out1, 4))
         # B in G2 (:302-315)
         msm(ctx, params.b2_small, 0, ni + 2, ss.p, slot(out2, 0, k2))
-        msm(ctx, params.b_g2_query, ni, n_aux, d_z.at(ni), slot(out2, 1, k2))
+        aux_msm("b2", d_z, ni, n_aux, slot(out2, 1, k2))
+        if sharder is not None:
+            sharder.reduce(g1, [slot(out1, 6), slot(out1, 5)])
+            sharder.reduce(g2, [slot(out2, 1, k2)])
         lib.check(lib.points_sum_dev(ctx.handle, g2, slot(out2, 0, k2), 2, slot(out2, 2, k2)))
 
         # second context: s * g_a + r * g1_b - rs * delta_g1 (:322-329) as one MSM over fresh bases

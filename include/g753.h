@@ -154,6 +154,14 @@ int g753_ntt_dev(g753_ctx* ctx, int field, void* d_data, unsigned log_n, int mod
 int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n);
 int g753_vec_scale_dev(g753_ctx* ctx, int field, void* d_a, const uint64_t* k_mont, size_t n);
 
+/* ---- mixed-radix domains (BASELINE config 4; no counterpart in the reference snapshot) ----------
+ * n = 2^a * m, m odd <= 1024, n | p - 1, a <= two-adicity: omega = GENERATOR^((p-1)/n),
+ * out[k] = sum_i in[i] omega^(i k) in natural order; the four modes scale as EvaluationDomain's do
+ * (1/n for the inverse, coset generator 17).  G753_ERR_DOMAIN when no such domain exists. */
+int g753_domain_check_mixed(int field, uint64_t n);
+int g753_ntt_mixed(g753_ctx* ctx, int field, uint64_t* data, uint64_t n, int mode);
+int g753_ntt_mixed_dev(g753_ctx* ctx, int field, void* d_data, uint64_t n, int mode);
+
 /* ---- NTT sharded over `world` GPUs (one process per GPU), four-step ------------
  * n = n1 * n2 (n1 = 2^ceil(log_n/2) >= n2); rank g owns cols = n2/world columns of the n1 x n2 view:
  *   input  shard  local[i2l][i1] = x[i1*n2 + g*cols + i2l]            (cols x n1 elements)

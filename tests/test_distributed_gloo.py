@@ -56,6 +56,32 @@ for field, log_n in ((ffi.FIELD_MNT4_FR, 4), (ffi.FIELD_MNT6_FR, 5), (ffi.FIELD_
         sh = dom.transform(dom.transform(dom.scatter(field_array(F, a)), ffi.IFFT), ffi.COSET_FFT)
         assert array_field(F, dom.gather(sh)) == ref.coset_fft(ref.ifft(a)), (rank, "chain")
     dom.close()
+# sharded Groth16 prover: heads everywhere, long queries split by point range, partial sums exchanged
+import test_groth16_emul as T16
+groth16 = importlib.import_module("ginger-lib_b200.groth16")
+n, ni, n_aux = 8, 3, 7
+key, z, a, b, c = T16.tiny_instance(0x6200, n, ni, n_aux)
+F = O.MNT4_FR
+r_, s_ = 0x1234567 << 500, F.p - 77
+want = O.groth16_create_proof(key, ni, z, O.witness_map(F, a, b, c, 1, 2, 3), r_, s_)
+one = lambda C, P: points_to_arrays(C, [P])[0][0]
+heads = {{"a": points_to_arrays(O.MNT4_G1, key.a_query[:ni]), "b1": points_to_arrays(O.MNT4_G1, key.b_g1_query[:ni]),
+         "b2": points_to_arrays(O.MNT4_G2, key.b_g2_query[:ni]), "h": points_to_arrays(O.MNT4_G1, key.h_query[:ni])}}
+shards = {{}}
+for name, C, grp, pts in (("a", O.MNT4_G1, ffi.MNT4_G1, key.a_query[ni:]), ("b1", O.MNT4_G1, ffi.MNT4_G1, key.b_g1_query[ni:]),
+                          ("b2", O.MNT4_G2, ffi.MNT4_G2, key.b_g2_query[ni:]), ("h", O.MNT4_G1, ffi.MNT4_G1, key.h_query[ni:]),
+                          ("l", O.MNT4_G1, ffi.MNT4_G1, key.l_query)):
+    lo, hi = groth16.shard_range(len(pts), rank, world)
+    co, inf = points_to_arrays(C, pts[lo:hi])
+    shards[name] = (ctx.upload_bases(grp, co, inf), lo)
+P = groth16.ShardedParameters(ctx, ffi.MNT4_G1, ffi.MNT4_G2, ffi.FIELD_MNT4_FR, one(O.MNT4_G1, key.alpha_g1),
+                              one(O.MNT4_G1, key.beta_g1), one(O.MNT4_G2, key.beta_g2), one(O.MNT4_G1, key.delta_g1),
+                              one(O.MNT4_G2, key.delta_g2), heads, shards, ni)
+proof = groth16.create_proof(P, field_array(F, z), field_array(F, a), field_array(F, b), field_array(F, c), 1, 2, 3, r_, s_)
+got = (T16.affine_of(O.MNT4_G1, proof.a, proof.infinity[0]), T16.affine_of(O.MNT4_G2, proof.b, proof.infinity[1]),
+       T16.affine_of(O.MNT4_G1, proof.c, proof.infinity[2]))
+assert got == want, (rank, "sharded groth16")
+P.free()
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")

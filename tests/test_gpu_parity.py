@@ -331,3 +331,43 @@ def test_msm_vs_cpp_restatement(ctx, group, log_n):
     want = ref753.msm(group, coords, None, sc)
     assert projective_to_point(C, got) == projective_to_point(C, want)
     bases.free()
+
+
+@pytest.mark.parametrize("field,n", [(ffi.FIELD_MNT6_FR, 40), (ffi.FIELD_MNT4_FR, 48 * 25)])
+def test_mixed_radix_ntt_vs_definition(ctx, field, n):
+    """BASELINE config 4 (mixed-radix FFT): the four transforms against the direct DFT definition;
+    parity unpinned - the reference has no mixed-radix domain"""
+    F = FIELDS[field]
+    p = F.p
+    dom = G.MixedRadixDomain.new(field, n, ctx=ctx)
+    assert dom is not None
+    w = O.mixed_radix_omega(F, n)
+    rng = O.SplitMix64(0x3B + n)
+    a = [O.random_field_element(rng, F) for _ in range(n)]
+    ninv = pow(n, -1, p)
+    arr = field_array(F, a)
+    assert array_field(F, dom.fft(arr)) == O.dft_naive(a, w, p)
+    inv = [x * ninv % p for x in O.dft_naive(a, pow(w, -1, p), p)]
+    assert array_field(F, dom.ifft(arr)) == inv
+    assert array_field(F, dom.coset_fft(arr)) == O.dft_naive(O.distribute_powers(a, F.generator, p), w, p)
+    assert array_field(F, dom.coset_ifft(arr)) == O.distribute_powers(inv, pow(F.generator, -1, p), p)
+
+
+@pytest.mark.parametrize("field,n", [(ffi.FIELD_MNT6_FR, (1 << 15) * 25), (ffi.FIELD_MNT4_FR, (1 << 18) * 5)])
+def test_mixed_radix_ntt_full_size_properties(ctx, field, n):
+    """SURVEY.md 8c candidate sizes (819 200 on mnt6753::Fr, 1 310 720 on mnt4753::Fr): round trips and
+    evaluation at the points omega^k of a polynomial given by a few coefficients"""
+    import bench
+    F = FIELDS[field]
+    p = F.p
+    dom = G.MixedRadixDomain.new(field, n, ctx=ctx)
+    raw = bench.random_scalars(n, 0x44)
+    raw[:, 11] &= np.uint64(0xFFFF)
+    assert (dom.ifft(dom.fft(raw)) == raw).all()
+    assert (dom.coset_ifft(dom.coset_fft(raw)) == raw).all()
+    coeffs = [3, 1, 4, 1, 5, 9, 2, 6]
+    ev = array_field(F, dom.fft(field_array(F, coeffs)))
+    w = O.mixed_radix_omega(F, n)
+    for k in (0, 1, 2, 12345, n - 1):
+        x = pow(w, k, p)
+        assert ev[k] == sum(c * pow(x, i, p) for i, c in enumerate(coeffs)) % p

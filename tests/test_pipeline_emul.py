@@ -236,3 +236,31 @@ def test_sharded_ntt_single_rank(ctx, field, log_n):
         out = dom.gather(dom.transform(dom.scatter(field_array(F, a)), mode))
         assert array_field(F, out) == want, mode
     dom.close()
+
+
+@pytest.mark.parametrize("field,n", [(ffi.FIELD_MNT4_FR, 12), (ffi.FIELD_MNT4_FR, 45), (ffi.FIELD_MNT6_FR, 40),
+                                     (ffi.FIELD_MNT6_FR, 7), (ffi.FIELD_MNT4_FR, 16)])
+def test_mixed_radix_ntt_vs_definition(ctx, field, n):
+    """mixed-radix domain (n = 2^a m): the four transforms against the direct DFT definition
+    (parity unpinned: the reference has no mixed-radix domain)"""
+    F = FIELDS[field]
+    p = F.p
+    dom = G.MixedRadixDomain.new(field, n, ctx=ctx)
+    assert dom is not None and dom.size() == n
+    w = O.mixed_radix_omega(F, n)
+    rng = O.SplitMix64(0x3A + n)
+    a = [O.random_field_element(rng, F) for _ in range(n)]
+    g, ninv = F.generator, pow(n, -1, p)
+    arr = field_array(F, a)
+    assert array_field(F, dom.fft(arr)) == O.dft_naive(a, w, p)
+    assert array_field(F, dom.ifft(arr)) == [x * ninv % p for x in O.dft_naive(a, pow(w, -1, p), p)]
+    assert array_field(F, dom.coset_fft(arr)) == O.dft_naive(O.distribute_powers(a, g, p), w, p)
+    inv = [x * ninv % p for x in O.dft_naive(a, pow(w, -1, p), p)]
+    assert array_field(F, dom.coset_ifft(arr)) == O.distribute_powers(inv, pow(g, -1, p), p)
+
+
+def test_mixed_radix_domain_none(ctx):
+    assert G.MixedRadixDomain.new(ffi.FIELD_MNT6_FR, 13 * 4, ctx=ctx) is None          # 13 does not divide p - 1
+    assert G.MixedRadixDomain.new(ffi.FIELD_MNT6_FR, (1 << 16) * 3, ctx=ctx) is None   # beyond the two-adicity
+    assert G.MixedRadixDomain.new(ffi.FIELD_MNT6_FR, (1 << 15) * 25, ctx=ctx) is not None
+    assert G.MixedRadixDomain.new(ffi.FIELD_MNT4_FR, (1 << 18) * 5, ctx=ctx) is not None
