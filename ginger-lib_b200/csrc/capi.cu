@@ -282,6 +282,8 @@ __global__ void __launch_bounds__(256) k_mac_probe(const Fq* seed, Fq* sink, int
     for (int k = 0; k < iters; k++) x = fq_mul<1>(x, y);
   } else if (VARIANT == 1) {
     for (int k = 0; k < iters; k++) x = fq_sqr<1>(x);
+  } else if (VARIANT == 3) {
+    for (int k = 0; k < iters; k++) x = fq_add<1>(fq_inv<1>(x), y);   // safegcd inversion chain
   } else {
     // 24 independent 64-bit accumulators, each a dependent IMAD.WIDE chain: 576 wide MACs / iter
     unsigned long long acc[NL];
@@ -350,6 +352,8 @@ int g753_ctx_create(int device, g753_ctx** out) {
 #endif
   const char* fc = getenv("G753_MSM_C");
   if (fc) ctx->forced_c = atoi(fc);
+  const char* fa = getenv("G753_MSM_AFFINE");
+  if (fa) ctx->forced_affine = atoi(fa) ? 1 : 0;
   *out = ctx;
   return G753_OK;
 }
@@ -934,6 +938,7 @@ int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iter
     cudaEventRecord(e0, ctx->stream);
     if (variant == 0) k_mac_probe<0><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
     else if (variant == 1) k_mac_probe<1><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
+    else if (variant == 3) k_mac_probe<3><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
     else k_mac_probe<2><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
     cudaEventRecord(e1, ctx->stream);
     ctx->launches++;

@@ -34,6 +34,7 @@ struct g753_ctx {
   uint64_t launches = 0;
   float phase_ms[MSM_PHASES] = {0, 0, 0, 0, 0};
   int forced_c = 0;
+  int forced_affine = -1;  // G753_MSM_AFFINE: 0 / 1 force the accumulation kernel, unset = by size
   std::mutex mu;
 #if !defined(G753_HOST_EMUL)
   cudaEvent_t ev[MSM_PHASES + 1];

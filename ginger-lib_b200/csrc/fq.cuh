@@ -378,11 +378,177 @@ G753_NI Fq fq_pow(const Fq& a, const uint32_t* e) {
   return r;
 }
 
-// a^-1 (Montgomery form in, Montgomery form out).  The reference uses a binary extended
-// Euclid (fp_768.rs:551-605); the inverse is unique, so Fermat gives identical limbs.
+// ------------------------------------------------------------------------------------
+// Inversion.  The reference uses a binary extended Euclid (fp_768.rs:551-605); the inverse is
+// unique, so any correct algorithm gives identical limbs.  Here: the Bernstein-Yang "safegcd"
+// divsteps in the batched form libsecp256k1's modinv32 made popular - 30 divsteps at a time are
+// decided on the low 30 bits of (f, g) alone and collected into a 2x2 matrix that is then applied to
+// the full-width (f, g) and, modulo p, to (d, e).  Branch-free, a fixed 62 x 30 = 1860 divsteps
+// (bound for 768-bit inputs: (45907 * 768 + 26313) / 19929 = 1771), about 30 multiplications' worth
+// of instructions instead of the ~1130 products of a Fermat exponentiation.
+// Numbers are 26 signed limbs of 30 bits.
+// ------------------------------------------------------------------------------------
+constexpr int SG_LIMBS = 26;
+constexpr int32_t SG_M30 = (int32_t)(0xffffffffu >> 2);
+struct Sg30 {
+  int32_t v[SG_LIMBS];
+};
+struct SgTrans {
+  int32_t u, v, q, r;
+};
+
+// limb i (30 bits) of a 768-bit little-endian u32 array
+G753_HD int32_t sg_limb30(const uint32_t* x, int i) {
+  const int bit = 30 * i, w = bit >> 5, sh = bit & 31;
+  uint64_t two = 0;
+  if (w < NL) two = x[w];
+  if (w + 1 < NL) two |= (uint64_t)x[w + 1] << 32;
+  return (int32_t)((uint32_t)(two >> sh) & (uint32_t)SG_M30);
+}
+
+G753_HD int32_t sg_divsteps_30(int32_t zeta, uint32_t f0, uint32_t g0, SgTrans& t) {
+  // u, v, q, r: the transition matrix, signed in [-2^30, 2^30], kept modulo 2^32
+  uint32_t u = 1, v = 0, q = 0, r = 1;
+  uint32_t f = f0, g = g0;
+  for (int i = 0; i < 30; ++i) {
+    uint32_t mask1 = (uint32_t)(zeta >> 31);   // zeta < 0
+    uint32_t mask2 = 0u - (g & 1u);            // g odd
+    uint32_t x = (f ^ mask1) - mask1, y = (u ^ mask1) - mask1, z = (v ^ mask1) - mask1;
+    g += x & mask2;
+    q += y & mask2;
+    r += z & mask2;
+    mask1 &= mask2;
+    zeta = (int32_t)(((uint32_t)zeta ^ mask1) - 1u);
+    f += g & mask1;
+    u += q & mask1;
+    v += r & mask1;
+    g >>= 1;
+    u <<= 1;
+    v <<= 1;
+  }
+  t.u = (int32_t)u;
+  t.v = (int32_t)v;
+  t.q = (int32_t)q;
+  t.r = (int32_t)r;
+  return zeta;
+}
+
+// (f, g) <- t * (f, g) / 2^30  (exact)
+G753_HD void sg_update_fg(Sg30& f, Sg30& g, const SgTrans& t) {
+  const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+  int64_t cf = u * f.v[0] + v * g.v[0];
+  int64_t cg = q * f.v[0] + r * g.v[0];
+  cf >>= 30;
+  cg >>= 30;
+#pragma unroll
+  for (int i = 1; i < SG_LIMBS; ++i) {
+    const int64_t fi = f.v[i], gi = g.v[i];
+    cf += u * fi + v * gi;
+    cg += q * fi + r * gi;
+    f.v[i - 1] = (int32_t)cf & SG_M30;
+    cf >>= 30;
+    g.v[i - 1] = (int32_t)cg & SG_M30;
+    cg >>= 30;
+  }
+  f.v[SG_LIMBS - 1] = (int32_t)cf;
+  g.v[SG_LIMBS - 1] = (int32_t)cg;
+}
+
+// (d, e) <- t * (d, e) / 2^30 mod p, both kept in (-2p, p)
+template <int FID>
+G753_HD void sg_update_de(Sg30& d, Sg30& e, const SgTrans& t) {
+  const int32_t u = t.u, v = t.v, q = t.q, r = t.r;
+  const uint32_t* P = G753_FC(FID).p;
+  const uint32_t pinv30 = (0u - G753_FC(FID).inv32) & (uint32_t)SG_M30;  // p^-1 mod 2^30
+  const int32_t sd = d.v[SG_LIMBS - 1] >> 31, se = e.v[SG_LIMBS - 1] >> 31;
+  int32_t md = (u & sd) + (v & se), me = (q & sd) + (r & se);
+  int64_t cd = (int64_t)u * d.v[0] + (int64_t)v * e.v[0];
+  int64_t ce = (int64_t)q * d.v[0] + (int64_t)r * e.v[0];
+  md -= (int32_t)((pinv30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)SG_M30);
+  me -= (int32_t)((pinv30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)SG_M30);
+  cd += (int64_t)sg_limb30(P, 0) * md;
+  ce += (int64_t)sg_limb30(P, 0) * me;
+  cd >>= 30;
+  ce >>= 30;
+#pragma unroll
+  for (int i = 1; i < SG_LIMBS; ++i) {
+    const int64_t di = d.v[i], ei = e.v[i], pi = sg_limb30(P, i);
+    cd += (int64_t)u * di + (int64_t)v * ei + pi * md;
+    ce += (int64_t)q * di + (int64_t)r * ei + pi * me;
+    d.v[i - 1] = (int32_t)cd & SG_M30;
+    cd >>= 30;
+    e.v[i - 1] = (int32_t)ce & SG_M30;
+    ce >>= 30;
+  }
+  d.v[SG_LIMBS - 1] = (int32_t)cd;
+  e.v[SG_LIMBS - 1] = (int32_t)ce;
+}
+
+// r in (-2p, p) -> sign-adjusted r in [0, p); sign < 0 requests negation
+template <int FID>
+G753_HD void sg_normalize(Sg30& r, int32_t sign) {
+  const uint32_t* P = G753_FC(FID).p;
+  int32_t cond_add = r.v[SG_LIMBS - 1] >> 31;
+  const int32_t cond_neg = sign >> 31;
+#pragma unroll
+  for (int i = 0; i < SG_LIMBS; ++i) {
+    int32_t x = r.v[i] + (sg_limb30(P, i) & cond_add);
+    r.v[i] = (x ^ cond_neg) - cond_neg;
+  }
+#pragma unroll
+  for (int i = 0; i < SG_LIMBS - 1; ++i) {
+    r.v[i + 1] += r.v[i] >> 30;
+    r.v[i] &= SG_M30;
+  }
+  cond_add = r.v[SG_LIMBS - 1] >> 31;
+#pragma unroll
+  for (int i = 0; i < SG_LIMBS; ++i) r.v[i] += sg_limb30(P, i) & cond_add;
+#pragma unroll
+  for (int i = 0; i < SG_LIMBS - 1; ++i) {
+    r.v[i + 1] += r.v[i] >> 30;
+    r.v[i] &= SG_M30;
+  }
+}
+
+// x^-1 mod p as plain integers (x canonical, < p); 0 -> 0
+template <int FID>
+G753_NI void fq_modinv_raw(Fq& out, const Fq& x) {
+  Sg30 d, e, f, g;
+#pragma unroll
+  for (int i = 0; i < SG_LIMBS; ++i) {
+    d.v[i] = 0;
+    e.v[i] = i == 0 ? 1 : 0;
+    f.v[i] = sg_limb30(G753_FC(FID).p, i);
+    g.v[i] = sg_limb30(x.l, i);
+  }
+  int32_t zeta = -1;
+  for (int it = 0; it < 62; ++it) {
+    SgTrans t;
+    zeta = sg_divsteps_30(zeta, (uint32_t)f.v[0], (uint32_t)g.v[0], t);
+    sg_update_de<FID>(d, e, t);
+    sg_update_fg(f, g, t);
+  }
+  sg_normalize<FID>(d, f.v[SG_LIMBS - 1]);
+  // 26 x 30 bits -> 24 x 32 bits
+#pragma unroll
+  for (int w = 0; w < NL; ++w) {
+    const int bit = 32 * w, i = bit / 30, sh = bit % 30;
+    uint64_t acc = (uint64_t)(uint32_t)d.v[i] >> sh;
+    if (i + 1 < SG_LIMBS) acc |= (uint64_t)(uint32_t)d.v[i + 1] << (30 - sh);
+    if (i + 2 < SG_LIMBS && 60 - sh < 32) acc |= (uint64_t)(uint32_t)d.v[i + 2] << (60 - sh);
+    out.l[w] = (uint32_t)acc;
+  }
+}
+
+// a^-1 (Montgomery form in, Montgomery form out): (aR)^-1 = a^-1 R^-1, times R^3 / R = a^-1 R
 template <int FID>
 G753_HD Fq fq_inv(const Fq& a) {
-  return fq_pow<FID>(a, G753_FC(FID).p_minus_2);
+  Fq t;
+  fq_modinv_raw<FID>(t, a);
+  Fq r3;
+#pragma unroll
+  for (int i = 0; i < NL; i++) r3.l[i] = G753_FC(FID).r3[i];
+  return fq_mul<FID>(t, r3);
 }
 
 template <int FID>

@@ -25,6 +25,8 @@
 //   k_window_combine  K6  Horner fold of the window sums, XYZZ -> homogeneous projective
 //   k_points_sum      K6  fold of per-shard partial results (multi-GPU)
 #pragma once
+#include <type_traits>
+
 #include "device.cuh"
 #include "ec_slots.cuh"
 
@@ -49,10 +51,10 @@ template <int GID> struct MsmCfg;
 #define G753_TP2 4
 #define G753_TP3 8
 #endif
-template <> struct MsmCfg<0> { static constexpr int K = 1, TP = 1, NC_ACC = 128, NC_RED = 128; template <int NC> using SC = SCurveM4G1<Lay<NC, 1>>; };
-template <> struct MsmCfg<1> { static constexpr int K = 2, TP = G753_TP2, NC_ACC = 48, NC_RED = 32; template <int NC> using SC = SCurveM4G2<Lay<NC, G753_TP2>>; };
-template <> struct MsmCfg<2> { static constexpr int K = 1, TP = 1, NC_ACC = 128, NC_RED = 128; template <int NC> using SC = SCurveM6G1<Lay<NC, 1>>; };
-template <> struct MsmCfg<3> { static constexpr int K = 3, TP = G753_TP3, NC_ACC = 32, NC_RED = 16; template <int NC> using SC = SCurveM6G2<Lay<NC, G753_TP3>>; };
+template <> struct MsmCfg<0> { static constexpr bool AFFINE = true; static constexpr int K = 1, TP = 1, NC_ACC = 128, NC_RED = 128; template <int NC> using SC = SCurveM4G1<Lay<NC, 1>>; };
+template <> struct MsmCfg<1> { static constexpr bool AFFINE = false; static constexpr int K = 2, TP = G753_TP2, NC_ACC = 48, NC_RED = 32; template <int NC> using SC = SCurveM4G2<Lay<NC, G753_TP2>>; };
+template <> struct MsmCfg<2> { static constexpr bool AFFINE = true; static constexpr int K = 1, TP = 1, NC_ACC = 128, NC_RED = 128; template <int NC> using SC = SCurveM6G1<Lay<NC, 1>>; };
+template <> struct MsmCfg<3> { static constexpr bool AFFINE = false; static constexpr int K = 3, TP = G753_TP3, NC_ACC = 32, NC_RED = 16; template <int NC> using SC = SCurveM6G2<Lay<NC, G753_TP3>>; };
 
 struct MsmPlan {
   unsigned c;       // window bits
@@ -269,6 +271,163 @@ k_bucket_acc(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
   E::stg(points + (size_t)it.dest * E::PT, 0);
 }
 
+// ------------------------------------------------------------------------------------
+// K5b': bucket accumulation in AFFINE coordinates with shared inversions.
+// An affine addition is lambda = (y2 - y1) / (x2 - x1), x3 = lambda^2 - x1 - x2,
+// y3 = lambda (x1 - x3) - y1: 1 inversion + 2 products + 1 squaring.  Every thread runs AFF_G work
+// items in lockstep; at step k it has up to AFF_G independent additions (item g: acc_g += base k of
+// item g), inverts the PRODUCT of their denominators once (Montgomery's trick: 3 products per
+// addition) with the safegcd inversion (~30 products' worth of instructions), so an addition costs
+// 6 products + 30 / AFF_G instead of the 10 of the XYZZ mixed addition.  The reference's
+// batch_normalization uses the same trick for its Z inversions (short_weierstrass_projective.rs:
+// 402-442).  Exceptional pairs take no part in the shared inversion except the doubling
+// (denominator 2 y1): empty accumulator (acc = Q), Q = -acc (acc becomes empty).
+// Accumulators and prefix products live in a global scratch laid out like the slots
+// ([item g][element][16-byte chunk][column], coalesced per chunk); items are length-sorted, so the
+// items of one thread (consecutive positions) have non-increasing lengths.
+// Prime-field curves only (K = 1): G2 keeps the XYZZ kernel.
+// STATUS: correct (parity tests run it with G753_MSM_AFFINE=1) but NOT the default: measured on a
+// B200 at 2^22 it takes 310 ms against the XYZZ kernel's 237 ms.  The arithmetic is ~15 % lighter
+// (6 products + 45 / 16 per addition; the inversion measures 45 products' worth, not 30), but every
+// addition makes two dependent trips to HBM / L2 (base gather, accumulator, prefix product, in both
+// phases) and the 864 B of slots per thread cap the SM at 8 warps, too few to hide them.
+// ------------------------------------------------------------------------------------
+constexpr int AFF_G = 16;
+constexpr int AFF_GSLOTS = 3;  // x, y, prefix product per item
+
+template <class L>
+G753_D void gs_to_slot(int slot, const uint4* gbase, int gslot) {
+  const uint4* p = gbase + (size_t)gslot * SLOT_CHUNKS * L::NC + L::col();
+  uint4* q = slot_ptr<L>(slot);
+#pragma unroll
+  for (int c = 0; c < SLOT_CHUNKS; c++) q[c * L::NC] = p[c * L::NC];
+}
+template <class L>
+G753_D void slot_to_gs(uint4* gbase, int gslot, int slot) {
+  uint4* p = gbase + (size_t)gslot * SLOT_CHUNKS * L::NC + L::col();
+  const uint4* q = slot_ptr<L>(slot);
+#pragma unroll
+  for (int c = 0; c < SLOT_CHUNKS; c++) p[c * L::NC] = q[c * L::NC];
+}
+
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_bucket_acc_affine(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                    const MsmItem* __restrict__ items, const uint32_t* __restrict__ item_total,
+                    Fq* __restrict__ points, uint4* __restrict__ scratch) {
+  typedef EcS<SC> E;
+  typedef typename E::M M;
+  typedef typename M::T L;
+  static_assert(E::K == 1, "affine accumulation is implemented for the prime-field curves");
+  enum { X1 = 0, Y1 = 1, X2 = 2, Y2 = 3, NUM = 4, DEN = 5, RUN = 6, INV = 7, TMP = 8 };  // Tw1 ops need no scratch
+  const unsigned total = *item_total;
+  const unsigned first = L::item() * AFF_G;
+  if (first >= total) return;
+  const unsigned cnt = total - first < (unsigned)AFF_G ? total - first : (unsigned)AFF_G;
+  uint4* my = scratch + (size_t)blockIdx.x * ((size_t)AFF_G * AFF_GSLOTS * SLOT_CHUNKS * L::NC);
+  const unsigned maxlen = items[first].len;
+  uint32_t empty = 0xffffffffu;  // bit g: accumulator g holds no point yet (or cancelled to infinity)
+
+  // loads base k of item g into X2, Y2 (sign applied); returns false when the item has fewer entries
+  auto load_q = [&](unsigned g, unsigned k) -> bool {
+    const MsmItem it = items[first + g];
+    if (k >= it.len) return false;
+    const uint32_t e = sorted[it.start + k];
+    const Fq* q = bases + (size_t)(e & 0x7fffffffu) * 2;
+    M::ldg(X2, q);
+    M::ldg(Y2, q + 1);
+    if (e >> 31) M::neg(Y2, Y2);
+    return true;
+  };
+  // with acc in X1, Y1 and Q in X2, Y2: 0 = ordinary addition, 1 = doubling, 2 = cancellation;
+  // leaves the denominator in DEN (cases 0, 1)
+  auto classify = [&]() -> int {
+    M::sub(DEN, X2, X1);
+    if (!M::is_zero(DEN)) return 0;
+    M::sub(NUM, Y2, Y1);
+    if (!M::is_zero(NUM) || M::is_zero(Y1)) return 2;
+    M::dbl(DEN, Y1);
+    return 1;
+  };
+
+  for (unsigned k = 0; k < maxlen; k++) {
+    // ---- phase 1: denominators and their running product -------------------------------------
+    M::set_one(RUN);
+    unsigned active = 0;
+    bool any = false;
+    for (unsigned g = 0; g < cnt; g++) {
+      if (!load_q(g, k)) break;           // lengths are non-increasing within a thread
+      active = g + 1;
+      if ((empty >> g) & 1) continue;
+      gs_to_slot<L>(X1, my, g * AFF_GSLOTS);
+      gs_to_slot<L>(Y1, my, g * AFF_GSLOTS + 1);
+      if (classify() == 2) continue;
+      slot_to_gs<L>(my, g * AFF_GSLOTS + 2, RUN);
+      M::mul(RUN, RUN, DEN, TMP);
+      any = true;
+    }
+    if (any) M::inv(INV, RUN, TMP);
+    // ---- phase 2: walk back, peel the individual inverses off, finish the additions ----------
+    for (int g = (int)active - 1; g >= 0; g--) {
+      load_q((unsigned)g, k);
+      if ((empty >> g) & 1) {
+        slot_to_gs<L>(my, g * AFF_GSLOTS, X2);
+        slot_to_gs<L>(my, g * AFF_GSLOTS + 1, Y2);
+        empty &= ~(1u << g);
+        continue;
+      }
+      gs_to_slot<L>(X1, my, g * AFF_GSLOTS);
+      gs_to_slot<L>(Y1, my, g * AFF_GSLOTS + 1);
+      const int kind = classify();
+      if (kind == 2) {
+        empty |= 1u << g;
+        continue;
+      }
+      if (kind == 1) {                    // lambda = (3 x1^2 + a) / (2 y1)
+        M::sqr(NUM, X1, TMP);
+        M::dbl(TMP, NUM);
+        M::add(NUM, NUM, TMP);
+        M::set_one(TMP);
+        SC::mul_by_a(TMP, TMP);
+        M::add(NUM, NUM, TMP);
+      } else {
+        M::sub(NUM, Y2, Y1);
+      }
+      gs_to_slot<L>(TMP, my, g * AFF_GSLOTS + 2);   // product of the denominators before this one
+      M::mul(TMP, TMP, INV, TMP);                // 1 / DEN
+      M::mul(INV, INV, DEN, TMP);                // inverse of the product of the earlier ones
+      M::mul(NUM, NUM, TMP, TMP);                // lambda
+      M::sqr(TMP, NUM, TMP);
+      M::sub(TMP, TMP, X1);
+      M::sub(TMP, TMP, X2);                          // x3
+      M::sub(X1, X1, TMP);
+      M::mul(X1, X1, NUM, TMP);
+      M::sub(Y1, X1, Y1);                            // y3 = lambda (x1 - x3) - y1
+      slot_to_gs<L>(my, g * AFF_GSLOTS, TMP);
+      slot_to_gs<L>(my, g * AFF_GSLOTS + 1, Y1);
+    }
+  }
+  // ---- results: XYZZ (x, y, 1, 1), or all-zero limbs for an empty sum ---------------------------
+  for (unsigned g = 0; g < cnt; g++) {
+    const MsmItem it = items[first + g];
+    Fq* out = points + (size_t)it.dest * E::PT;
+    if ((empty >> g) & 1) {
+      M::set_zero(X1);
+      for (int i = 0; i < 4; i++) M::stg(out + i, X1);
+    } else {
+      gs_to_slot<L>(X1, my, g * AFF_GSLOTS);
+      gs_to_slot<L>(Y1, my, g * AFF_GSLOTS + 1);
+      M::set_one(X2);
+      M::stg(out, X1);
+      M::stg(out + 1, Y1);
+      M::stg(out + 2, X2);
+      M::stg(out + 3, X2);
+    }
+  }
+}
+constexpr int AFF_SLOTS = 9;   // X1 .. TMP: 864 B per thread, two 128-thread blocks per SM
+
+
 // Buckets that were cut into several items: points[t] = sum of their partial results
 // points[NB + item_off[t] + j], j < item_cnt[t].  A bucket can hold a large share of all points
 // (the top window of a 753-bit scalar has only a few significant bits; real witnesses are full of
@@ -399,7 +558,7 @@ struct MsmWorkspace {
 };
 
 template <int GID>
-static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n) {
+static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n, bool affine = false) {
   constexpr size_t PT_BYTES = sizeof(Fq) * 4 * MsmCfg<GID>::K;
   MsmWorkspace s;
   const size_t len = (size_t)pl.B + 1;
@@ -426,6 +585,9 @@ static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n) {
   t += Carver::pad(sizeof(uint32_t) * s.max_items);                     // item id -> bucket
   t += Carver::pad(PT_BYTES * (NB + s.max_items));                      // buckets + item partials
   t += Carver::pad(PT_BYTES * pl.rows * entries) * 2;                   // reduction levels
+  if (affine)                                                            // accumulators + prefix products
+    t += Carver::pad((size_t)div_up(div_up(s.max_items, AFF_G), MsmCfg<GID>::NC_ACC) * MsmCfg<GID>::NC_ACC * AFF_G *
+                     AFF_GSLOTS * sizeof(Fq));
   s.total = t + 8192;
   return s;
 }
@@ -463,7 +625,17 @@ struct MsmKey {
   unsigned copies = 1;
   int c = 0;          // window bits the tables were built for (0 = choose per call)
   unsigned rows = 0;  // bucket rows the tables were built for (0 = derive)
+  int affine = -1;    // accumulation kernel: -1 = by size, 0 = XYZZ, 1 = affine with shared inversions
 };
+
+struct MsmHooks;
+template <int GID>
+static inline typename std::enable_if<MsmCfg<GID>::AFFINE>::type msm_launch_affine(
+    MsmHooks& hooks, cudaStream_t stream, unsigned blocks, const Fq* bases, const uint32_t* sorted,
+    const MsmItem* items, const uint32_t* item_total, Fq* points, uint4* scratch);
+template <int GID>
+static inline typename std::enable_if<!MsmCfg<GID>::AFFINE>::type msm_launch_affine(
+    MsmHooks&, cudaStream_t, unsigned, const Fq*, const uint32_t*, const MsmItem*, const uint32_t*, Fq*, uint4*) {}
 
 // d_scalars: count x 24 u32 canonical (device); d_out: 3K Fq (device)
 template <int GID>
@@ -489,7 +661,8 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   const unsigned n = (unsigned)count;
   const MsmPlan pl = msm_plan(n, key.copies, key.c, key.rows);
   if (pl.c == 0) return G753_ERR_BAD_ARG;
-  const MsmWorkspace ws = msm_workspace<GID>(pl, n);
+  const bool affine = Cfg::AFFINE && key.affine > 0;  // opt-in (G753_MSM_AFFINE=1): measured slower, see header
+  const MsmWorkspace ws = msm_workspace<GID>(pl, n, affine);
   if ((uint64_t)pl.W * n >= 0xffffffffull || (uint64_t)pl.rows * ws.row_cap >= 0xffffffffull ||
       (uint64_t)(pl.copies - 1) * key.copy_stride + n > 0x7fffffffull)
     return G753_ERR_BAD_ARG;
@@ -515,6 +688,8 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   Fq* points = cv.take<Fq>(PT * ((size_t)NB + ws.max_items));
   Fq* lvl_r = cv.take<Fq>(PT * R * ws.level_entries);
   Fq* lvl_y = cv.take<Fq>(PT * R * ws.level_entries);
+  const unsigned aff_blocks = div_up(div_up(ws.max_items, AFF_G), CA);
+  uint4* aff_scratch = affine ? (uint4*)cv.take<Fq>((size_t)aff_blocks * CA * AFF_G * AFF_GSLOTS) : nullptr;
 
   if (hooks.mark) hooks.mark(hooks.user, 0);
   G753_TRY(dev_memset(hist, 0, sizeof(uint32_t) * NB, stream));
@@ -544,8 +719,11 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   G753_MSM_LAUNCH(hooks, k_item_emit, div_up(NB, 256), 256, stream, offsets, cursor, item_cnt, item_off, NB,
                   pl.B, ws.row_cap, len_cursor, items, part_bucket);
   if (hooks.mark) hooks.mark(hooks.user, 2);
-  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc<SCA>, div_up(ws.max_items, CA), TA, SMEM_ACC, stream, key.bases,
-                       sorted, items, item_total, points);
+  if (affine)
+    msm_launch_affine<GID>(hooks, stream, aff_blocks, key.bases, sorted, items, item_total, points, aff_scratch);
+  else
+    G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc<SCA>, div_up(ws.max_items, CA), TA, SMEM_ACC, stream, key.bases,
+                         sorted, items, item_total, points);
   // a bucket holds at most row_cap points = row_cap / ITEM_LEN + 1 partials
   for (size_t stride = 1; stride <= ws.row_cap / ITEM_LEN; stride *= FIX_FAN)
     G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup_level<SCA>, div_up(ws.max_items, CA), TA, SMEM_FIX, stream, item_cnt,
@@ -583,6 +761,17 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
                        d_out);
   if (hooks.mark) hooks.mark(hooks.user, 5);
   return launch_check("msm_run");
+}
+
+template <int GID>
+static inline typename std::enable_if<MsmCfg<GID>::AFFINE>::type msm_launch_affine(
+    MsmHooks& hooks, cudaStream_t stream, unsigned blocks, const Fq* bases, const uint32_t* sorted,
+    const MsmItem* items, const uint32_t* item_total, Fq* points, uint4* scratch) {
+  typedef MsmCfg<GID> Cfg;
+  constexpr int CA = Cfg::NC_ACC, TA = CA * Cfg::TP;
+  typedef typename Cfg::template SC<CA> SCA;
+  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc_affine<SCA>, blocks, TA, (slot_bytes<EcS<SCA>, CA>(AFF_SLOTS)), stream, bases,
+                       sorted, items, item_total, points, scratch);
 }
 
 }  // namespace g753

@@ -20,6 +20,7 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
   key.bases = (const Fq*)b->d_points + first * 2 * MsmCfg<GID>::K;
   key.inf = b->d_inf ? b->d_inf + first : nullptr;
   key.copy_stride = key.inf_stride = b->n;
+  key.affine = ctx->forced_affine;
   // the precomputed copies pay off when the slice is a sizeable part of the key they were sized
   // for; short slices (the prover's input-query views) run the plain pipeline on copy 0
   if (b->copies > 1 && count * 4 >= b->n) {

@@ -213,7 +213,8 @@ int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uin
                   uint64_t* out_xyz);
 /* Run `iters` dependent Montgomery multiplications per thread on `blocks` x `threads`
  * threads and report the kernel time in ms (CUDA events): the integer-pipe roofline probe
- * of SURVEY.md 8d.  variant 0 = fq_mul, 1 = fq_sqr, 2 = raw independent IMAD.WIDE stream */
+ * of SURVEY.md 8d.  variant 0 = fq_mul, 1 = fq_sqr, 2 = raw independent IMAD.WIDE stream,
+ * 3 = fq_inv (safegcd) */
 int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms);
 /* debugging aid: copy the first `bytes` of the MSM workspace to the host; *cap = its size */
 int g753_debug_scratch(g753_ctx* ctx, void* h_dst, size_t bytes, size_t* cap);
