@@ -338,9 +338,86 @@ G753_HD Fq fq_mul(const Fq& a, const Fq& b) {
   return r;
 }
 
+// Dedicated squaring (replaces Fp768::square_in_place, fp_768.rs:339-548: the reference also
+// computes the cross products once, doubles them and adds the squares before reducing).
+//   a^2 = 2 * sum_{i<j} a_i a_j 2^(32 (i+j)) + sum_i a_i^2 2^(64 i):   276 + 24 products instead of 576,
+// then a separate word-by-word Montgomery reduction (576 products): 876 limb-MACs against the 1152
+// of fq_mul, i.e. 25 % fewer instructions on the binding IMAD pipe.  Every product is still one
+// mad.lo.cc / madc.hi.cc pair on a carry chain: within one row the products of equal parity of
+// (i + j) occupy consecutive column pairs.  Carries leaving a chain are counted in small per-column
+// counters and folded in with one addition chain at the end (IADD3s run on the idle ALU pipe).
 template <int FID>
 G753_HD Fq fq_sqr(const Fq& a) {
-  return fq_mul<FID>(a, a);
+  uint32_t T[2 * NL];      // columns 0 .. 47 of the product
+  uint32_t K[2 * NL + 2];  // deferred carries into columns (tiny counts)
+#pragma unroll
+  for (int c = 0; c < 2 * NL; c++) T[c] = 0;
+#pragma unroll
+  for (int c = 0; c < 2 * NL + 2; c++) K[c] = 0;
+  // ---- cross products, each once -------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < NL - 1; i++) {
+#pragma unroll
+    for (int par = 1; par <= 2; par++) {       // j = i + par, i + par + 2, ...
+      if (i + par >= NL) continue;
+      int last = i + par;
+      T[i + last] = mad_lo_cc(a.l[i], a.l[last], T[i + last]);
+      T[i + last + 1] = madc_hi_cc(a.l[i], a.l[last], T[i + last + 1]);
+#pragma unroll
+      for (int j = i + par + 2; j < NL; j += 2) {
+        T[i + j] = madc_lo_cc(a.l[i], a.l[j], T[i + j]);
+        T[i + j + 1] = madc_hi_cc(a.l[i], a.l[j], T[i + j + 1]);
+        last = j;
+      }
+      K[i + last + 2] += addc(0, 0);
+    }
+  }
+  // ---- T = 2 T + 2 K + squares ----------------------------------------------------------------
+  T[0] = add_cc(T[0], T[0]);
+#pragma unroll
+  for (int c = 1; c < 2 * NL; c++) T[c] = addc_cc(T[c], T[c]);
+  T[0] = add_cc(T[0], K[0] << 1);
+#pragma unroll
+  for (int c = 1; c < 2 * NL; c++) T[c] = addc_cc(T[c], K[c] << 1);
+  T[0] = mad_lo_cc(a.l[0], a.l[0], T[0]);
+  T[1] = madc_hi_cc(a.l[0], a.l[0], T[1]);
+#pragma unroll
+  for (int i = 1; i < NL; i++) {
+    T[2 * i] = madc_lo_cc(a.l[i], a.l[i], T[2 * i]);
+    T[2 * i + 1] = madc_hi_cc(a.l[i], a.l[i], T[2 * i + 1]);
+  }
+  // ---- Montgomery reduction: 24 rows m_i * p, two parity chains per row --------------------------
+#pragma unroll
+  for (int c = 0; c < 2 * NL + 2; c++) K[c] = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    const uint32_t m = mul_lo(T[i], G753_FC(FID).inv32);
+    T[i] = mad_lo_cc(m, G753_FC(FID).p[0], T[i]);
+    T[i + 1] = madc_hi_cc(m, G753_FC(FID).p[0], T[i + 1]);
+#pragma unroll
+    for (int j = 2; j < NL; j += 2) {
+      T[i + j] = madc_lo_cc(m, G753_FC(FID).p[j], T[i + j]);
+      T[i + j + 1] = madc_hi_cc(m, G753_FC(FID).p[j], T[i + j + 1]);
+    }
+    K[i + NL] += addc(0, 0);
+    T[i + 1] = mad_lo_cc(m, G753_FC(FID).p[1], T[i + 1]);
+    T[i + 2] = madc_hi_cc(m, G753_FC(FID).p[1], T[i + 2]);
+#pragma unroll
+    for (int j = 3; j < NL; j += 2) {
+      T[i + j] = madc_lo_cc(m, G753_FC(FID).p[j], T[i + j]);
+      if (i + j + 1 < 2 * NL)
+        T[i + j + 1] = madc_hi_cc(m, G753_FC(FID).p[j], T[i + j + 1]);
+      // i = 23, j = 23: the high word would land in column 48; it is zero because T + M p < 2^1536
+    }
+    if (i + NL + 1 < 2 * NL + 2) K[i + NL + 1] += addc(0, 0);
+  }
+  Fq r;
+  r.l[0] = add_cc(T[NL], K[NL]);
+#pragma unroll
+  for (int c = 1; c < NL - 1; c++) r.l[c] = addc_cc(T[NL + c], K[NL + c]);
+  r.l[NL - 1] = addc(T[2 * NL - 1], K[2 * NL - 1]);
+  fq_reduce_once<FID>(r.l);
+  return r;
 }
 
 // Out-of-line entry points: the curve code calls the multiplier hundreds of times per group

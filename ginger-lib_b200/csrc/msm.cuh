@@ -44,17 +44,37 @@ constexpr unsigned ITEM_REP = 16;          // replicated length counters (spread
 // that the slot footprint (accumulate: 8K + NTMP slots, reduce: 13K + NTMP slots of 96 B per column)
 // leaves >= 8 warps per SM inside the 227 KB of shared memory
 template <int GID> struct MsmCfg;
+// TPA lanes per column in the accumulation kernels, TP in all others (reduction, fold, key set-up);
+// the TEST-ONLY host build runs one lane everywhere
 #if defined(G753_HOST_EMUL)
+#define G753_TP2A 1
 #define G753_TP2 1
 #define G753_TP3 1
 #else
+#define G753_TP2A 2
 #define G753_TP2 4
 #define G753_TP3 8
 #endif
-template <> struct MsmCfg<0> { static constexpr bool AFFINE = true; static constexpr int K = 1, TP = 1, NC_ACC = 128, NC_RED = 128; template <int NC> using SC = SCurveM4G1<Lay<NC, 1>>; };
-template <> struct MsmCfg<1> { static constexpr bool AFFINE = false; static constexpr int K = 2, TP = G753_TP2, NC_ACC = 48, NC_RED = 32; template <int NC> using SC = SCurveM4G2<Lay<NC, G753_TP2>>; };
-template <> struct MsmCfg<2> { static constexpr bool AFFINE = true; static constexpr int K = 1, TP = 1, NC_ACC = 128, NC_RED = 128; template <int NC> using SC = SCurveM6G1<Lay<NC, 1>>; };
-template <> struct MsmCfg<3> { static constexpr bool AFFINE = false; static constexpr int K = 3, TP = G753_TP3, NC_ACC = 32, NC_RED = 16; template <int NC> using SC = SCurveM6G2<Lay<NC, G753_TP3>>; };
+template <> struct MsmCfg<0> {
+  static constexpr bool AFFINE = true;
+  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = 128, NC_RED = 128;
+  template <int NC, int LANES = 1> using SC = SCurveM4G1<Lay<NC, LANES>>;
+};
+template <> struct MsmCfg<1> {
+  static constexpr bool AFFINE = false;
+  static constexpr int K = 2, TP = G753_TP2, TPA = G753_TP2A, NC_ACC = 16, NC_RED = 32;
+  template <int NC, int LANES = G753_TP2> using SC = SCurveM4G2<Lay<NC, LANES>>;
+};
+template <> struct MsmCfg<2> {
+  static constexpr bool AFFINE = true;
+  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = 128, NC_RED = 128;
+  template <int NC, int LANES = 1> using SC = SCurveM6G1<Lay<NC, LANES>>;
+};
+template <> struct MsmCfg<3> {
+  static constexpr bool AFFINE = false;
+  static constexpr int K = 3, TP = G753_TP3, TPA = G753_TP3, NC_ACC = 32, NC_RED = 16;
+  template <int NC, int LANES = G753_TP3> using SC = SCurveM6G2<Lay<NC, LANES>>;
+};
 
 struct MsmPlan {
   unsigned c;       // window bits
@@ -643,9 +663,9 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
                    size_t count, Fq* d_out, MsmHooks hooks) {
   typedef MsmCfg<GID> Cfg;
   constexpr int CA = Cfg::NC_ACC, CR = Cfg::NC_RED;        // columns (curve operations) per block
-  constexpr int TA = CA * Cfg::TP, TR = CR * Cfg::TP;      // threads per block
-  typedef typename Cfg::template SC<CA> SCA;
-  typedef typename Cfg::template SC<CR> SCR;
+  constexpr int TA = CA * Cfg::TPA, TR = CR * Cfg::TP;     // threads per block
+  typedef typename Cfg::template SC<CA, Cfg::TPA> SCA;
+  typedef typename Cfg::template SC<CR, Cfg::TP> SCR;
   typedef EcS<SCA> EA;
   typedef EcS<SCR> ER;
   constexpr size_t PT = 4 * Cfg::K;  // Fq per XYZZ point
@@ -768,8 +788,8 @@ static inline typename std::enable_if<MsmCfg<GID>::AFFINE>::type msm_launch_affi
     MsmHooks& hooks, cudaStream_t stream, unsigned blocks, const Fq* bases, const uint32_t* sorted,
     const MsmItem* items, const uint32_t* item_total, Fq* points, uint4* scratch) {
   typedef MsmCfg<GID> Cfg;
-  constexpr int CA = Cfg::NC_ACC, TA = CA * Cfg::TP;
-  typedef typename Cfg::template SC<CA> SCA;
+  constexpr int CA = Cfg::NC_ACC, TA = CA * Cfg::TPA;
+  typedef typename Cfg::template SC<CA, Cfg::TPA> SCA;
   G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc_affine<SCA>, blocks, TA, (slot_bytes<EcS<SCA>, CA>(AFF_SLOTS)), stream, bases,
                        sorted, items, item_total, points, scratch);
 }
