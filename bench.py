@@ -386,6 +386,12 @@ def run_ours(args):
                          "variable_base.rs:10-83, 1 run of %.1f s; result equal to the CUDA path's" %
                          (args.cpu_log_n, times[0])}
 
+    # ---- config 4: MNT6-753 G2 (Fq3) MSM at 2^20 + a mixed-radix transform (rank 0, N = 1) ----
+    cfg4 = None
+    if rank == 0 and world == 1 and not args.no_config4:
+        bases.free()
+        cfg4 = run_config4(ctx, G, ffi, params, args)
+
     # ---- config 5: end-to-end Groth16 proof; N > 1: the long MSMs sharded by point range -------
     g16 = None
     if not args.no_groth16:
@@ -437,7 +443,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 288,
                     "path": "g753_msm: pinned host scalars -> H2D -> MSM -> D2H result; bases resident (proving key)"},
             "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "fft": fft, "groth16": g16,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "fft": fft, "config4": cfg4, "groth16": g16,
             "setup_s": setup_s, "key_precompute_s": precompute_s,
         }
         print(json.dumps(line), flush=True)
@@ -445,6 +451,67 @@ def run_ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_config4(ctx, G, ffi, params, args):
+    """BASELINE config 4: MNT6-753 G2 (over Fq3) MSM at 2^20 points on a resident synthetic key, verified
+    by its discrete logs, and the mixed-radix transform at 2^15 * 25 = 819 200 points on mnt6753::Fr
+    (round trip checked; parity unpinned - the reference has no mixed-radix domain)"""
+    import torch
+    group, log_n = ffi.MNT6_G2, 20
+    n = 1 << log_n
+    t0 = time.perf_counter()
+    bases = ctx.generate_bases(group, n, 0xC4)
+    bases.precompute(args.copies)
+    ctx.sync()
+    key_s = time.perf_counter() - t0
+    sc = random_scalars(n, 0xC5)
+    r = params.GROUP_ORDER[group]
+    p = params.GROUP_BASE_MODULUS[group]
+    out = None
+    times = []
+    for it in range(3):
+        t1 = time.perf_counter()
+        out = G.VariableBaseMSM.multi_scalar_mul(bases, sc)        # host scalars in, host point out
+        times.append(time.perf_counter() - t1)
+    phases = ctx.last_msm_phases()
+    k = dot_mod(sc, G.Bases.generated_logs(n, 0xC4), r)
+    gen = np.stack([int_to_limbs(v) for v in params.GENERATOR_MONT[group]]).reshape(-1)
+    expect = np.zeros((3, 36), dtype=np.uint64)
+    ctx.lib.check(ctx.lib.point_op(ctx.handle, group, 2, ffi.ptr(gen), ffi.ptr(int_to_limbs(k)), ffi.ptr(expect)))
+    xy = np.zeros((2, 72), dtype=np.uint64)
+    inf = np.zeros(2, dtype=np.uint8)
+    both = np.ascontiguousarray(np.stack([out.reshape(-1), expect.reshape(-1)]))
+    ctx.lib.check(ctx.lib.batch_normalize(ctx.handle, group, ffi.ptr(both), 2, ffi.ptr(xy), ffi.ptr(inf)))
+    if not (xy[0] == xy[1]).all():
+        raise SystemExit("config 4: MNT6 G2 MSM differs from (sum s_i a_i) * G")
+    bases.free()
+    # mixed-radix transform
+    N = (1 << 15) * 25
+    field = ffi.FIELD_MNT6_FR
+    raw = random_scalars(N, 0xC6)
+    raw[:, 11] &= np.uint64(0xFFFF)
+    vec = G.DeviceVector(ctx, field, N, raw)
+    lib = ctx.lib
+    for mode in (ffi.FFT, ffi.IFFT):
+        lib.check(lib.ntt_mixed_dev(ctx.handle, field, vec.ptr, N, mode))
+    if not (vec.download() == raw).all():
+        raise SystemExit("config 4: mixed-radix ifft(fft(x)) != x")
+    ctx.sync()
+    t1 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        lib.check(lib.ntt_mixed_dev(ctx.handle, field, vec.ptr, N, ffi.FFT))
+    ctx.sync()
+    mixed_ms = (time.perf_counter() - t1) / reps * 1e3
+    vec.free()
+    return {"msm": {"workload": "MNT6-753 G2 (Fq3) MSM, 2^20 points, resident key with %d copies (built in %.1f s)"
+                                % (args.copies, key_s),
+                    "ms": min(times) * 1e3, "mpts_per_s": n / min(times) / 1e6, "phases_ms": phases,
+                    "verified": "result == (sum s_i a_i mod r) * G2 generator"},
+            "mixed_radix_fft": {"field": "mnt6753::Fr", "n": N, "factorisation": "2^15 * 5^2", "ms": mixed_ms,
+                                "elements_per_s": N / (mixed_ms * 1e-3), "verified": "ifft(fft(x)) == x",
+                                "parity": "unpinned: no mixed-radix domain in the reference"}}
 
 
 def main():
@@ -462,6 +529,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fft", action="store_true")
     ap.add_argument("--no-groth16", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--groth16-log-n", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -49,10 +49,12 @@ template <int GID> struct MsmCfg;
 #if defined(G753_HOST_EMUL)
 #define G753_TP2A 1
 #define G753_TP2 1
+#define G753_TP3A 1
 #define G753_TP3 1
 #else
 #define G753_TP2A 2
 #define G753_TP2 4
+#define G753_TP3A 4
 #define G753_TP3 8
 #endif
 template <> struct MsmCfg<0> {
@@ -72,7 +74,7 @@ template <> struct MsmCfg<2> {
 };
 template <> struct MsmCfg<3> {
   static constexpr bool AFFINE = false;
-  static constexpr int K = 3, TP = G753_TP3, TPA = G753_TP3, NC_ACC = 32, NC_RED = 16;
+  static constexpr int K = 3, TP = G753_TP3, TPA = G753_TP3A, NC_ACC = 32, NC_RED = 16;
   template <int NC, int LANES = G753_TP3> using SC = SCurveM6G2<Lay<NC, LANES>>;
 };
 

@@ -537,21 +537,26 @@ template <int FID, class L, unsigned NR>
 struct Tw3C {
   typedef L T;
   static constexpr int K = 3, NTMP = 9, FIELD = FID;
-  static_assert(L::TP >= 6, "Fq3 needs six product lanes");
-  // Karatsuba (fp3.rs:451-478): v0, v1, v2 on lanes 0..2, the three cross products on lanes 3..5.
-  // scratch: t+0..2 = v0, v1, v2; t+3.. = (a1+a2, b1+b2), (a0+a1, b0+b1), (a0+a2, b0+b2)
+  static_assert(L::TP == 4 || L::TP == 8, "Fq3 runs on four or eight lanes");
+  // Karatsuba (fp3.rs:451-478): v0 = a0 b0, v1 = a1 b1, v2 = a2 b2 and the cross products
+  // m12 = (a1+a2)(b1+b2), m01 = (a0+a1)(b0+b1), m02 = (a0+a2)(b0+b2).
+  //   TP = 8: all six products in one round (lanes 0..5);
+  //   TP = 4: v0, v1, v2, m12 in the first round, m01, m02 (lanes 1, 2) in the second.
+  // scratch: t+0..2 = v0, v1, v2; t+3.. = the operand sums of m12, m01, m02 (product over the first)
   static G753_NI void mul(int d, int a, int b, int t) {
     const int r = L::role();
-    if (r >= 3 && r < 6) {
-      const int j = r - 3;                                    // 0: (1,2)  1: (0,1)  2: (0,2)
-      const int x = j == 0 ? 1 : 0, y = j == 1 ? 1 : 2;
+    const int j = L::TP == 8 ? r - 3 : (r == 3 ? 0 : r);   // which cross product this lane prepares
+    if (L::TP == 8 ? (r >= 3 && r < 6) : (r >= 1)) {
+      const int x = j == 0 ? 1 : 0, y = j == 1 ? 1 : 2;     // j = 0: (1,2)  1: (0,1)  2: (0,2)
       s_add<FID, L>(t + 3 + 2 * j, a + x, a + y);
       s_add<FID, L>(t + 4 + 2 * j, b + x, b + y);
     }
     L::sync();
-    if (r < 6) {
-      const int j = r - 3;
-      s_mul<FID, L>(r < 3 ? t + r : t + 3 + 2 * j, r < 3 ? a + r : t + 3 + 2 * j, r < 3 ? b + r : t + 4 + 2 * j);
+    if (L::TP == 8) {
+      if (r < 6) s_mul<FID, L>(r < 3 ? t + r : t + 3 + 2 * j, r < 3 ? a + r : t + 3 + 2 * j, r < 3 ? b + r : t + 4 + 2 * j);
+    } else {
+      s_mul<FID, L>(r < 3 ? t + r : t + 3, r < 3 ? a + r : t + 3, r < 3 ? b + r : t + 4);
+      if (r == 1 || r == 2) s_mul<FID, L>(t + 3 + 2 * r, t + 3 + 2 * r, t + 4 + 2 * r);
     }
     L::sync();
     // m12 = t+3, m01 = t+5, m02 = t+7; one output coordinate per lane 0..2
@@ -565,6 +570,7 @@ struct Tw3C {
     L::sync();
   }
   // Chung-Hasan SQR2 (fp3.rs:165-185): a0^2, a0 a1, (a0 - a1 + a2)^2, a1 a2, a2^2 on lanes 0..4
+  // (TP = 4: the fifth product in a second round on lane 0)
   static G753_NI void sqr(int d, int a, int t) {
     const int r = L::role();
     if (r == 2) {
@@ -572,11 +578,12 @@ struct Tw3C {
       s_add<FID, L>(t + 5, t + 5, a + 2);
     }
     L::sync();
-    if (r < 5) {
+    if (r < (L::TP == 8 ? 5 : 4)) {
       const int x = r == 0 ? a : r == 1 ? a : r == 2 ? t + 5 : r == 3 ? a + 1 : a + 2;
       const int y = r == 0 ? a : r == 1 ? a + 1 : r == 2 ? t + 5 : r == 3 ? a + 2 : a + 2;
       s_mul<FID, L>(t + r, x, y);
     }
+    if (L::TP == 4 && r == 0) s_mul<FID, L>(t + 4, a + 2, a + 2);
     L::sync();
     if (r == 1 || r == 3) s_dbl<FID, L>(t + r, t + r);        // s1 = 2 a0 a1, s3 = 2 a1 a2
     L::sync();
