@@ -84,7 +84,15 @@ class Parameters:
         for b in (self.a_query, self.b_g1_query, self.b_g2_query, self.h_query, self.l_query, self.a_small,
                   self.b1_small, self.b2_small, self.fresh):
             b.free()
+        self._free_ws()
         self.ctx2.close()
+
+    def _free_ws(self):
+        ws = getattr(self, "_ws", None)
+        if ws is not None:
+            for dv in ws["bufs"]:
+                dv.free()
+            self._ws = None
 
 
 def shard_range(n, rank, world):
@@ -141,6 +149,7 @@ class ShardedParameters(Parameters):
     def free(self):
         for b in [v[0] for v in self.aux.values()] + [self.a_small, self.b1_small, self.b2_small, self.h_head, self.fresh]:
             b.free()
+        self._free_ws()
         self.ctx2.close()
 
 
@@ -256,14 +265,18 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
     n_vars = z.shape[0]
     n_aux = n_vars - ni
 
-    # every device buffer of the proof is allocated before anything is queued (cudaFree synchronises)
-    dev = [_Dev(ctx, n) for _ in range(3)]
-    d_h = _Dev(ctx, n + 1)
-    d_z = _Dev(ctx, n_vars + 1)
-    sr, ss = _Dev(ctx, ni + 2), _Dev(ctx, ni + 2)
-    sc3 = _Dev(ctx, 3)
-    out1 = _Dev(ctx, 3 * 16)        # G1 partial results, 3 Fq each
-    out2 = _Dev(ctx, 3 * k2 * 4)    # G2 partial results
+    # every device buffer of the proof is allocated before anything is queued and kept with the key
+    # for the next proof of the same shape (cudaMalloc / cudaFree synchronise the device)
+    ws = getattr(params, "_ws", None)
+    if ws is None or ws["shape"] != (n, n_vars, ni):
+        if ws is not None:
+            for dv in ws["bufs"]:
+                dv.free()
+        bufs = [_Dev(ctx, n) for _ in range(3)] + [_Dev(ctx, n + 1), _Dev(ctx, n_vars + 1), _Dev(ctx, ni + 2),
+                                                    _Dev(ctx, ni + 2), _Dev(ctx, 3), _Dev(ctx, 3 * 16), _Dev(ctx, 3 * k2 * 4)]
+        ws = params._ws = {"shape": (n, n_vars, ni), "bufs": bufs}
+    bufs = ws["bufs"]
+    dev, d_h, d_z, sr, ss, sc3, out1, out2 = bufs[:3], bufs[3], bufs[4], bufs[5], bufs[6], bufs[7], bufs[8], bufs[9]
     slot = lambda o, i, k=1: o.at(3 * k * i)
     try:
         # ---- witness map on the device, then into_repr of h and the assignment (prover.rs:241-267) ----
@@ -353,5 +366,3 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
                      (bool(inf[0]), bool(infb[0]), bool(infc[0])))
     finally:
         ctx2.sync()
-        for dv in dev + [d_h, d_z, sr, ss, sc3, out1, out2]:
-            dv.free()
