@@ -10,8 +10,7 @@
 // reference's mixed addition, P + (-P) and P + P are both handled explicitly.
 //
 // A point occupies 4 tower elements = 4K slots in the order X, Y, ZZ, ZZZ; infinity <=> ZZ == 0.
-// `W` is the first scratch slot: madd_g / mdbl_g need 4K + NTMP, add / add_g / dbl need
-// 5K + NTMP scratch slots.
+// `W` is the first scratch slot: every operation needs 4K + NTMP scratch slots.
 #pragma once
 #include "slots.cuh"
 
@@ -87,7 +86,7 @@ struct EcS {
   static constexpr int K = M::K;
   static constexpr int PT = 4 * K;                      // slots per XYZZ point
   static constexpr int MADD_SCRATCH = 4 * K + M::NTMP;  // scratch slots of madd_g / mdbl_g
-  static constexpr int ADD_SCRATCH = 5 * K + M::NTMP;   // scratch slots of add / add_g / dbl
+  static constexpr int ADD_SCRATCH = 4 * K + M::NTMP;   // scratch slots of add / add_g / dbl
 
   static G753_D bool is_inf(int P) { return M::is_zero(P + 2 * K); }
   static G753_D void set_inf(int P) {
@@ -179,10 +178,10 @@ struct EcS {
     M::sub(Y, Y, t2);          // Y3 = R (Q - X3) - Y1 PPP
   }
 
-  // P = 2P: dbl-2008-s-1
+  // P = 2P: dbl-2008-s-1.  Four temporaries: V's slot is recycled once ZZ3 = V ZZ1 is formed.
   static G753_NI void dbl(int P, int W) {
     const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
-    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, t4 = W + 4 * K, tt = W + 5 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, tt = W + 4 * K;
     if (M::is_zero(ZZ)) return;
     M::dbl(t0, Y);             // U = 2 Y1
     if (M::is_zero(t0)) {
@@ -192,27 +191,28 @@ struct EcS {
     M::sqr(t1, t0, tt);        // V
     M::mul(t0, t0, t1, tt);    // W
     M::mul(t2, X, t1, tt);     // S = X1 V
-    M::sqr(t3, ZZ, tt);
-    SC::mul_by_a(t4, t3);      // a ZZ1^2
+    M::sqr(t3, ZZ, tt);        // ZZ1^2
+    M::mul(ZZ, ZZ, t1, tt);    // ZZ3 = V ZZ1
+    SC::mul_by_a(t1, t3);      // a ZZ1^2   (t1 != t3: the Fq3 twist permutes coordinates)
     M::sqr(t3, X, tt);
-    M::add(t4, t4, t3);
+    M::add(t1, t1, t3);
     M::dbl(t3, t3);
-    M::add(t3, t3, t4);        // M = 3 X1^2 + a ZZ1^2
-    M::mul(ZZ, ZZ, t1, tt);
-    M::mul(ZZZ, ZZZ, t0, tt);
+    M::add(t3, t3, t1);        // M = 3 X1^2 + a ZZ1^2
+    M::mul(ZZZ, ZZZ, t0, tt);  // ZZZ3 = W ZZZ1
     M::sqr(X, t3, tt);
-    M::dbl(t4, t2);
-    M::sub(X, X, t4);          // X3 = M^2 - 2S
+    M::dbl(t1, t2);
+    M::sub(X, X, t1);          // X3 = M^2 - 2S
     M::sub(t2, t2, X);
     M::mul(t2, t3, t2, tt);    // M (S - X3)
-    M::mul(t4, t0, Y, tt);     // W Y1
-    M::sub(Y, t2, t4);
+    M::mul(t1, t0, Y, tt);     // W Y1
+    M::sub(Y, t2, t1);
   }
 
-  // P += Q (both on slots, Q preserved): add-2008-s, 12M + 2S
+  // P += Q (both on slots, Q preserved): add-2008-s, 12M + 2S.  Four temporaries: once U1, S1, P, R
+  // exist, X1 and Y1 are dead and their slots carry PP and the later intermediates.
   static G753_NI void add(int P, int Q, int W) {
     const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
-    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, t4 = W + 4 * K, tt = W + 5 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, tt = W + 4 * K;
     if (M::is_zero(Q + 2 * K)) return;
     if (M::is_zero(ZZ)) {
       copy(P, Q);
@@ -229,39 +229,40 @@ struct EcS {
       else set_inf(P);
       return;
     }
-    M::sqr(t4, t2, tt);             // PP
-    M::mul(t2, t2, t4, tt);         // PPP
-    M::mul(t0, t0, t4, tt);         // Q = U1 PP
     M::mul(ZZ, ZZ, Q + 2 * K, tt);
-    M::mul(ZZ, ZZ, t4, tt);
     M::mul(ZZZ, ZZZ, Q + 3 * K, tt);
+    M::sqr(X, t2, tt);              // PP
+    M::mul(t2, t2, X, tt);          // PPP
+    M::mul(t0, t0, X, tt);          // Q = U1 PP
+    M::mul(ZZ, ZZ, X, tt);
     M::mul(ZZZ, ZZZ, t2, tt);
     M::sqr(X, t3, tt);
     M::sub(X, X, t2);
-    M::dbl(t4, t0);
-    M::sub(X, X, t4);               // X3 = R^2 - PPP - 2Q
-    M::mul(t4, t1, t2, tt);         // S1 PPP
+    M::dbl(Y, t0);
+    M::sub(X, X, Y);                // X3 = R^2 - PPP - 2Q
     M::sub(t0, t0, X);
-    M::mul(Y, t3, t0, tt);
-    M::sub(Y, Y, t4);
+    M::mul(t0, t3, t0, tt);         // R (Q - X3)
+    M::mul(Y, t1, t2, tt);          // S1 PPP
+    M::sub(Y, t0, Y);
   }
 
-  // P += q, q an XYZZ point in global memory (4K Fq, order X, Y, ZZ, ZZZ)
+  // P += q, q an XYZZ point in global memory (4K Fq, order X, Y, ZZ, ZZZ); q's coordinates are
+  // (re)loaded where they are used
   static G753_NI void add_g(int P, const Fq* q, int W) {
     const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
-    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, t4 = W + 4 * K, tt = W + 5 * K;
-    M::ldg(t4, q + 2 * K);          // ZZ2
-    if (M::is_zero(t4)) return;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, tt = W + 4 * K;
+    M::ldg(t0, q + 2 * K);          // ZZ2
+    if (M::is_zero(t0)) return;
     if (M::is_zero(ZZ)) {
       ldg(P, q);
       return;
     }
-    M::mul(t0, X, t4, tt);          // U1 = X1 ZZ2
+    M::mul(t0, X, t0, tt);          // U1 = X1 ZZ2
+    M::ldg(t1, q + 3 * K);
+    M::mul(t1, Y, t1, tt);          // S1 = Y1 ZZZ2
     M::ldg(t2, q);
     M::mul(t2, t2, ZZ, tt);
     M::sub(t2, t2, t0);             // P = X2 ZZ1 - U1
-    M::ldg(t3, q + 3 * K);          // ZZZ2
-    M::mul(t1, Y, t3, tt);          // S1 = Y1 ZZZ2
     M::ldg(t3, q + K);
     M::mul(t3, t3, ZZZ, tt);
     M::sub(t3, t3, t1);             // R = Y2 ZZZ1 - S1
@@ -270,22 +271,23 @@ struct EcS {
       else set_inf(P);
       return;
     }
-    M::mul(ZZ, ZZ, t4, tt);         // ZZ1 ZZ2
-    M::ldg(t4, q + 3 * K);
-    M::mul(ZZZ, ZZZ, t4, tt);       // ZZZ1 ZZZ2
-    M::sqr(t4, t2, tt);             // PP
-    M::mul(t2, t2, t4, tt);         // PPP
-    M::mul(t0, t0, t4, tt);         // Q = U1 PP
-    M::mul(ZZ, ZZ, t4, tt);
+    M::ldg(X, q + 2 * K);
+    M::mul(ZZ, ZZ, X, tt);          // ZZ1 ZZ2
+    M::ldg(X, q + 3 * K);
+    M::mul(ZZZ, ZZZ, X, tt);        // ZZZ1 ZZZ2
+    M::sqr(X, t2, tt);              // PP
+    M::mul(t2, t2, X, tt);          // PPP
+    M::mul(t0, t0, X, tt);          // Q = U1 PP
+    M::mul(ZZ, ZZ, X, tt);
     M::mul(ZZZ, ZZZ, t2, tt);
     M::sqr(X, t3, tt);
     M::sub(X, X, t2);
-    M::dbl(t4, t0);
-    M::sub(X, X, t4);
-    M::mul(t4, t1, t2, tt);
+    M::dbl(Y, t0);
+    M::sub(X, X, Y);
     M::sub(t0, t0, X);
-    M::mul(Y, t3, t0, tt);
-    M::sub(Y, Y, t4);
+    M::mul(t0, t3, t0, tt);
+    M::mul(Y, t1, t2, tt);
+    M::sub(Y, t0, Y);
   }
 
   // XYZZ -> the reference's homogeneous projective (X:Y:Z) = (X ZZZ : Y ZZ : ZZ ZZZ), in place

@@ -28,6 +28,7 @@ def test_proof_tiny_vs_oracle(ctx):
     check_instance(ctx, 0x6107, 8, 3, 6, 0, 0, 0, 0x1234567 << 600, F.p - 3)
     check_instance(ctx, 0x6108, 4, 2, 3, 5, 7, 11, 3, 4)
     check_instance(ctx, 0x6109, 32, 3, 40, 1, 2, 3, F.p - 1, 12345)   # more variables than constraints
+    check_instance(ctx, 0x6601, 8, 2, 9, 1, 2, 3, O.MNT6_FR.p - 5, 0x77 << 700, engine="mnt6")   # G2 over Fq3
 
 
 def _mont_random(n, seed):
