@@ -234,7 +234,7 @@ def run_ours(args):
     t_setup = time.perf_counter()
     bases = ctx.generate_bases(GROUP, n_local, seed)           # bases[i] = a_i * G, resident
     t_pre = time.perf_counter()
-    if args.copies > 1:
+    if args.copies != 1:
         bases.precompute(args.copies)                          # once per key: shifted copies 2^(j*rows*c) * P_i
         ctx.sync()
     precompute_s = time.perf_counter() - t_pre
@@ -432,8 +432,9 @@ def run_ours(args):
                                    % args.log_n,
                        "points_total": n_global, "points_per_gpu": n_local,
                        "bases": "a_i*G, a_i = splitmix64 (g753_bases_generate), resident in HBM" +
-                                (" with %d precomputed shifted copies (g753_bases_precompute, %.1f s once per key)"
-                                 % (args.copies, precompute_s) if args.copies > 1 else ""),
+                                (" with precomputed shifted copies (g753_bases_precompute, %s, %.1f s once per key)"
+                                 % ("%d copies" % args.copies if args.copies else "as many as fit 6 GiB", precompute_s)
+                                 if args.copies != 1 else ""),
                        "scalars": "uniform 752-bit canonical", "l2": "inputs (%.0f MiB/GPU) larger than L2" %
                        ((n_local * 288) / 2**20),
                        "parallelism": "point-range shards x%d, NCCL all-gather of partial points + device fold" % world
@@ -505,8 +506,8 @@ def run_config4(ctx, G, ffi, params, args):
     ctx.sync()
     mixed_ms = (time.perf_counter() - t1) / reps * 1e3
     vec.free()
-    return {"msm": {"workload": "MNT6-753 G2 (Fq3) MSM, 2^20 points, resident key with %d copies (built in %.1f s)"
-                                % (args.copies, key_s),
+    return {"msm": {"workload": "MNT6-753 G2 (Fq3) MSM, 2^20 points, resident key with precomputed copies (built in %.1f s)"
+                                % key_s,
                     "ms": min(times) * 1e3, "mpts_per_s": n / min(times) / 1e6, "phases_ms": phases,
                     "verified": "result == (sum s_i a_i mod r) * G2 generator"},
             "mixed_radix_fft": {"field": "mnt6753::Fr", "n": N, "factorisation": "2^15 * 5^2", "ms": mixed_ms,
@@ -524,8 +525,8 @@ def main():
     ap.add_argument("--fft-log-n", type=int, default=22)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--cpu-log-n", type=int, default=16, help="log2 of the CPU baseline's bounded sample")
-    ap.add_argument("--copies", type=int, default=8,
-                    help="precomputed shifted copies of the resident key (1 = plain key)")
+    ap.add_argument("--copies", type=int, default=0,
+                    help="precomputed shifted copies of the resident key (0 = auto by memory budget, 1 = plain key)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fft", action="store_true")
     ap.add_argument("--no-groth16", action="store_true")

@@ -38,7 +38,7 @@ def gen_range(ctx, group, seed, first, count):
     return ctx.generate_bases(group, count, (seed + first * GOLDEN) & 0xFFFFFFFFFFFFFFFF)
 
 
-def run(ctx, log_n=20, steps=3, warmup=1, copies=8, verify=True, rank=0, world=1, barrier=None):
+def run(ctx, log_n=20, steps=3, warmup=1, copies=0, verify=True, rank=0, world=1, barrier=None):
     import torch
     G = importlib.import_module("ginger-lib_b200")
     groth16 = importlib.import_module("ginger-lib_b200.groth16")
@@ -111,7 +111,8 @@ def run(ctx, log_n=20, steps=3, warmup=1, copies=8, verify=True, rank=0, world=1
         "config": {"workload": "MNT4-753 Groth16 create_proof after constraint synthesis, domain 2^%d "
                                "(%d constraints, 3 inputs, num_aux = num_constraints; BASELINE config 5)" % (log_n, n - ni),
                    "transforms": 7, "msms": "A, B1, H, L in G1 + B2 in G2 (Fq2), ~2^%d points each, + 4 short ones" % log_n,
-                   "key": "synthetic, resident, %d precomputed copies; built in %.1f s" % (copies, key_s),
+                   "key": "synthetic, resident, precomputed copies (%s); built in %.1f s"
+                          % ("%d" % copies if copies else "auto, 6 GiB per query", key_s),
                    "host_io": "a, b, c, assignment in pinned host memory (%d MiB H2D per proof); proof to host"
                               % ((3 * n + n_vars) * 96 >> 20)},
         "h2d_bytes_per_step": (3 * n + n_vars) * 96, "d2h_bytes_per_step": 2 * 96 * 2 + 4 * 96,
@@ -175,7 +176,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
-    ap.add_argument("--copies", type=int, default=8)
+    ap.add_argument("--copies", type=int, default=0)
     args = ap.parse_args()
     G = importlib.import_module("ginger-lib_b200")
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))

@@ -477,7 +477,16 @@ int g753_bases_generate(g753_ctx* ctx, int group, const uint64_t* gen_xy, uint64
 int g753_bases_precompute(g753_ctx* ctx, g753_bases* b, unsigned copies) {
   CHECK_CTX(ctx);
   if (!b) return fail(G753_ERR_BAD_ARG, "null bases");
-  if (copies == 0) copies = 8;
+  if (copies == 0) {
+    // auto: as many copies as fit a per-key memory budget (default 6 GiB, G753_KEY_BUDGET_MB): the
+    // set-up cost is ~W*c doublings per point whatever the count, only memory grows with it
+    size_t budget_mb = 6144;
+    const char* env = getenv("G753_KEY_BUDGET_MB");
+    if (env && atol(env) > 0) budget_mb = (size_t)atol(env);
+    const size_t key_bytes = (size_t)2 * group_k(b->group) * 96 * (b->n ? b->n : 1);
+    size_t fit = (budget_mb << 20) / key_bytes;
+    copies = fit < 2 ? 1 : fit > 64 ? 64 : (unsigned)fit;
+  }
   if (copies > 64) return fail(G753_ERR_BAD_ARG, "too many copies");
   if (b->copies > 1 || copies == 1) return G753_OK;
   std::lock_guard<std::mutex> lock(ctx->mu);

@@ -38,14 +38,14 @@ class Parameters:
     its first num_inputs).  vk points: (2*k*12,) Montgomery affine limbs."""
 
     def __init__(self, ctx, g1, g2, field, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, a_query, b_g1_query,
-                 b_g2_query, h_query, l_query, num_inputs, precompute=0):
+                 b_g2_query, h_query, l_query, num_inputs, precompute=1):
         self.ctx, self.g1, self.g2, self.field, self.num_inputs = ctx, g1, g2, field, num_inputs
         k2 = ffi.GROUP_K[g2]
         ni = num_inputs
 
         def up(group, q):
             b = q if isinstance(q, Bases) else Bases(ctx, group, q[0], q[1])
-            if precompute and len(b) >= 1 << 12:
+            if precompute is not None and precompute != 1 and len(b) >= 1 << 12:
                 b.precompute(precompute)
             return b
 
@@ -114,7 +114,7 @@ class ShardedParameters(Parameters):
     first base counted from the start of the long part (query[num_inputs + lo], l_query[lo])."""
 
     def __init__(self, ctx, g1, g2, field, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, heads, shards, num_inputs,
-                 process_group=None, precompute=0):
+                 process_group=None, precompute=1):
         import torch.distributed as dist
         self.ctx, self.g1, self.g2, self.field, self.num_inputs = ctx, g1, g2, field, num_inputs
         k2 = ffi.GROUP_K[g2]
@@ -137,7 +137,7 @@ class ShardedParameters(Parameters):
             b.precompute(64)
         self.aux = {}
         for name, (bases, lo) in shards.items():
-            if precompute and len(bases) >= 1 << 12:
+            if precompute is not None and precompute != 1 and len(bases) >= 1 << 12:
                 bases.precompute(precompute)
             self.aux[name] = (bases, 0, lo)
         self.delta_g1 = ffi.as_u64(delta_g1).reshape(1, 2 * LIMBS)

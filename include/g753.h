@@ -96,7 +96,8 @@ int g753_bases_free(g753_ctx* ctx, g753_bases* bases);
  * normalised to affine.  sum_i s_i bases[i] = (sum_i s_i a_i mod r) * G at any size. */
 int g753_bases_generate(g753_ctx* ctx, int group, const uint64_t* gen_xy, uint64_t seed, size_t n,
                         g753_bases** out);
-/* Optional, once per resident key: build `copies` (0 = default 8) tables 2^(j*shift) * P_i next to
+/* Optional, once per resident key: build `copies` (0 = as many as fit a 6 GiB per-key budget, at most
+ * 64) tables 2^(j*shift) * P_i next to
  * the key so that an MSM over (most of) it needs W/copies bucket rows instead of W: the bucket
  * reduction and the serial window fold of variable_base.rs:60-82 shrink accordingly.  Costs
  * copies x the key's memory and ~(copies-1) * 760 doublings per point, once; results of later
