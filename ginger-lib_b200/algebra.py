@@ -96,6 +96,23 @@ class Bases:
         return self.n
 
     @classmethod
+    def from_wire(cls, ctx, group, data):
+        """bases from the reference's serialisation (`GroupAffine::write`: x || y || infinity byte,
+        canonical little-endian coordinates) - the proving-key loader of SURVEY.md 8f-2"""
+        k = ffi.GROUP_K[group]
+        rec = 2 * k * 96 + 1
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        if buf.size % rec:
+            raise ValueError("wire data is not a whole number of %d-byte points" % rec)
+        self = cls.__new__(cls)
+        self.ctx, self.group, self.k, self.n = ctx, group, k, buf.size // rec
+        h = ctypes.c_void_p()
+        ctx.lib.check(ctx.lib.bases_upload_wire(ctx.handle, group, ffi.ptr(np.ascontiguousarray(buf)), self.n,
+                                                ctypes.byref(h)))
+        self.handle = h
+        return self
+
+    @classmethod
     def generate(cls, ctx, group, n, seed):
         from . import params
         self = cls.__new__(cls)

@@ -33,6 +33,33 @@ __global__ void k_bases_sanitize(Fq* __restrict__ bases, const uint8_t* __restri
   }
 }
 
+// Proving-key loader: the reference's wire format of an affine point is
+// x || y || infinity (GroupAffine::write, curves/models/short_weierstrass_projective.rs:185-192), each
+// coordinate element as its CANONICAL integer, 12 little-endian u64 = 96 bytes (Fp768::write,
+// fields/models/fp_768.rs:784-789; bytes.rs:70-78), the flag one byte (bytes.rs:220-225).  One
+// thread per base-field element: gather the 96 unaligned bytes, convert to Montgomery form
+// (from_repr, fp_768.rs:627-635) and store into the resident layout.
+template <int FID>
+__global__ void __launch_bounds__(128)
+k_bases_from_wire(const uint8_t* __restrict__ wire, unsigned n, unsigned fq_per_point, Fq* __restrict__ out,
+                  uint8_t* __restrict__ inf) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * fq_per_point) return;
+  const unsigned i = (unsigned)(t / fq_per_point), e = (unsigned)(t % fq_per_point);
+  const size_t rec = (size_t)fq_per_point * 96 + 1;
+  const uint8_t* src = wire + (size_t)i * rec + (size_t)e * 96;
+  Fq v;
+#pragma unroll
+  for (int w = 0; w < NL; w++)
+    v.l[w] = (uint32_t)src[4 * w] | ((uint32_t)src[4 * w + 1] << 8) | ((uint32_t)src[4 * w + 2] << 16) |
+             ((uint32_t)src[4 * w + 3] << 24);
+  const bool is_inf = wire[(size_t)i * rec + rec - 1] != 0;
+  if (is_inf) v = fq_zero<FID>();   // infinite bases are stored as (0, 0), see k_bases_sanitize
+  else v = fq_to_mont<FID>(v);
+  out[t] = v;
+  if (e == 0) inf[i] = is_inf ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------
 // dispatch helpers
 // ------------------------------------------------------------------------------------
@@ -407,6 +434,48 @@ int g753_bases_upload(g753_ctx* ctx, int group, const uint64_t* coords, const ui
     }
   }
   if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  if (rc != G753_OK) {
+    dev_free(b->d_points);
+    dev_free(b->d_inf);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return G753_OK;
+}
+
+int g753_bases_upload_wire(g753_ctx* ctx, int group, const uint8_t* wire, size_t n, g753_bases** out) {
+  CHECK_CTX(ctx);
+  if (!out) return fail(G753_ERR_BAD_ARG, "null out");
+  *out = nullptr;
+  const int k = group_k(group);
+  if (k == 0) return fail(G753_ERR_BAD_ARG, "unknown group");
+  if (n && !wire) return fail(G753_ERR_BAD_ARG, "null data");
+  if (n > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "too many bases");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  g753_bases* b = new (std::nothrow) g753_bases();
+  if (!b) return fail(G753_ERR_OOM, "host allocation failed");
+  b->group = group;
+  b->n = n;
+  const size_t rec = (size_t)2 * k * 96 + 1;
+  uint8_t* d_wire = nullptr;
+  int rc = dev_alloc(&b->d_points, (size_t)2 * k * 96 * n);
+  if (rc == G753_OK) rc = dev_alloc((void**)&b->d_inf, n ? n : 1);
+  if (rc == G753_OK && n) rc = dev_alloc((void**)&d_wire, rec * n);
+  if (rc == G753_OK && n) rc = h2d(d_wire, wire, rec * n, ctx->stream);
+  if (rc == G753_OK && n) {
+    const bool mnt4 = (group == G753_MNT4_G1 || group == G753_MNT4_G2);   // base field id = 0 for MNT4
+    if (mnt4)
+      G753_LAUNCH(k_bases_from_wire<0>, div_up(n * 2 * k, 128), 128, ctx->stream, d_wire, (unsigned)n, (unsigned)(2 * k),
+                  (Fq*)b->d_points, b->d_inf);
+    else
+      G753_LAUNCH(k_bases_from_wire<1>, div_up(n * 2 * k, 128), 128, ctx->stream, d_wire, (unsigned)n, (unsigned)(2 * k),
+                  (Fq*)b->d_points, b->d_inf);
+    ctx->launches++;
+    rc = launch_check("k_bases_from_wire");
+  }
+  if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  dev_free(d_wire);
   if (rc != G753_OK) {
     dev_free(b->d_points);
     dev_free(b->d_inf);

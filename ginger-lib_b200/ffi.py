@@ -31,6 +31,7 @@ SYMBOLS = [
     ("g753_last_error", ctypes.c_char_p, []),
     ("g753_version", ctypes.c_char_p, []),
     ("g753_bases_upload", _i, [_vp, _i, _vp, _vp, _sz, _pvp]),
+    ("g753_bases_upload_wire", _i, [_vp, _i, _vp, _sz, _pvp]),
     ("g753_bases_free", _i, [_vp, _vp]),
     ("g753_bases_len", _sz, [_vp]),
     ("g753_bases_generate", _i, [_vp, _i, _vp, ctypes.c_uint64, _sz, _pvp]),

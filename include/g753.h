@@ -89,6 +89,12 @@ const char* g753_version(void);
  * proof-systems/src/groth16/mod.rs:313-371); they stay resident in HBM. */
 int g753_bases_upload(g753_ctx* ctx, int group, const uint64_t* coords, const uint8_t* infinity,
                       size_t n, g753_bases** out);
+/* same from the reference's WIRE format (Parameters::read / GroupAffine::read, proof-systems/src/
+ * groth16/mod.rs:211-239, curves/models/short_weierstrass_projective.rs:185-202): n records of
+ * x || y || infinity, every coordinate element 96 bytes canonical little-endian (fp_768.rs:784-789),
+ * the flag one byte; the conversion to Montgomery form runs on the device.  No curve check, as
+ * `read_affine_vec(len, false, ..)` does none. */
+int g753_bases_upload_wire(g753_ctx* ctx, int group, const uint8_t* wire, size_t n, g753_bases** out);
 int g753_bases_free(g753_ctx* ctx, g753_bases* bases);
 /* synthetic key for benchmarks / full-size parity checks: bases[i] = a_i * G on the
  * device, a_i = splitmix64(seed + (i+1) * 0x9E3779B97F4A7C15) | 1 (64 bits), G = gen_xy (affine,

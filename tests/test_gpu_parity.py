@@ -371,3 +371,29 @@ def test_mixed_radix_ntt_full_size_properties(ctx, field, n):
     for k in (0, 1, 2, 12345, n - 1):
         x = pow(w, k, p)
         assert ev[k] == sum(c * pow(x, i, p) for i, c in enumerate(coeffs)) % p
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_bases_from_wire_format(ctx, group):
+    """SURVEY.md 8f-2, proving-key loader: GroupAffine::write records (x || y || infinity byte, canonical
+    little-endian) are converted to the resident Montgomery layout on the device"""
+    from util753 import sample_points
+    C = GROUPS[group]
+    k = C.F.k
+    pts = sample_points(C, 9, 0x3C0 + group)
+    pts[4] = None
+    wire = b""
+    for P in pts:
+        if P is None:
+            wire += O.int_to_bytes96(0) * k + O.int_to_bytes96(1) + O.int_to_bytes96(0) * (k - 1) + b"\x01"
+        else:
+            wire += b"".join(O.int_to_bytes96(c) for c in P[0]) + b"".join(O.int_to_bytes96(c) for c in P[1]) + b"\x00"
+    bases = G.Bases.from_wire(ctx, group, wire)
+    coords, inf = points_to_arrays(C, pts)
+    ref = ctx.upload_bases(group, coords, inf)
+    assert (bases.download() == ref.download()).all()
+    sc = sample_scalars(C, 9, 0x3D0 + group)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    bases.free()
+    ref.free()

@@ -301,3 +301,30 @@ def test_msm_affine_accumulation(ctx, monkeypatch, group):
     bases.free()
     b2.free()
     cx.close()
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_bases_from_wire_format(ctx, group):
+    """proving-key loader: the reference's serialisation of affine points (x || y || infinity byte,
+    canonical little-endian 96-byte elements; byte order pinned by the reference's *_tobyte fixtures
+    through oracle.int_to_bytes96) lands in the same resident layout as the limb upload"""
+    C = GROUPS[group]
+    k = C.F.k
+    pts = sample_points(C, 6, 0x3C0 + group)
+    pts[2] = None
+    wire = b""
+    for P in pts:
+        if P is None:
+            wire += O.int_to_bytes96(0) * k + O.int_to_bytes96(1) + O.int_to_bytes96(0) * (k - 1) + b"\x01"   # zero() = (0, 1, true)
+        else:
+            wire += b"".join(O.int_to_bytes96(c) for c in P[0]) + b"".join(O.int_to_bytes96(c) for c in P[1]) + b"\x00"
+    bases = G.Bases.from_wire(ctx, group, wire)
+    coords, inf = points_to_arrays(C, pts)
+    ref = ctx.upload_bases(group, coords, inf)
+    assert len(bases) == 6
+    assert (bases.download() == ref.download()).all()
+    sc = sample_scalars(C, 6, 0x3D0 + group)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    bases.free()
+    ref.free()
