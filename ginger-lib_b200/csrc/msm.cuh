@@ -529,6 +529,63 @@ k_reduce_level(const Fq* __restrict__ X, size_t x_stride, const Fq* __restrict__
   E::stg(Yout + (size_t)t * E::PT, ACC);
 }
 
+// ---- reduction tail ----------------------------------------------------------------------------
+// Once a row is down to n_in <= REDUCE_TAIL_MAX entries the remaining running-sum levels are pure
+// latency (a dozen serial additions per level on a handful of threads).  The tail computes
+//   G = sum_i Y_i + 2^log2f * sum_i i * X_i
+// by bit planes instead: S_t = sum_{i : bit t of i set} X_i for every bit t, and sum_i Y_i, each
+// by a pairwise tree (one addition of latency per halving, all planes and rows in one launch),
+// then 2^(t + log2f) S_t per plane in parallel and a last tree over the planes.
+constexpr unsigned REDUCE_TAIL_MAX = 16384;
+
+// first halving: T[(row * P + plane) * half + p] = masked X (or Y on the last plane) of entries 2p, 2p+1
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_tail_planes(const Fq* __restrict__ X, const Fq* __restrict__ Y, unsigned n_in, unsigned nbits, unsigned rows,
+              Fq* __restrict__ T) {
+  typedef EcS<SC> E;
+  const unsigned P = nbits + 1, half = (n_in + 1) / 2;
+  unsigned t = E::M::T::item();
+  if (t >= rows * P * half) return;
+  const unsigned p = t % half, plane = (t / half) % P, row = t / (half * P);
+  const Fq* x = (plane < nbits ? X : Y) + (size_t)row * n_in * E::PT;
+  E::set_inf(0);
+  for (unsigned k = 0; k < 2; k++) {
+    const unsigned i = 2 * p + k;
+    if (i < n_in && (plane == nbits || ((i >> plane) & 1))) E::add_g(0, x + (size_t)i * E::PT, E::PT);
+  }
+  E::stg(T + (size_t)t * E::PT, 0);
+}
+// out[g * half + p] = in[g * m_in + 2p] + in[g * m_in + 2p + 1]
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_pair_sum(const Fq* __restrict__ in, unsigned groups, unsigned m_in, Fq* __restrict__ out) {
+  typedef EcS<SC> E;
+  const unsigned half = (m_in + 1) / 2;
+  unsigned t = E::M::T::item();
+  if (t >= groups * half) return;
+  const unsigned p = t % half, g = t / half;
+  const Fq* x = in + (size_t)g * m_in * E::PT;
+  E::set_inf(0);
+  E::add_g(0, x + (size_t)(2 * p) * E::PT, E::PT);
+  if (2 * p + 1 < m_in) E::add_g(0, x + (size_t)(2 * p + 1) * E::PT, E::PT);
+  E::stg(out + (size_t)t * E::PT, 0);
+}
+// Z[row * P + plane] = 2^(plane + log2f) * S[row * P + plane] (the Y plane, plane == nbits, is copied)
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_tail_scale(const Fq* __restrict__ S, unsigned nbits, unsigned rows, unsigned log2f, Fq* __restrict__ Z) {
+  typedef EcS<SC> E;
+  const unsigned P = nbits + 1;
+  unsigned t = E::M::T::item();
+  if (t >= rows * P) return;
+  const unsigned plane = t % P;
+  E::ldg(0, S + (size_t)t * E::PT);
+  if (plane < nbits)
+    for (unsigned k = 0; k < plane + log2f; k++) E::dbl(0, E::PT);
+  E::stg(Z + (size_t)t * E::PT, 0);
+}
+
 // Horner fold over the W window sums (stride between windows given, in points), then convert
 // to the reference's homogeneous projective layout.  One thread: W*c doublings are a serial chain.
 template <class SC>
@@ -575,6 +632,7 @@ k_points_sum(const Fq* __restrict__ pts, unsigned count, Fq* __restrict__ out_xy
 // ------------------------------------------------------------------------------------
 struct MsmWorkspace {
   unsigned n_chunks, nb_chunks, level_entries, max_items;
+  size_t tail_points;  // points per ping-pong buffer of the reduction tail
   size_t row_cap;  // entries per row of sorted[]
   size_t total;
 };
@@ -596,6 +654,18 @@ static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n, bool affin
   }
   if (entries == 0) entries = 1;
   s.level_entries = entries;
+  // reduction tail: two ping-pong buffers of rows x (bits + 1) planes x ceil(n_in / 2) points, n_in being
+  // the first level size <= REDUCE_TAIL_MAX (at least one running-sum level always runs first)
+  s.tail_points = 0;
+  {
+    size_t m = div_up(len, REDUCE_SEG);
+    while (m > REDUCE_TAIL_MAX) m = div_up(m, REDUCE_SEG);
+    if (m > 1) {
+      unsigned nbits = 0;
+      while (((size_t)1 << nbits) < m) nbits++;
+      s.tail_points = (size_t)pl.rows * (nbits + 1) * ((m + 1) / 2);
+    }
+  }
   size_t t = 0;
   t += Carver::pad(sizeof(uint32_t) * pl.W * n);                        // digits
   t += Carver::pad(sizeof(uint32_t) * pl.rows * s.row_cap);             // sorted
@@ -607,6 +677,7 @@ static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n, bool affin
   t += Carver::pad(sizeof(uint32_t) * s.max_items);                     // item id -> bucket
   t += Carver::pad(PT_BYTES * (NB + s.max_items));                      // buckets + item partials
   t += Carver::pad(PT_BYTES * pl.rows * entries) * 2;                   // reduction levels
+  t += Carver::pad(PT_BYTES * (s.tail_points + 1)) * 2;                 // reduction tail
   if (affine)                                                            // accumulators + prefix products
     t += Carver::pad((size_t)div_up(div_up(s.max_items, AFF_G), MsmCfg<GID>::NC_ACC) * MsmCfg<GID>::NC_ACC * AFF_G *
                      AFF_GSLOTS * sizeof(Fq));
@@ -710,6 +781,8 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   Fq* points = cv.take<Fq>(PT * ((size_t)NB + ws.max_items));
   Fq* lvl_r = cv.take<Fq>(PT * R * ws.level_entries);
   Fq* lvl_y = cv.take<Fq>(PT * R * ws.level_entries);
+  Fq* tail_a = cv.take<Fq>(PT * (ws.tail_points + 1));
+  Fq* tail_b = cv.take<Fq>(PT * (ws.tail_points + 1));
   const unsigned aff_blocks = div_up(div_up(ws.max_items, AFF_G), CA);
   uint4* aff_scratch = affine ? (uint4*)cv.take<Fq>((size_t)aff_blocks * CA * AFF_G * AFF_GSLOTS) : nullptr;
 
@@ -775,6 +848,42 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
     log2f += REDUCE_SEG_LOG;
     if (n_out == 1) {
       window_sums = Yo;
+      break;
+    }
+    if (n_out <= REDUCE_TAIL_MAX) {
+      // tail: bit planes + pairwise trees (see k_tail_planes)
+      unsigned nbits = 0;
+      while ((1u << nbits) < n_out) nbits++;
+      const unsigned P = nbits + 1;
+      unsigned m = div_up(n_out, 2);
+      G753_MSM_LAUNCH_SMEM(hooks, k_tail_planes<SCR>, div_up((size_t)R * P * m, CR), TR, SMEM_RED, stream, X, Y, n_out,
+                           nbits, R, tail_a);
+      Fq *cur = tail_a, *oth = tail_b;
+      while (m > 1) {
+        G753_MSM_LAUNCH_SMEM(hooks, k_pair_sum<SCR>, div_up((size_t)R * P * div_up(m, 2), CR), TR, SMEM_RED, stream, cur,
+                             R * P, m, oth);
+        m = div_up(m, 2);
+        Fq* t2 = cur;
+        cur = oth;
+        oth = t2;
+      }
+      G753_MSM_LAUNCH_SMEM(hooks, k_tail_scale<SCR>, div_up((size_t)R * P, CR), TR, SMEM_RED, stream, cur, nbits, R, log2f,
+                           oth);
+      {
+        Fq* t2 = cur;
+        cur = oth;
+        oth = t2;
+      }
+      m = P;
+      while (m > 1) {
+        G753_MSM_LAUNCH_SMEM(hooks, k_pair_sum<SCR>, div_up((size_t)R * div_up(m, 2), CR), TR, SMEM_RED, stream, cur, R, m,
+                             oth);
+        m = div_up(m, 2);
+        Fq* t2 = cur;
+        cur = oth;
+        oth = t2;
+      }
+      window_sums = cur;
       break;
     }
   }
