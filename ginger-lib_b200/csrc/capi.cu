@@ -376,6 +376,9 @@ int g753_ctx_create(int device, g753_ctx** out) {
   ctx->ev_ok = true;
   for (int i = 0; i <= MSM_PHASES; i++)
     if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) ctx->ev_ok = false;
+  ctx->copy_ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < g753_ctx::MAX_CHUNKS && ctx->copy_ok; i++)
+    if (cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) ctx->copy_ok = false;
 #endif
   const char* fc = getenv("G753_MSM_C");
   if (fc) ctx->forced_c = atoi(fc);
@@ -398,6 +401,10 @@ int g753_ctx_destroy(g753_ctx* ctx) {
 #if !defined(G753_HOST_EMUL)
   if (ctx->ev_ok)
     for (int i = 0; i <= MSM_PHASES; i++) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->copy_ok) {
+    for (int i = 0; i < g753_ctx::MAX_CHUNKS; i++) cudaEventDestroy(ctx->chunk_ev[i]);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
 #endif
   delete ctx;
@@ -640,8 +647,33 @@ int g753_msm(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, con
   Carver cv(ctx->scratch_io.ptr);
   uint32_t* d_scalars = cv.take<uint32_t>(count * NL);
   uint32_t* d_out = cv.take<uint32_t>(out_bytes / 4);
-  if (count) G753_TRY(h2d(d_scalars, scalars, count * 96, ctx->stream));
-  G753_TRY(msm_any(ctx, b, first, count, d_scalars, d_out));
+#if !defined(G753_HOST_EMUL)
+  // upload the scalars in pieces on the copy stream; the digit extraction of piece j waits for
+  // piece j only, so the transfer overlaps the start of the pipeline
+  unsigned chunks = 1;
+  if (ctx->copy_ok && count >= ((size_t)1 << 18)) chunks = g753_ctx::MAX_CHUNKS;
+  if (chunks > 1) {
+    cudaEvent_t ready;
+    if (cudaEventCreateWithFlags(&ready, cudaEventDisableTiming) == cudaSuccess) {
+      cudaEventRecord(ready, ctx->stream);              // the staging buffer is free once earlier work is done
+      cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
+      cudaEventDestroy(ready);
+    }
+    for (unsigned j = 0; j < chunks; j++) {
+      const size_t lo = count * j / chunks, hi = count * (j + 1) / chunks;
+      G753_TRY(h2d((char*)d_scalars + lo * 96, (const char*)scalars + lo * 96, (hi - lo) * 96, ctx->copy_stream));
+      cudaEventRecord(ctx->chunk_ev[j], ctx->copy_stream);
+    }
+    ctx->scalar_chunks = chunks;
+    int rc = msm_any(ctx, b, first, count, d_scalars, d_out);
+    ctx->scalar_chunks = 1;
+    G753_TRY(rc);
+  } else
+#endif
+  {
+    if (count) G753_TRY(h2d(d_scalars, scalars, count * 96, ctx->stream));
+    G753_TRY(msm_any(ctx, b, first, count, d_scalars, d_out));
+  }
   G753_TRY(d2h(out_xyz, d_out, out_bytes, ctx->stream));
   G753_TRY(stream_sync(ctx->stream));
   return G753_OK;

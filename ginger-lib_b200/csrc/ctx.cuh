@@ -36,9 +36,14 @@ struct g753_ctx {
   int forced_c = 0;
   int forced_affine = -1;  // G753_MSM_AFFINE: 0 / 1 force the accumulation kernel, unset = by size
   std::mutex mu;
+  unsigned scalar_chunks = 1;  // > 1 while g753_msm feeds the scalars of the running MSM in pieces
 #if !defined(G753_HOST_EMUL)
   cudaEvent_t ev[MSM_PHASES + 1];
   bool ev_ok = false;
+  enum { MAX_CHUNKS = 8 };
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ev[MAX_CHUNKS];
+  bool copy_ok = false;
 #endif
 };
 
@@ -69,6 +74,11 @@ static inline int use_device(g753_ctx* ctx) {
 static inline void phase_mark(void* user, int phase) {
   g753_ctx* ctx = (g753_ctx*)user;
   if (ctx->ev_ok && phase <= MSM_PHASES) cudaEventRecord(ctx->ev[phase], ctx->stream);
+}
+static inline void chunk_wait(void* user, int chunk) {
+  g753_ctx* ctx = (g753_ctx*)user;
+  if (ctx->copy_ok && ctx->scalar_chunks > 1 && chunk < g753_ctx::MAX_CHUNKS)
+    cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[chunk], 0);
 }
 #else
 static inline int use_device(g753_ctx*) { return G753_OK; }

@@ -116,11 +116,12 @@ static inline MsmPlan msm_plan(size_t n, unsigned copies = 1, int forced_c = 0, 
 // ------------------------------------------------------------------------------------
 // window w = j * rows + r: histogram row r; inf (may be null) holds one flag per (copy, point):
 // inf[j * inf_stride + i]
+// handles scalars [first, last) of the n (chunks let the upload of the next scalars overlap)
 static __global__ void k_msm_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ inf,
-                             size_t inf_stride, unsigned n, unsigned c, unsigned W, unsigned B, unsigned rows,
-                             uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                             size_t inf_stride, unsigned n, unsigned first, unsigned last, unsigned c, unsigned W,
+                             unsigned B, unsigned rows, uint32_t* __restrict__ digits, uint32_t* __restrict__ hist) {
+  unsigned i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= last) return;
   const uint32_t* s = scalars + (size_t)i * NL;
   const uint32_t half = 1u << (c - 1);
   const uint32_t mask = (1u << c) - 1;
@@ -687,6 +688,8 @@ static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n, bool affin
 
 struct MsmHooks {  // phase timing hooks; the emulation build leaves them null
   void (*mark)(void* user, int phase) = nullptr;
+  void (*wait_chunk)(void* user, int chunk) = nullptr;  // order the stream after the upload of scalar chunk j
+  unsigned scalar_chunks = 1;
   void* user = nullptr;
   uint64_t* launches = nullptr;
 };
@@ -791,8 +794,18 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   G753_TRY(dev_memset(len_hist, 0, sizeof(uint32_t) * ITEM_LEN * ITEM_REP, stream));
   // empty buckets are never written by the accumulation: all-zero limbs = ZZ == 0 = infinity
   G753_TRY(dev_memset(points, 0, sizeof(Fq) * PT * NB, stream));
-  G753_MSM_LAUNCH(hooks, k_msm_digits, div_up(n, 256), 256, stream, d_scalars, key.inf, key.inf_stride, n, pl.c,
-                  pl.W, pl.B, R, digits, hist);
+  {
+    // scalar chunks: the host-buffer entry point uploads the scalars in pieces on a copy stream and
+    // makes this stream wait for piece j right before its digits are extracted
+    const unsigned chunks = hooks.scalar_chunks > 1 ? hooks.scalar_chunks : 1;
+    for (unsigned j = 0; j < chunks; j++) {
+      const unsigned lo = (unsigned)((uint64_t)n * j / chunks), hi = (unsigned)((uint64_t)n * (j + 1) / chunks);
+      if (hooks.wait_chunk) hooks.wait_chunk(hooks.user, (int)j);
+      if (hi > lo)
+        G753_MSM_LAUNCH(hooks, k_msm_digits, div_up(hi - lo, 256), 256, stream, d_scalars, key.inf, key.inf_stride, n, lo,
+                        hi, pl.c, pl.W, pl.B, R, digits, hist);
+    }
+  }
   if (hooks.mark) hooks.mark(hooks.user, 1);
   G753_MSM_LAUNCH(hooks, k_scan_chunks, div_up((size_t)R * ws.n_chunks, 128), 128, stream, hist,
                   (unsigned)len, ws.n_chunks, R, chunk_sums);

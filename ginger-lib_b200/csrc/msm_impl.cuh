@@ -14,6 +14,8 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
   hooks.launches = &ctx->launches;
 #if !defined(G753_HOST_EMUL)
   hooks.mark = phase_mark;
+  hooks.wait_chunk = chunk_wait;
+  hooks.scalar_chunks = ctx->scalar_chunks;
   hooks.user = ctx;
 #endif
   MsmKey key;
