@@ -177,6 +177,51 @@ static int shard_step1(g753_ctx* ctx, const g753_ntt_shard* p, Fq* data, Fq* sen
   return launch_check("shard_step1");
 }
 
+#if !defined(G753_HOST_EMUL)
+// step 1 with the exchange fused into the last butterfly pass (NttScatter): peer_z[h] is rank h's
+// row buffer Z (rows x n2 elements), mapped into this process
+template <int FID>
+static int shard_step1_fused(g753_ctx* ctx, const g753_ntt_shard* p, Fq* data, void* const* peer_z, int mode) {
+  const NttTables* T = nullptr;
+  G753_TRY(ntt_tables_get<FID>(ctx, p->log_n1, &T));
+  NttCall c;
+  c.inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
+  c.batch = (unsigned)p->cols;
+  if (mode == G753_COSET_FFT) {
+    c.pre = p->cp;
+    c.pre_stride = p->n1;
+  }
+  c.post = c.inverse ? p->t1i : p->t1f;
+  c.post_stride = p->n1;
+  NttScatter sc;
+  for (unsigned h = 0; h < 8; h++) sc.peer[h] = h < p->world ? (Fq*)peer_z[h] : nullptr;
+  sc.rows = (unsigned)p->rows;
+  sc.cols = (unsigned)p->cols;
+  sc.rank = p->rank;
+  sc.n2 = p->n2;
+  sc.enabled = 1;
+  c.scatter = &sc;
+  G753_TRY(ctx->scratch_io.reserve(sizeof(Fq) * p->cols * p->n1 + 1024));
+  return ntt_run<FID>(*T, ctx->stream, data, (Fq*)ctx->scratch_io.ptr, c, &ctx->launches);
+}
+#endif
+
+// step 2 on a row buffer that already holds Z[k1l][i2] (written by the peers' fused step 1)
+template <int FID>
+static int shard_step2_local(g753_ctx* ctx, const g753_ntt_shard* p, Fq* z, int mode) {
+  const NttTables* T = nullptr;
+  G753_TRY(ntt_tables_get<FID>(ctx, p->log_n2, &T));
+  NttCall c;
+  c.inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
+  c.batch = (unsigned)p->rows;
+  if (mode == G753_COSET_IFFT) {
+    c.post = p->cq;
+    c.post_stride = p->n2;
+  }
+  G753_TRY(ctx->scratch_io.reserve(sizeof(Fq) * p->rows * p->n2 + 1024));
+  return ntt_run<FID>(*T, ctx->stream, z, (Fq*)ctx->scratch_io.ptr, c, &ctx->launches);
+}
+
 template <int FID>
 static int shard_step2(g753_ctx* ctx, const g753_ntt_shard* p, const Fq* recv, Fq* data, int mode) {
   const NttTables* T = nullptr;
@@ -865,6 +910,31 @@ int g753_ntt_shard_step1(g753_ctx* ctx, const g753_ntt_shard* plan, void* d_data
   std::lock_guard<std::mutex> lock(ctx->mu);
   return plan->field == 0 ? shard_step1<0>(ctx, plan, (Fq*)d_data, (Fq*)d_send, mode)
                           : shard_step1<1>(ctx, plan, (Fq*)d_data, (Fq*)d_send, mode);
+}
+
+int g753_ntt_shard_step1_fused(g753_ctx* ctx, const g753_ntt_shard* plan, void* d_data, void* const* peer_z,
+                               int mode) {
+  CHECK_CTX(ctx);
+  if (!plan || !d_data || !peer_z) return fail(G753_ERR_BAD_ARG, "null pointer");
+  if (mode < G753_FFT || mode > G753_COSET_IFFT) return fail(G753_ERR_BAD_ARG, "unknown transform");
+#if defined(G753_HOST_EMUL)
+  return fail(G753_ERR_NO_DEVICE, "peer-memory exchange needs GPUs");
+#else
+  if (plan->world > 8 || plan->log_n1 == 0) return fail(G753_ERR_BAD_ARG, "fused exchange: 2..8 ranks, n1 >= 2");
+  for (unsigned h = 0; h < plan->world; h++)
+    if (!peer_z[h]) return fail(G753_ERR_BAD_ARG, "null peer buffer");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return plan->field == 0 ? shard_step1_fused<0>(ctx, plan, (Fq*)d_data, peer_z, mode)
+                          : shard_step1_fused<1>(ctx, plan, (Fq*)d_data, peer_z, mode);
+#endif
+}
+
+int g753_ntt_shard_step2_local(g753_ctx* ctx, const g753_ntt_shard* plan, void* d_z, int mode) {
+  CHECK_CTX(ctx);
+  if (!plan || !d_z) return fail(G753_ERR_BAD_ARG, "null pointer");
+  if (mode < G753_FFT || mode > G753_COSET_IFFT) return fail(G753_ERR_BAD_ARG, "unknown transform");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return plan->field == 0 ? shard_step2_local<0>(ctx, plan, (Fq*)d_z, mode) : shard_step2_local<1>(ctx, plan, (Fq*)d_z, mode);
 }
 
 int g753_ntt_shard_step2(g753_ctx* ctx, const g753_ntt_shard* plan, const void* d_recv, void* d_data, int mode) {

@@ -160,6 +160,16 @@ static int ntt_tables_build(NttTables& T, unsigned log_n, cudaStream_t stream, u
 // pre  (first pass): inputs are multiplied by pre[index]            (coset_fft: g^i)
 // post (last pass):  outputs are multiplied by post[index] or *post_const (ifft: n^-1,
 //                    coset_ifft: g^-i n^-1)
+// Fused exchange of the sharded four-step transform: the LAST pass of the column transforms stores
+// every output straight into its final place on the destination GPU (peer memory mapped over
+// NVLink), so the transpose + all-to-all costs no kernel and no collective call of its own.
+// Output k1 of column bi goes to rank h = k1 / rows, element (k1 % rows) * n2 + rank * cols + bi.
+struct NttScatter {
+  Fq* peer[8];
+  unsigned rows, cols, rank, enabled;
+  size_t n2;
+};
+
 constexpr int NTT_T = 128;            // threads per block = butterflies per stage per block
 constexpr int NTT_E = 2 * NTT_T;      // elements per block (columns x 2^q)
 constexpr unsigned NTT_MAX_Q = 8;     // 2^q <= NTT_E
@@ -222,7 +232,7 @@ template <int FID>
 __global__ void __launch_bounds__(NTT_T, 4)
 k_ntt_pass(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restrict__ tw, unsigned L, unsigned s,
            unsigned q, const Fq* __restrict__ pre, size_t pre_stride, const Fq* __restrict__ post,
-           size_t post_stride, const Fq* __restrict__ post_const) {
+           size_t post_stride, const Fq* __restrict__ post_const, const NttScatter sc) {
   extern __shared__ uint4 ntt_sm[];
   const unsigned tid = threadIdx.x;
   {  // blockIdx.y = index of the vector within a batch of equal-length transforms
@@ -280,8 +290,14 @@ k_ntt_pass(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restrict
           x = fq_mul<FID>(x, cst);
           y = fq_mul<FID>(y, cst);
         }
-        ntt_stg(out + o0, x);
-        ntt_stg(out + o1, y);
+        if (sc.enabled) {
+          const size_t col = (size_t)sc.rank * sc.cols + blockIdx.y;
+          ntt_stg(sc.peer[o0 / sc.rows] + (o0 % sc.rows) * sc.n2 + col, x);
+          ntt_stg(sc.peer[o1 / sc.rows] + (o1 % sc.rows) * sc.n2 + col, y);
+        } else {
+          ntt_stg(out + o0, x);
+          ntt_stg(out + o1, y);
+        }
       }
     }
     if (d + 1 < q) __syncthreads();
@@ -420,6 +436,7 @@ struct NttCall {
   size_t post_stride = 0;
   const Fq* post_const = nullptr;   // outputs *= *post_const (when post == nullptr)
   unsigned batch = 1;               // contiguous vectors of n elements each
+  const NttScatter* scatter = nullptr;  // last pass stores to peer memory instead (device build, log_n >= 1)
 };
 
 static inline NttCall ntt_call_for_mode(const NttTables& T, int mode) {
@@ -483,15 +500,19 @@ static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tm
     const size_t n_cols = n >> q;
     const unsigned cols_per_block = NTT_E >> q;
     dim3 grid(div_up(n_cols, cols_per_block), call.batch);
+    NttScatter sc;
+    sc.enabled = 0;
+    if (last && call.scatter) sc = *call.scatter;
     k_ntt_pass<FID><<<grid, NTT_T, NTT_SMEM, stream>>>(src, dst, tw, log_n, s, q, first ? call.pre : nullptr,
                                                        call.pre_stride, last ? call.post : nullptr, call.post_stride,
-                                                       last ? call.post_const : nullptr);
+                                                       last ? call.post_const : nullptr, sc);
     if (launches) ++*launches;
     s += q;
     Fq* t = src;
     src = dst;
     dst = t;
   }
+  if (call.scatter) return launch_check("ntt_run (scattered)");   // the results live in peer memory
 #endif
   if (src != d_data) G753_TRY(d2d(d_data, src, sizeof(Fq) * n * call.batch, stream));
   return launch_check("ntt_run");

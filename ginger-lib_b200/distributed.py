@@ -215,3 +215,47 @@ class ShardedEvaluationDomain:
         if getattr(self, "plan", None):
             self.ctx.lib.ntt_shard_destroy(self.ctx.handle, self.plan)
             self.plan = None
+
+
+class FusedShardedNTT:
+    """The sharded transform with the exchange fused into the compute kernel (NVLink peer memory).
+
+    Two row buffers per rank live in symmetric memory (`torch.distributed._symmetric_memory`: every
+    rank maps every peer's buffer).  A transform reads the current buffer, and the LAST butterfly pass
+    of its column transforms stores each output directly into the OTHER buffer of the destination
+    GPU, already in row order (`g753_ntt_shard_step1_fused`); one device-side barrier later the row
+    transforms run in place there (`g753_ntt_shard_step2_local`).  No pack / unpack kernels and no
+    collective call: the only cross-GPU traffic is the kernel's own stores.  Ping-ponging the two
+    buffers makes one barrier per transform sufficient when transforms chain (n1 == n2)."""
+
+    def __init__(self, dom, stream):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        self.torch, self.dom, self.stream = torch, dom, stream
+        dev = torch.device("cuda", dom.ctx.device)
+        group = dom.pg if dom.pg is not None else dom.dist.group.WORLD
+        self.bufs = [symm_mem.empty(dom.local * LIMBS, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.hdls = [symm_mem.rendezvous(b, group) for b in self.bufs]
+        self.peers = [(ctypes.c_void_p * dom.world)(*[int(h.buffer_ptrs[r]) for r in range(dom.world)]) for h in self.hdls]
+        self.cur = 0
+
+    def load(self, shard):
+        """host input shard (local, 12) -> the current buffer"""
+        t = self.torch.from_numpy(ffi.as_u64(shard).reshape(-1).view(np.int64).copy())
+        with self.torch.cuda.stream(self.stream):
+            self.bufs[self.cur].copy_(t, non_blocking=False)
+        self.stream.synchronize()
+
+    def store(self):
+        self.stream.synchronize()
+        return self.bufs[self.cur].cpu().numpy().view(np.uint64).reshape(self.dom.local, LIMBS)
+
+    def transform(self, mode):
+        lib, ctx, dom = self.dom.ctx.lib, self.dom.ctx, self.dom
+        src, dst = self.cur, 1 - self.cur
+        lib.check(lib.ntt_shard_step1_fused(ctx.handle, dom.plan, ctypes.c_void_p(self.bufs[src].data_ptr()),
+                                            self.peers[dst], mode))
+        with self.torch.cuda.stream(self.stream):
+            self.hdls[dst].barrier(channel=0)
+        lib.check(lib.ntt_shard_step2_local(ctx.handle, dom.plan, ctypes.c_void_p(self.bufs[dst].data_ptr()), mode))
+        self.cur = dst

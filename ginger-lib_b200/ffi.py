@@ -55,6 +55,8 @@ SYMBOLS = [
     ("g753_ntt_shard_shape", _i, [_vp, ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
     ("g753_ntt_shard_step1", _i, [_vp, _vp, _vp, _vp, _i]),
     ("g753_ntt_shard_step2", _i, [_vp, _vp, _vp, _vp, _i]),
+    ("g753_ntt_shard_step1_fused", _i, [_vp, _vp, _vp, _vp, _i]),
+    ("g753_ntt_shard_step2_local", _i, [_vp, _vp, _vp, _i]),
     ("g753_vec_op_dev", _i, [_vp, _i, _i, _vp, _vp, _sz]),
     ("g753_vec_scale_dev", _i, [_vp, _i, _vp, _vp, _sz]),
     ("g753_witness_map", _i, [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp]),

@@ -184,6 +184,15 @@ int g753_ntt_shard_destroy(g753_ctx* ctx, g753_ntt_shard* plan);
 int g753_ntt_shard_shape(const g753_ntt_shard* plan, size_t* n1, size_t* n2, size_t* cols, size_t* rows);
 int g753_ntt_shard_step1(g753_ctx* ctx, const g753_ntt_shard* plan, void* d_data, void* d_send, int mode);
 int g753_ntt_shard_step2(g753_ctx* ctx, const g753_ntt_shard* plan, const void* d_recv, void* d_data, int mode);
+/* Fused compute + exchange over peer memory (NVLink / NVSwitch P2P): peer_z[h] (host array of `world`
+ * device pointers) is rank h's row buffer of rows*n2 elements mapped into this process (CUDA IPC /
+ * symmetric memory).  step1_fused runs the column transforms and its LAST butterfly pass stores every
+ * output, twiddled, straight into its final place Z[k1l][rank*cols + i2l] on the destination GPU: no
+ * pack kernel, no collective call, no unpack.  After a cross-rank barrier step2_local transforms the
+ * rows of this rank's Z in place (the output shard).  2..8 ranks. */
+int g753_ntt_shard_step1_fused(g753_ctx* ctx, const g753_ntt_shard* plan, void* d_data, void* const* peer_z,
+                               int mode);
+int g753_ntt_shard_step2_local(g753_ctx* ctx, const g753_ntt_shard* plan, void* d_z, int mode);
 
 /* R1CStoQAP::witness_map from the evaluated constraints onwards (proof-systems/src/groth16/
  * r1cs_to_qap.rs:121-166): a, b, c = the n = 2^log_n evaluations <A_i,z>, <B_i,z>, <C_i,z> padded as
