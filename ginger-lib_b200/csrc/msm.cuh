@@ -37,7 +37,7 @@ constexpr unsigned SCAN_CHUNK = 256;
 constexpr unsigned REDUCE_SEG_LOG = 3;     // running-sum segment = 8 buckets: short serial chains, more levels
 constexpr unsigned REDUCE_SEG = 1u << REDUCE_SEG_LOG;
 constexpr unsigned MSM_MAX_C = 20;
-constexpr unsigned ITEM_LEN = 64;          // longest run one thread accumulates
+constexpr unsigned ITEM_LEN = 128;         // longest run one thread accumulates
 constexpr unsigned ITEM_REP = 16;          // replicated length counters (spreads the atomics)
 
 // per-group launch shapes: NC_* columns (curve operations) per block, TP lanes per column; chosen so

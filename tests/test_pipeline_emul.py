@@ -98,11 +98,11 @@ def test_msm_heavy_buckets(ctx, group):
 
 
 def test_msm_very_heavy_bucket_tree_fixup(ctx):
-    """one bucket holding 700 points (11 work items): the partial sums are joined by the in-place
-    tree of k_bucket_fixup_level over two levels"""
+    """one bucket holding 1300 points (11 work items of <= 128): the partial sums are joined by the
+    in-place tree of k_bucket_fixup_level over two levels"""
     C = O.MNT4_G1
     base = sample_points(C, 5, 0x99)
-    n = 700
+    n = 1300
     pts = [base[i % 5] for i in range(n)]
     sc = [3] * n
     sc[10] = C.r - 3
