@@ -370,6 +370,8 @@ def run_ours(args):
                                 "peak": peak_mac_per_s / 1e12, "unit": "Tlimb-MAC/s",
                                 "frac": muls * LIMB_MACS_PER_MUL / (fft_ms * 1e-3) / peak_mac_per_s}}
         vec.free()
+        if world > 1:
+            fft["sharded"] = sharded_fft(ctx, stream, ffi, args.fft_log_n, world, max(args.steps, 5))
 
     # ---- CPU baseline beside it (rank 0, N = 1): same bases / scalars, bounded sample ------
     cpu = None
@@ -452,6 +454,53 @@ def run_ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_fft(ctx, stream, ffi, log_n, world, reps):
+    """the 2^log_n transform sharded over all ranks (four-step): exchange fused into the
+    last butterfly pass over peer memory when symmetric memory is available, else NCCL all-to-all.
+    Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    D = importlib.import_module("ginger-lib_b200.distributed")
+    field = ffi.FIELD_MNT4_FR
+    n = 1 << log_n
+    dom = D.ShardedEvaluationDomain(ctx, field, log_n)
+    raw = random_scalars(dom.local, 123)
+    raw[:, 11] &= np.uint64(0xFFFF)
+    dev = torch.device("cuda", ctx.device)
+    path = "fused: last butterfly pass stores into peer memory (symmetric memory over NVLink), one barrier"
+    try:
+        fused = D.FusedShardedNTT(dom, stream)
+        fused.load(raw)
+        one = lambda: fused.transform(ffi.FFT)
+    except Exception as ex:                                   # no symmetric memory on this box / build
+        path = "NCCL all_to_all_single between the column and row passes (%s)" % type(ex).__name__
+        with torch.cuda.stream(stream):
+            t_data = torch.from_numpy(raw.view(np.int64).reshape(-1).copy()).to(dev)
+            t_send, t_recv = torch.empty_like(t_data), torch.empty_like(t_data)
+        stream.synchronize()
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+
+        def exchange():
+            with torch.cuda.stream(stream):
+                dist.all_to_all_single(t_recv, t_send)
+        one = lambda: dom.transform_dev(p(t_data), p(t_send), p(t_recv), ffi.FFT, exchange)
+    for _ in range(3):
+        one()
+    stream.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        one()
+    e1.record(stream)
+    stream.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"n_gpus": world, "log_n": log_n, "ms": ms, "value": n / (ms * 1e-3), "unit": "elements/s", "exchange": path,
+            "exchange_bytes_per_rank": (n // world) * 96 * (world - 1) // world}
 
 
 def run_config4(ctx, G, ffi, params, args):
