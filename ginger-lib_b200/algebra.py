@@ -196,6 +196,25 @@ class VariableBaseMSM:
         return out
 
 
+class FixedBaseMSM:
+    """algebra/src/msm/fixed_base.rs:4-80 with the normalisation the key generator applies to its
+    results (groth16/generator.rs:225-319): `multi_scalar_mul(group, base, scalars)` returns the affine
+    points scalars[i] * base, (n, 2*k*12) Montgomery limbs + infinity flags."""
+
+    @staticmethod
+    def multi_scalar_mul(group, base_xy, scalars, ctx=None):
+        ctx = ctx or default_context()
+        k = ffi.GROUP_K[group]
+        base = ffi.as_u64(base_xy).reshape(2 * k * LIMBS)
+        scalars = ffi.as_u64(scalars).reshape(-1, LIMBS)
+        n = scalars.shape[0]
+        out = np.zeros((n, 2 * k * LIMBS), dtype=np.uint64)
+        inf = np.zeros(n, dtype=np.uint8)
+        ctx.lib.check(ctx.lib.fixed_base_msm(ctx.handle, group, ffi.ptr(base), ffi.ptr(scalars), n, ffi.ptr(out),
+                                             ffi.ptr(inf)))
+        return out, inf
+
+
 class EvaluationDomain:
     """algebra/src/fft/domain.rs:24-179 for the two 753-bit scalar fields.
 

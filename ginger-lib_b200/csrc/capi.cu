@@ -767,6 +767,22 @@ int g753_batch_normalize(g753_ctx* ctx, int group, const uint64_t* xyz, size_t c
   return fail(G753_ERR_BAD_ARG, "unknown group");
 }
 
+int g753_fixed_base_msm(g753_ctx* ctx, int group, const uint64_t* base_xy, const uint64_t* scalars, size_t n,
+                        uint64_t* out_xy, uint8_t* out_infinity) {
+  CHECK_CTX(ctx);
+  if (!base_xy || (n && (!scalars || !out_xy || !out_infinity))) return fail(G753_ERR_BAD_ARG, "null pointer");
+  if (n > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "too many scalars");
+  if (n == 0) return G753_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  switch (group) {
+    case G753_MNT4_G1: return fixed_base_impl<0>(ctx, base_xy, scalars, n, out_xy, out_infinity);
+    case G753_MNT4_G2: return fixed_base_impl<1>(ctx, base_xy, scalars, n, out_xy, out_infinity);
+    case G753_MNT6_G1: return fixed_base_impl<2>(ctx, base_xy, scalars, n, out_xy, out_infinity);
+    case G753_MNT6_G2: return fixed_base_impl<3>(ctx, base_xy, scalars, n, out_xy, out_infinity);
+  }
+  return fail(G753_ERR_BAD_ARG, "unknown group");
+}
+
 // ---- NTT ---------------------------------------------------------------------------------
 int g753_domain_check(int field, unsigned log_n) {
   if (field != 0 && field != 1) return fail(G753_ERR_BAD_ARG, "unknown field");

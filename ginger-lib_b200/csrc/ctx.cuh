@@ -105,3 +105,6 @@ template <int GID>
 int bases_precompute_impl(g753_ctx* ctx, g753_bases* b, unsigned copies);
 template <int GID>
 int batch_normalize_impl(g753_ctx* ctx, const uint64_t* xyz, size_t count, uint64_t* xy, uint8_t* infinity);
+template <int GID>
+int fixed_base_impl(g753_ctx* ctx, const uint64_t* base_xy, const uint64_t* scalars, size_t n, uint64_t* out_xy,
+                    uint8_t* out_inf);

@@ -299,10 +299,139 @@ int batch_normalize_impl(g753_ctx* ctx, const uint64_t* xyz, size_t count, uint6
   return stream_sync(ctx->stream);
 }
 
+// FixedBaseMSM (algebra/src/msm/fixed_base.rs:6-80) + batch_normalization + into_affine
+// (proof-systems/src/groth16/generator.rs:225-319 computes every query of a key this way): out[i] =
+// scalars[i] * G in affine form.  The window table (8-bit windows: entry (w, j) = j * 2^(8w) * G, affine)
+// is built per call on the device; the reference picks its window from the number of scalars
+// (fixed_base.rs:7-13) - the resulting points do not depend on it.
+constexpr unsigned FB_WINDOW = 8, FB_WINDOWS = (SCALAR_BITS + FB_WINDOW - 1) / FB_WINDOW, FB_ENTRIES = (1u << FB_WINDOW) - 1;
+
+// window bases: wb[w] = 2^(8 w) * G, affine (one serial chain of 8 doublings per window)
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_fb_bases(const Fq* __restrict__ g, Fq* __restrict__ wb) {
+  typedef EcS<SC> E;
+  typedef typename E::M M;
+  constexpr int K = E::K, P = 0, S = E::PT;
+  if (E::M::T::item() != 0) return;
+  E::set_inf(P);
+  E::madd_g(P, g, false, S);
+  for (unsigned w = 0; w < FB_WINDOWS; w++) {
+    Fq* o = wb + (size_t)w * 2 * K;
+    if (E::is_inf(P)) {
+      M::set_zero(S);
+      M::stg(o, S);
+      M::stg(o + K, S);
+    } else {
+      E::to_affine(P, S);
+      M::stg(o, P);
+      M::stg(o + K, P + K);
+    }
+    for (unsigned k = 0; k < FB_WINDOW; k++) E::dbl(P, S);
+  }
+}
+// table[w * FB_ENTRIES + j - 1] = j * wb[w], affine: one thread per window, running sum
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_fb_rows(const Fq* __restrict__ wb, Fq* __restrict__ table) {
+  typedef EcS<SC> E;
+  typedef typename E::M M;
+  constexpr int K = E::K, P = 0, Q = E::PT, S = 2 * E::PT;
+  unsigned w = E::M::T::item();
+  if (w >= FB_WINDOWS) return;
+  const Fq* base = wb + (size_t)w * 2 * K;
+  M::ldg(S, base);
+  M::ldg(S + K, base + K);
+  const bool base_inf = M::is_zero(S) && M::is_zero(S + K);
+  E::set_inf(P);
+  for (unsigned j = 1; j <= FB_ENTRIES; j++) {
+    Fq* o = table + ((size_t)w * FB_ENTRIES + j - 1) * 2 * K;
+    if (!base_inf) E::madd_g(P, base, false, S);
+    if (E::is_inf(P)) {
+      M::set_zero(S);
+      M::stg(o, S);
+      M::stg(o + K, S);
+      continue;
+    }
+    E::copy(Q, P);
+    E::to_affine(Q, S);
+    M::stg(o, Q);
+    M::stg(o + K, Q + K);
+  }
+}
+
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_fixed_base(const Fq* __restrict__ table, const uint32_t* __restrict__ scalars, unsigned n, Fq* __restrict__ out_xy,
+             uint8_t* __restrict__ out_inf) {
+  typedef EcS<SC> E;
+  typedef typename E::M M;
+  constexpr int K = E::K, P = 0, S = E::PT;
+  unsigned i = E::M::T::item();
+  if (i >= n) return;
+  const uint32_t* s = scalars + (size_t)i * NL;
+  E::set_inf(P);
+  for (unsigned w = 0; w < FB_WINDOWS; w++) {
+    const unsigned bit = w * FB_WINDOW;
+    const uint32_t d = (s[bit >> 5] >> (bit & 31)) & 0xffu;      // 8-bit windows never straddle a limb
+    if (!d) continue;
+    const Fq* q = table + (size_t)(w * FB_ENTRIES + d - 1) * 2 * K;
+    M::ldg(S, q);
+    M::ldg(S + K, q + K);
+    if (M::is_zero(S) && M::is_zero(S + K)) continue;            // table entry at infinity
+    E::madd_g(P, q, false, S);
+  }
+  Fq* o = out_xy + (size_t)i * 2 * K;
+  if (E::is_inf(P)) {            // GroupAffine::zero() = (0, 1, true)
+    M::set_zero(S);
+    M::stg(o, S);
+    M::set_one(S);
+    M::stg(o + K, S);
+    out_inf[i] = 1;
+    return;
+  }
+  E::to_affine(P, S);
+  M::stg(o, P);
+  M::stg(o + K, P + K);
+  out_inf[i] = 0;
+}
+
+template <int GID>
+int fixed_base_impl(g753_ctx* ctx, const uint64_t* base_xy, const uint64_t* scalars, size_t n, uint64_t* out_xy,
+                    uint8_t* out_inf) {
+  constexpr int K = MsmCfg<GID>::K, T = 32;
+  typedef typename MsmCfg<GID>::template SC<T> SC;
+  typedef EcS<SC> E;
+  const size_t aff = sizeof(Fq) * 2 * K;
+  const size_t entries = (size_t)FB_WINDOWS * FB_ENTRIES;
+  G753_TRY(ctx->scratch.reserve(aff * (entries + 1 + FB_WINDOWS + n) + 96 * n + n + 8192));
+  Carver cv(ctx->scratch.ptr);
+  Fq* d_g = cv.take<Fq>(2 * K);
+  Fq* d_table = cv.take<Fq>(2 * K * entries);
+  uint32_t* d_sc = cv.take<uint32_t>(NL * n);
+  Fq* d_out = cv.take<Fq>(2 * K * n);
+  uint8_t* d_inf = cv.take<uint8_t>(n);
+  G753_TRY(h2d(d_g, base_xy, aff, ctx->stream));
+  G753_TRY(h2d(d_sc, scalars, 96 * n, ctx->stream));
+  const size_t smem = slot_bytes<E, T>(2 * E::PT + E::ADD_SCRATCH);
+  Fq* d_wb = cv.take<Fq>(2 * K * FB_WINDOWS);
+  G753_LAUNCH_SMEM(k_fb_bases<SC>, 1, T * MsmCfg<GID>::TP, smem, ctx->stream, d_g, d_wb);
+  G753_LAUNCH_SMEM(k_fb_rows<SC>, div_up(FB_WINDOWS, T), T * MsmCfg<GID>::TP, smem, ctx->stream, d_wb, d_table);
+  ctx->launches++;
+  G753_LAUNCH_SMEM(k_fixed_base<SC>, div_up(n, T), T * MsmCfg<GID>::TP, smem, ctx->stream, d_table, d_sc, (unsigned)n, d_out,
+                   d_inf);
+  ctx->launches += 2;
+  G753_TRY(launch_check("k_fixed_base"));
+  G753_TRY(d2h(out_xy, d_out, aff * n, ctx->stream));
+  G753_TRY(d2h(out_inf, d_inf, n, ctx->stream));
+  return stream_sync(ctx->stream);
+}
+
 #define G753_INSTANTIATE_GROUP(GID)                                                                        \
   template int msm_dispatch<GID>(g753_ctx*, const g753_bases*, size_t, size_t, const uint32_t*, void*);   \
   template int point_op_impl<GID>(g753_ctx*, int, const uint64_t*, const uint64_t*, uint64_t*);            \
   template void points_sum_launch<GID>(g753_ctx*, const void*, size_t, void*);                               \
   template int bases_generate_impl<GID>(g753_ctx*, const uint64_t*, uint64_t, size_t, void*);                \
   template int bases_precompute_impl<GID>(g753_ctx*, g753_bases*, unsigned);                                 \
-  template int batch_normalize_impl<GID>(g753_ctx*, const uint64_t*, size_t, uint64_t*, uint8_t*);
+  template int batch_normalize_impl<GID>(g753_ctx*, const uint64_t*, size_t, uint64_t*, uint8_t*);        \
+  template int fixed_base_impl<GID>(g753_ctx*, const uint64_t*, const uint64_t*, size_t, uint64_t*, uint8_t*);

@@ -43,6 +43,7 @@ SYMBOLS = [
     ("g753_msm_host", _i, [_vp, _i, _vp, _vp, _sz, _vp, _sz, _vp]),
     ("g753_points_sum_dev", _i, [_vp, _i, _vp, _sz, _vp]),
     ("g753_batch_normalize", _i, [_vp, _i, _vp, _sz, _vp, _vp]),
+    ("g753_fixed_base_msm", _i, [_vp, _i, _vp, _vp, _sz, _vp, _vp]),
     ("g753_group_coord_limbs", _i, [_i]),
     ("g753_domain_check", _i, [_i, _u]),
     ("g753_ntt", _i, [_vp, _i, _vp, _u, _i]),

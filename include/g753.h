@@ -142,6 +142,14 @@ int g753_points_sum_dev(g753_ctx* ctx, int group, const void* d_points_xyz, size
  * This is the normalisation that defines bit-exactness of a proof (prover.rs:340-345). */
 int g753_batch_normalize(g753_ctx* ctx, int group, const uint64_t* xyz, size_t count, uint64_t* xy,
                          uint8_t* infinity);
+/* FixedBaseMSM::multi_scalar_mul followed by batch_normalization / into_affine (algebra/src/msm/
+ * fixed_base.rs:66-79; proof-systems/src/groth16/generator.rs:225-319 builds every query of a key
+ * this way): out[i] = scalars[i] * base, affine (2*k*12 limbs, fully reduced) + infinity flag
+ * ((0, 1, true) for a zero scalar).  base_xy: one affine point; scalars: n x 12 canonical limbs.
+ * The window table is internal (the reference's window size, fixed_base.rs:7-13, does not change
+ * the points). */
+int g753_fixed_base_msm(g753_ctx* ctx, int group, const uint64_t* base_xy, const uint64_t* scalars, size_t n,
+                        uint64_t* out_xy, uint8_t* out_infinity);
 /* limbs per coordinate element (12 * k) of a group */
 int g753_group_coord_limbs(int group);
 

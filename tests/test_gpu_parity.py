@@ -397,3 +397,29 @@ def test_bases_from_wire_format(ctx, group):
     assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
     bases.free()
     ref.free()
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_fixed_base_msm(ctx, group):
+    """SURVEY.md 8f-3: FixedBaseMSM::multi_scalar_mul + batch normalisation (fixed_base.rs:66-79,
+    generator.rs:243-284) - scalars[i] * G, affine, against the oracle, then 2^12 scalars against the
+    variable-base MSM (sum_i t_i (s_i G) == (sum_i t_i s_i) G)"""
+    import bench
+    from util753 import sample_points
+    C = GROUPS[group]
+    base = sample_points(C, 1, 0x4F0 + group)[0]
+    sc = [0, 1, C.r - 1, 255, 256, (1 << 752) + 12345] + sample_scalars(C, 3, 0x4F1)
+    coords, _ = points_to_arrays(C, [base])
+    out, inf = G.FixedBaseMSM.multi_scalar_mul(group, coords[0], ints_to_array(sc), ctx=ctx)
+    want_c, want_inf = points_to_arrays(C, [C.mul(base, s) for s in sc])
+    assert (inf == want_inf).all() and (out == want_c).all()
+    n = 1 << 12
+    s_arr = bench.random_scalars(n, 0x4F2 + group)
+    pts, inf = G.FixedBaseMSM.multi_scalar_mul(group, coords[0], s_arr, ctx=ctx)
+    assert not inf.any()
+    t_arr = bench.random_scalars(n, 0x4F3 + group)
+    bases = ctx.upload_bases(group, pts)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, t_arr)
+    k = sum(int(a) * int(b) for a, b in zip(array_to_ints(s_arr), array_to_ints(t_arr))) % C.r
+    assert projective_to_point(C, got) == C.mul(base, k)
+    bases.free()

@@ -328,3 +328,17 @@ def test_bases_from_wire_format(ctx, group):
     assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
     bases.free()
     ref.free()
+
+
+@pytest.mark.parametrize("group", [ffi.MNT4_G1, ffi.MNT6_G2])
+def test_fixed_base_msm(ctx, group):
+    """FixedBaseMSM::multi_scalar_mul + normalisation (fixed_base.rs:66-79, generator.rs:243-284):
+    scalars[i] * G for 0, 1, r - 1, a full-width and some small scalars"""
+    C = GROUPS[group]
+    base = sample_points(C, 1, 0x4F0 + group)[0]
+    sc = [0, 1, C.r - 1, 255, 256, (1 << 752) + 12345] + sample_scalars(C, 2, 0x4F1)
+    coords, _ = points_to_arrays(C, [base])
+    out, inf = G.FixedBaseMSM.multi_scalar_mul(group, coords[0], ints_to_array(sc), ctx=ctx)
+    want_c, want_inf = points_to_arrays(C, [C.mul(base, s) for s in sc])
+    assert (inf == want_inf).all()
+    assert (out == want_c).all()
