@@ -471,11 +471,16 @@ def sharded_fft(ctx, stream, ffi, log_n, world, reps):
     dev = torch.device("cuda", ctx.device)
     path = "fused: last butterfly pass stores into peer memory (symmetric memory over NVLink), one barrier"
     try:
+        # measured (profiles/r01_ntt_sharded_fused_n{2,4,8}.json): the fused exchange wins on 2 GPUs (3.36 vs
+        # 3.79 ms), ties on 4 and loses 5 % on 8, where its 96-byte remote stores cost more than NCCL's bulk
+        # copies save
+        if world > 4:
+            raise RuntimeError("NCCL preferred above 4 ranks")
         fused = D.FusedShardedNTT(dom, stream)
         fused.load(raw)
         one = lambda: fused.transform(ffi.FFT)
     except Exception as ex:                                   # no symmetric memory on this box / build
-        path = "NCCL all_to_all_single between the column and row passes (%s)" % type(ex).__name__
+        path = "NCCL all_to_all_single between the column and row passes (%s)" % str(ex)[:60]
         with torch.cuda.stream(stream):
             t_data = torch.from_numpy(raw.view(np.int64).reshape(-1).copy()).to(dev)
             t_send, t_recv = torch.empty_like(t_data), torch.empty_like(t_data)
