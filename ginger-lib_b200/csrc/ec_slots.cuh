@@ -10,7 +10,7 @@
 // reference's mixed addition, P + (-P) and P + P are both handled explicitly.
 //
 // A point occupies 4 tower elements = 4K slots in the order X, Y, ZZ, ZZZ; infinity <=> ZZ == 0.
-// `W` is the first scratch slot: every operation needs 4K + NTMP scratch slots.
+// `W` is the first scratch slot: madd_g / mdbl_g need 3K + NTMP scratch slots, add / add_g / dbl 4K + NTMP.
 #pragma once
 #include "slots.cuh"
 
@@ -85,7 +85,7 @@ struct EcS {
   typedef typename SC::M M;
   static constexpr int K = M::K;
   static constexpr int PT = 4 * K;                      // slots per XYZZ point
-  static constexpr int MADD_SCRATCH = 4 * K + M::NTMP;  // scratch slots of madd_g / mdbl_g
+  static constexpr int MADD_SCRATCH = 3 * K + M::NTMP;  // scratch slots of madd_g / mdbl_g
   static constexpr int ADD_SCRATCH = 4 * K + M::NTMP;   // scratch slots of add / add_g / dbl
 
   static G753_D bool is_inf(int P) { return M::is_zero(P + 2 * K); }
@@ -105,10 +105,11 @@ struct EcS {
     for (int i = 0; i < 4; i++) M::stg(g + i * K, P + i * K);
   }
 
-  // P = 2 * (+-q), q affine (x, y) in global memory, finite: mdbl-2008-s-1 with general a
+  // P = 2 * (+-q), q affine (x, y) in global memory, finite: mdbl-2008-s-1 with general a.
+  // Three temporaries (P's own slots hold V, W and, briefly, the coefficient a).
   static G753_NI void mdbl_g(int P, const Fq* q, bool negq, int W) {
     const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
-    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, tt = W + 4 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, tt = W + 3 * K;
     M::ldg(t0, q + K);
     if (negq) M::neg(t0, t0);  // y
     M::dbl(t1, t0);            // U = 2y
@@ -121,24 +122,26 @@ struct EcS {
     M::ldg(t1, q);             // x
     M::mul(t2, t1, ZZ, tt);    // S = x V
     M::sqr(t1, t1, tt);        // x^2
-    M::dbl(t3, t1);
-    M::add(t1, t3, t1);        // 3 x^2
+    M::dbl(Y, t1);
+    M::add(t1, Y, t1);         // 3 x^2
     M::set_one(X);
-    SC::mul_by_a(t3, X);       // a
-    M::add(t1, t1, t3);        // M = 3 x^2 + a
+    SC::mul_by_a(Y, X);        // a
+    M::add(t1, t1, Y);         // M = 3 x^2 + a
     M::sqr(X, t1, tt);
-    M::dbl(t3, t2);
-    M::sub(X, X, t3);          // X3 = M^2 - 2S
+    M::dbl(Y, t2);
+    M::sub(X, X, Y);           // X3 = M^2 - 2S
     M::sub(t2, t2, X);
     M::mul(t2, t1, t2, tt);    // M (S - X3)
-    M::mul(t3, ZZZ, t0, tt);   // W y
-    M::sub(Y, t2, t3);
+    M::mul(t1, ZZZ, t0, tt);   // W y
+    M::sub(Y, t2, t1);
   }
 
-  // P += (+-q), q affine in global memory, finite: madd-2008-s, 8M + 2S
+  // P += (+-q), q affine in global memory, finite: madd-2008-s, 8M + 2S.
+  // Three temporaries: Q = X1 PP replaces X1 in place and Q - X3 is formed as 3Q - (R^2 - PPP), so
+  // the accumulation kernels need 7K + NTMP slots per column.
   static G753_NI void madd_g(int P, const Fq* q, bool negq, int W) {
     const int X = P, Y = P + K, ZZ = P + 2 * K, ZZZ = P + 3 * K;
-    const int t0 = W, t1 = W + K, t2 = W + 2 * K, t3 = W + 3 * K, tt = W + 4 * K;
+    const int t0 = W, t1 = W + K, t2 = W + 2 * K, tt = W + 3 * K;
     if (M::is_zero(ZZ)) {
       M::ldg(X, q);
       M::ldg(Y, q + K);
@@ -165,17 +168,19 @@ struct EcS {
     }
     M::sqr(t2, t0, tt);        // PP
     M::mul(t0, t0, t2, tt);    // PPP
-    M::mul(t3, X, t2, tt);     // Q = X1 PP
-    M::mul(ZZ, ZZ, t2, tt);
-    M::mul(ZZZ, ZZZ, t0, tt);
-    M::sqr(X, t1, tt);
-    M::sub(X, X, t0);
-    M::dbl(t2, t3);
-    M::sub(X, X, t2);          // X3 = R^2 - PPP - 2Q
-    M::mul(t2, Y, t0, tt);     // Y1 PPP
-    M::sub(t3, t3, X);
-    M::mul(Y, t1, t3, tt);
-    M::sub(Y, Y, t2);          // Y3 = R (Q - X3) - Y1 PPP
+    M::mul(X, X, t2, tt);      // Q = X1 PP   (X1 is dead from here on)
+    M::mul(ZZ, ZZ, t2, tt);    // ZZ3
+    M::mul(ZZZ, ZZZ, t0, tt);  // ZZZ3
+    M::sqr(t2, t1, tt);
+    M::sub(t2, t2, t0);        // R^2 - PPP
+    M::mul(Y, Y, t0, tt);      // Y1 PPP      (PPP is dead from here on)
+    M::dbl(t0, X);
+    M::add(t0, t0, X);
+    M::sub(t0, t0, t2);        // 3Q - (R^2 - PPP) = Q - X3
+    M::mul(t0, t1, t0, tt);    // R (Q - X3)
+    M::sub(Y, t0, Y);          // Y3
+    M::dbl(X, X);
+    M::sub(X, t2, X);          // X3 = R^2 - PPP - 2Q
   }
 
   // P = 2P: dbl-2008-s-1.  Four temporaries: V's slot is recycled once ZZ3 = V ZZ1 is formed.

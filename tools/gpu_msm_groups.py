@@ -19,7 +19,7 @@ for g in groups:
     sc = bench.random_scalars(n, 0x77 + g)
     for copies in copies_list:
         t0 = time.time()
-        if copies > 1:
+        if copies != 1:
             bases.precompute(copies)
             ctx.sync()
         pre_s = time.time() - t0
