@@ -41,7 +41,7 @@ constexpr unsigned ITEM_LEN = 128;         // longest run one thread accumulates
 constexpr unsigned ITEM_REP = 16;          // replicated length counters (spreads the atomics)
 
 // per-group launch shapes: NC_* columns (curve operations) per block, TP lanes per column; chosen so
-// that the slot footprint (accumulate: 7K + NTMP slots, reduce: 12K + NTMP slots of 96 B per column)
+// that the slot footprint (accumulate: 8 slots on G1, 7K + NTMP on G2; reduce: 12K + NTMP slots of 96 B per column)
 // leaves >= 8 warps per SM inside the 227 KB of shared memory
 template <int GID> struct MsmCfg;
 // TPA lanes per column in the accumulation kernels, TP in all others (reduction, fold, key set-up);
@@ -59,7 +59,7 @@ template <int GID> struct MsmCfg;
 #endif
 template <> struct MsmCfg<0> {
   static constexpr bool AFFINE = true;
-  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = 160, NC_RED = 96;
+  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = 128, NC_RED = 96;
   template <int NC, int LANES = 1> using SC = SCurveM4G1<Lay<NC, LANES>>;
 };
 template <> struct MsmCfg<1> {
@@ -69,12 +69,12 @@ template <> struct MsmCfg<1> {
 };
 template <> struct MsmCfg<2> {
   static constexpr bool AFFINE = true;
-  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = 160, NC_RED = 96;
+  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = 128, NC_RED = 96;
   template <int NC, int LANES = 1> using SC = SCurveM6G1<Lay<NC, LANES>>;
 };
 template <> struct MsmCfg<3> {
   static constexpr bool AFFINE = false;
-  static constexpr int K = 3, TP = G753_TP3, TPA = G753_TP3A, NC_ACC = 24, NC_RED = 16;
+  static constexpr int K = 3, TP = G753_TP3, TPA = G753_TP3A, NC_ACC = 32, NC_RED = 16;
   template <int NC, int LANES = G753_TP3> using SC = SCurveM6G2<Lay<NC, LANES>>;
 };
 
