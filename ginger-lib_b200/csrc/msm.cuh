@@ -286,10 +286,22 @@ k_bucket_acc(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
   if (pos >= *item_total) return;
   const MsmItem it = items[pos];
   E::set_inf(0);
+  uint32_t e = sorted[it.start];
   for (uint32_t k = 0; k < it.len; k++) {
-    uint32_t e = sorted[it.start + k];
     const Fq* q = bases + (size_t)(e & 0x7fffffffu) * (2 * E::K);
-    E::madd_g(0, q, (e >> 31) != 0, E::PT);
+    const bool neg = (e >> 31) != 0;
+    if (k + 1 < it.len) {
+      // the gather of the NEXT base is the one long-latency load of the loop: pull its lines into
+      // L2 while this addition runs (no registers, no shared memory)
+      e = sorted[it.start + k + 1];
+#if defined(__CUDA_ARCH__)
+      const char* nq = (const char*)(bases + (size_t)(e & 0x7fffffffu) * (2 * E::K));
+#pragma unroll
+      for (int off = 0; off < (int)(2 * E::K * sizeof(Fq)); off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + off));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 2 * E::K * sizeof(Fq) - 1));
+#endif
+    }
+    E::madd_g(0, q, neg, E::PT);
   }
   E::stg(points + (size_t)it.dest * E::PT, 0);
 }
