@@ -246,6 +246,21 @@ def test_ntt_large_properties(ctx):
             assert vals[i] == acc
 
 
+@pytest.mark.parametrize("field,log_n", [(ffi.FIELD_MNT4_FR, 20), (ffi.FIELD_MNT6_FR, 14)])
+def test_ntt_config2_vs_cpp_restatement(ctx, field, log_n):
+    """BASELINE config 2 at its full sizes (2^20 on mnt4753::Fr, the 2^14 maximum of mnt6753::Fr): all four
+    transforms bit-exact, every limb, against the C++ restatement of domain.rs:120-179 / 305-416"""
+    from oracle import ref753
+    n = 1 << log_n
+    rng = np.random.default_rng(21 + log_n)
+    raw = rng.integers(0, 1 << 63, size=(n, 12), dtype=np.uint64)
+    raw[:, 11] &= np.uint64(0xFFFF)
+    dom = G.EvaluationDomain.new(field, n, ctx=ctx)
+    for mode, run in ((ffi.FFT, dom.fft), (ffi.IFFT, dom.ifft), (ffi.COSET_FFT, dom.coset_fft),
+                      (ffi.COSET_IFFT, dom.coset_ifft)):
+        assert np.array_equal(run(raw), ref753.fft(field, raw, mode)), mode
+
+
 # ---- synthetic key generator + full-size properties -------------------------------------------
 def _dot_mod(scalars, logs, r):
     return sum(int(s) * int(a) for s, a in zip(array_to_ints(scalars), logs)) % r
@@ -316,7 +331,7 @@ def test_msm_large_discrete_log_property(ctx, group, log_n):
     bases.free()
 
 
-@pytest.mark.parametrize("group,log_n", [(ffi.MNT4_G1, 14), (ffi.MNT6_G2, 10)])
+@pytest.mark.parametrize("group,log_n", [(ffi.MNT4_G1, 16), (ffi.MNT6_G1, 14), (ffi.MNT4_G2, 12), (ffi.MNT6_G2, 10)])
 def test_msm_vs_cpp_restatement(ctx, group, log_n):
     """CUDA MSM == the C++ restatement of the reference's Pippenger (oracle/ref753.cpp) on the same
     bases and scalars, after normalisation (BASELINE config 1 shape, smaller n)"""
@@ -329,6 +344,9 @@ def test_msm_vs_cpp_restatement(ctx, group, log_n):
     sc = bench.random_scalars(n, 0xBEEF + group)
     got = G.VariableBaseMSM.multi_scalar_mul(bases, sc)
     want = ref753.msm(group, coords, None, sc)
+    assert projective_to_point(C, got) == projective_to_point(C, want)
+    bases.precompute(0)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, sc)
     assert projective_to_point(C, got) == projective_to_point(C, want)
     bases.free()
 
