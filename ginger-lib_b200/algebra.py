@@ -278,6 +278,44 @@ class EvaluationDomain:
     def coset_ifft(self, evals):
         return self._run(evals, ffi.COSET_IFFT)
 
+    # the public fields of the struct (domain.rs:24-39), 12 Montgomery limbs each, computed on the device
+    _CONSTANTS = {"size_inv": 0, "group_gen": 1, "group_gen_inv": 2, "generator_inv": 3,
+                  "vanishing_on_coset_inv": 4}
+
+    def __getattr__(self, name):
+        which = EvaluationDomain._CONSTANTS.get(name)
+        if which is None:
+            raise AttributeError(name)
+        out = np.zeros(LIMBS, dtype=np.uint64)
+        self.ctx.lib.check(self.ctx.lib.domain_constant(self.ctx.handle, self.field, self.log_size_of_group,
+                                                        which, ffi.ptr(out)))
+        setattr(self, name, out)
+        return out
+
+    def mul_polynomials_in_evaluation_domain(self, self_evals, other_evals):
+        """Point-wise product of two evaluation vectors over the domain (domain.rs:289-302)."""
+        a = ffi.as_u64(self_evals).reshape(-1, LIMBS)
+        b = ffi.as_u64(other_evals).reshape(-1, LIMBS)
+        assert a.shape == b.shape
+        da = DeviceVector(self.ctx, self.field, a.shape[0], a)
+        db = DeviceVector(self.ctx, self.field, b.shape[0], b)
+        try:
+            da.op(ffi.OP_MUL, db)
+            return da.download()
+        finally:
+            da.free()
+            db.free()
+
+    def divide_by_vanishing_poly_on_coset_in_place(self, evals):
+        """evals *= (17^n - 1)^-1: Z is constant on the coset (domain.rs:245-256)."""
+        v = ffi.as_u64(evals).reshape(-1, LIMBS)
+        d = DeviceVector(self.ctx, self.field, v.shape[0], v)
+        try:
+            d.scale(self.vanishing_on_coset_inv)
+            return d.download()
+        finally:
+            d.free()
+
     # numpy arrays cannot be resized in place; the *_in_place forms return the resized vector
     fft_in_place = fft
     ifft_in_place = ifft

@@ -994,6 +994,26 @@ int g753_ntt_mixed(g753_ctx* ctx, int field, uint64_t* data, uint64_t n, int mod
   return rc;
 }
 
+int g753_domain_constant(g753_ctx* ctx, int field, unsigned log_n, int which, uint64_t* out) {
+  CHECK_CTX(ctx);
+  if (!out || which < 0 || which > 4) return fail(G753_ERR_BAD_ARG, "bad argument");
+  G753_TRY(g753_domain_check(field, log_n));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  // the constants alone: no O(n) twiddle tables for a domain that may never be transformed
+  Fq* consts = nullptr;
+  int rc = field == 0 ? ntt_consts_build<0>(&consts, log_n, ctx->stream, &ctx->launches)
+                      : ntt_consts_build<1>(&consts, log_n, ctx->stream, &ctx->launches);
+  if (rc == G753_OK) {
+    const unsigned L = log_n ? log_n : 1;
+    // consts layout: see k_ntt_setup
+    const unsigned idx[5] = {0u, 1u, 1u + L, 1u + 3 * L, 1u + 4 * L};
+    rc = d2h(out, consts + idx[which], sizeof(Fq), ctx->stream);
+    if (rc == G753_OK) rc = stream_sync(ctx->stream);
+  }
+  dev_free(consts);
+  return rc;
+}
+
 int g753_vec_op_dev(g753_ctx* ctx, int field, int op, void* d_a, const void* d_b, size_t n) {
   CHECK_CTX(ctx);
   if (!d_a || (field != 0 && field != 1)) return fail(G753_ERR_BAD_ARG, "bad argument");

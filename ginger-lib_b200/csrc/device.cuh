@@ -85,10 +85,13 @@ static inline int launch_check(const char*) { return G753_OK; }
 #include <cuda_runtime.h>
 #define G753_LAUNCH(kernel, grid, block, stream, ...) \
   kernel<<<(unsigned)(grid), (unsigned)(block), 0, (stream)>>>(__VA_ARGS__)
-// launch with `smem` bytes of dynamic shared memory (opt-in above 48 KB)
+// launch with `smem` bytes of dynamic shared memory (opt-in above 48 KB); the slot kernels are
+// occupancy-bound by shared memory, so the whole 228 KB of the SM is asked for as shared memory
 #define G753_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                                        \
   do {                                                                                                  \
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));             \
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,                        \
+                         (int)cudaSharedmemCarveoutMaxShared);                                          \
     kernel<<<(unsigned)(grid), (unsigned)(block), (size_t)(smem), (stream)>>>(__VA_ARGS__);             \
   } while (0)
 namespace g753 {

@@ -88,6 +88,8 @@ struct EcS {
   static constexpr int PT = 4 * K;                      // slots per XYZZ point
   static constexpr int MADD_SCRATCH = (K == 1 ? 4 : 3) * K + M::NTMP;  // scratch slots of madd_g / mdbl_g
   static constexpr int ADD_SCRATCH = 4 * K + M::NTMP;   // scratch slots of add / add_g / dbl
+  // scratch slots of madd_acc_g, the mixed addition of the accumulation kernel: two on the prime-field curves
+  static constexpr int ACC_SCRATCH = K == 1 ? 2 : MADD_SCRATCH;
 
   static G753_D bool is_inf(int P) { return M::is_zero(P + 2 * K); }
   static G753_D void set_inf(int P) {
@@ -201,6 +203,67 @@ struct EcS {
     M::sub(Y, t0, Y);          // Y3
     M::dbl(X, X);
     M::sub(X, t2, X);          // X3 = R^2 - PPP - 2Q
+  }
+
+  // ---- prime-field curves, six slots per column (P's four + two temporaries) --------------------
+  // Same madd-2008-s / mdbl-2008-s-1 values as madd_g / mdbl_g; PP and PPP live in registers as the
+  // common factor of consecutive products (s_mul_many) instead of in slots.
+  static G753_NI void mdbl6_g(int P, const Fq* q, bool negq, int W) {
+    const int X = P, Y = P + 1, ZZ = P + 2, ZZZ = P + 3, t0 = W, t1 = W + 1;
+    M::ldg(t0, q + 1);
+    if (negq) M::neg(t0, t0);  // y
+    M::dbl(t1, t0);            // U = 2y
+    if (M::is_zero(t1)) {
+      set_inf(P);
+      return;
+    }
+    M::sqr(ZZ, t1, 0);         // V
+    M::mul(ZZZ, t1, ZZ, 0);    // W
+    M::ldg(t1, q);             // x
+    M::mul(Y, t1, ZZ, 0);      // S = x V
+    M::sqr(t1, t1, 0);         // x^2
+    M::dbl(X, t1);
+    M::add(t1, X, t1);         // 3 x^2
+    M::set_one(X);
+    SC::mul_by_a(X, X);        // a (the prime-field forms read their operand before writing)
+    M::add(t1, t1, X);         // M = 3 x^2 + a
+    M::sqr(X, t1, 0);
+    M::sub(X, X, Y);
+    M::sub(X, X, Y);           // X3 = M^2 - 2S
+    M::sub(Y, Y, X);
+    M::mul(Y, t1, Y, 0);       // M (S - X3)
+    M::mul(t1, ZZZ, t0, 0);    // W y
+    M::sub(Y, Y, t1);
+  }
+  static G753_NI void madd6_g(int P, const Fq* q, bool negq, int W) {
+    typedef typename M::T L;
+    constexpr int F = M::FIELD;
+    const int X = P, Y = P + 1, ZZ = P + 2, ZZZ = P + 3, t0 = W, t1 = W + 1;
+    if (M::is_zero(ZZ)) {
+      M::ldg(X, q);
+      M::ldg(Y, q + 1);
+      if (negq) M::neg(Y, Y);
+      M::set_one(ZZ);
+      M::set_one(ZZZ);
+      return;
+    }
+    const bool p0 = s_gmul_sub<F, L>(t0, q, ZZ, X, false);      // P = x2 ZZ1 - X1
+    const bool r0 = s_gmul_sub<F, L>(t1, q + 1, ZZZ, Y, negq);  // R = +-(y2 ZZZ1) - Y1
+    if (p0) {
+      if (r0) mdbl6_g(P, q, negq, W);
+      else set_inf(P);
+      return;
+    }
+    s_mul_many<F, L>(t0, true, (unsigned)X | (unsigned)ZZ << 8 | (unsigned)t0 << 16, 3);  // PP: Q, ZZ3, PPP
+    s_mul_many<F, L>(t0, false, (unsigned)ZZZ | (unsigned)Y << 8, 2);                     // PPP: ZZZ3, Y1 PPP
+    s_sqr_sub<F, L>(t0, t1, t0);                                                          // R^2 - PPP
+    s_x3<F, L>(X, t0);                                                                    // X3, Q - X3
+    s_mul_sub<F, L>(Y, t1, t0, Y);                                                        // Y3
+  }
+  // the accumulation kernel's mixed addition: needs ACC_SCRATCH slots at W
+  static G753_D void madd_acc_g(int P, const Fq* q, bool negq, int W) {
+    if constexpr (K == 1) madd6_g(P, q, negq, W);
+    else madd_g(P, q, negq, W);
   }
 
   // P = 2P: dbl-2008-s-1.  Four temporaries: V's slot is recycled once ZZ3 = V ZZ1 is formed.

@@ -301,7 +301,7 @@ k_bucket_acc(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
       asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + 2 * E::K * sizeof(Fq) - 1));
 #endif
     }
-    E::madd_g(0, q, neg, E::PT);
+    E::madd_acc_g(0, q, neg, E::PT);
   }
   E::stg(points + (size_t)it.dest * E::PT, 0);
 }
@@ -757,7 +757,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   typedef EcS<SCA> EA;
   typedef EcS<SCR> ER;
   constexpr size_t PT = 4 * Cfg::K;  // Fq per XYZZ point
-  constexpr size_t SMEM_ACC = slot_bytes<EA, CA>(EA::PT + EA::MADD_SCRATCH);
+  constexpr size_t SMEM_ACC = slot_bytes<EA, CA>(EA::PT + EA::ACC_SCRATCH);
   constexpr size_t SMEM_FIX = slot_bytes<EA, CA>(EA::PT + EA::ADD_SCRATCH);
   constexpr size_t SMEM_RED = slot_bytes<ER, CR>(2 * ER::PT + ER::ADD_SCRATCH);
   static_assert(SMEM_ACC <= 232448 && SMEM_FIX <= 232448 && SMEM_RED <= 232448, "slot footprint exceeds 227 KB");

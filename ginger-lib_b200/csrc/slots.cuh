@@ -98,7 +98,7 @@ G753_D void s_st(int s, const Fq& a) {
   }
 }
 // global <-> register, 16-byte vector accesses (Fq is 16-byte aligned)
-G753_D Fq g_ld(const Fq* g) {
+G753_HD Fq g_ld(const Fq* g) {
   const uint4* p = (const uint4*)g;
   Fq r;
 #pragma unroll
@@ -201,6 +201,55 @@ G753_D void s_stg(Fq* g, int a) {
   const uint4* q = slot_ptr<T>(a);
 #pragma unroll
   for (int k = 0; k < SLOT_CHUNKS; k++) p[k] = q[k * T::NC];
+}
+
+// ---- fused forms for the six-slot mixed addition of the prime-field curves (EcS::madd6_g) ----
+// A product reads two slots and writes one; the formulas of a mixed addition reuse PP and PPP as a
+// factor of three / two products, so keeping that factor in registers across the products removes
+// its slot (and its reloads), and folding the subtraction that follows a product into the same
+// call removes a round trip through shared memory.  Six slots per thread instead of eight puts
+// three 128-thread blocks (12 warps) on an SM instead of two.
+// d = +-(g * b) - c with g in global memory; returns d == 0
+template <int FID, class T>
+G753_NI bool s_gmul_sub(int d, const Fq* g, int b, int c, bool negate) {
+  Fq r = fq_mul<FID>(g_ld(g), s_ld<T>(b));
+  const Fq cc = s_ld<T>(c);
+  r = negate ? fq_neg<FID>(fq_add<FID>(r, cc)) : fq_sub<FID>(r, cc);
+  s_st<T>(d, r);
+  uint32_t t = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) t |= r.l[i];
+  return t == 0;
+}
+// f = slot[fsrc] (squared first when `square`); slot[d_i] *= f for the nd slots packed 8 bits each
+// in dpack.  f is read before any destination is written, so fsrc may be one of them.
+template <int FID, class T>
+G753_NI void s_mul_many(int fsrc, bool square, unsigned dpack, int nd) {
+  Fq f = s_ld<T>(fsrc);
+  if (square) f = fq_sqr<FID>(f);
+#pragma unroll 1
+  for (int i = 0; i < nd; i++) {
+    const int d = (int)((dpack >> (8 * i)) & 0xffu);
+    s_st<T>(d, fq_mul<FID>(s_ld<T>(d), f));
+  }
+}
+// d = a^2 - c
+template <int FID, class T>
+G753_NI void s_sqr_sub(int d, int a, int c) {
+  s_st<T>(d, fq_sub<FID>(fq_sqr<FID>(s_ld<T>(a)), s_ld<T>(c)));
+}
+// d = a * b - c
+template <int FID, class T>
+G753_NI void s_mul_sub(int d, int a, int b, int c) {
+  s_st<T>(d, fq_sub<FID>(fq_mul<FID>(s_ld<T>(a), s_ld<T>(b)), s_ld<T>(c)));
+}
+// (x, u) <- (u - 2x, x - (u - 2x)): X3 = (R^2 - PPP) - 2Q and Q - X3 from x = Q, u = R^2 - PPP
+template <int FID, class T>
+G753_NI void s_x3(int x, int u) {
+  const Fq q = s_ld<T>(x);
+  const Fq x3 = fq_sub<FID>(fq_sub<FID>(s_ld<T>(u), q), q);
+  s_st<T>(x, x3);
+  s_st<T>(u, fq_sub<FID>(q, x3));
 }
 
 // ---- towers: an element is K consecutive slots; `t` is the first of NTMP scratch slots ----

@@ -46,6 +46,7 @@ SYMBOLS = [
     ("g753_fixed_base_msm", _i, [_vp, _i, _vp, _vp, _sz, _vp, _vp]),
     ("g753_group_coord_limbs", _i, [_i]),
     ("g753_domain_check", _i, [_i, _u]),
+    ("g753_domain_constant", _i, [_vp, _i, _u, _i, _vp]),
     ("g753_ntt", _i, [_vp, _i, _vp, _u, _i]),
     ("g753_ntt_dev", _i, [_vp, _i, _vp, _u, _i]),
     ("g753_domain_check_mixed", _i, [_i, ctypes.c_uint64]),

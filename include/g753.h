@@ -157,6 +157,10 @@ int g753_group_coord_limbs(int group);
 /* 0 if a radix-2 domain of size 2^log_n exists for the field (domain.rs:70-72), else
  * G753_ERR_DOMAIN - the `None` of EvaluationDomain::new */
 int g753_domain_check(int field, unsigned log_n);
+/* the public fields of EvaluationDomain (domain.rs:24-39) and the coset constant, 12 Montgomery limbs:
+ * which = 0 size_inv, 1 group_gen, 2 group_gen_inv, 3 generator_inv (17^-1),
+ * 4 (17^n - 1)^-1, the factor of divide_by_vanishing_poly_on_coset_in_place (domain.rs:245-256) */
+int g753_domain_constant(g753_ctx* ctx, int field, unsigned log_n, int which, uint64_t* out);
 /* in place on host memory: data = n = 2^log_n elements, already resized by the caller
  * (domain.rs:121 zero-pads or truncates).  mode is one of G753_FFT..G753_COSET_IFFT */
 int g753_ntt(g753_ctx* ctx, int field, uint64_t* data, unsigned log_n, int mode);

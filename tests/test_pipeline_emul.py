@@ -63,6 +63,24 @@ def test_msm_small(ctx, group):
     bases.free()
 
 
+@pytest.mark.parametrize("group", [ffi.MNT4_G1, ffi.MNT6_G1])
+def test_msm_accumulate_exceptions(ctx, group):
+    """the branches of the six-slot mixed addition (EcS::madd6_g): acc + (-acc) -> infinity and on from
+    there, acc + acc -> doubling (also of a negated base), in one bucket each"""
+    C = GROUPS[group]
+    P, Q, R = sample_points(C, 3, 0xE0 + group)
+    s, t = sample_scalars(C, 2, 0xE8 + group)
+    for pts, sc in (([P, C.neg(P)], [s, s]),
+                    ([P, C.neg(P), Q], [s, s, s]),
+                    ([P, P], [s, s]),
+                    ([P, P, C.neg(P), C.neg(P), R], [s, s, s, s, t]),
+                    ([P, C.neg(P), C.neg(P)], [s, s, s]),
+                    ([P, P], [C.r - s, C.r - s])):
+        coords, inf = points_to_arrays(C, pts)
+        got = G.VariableBaseMSM.multi_scalar_mul(coords, ints_to_array(sc), group=group, infinity=inf, ctx=ctx)
+        assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+
+
 def test_msm_window_sizes(ctx, monkeypatch):
     """force several window widths through the same input (exercises multi-level reduction)"""
     C = O.MNT4_G1
@@ -146,6 +164,34 @@ def test_domain_new_none(ctx):
     assert G.EvaluationDomain.new(ffi.FIELD_MNT6_FR, (1 << 14) + 1, ctx=ctx) is None
     assert G.EvaluationDomain.new(ffi.FIELD_MNT6_FR, 1 << 14, ctx=ctx) is not None
     assert G.EvaluationDomain.new(ffi.FIELD_MNT4_FR, (1 << 29) + 1, ctx=ctx) is None
+
+
+@pytest.mark.parametrize("field", sorted(FIELDS))
+def test_domain_public_fields_and_pointwise(ctx, field):
+    """EvaluationDomain's public fields (domain.rs:24-39), mul_polynomials_in_evaluation_domain
+    (:289-302) and divide_by_vanishing_poly_on_coset_in_place (:245-256)"""
+    F = FIELDS[field]
+    rng = O.SplitMix64(0xD7 + field)
+    for n in (1, 2, 8, 1 << 13):
+        dom = G.EvaluationDomain.new(field, n, ctx=ctx)
+        ref = O.EvaluationDomain(F, n)
+        assert array_field(F, dom.size_inv) == [ref.size_inv]
+        assert array_field(F, dom.group_gen) == [ref.group_gen]
+        assert array_field(F, dom.group_gen_inv) == [ref.group_gen_inv]
+        assert array_field(F, dom.generator_inv) == [ref.generator_inv]
+        zinv = pow(pow(ref.generator, n, F.p) - 1, -1, F.p)
+        assert array_field(F, dom.vanishing_on_coset_inv) == [zinv]
+    with pytest.raises(AttributeError):
+        dom.no_such_field
+    n = 8
+    dom = G.EvaluationDomain.new(field, n, ctx=ctx)
+    a = [O.random_field_element(rng, F) for _ in range(n)]
+    b = [O.random_field_element(rng, F) for _ in range(n)]
+    got = dom.mul_polynomials_in_evaluation_domain(field_array(F, a), field_array(F, b))
+    assert array_field(F, got) == [x * y % F.p for x, y in zip(a, b)]
+    zinv = pow(pow(F.generator, n, F.p) - 1, -1, F.p)
+    got = dom.divide_by_vanishing_poly_on_coset_in_place(field_array(F, a))
+    assert array_field(F, got) == [x * zinv % F.p for x in a]
 
 
 def test_device_vector_chain(ctx):
