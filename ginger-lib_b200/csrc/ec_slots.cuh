@@ -206,8 +206,7 @@ struct EcS {
   }
 
   // ---- prime-field curves, six slots per column (P's four + two temporaries) --------------------
-  // Same madd-2008-s / mdbl-2008-s-1 values as madd_g / mdbl_g; PP and PPP live in registers as the
-  // common factor of consecutive products (s_mul_many) instead of in slots.
+  // Same madd-2008-s / mdbl-2008-s-1 values as madd_g / mdbl_g; see s_madd6 (slots.cuh).
   static G753_NI void mdbl6_g(int P, const Fq* q, bool negq, int W) {
     const int X = P, Y = P + 1, ZZ = P + 2, ZZZ = P + 3, t0 = W, t1 = W + 1;
     M::ldg(t0, q + 1);
@@ -238,7 +237,7 @@ struct EcS {
   static G753_NI void madd6_g(int P, const Fq* q, bool negq, int W) {
     typedef typename M::T L;
     constexpr int F = M::FIELD;
-    const int X = P, Y = P + 1, ZZ = P + 2, ZZZ = P + 3, t0 = W, t1 = W + 1;
+    const int X = P, Y = P + 1, ZZ = P + 2, ZZZ = P + 3;
     if (M::is_zero(ZZ)) {
       M::ldg(X, q);
       M::ldg(Y, q + 1);
@@ -247,18 +246,13 @@ struct EcS {
       M::set_one(ZZZ);
       return;
     }
-    const bool p0 = s_gmul_sub<F, L>(t0, q, ZZ, X, false);      // P = x2 ZZ1 - X1
-    const bool r0 = s_gmul_sub<F, L>(t1, q + 1, ZZZ, Y, negq);  // R = +-(y2 ZZZ1) - Y1
-    if (p0) {
-      if (r0) mdbl6_g(P, q, negq, W);
+    const unsigned z = s_madd6<F, L>(P, W, q, negq, 0);   // P = x2 ZZ1 - X1, R = +-(y2 ZZZ1) - Y1
+    if (z & 1u) {
+      if (z & 2u) mdbl6_g(P, q, negq, W);
       else set_inf(P);
       return;
     }
-    s_mul_many<F, L>(t0, true, (unsigned)X | (unsigned)ZZ << 8 | (unsigned)t0 << 16, 3);  // PP: Q, ZZ3, PPP
-    s_mul_many<F, L>(t0, false, (unsigned)ZZZ | (unsigned)Y << 8, 2);                     // PPP: ZZZ3, Y1 PPP
-    s_sqr_sub<F, L>(t0, t1, t0);                                                          // R^2 - PPP
-    s_x3<F, L>(X, t0);                                                                    // X3, Q - X3
-    s_mul_sub<F, L>(Y, t1, t0, Y);                                                        // Y3
+    s_madd6<F, L>(P, W, q, negq, 1);
   }
   // the accumulation kernel's mixed addition: needs ACC_SCRATCH slots at W
   static G753_D void madd_acc_g(int P, const Fq* q, bool negq, int W) {

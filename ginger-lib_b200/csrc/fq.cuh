@@ -338,6 +338,56 @@ G753_HD Fq fq_mul(const Fq& a, const Fq& b) {
   return r;
 }
 
+// Two products under ONE Montgomery reduction: (a b + c d) / R mod p, the lazy reduction of
+// sums of products (a0 b0 + NR a1 b1 of an Fq2 product, R (Q - X3) - Y1 PPP of a mixed addition).
+// 2 x 576 + 600 limb-MACs instead of 2 x 1176.  Same interleaved accumulators as fq_mul with a second
+// row of partial products per step; the running total stays below 4 p 2^32 < 2^(32 (NL + 1)), so no
+// chain carries out of its array (the argument of mont_step), and the result
+// (a b + c d + M p) / R < p (1 + 2 p / R) < 2 p needs the same single conditional subtraction.
+// The multipliers b, d are consumed one limb per step, so callers may stream them from shared
+// memory (s_mul2, slots.cuh) and keep only a and c in registers.
+template <int FID, bool FIRST>
+G753_HD void mont2_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, const uint32_t* c, uint32_t di) {
+  if (FIRST) {
+    row_mul(O, a + 1, bi);
+    row_mul(E, a, bi);
+  } else {
+    E[0] = add_cc(E[0], O[1]);
+    row_mad_shift(O, a + 1, bi);
+    row_mad(E, a, bi);
+    O[NL - 1] = addc(O[NL - 1], 0);
+  }
+  row_mad(O, c + 1, di);
+  row_mad(E, c, di);
+  O[NL - 1] = addc(O[NL - 1], 0);
+  uint32_t m = mul_lo(E[0], G753_FC(FID).inv32);
+  row_mad(O, G753_FC(FID).p + 1, m);
+  row_mad(E, G753_FC(FID).p, m);
+  O[NL - 1] = addc(O[NL - 1], 0);
+}
+// the accumulators after the last step -> canonical element (NL is even: `even` holds the columns)
+template <int FID>
+G753_HD Fq mont_finish(const uint32_t* even, const uint32_t* odd) {
+  Fq r;
+  r.l[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+  for (int i = 1; i < NL - 1; i++) r.l[i] = addc_cc(even[i], odd[i + 1]);
+  r.l[NL - 1] = addc(even[NL - 1], 0);
+  fq_reduce_once<FID>(r.l);
+  return r;
+}
+template <int FID>
+G753_HD Fq fq_mul2(const Fq& a, const Fq& b, const Fq& c, const Fq& d) {
+  uint32_t even[NL], odd[NL];
+  mont2_step<FID, true>(even, odd, a.l, b.l[0], c.l, d.l[0]);
+#pragma unroll
+  for (int i = 1; i < NL; i += 2) {
+    mont2_step<FID, false>(odd, even, a.l, b.l[i], c.l, d.l[i]);
+    if (i + 1 < NL) mont2_step<FID, false>(even, odd, a.l, b.l[i + 1], c.l, d.l[i + 1]);
+  }
+  return mont_finish<FID>(even, odd);
+}
+
 // Dedicated squaring (replaces Fp768::square_in_place, fp_768.rs:339-548: the reference also
 // computes the cross products once, doubles them and adds the squares before reducing).
 //   a^2 = 2 * sum_{i<j} a_i a_j 2^(32 (i+j)) + sum_i a_i^2 2^(64 i):   276 + 24 products instead of 576,

@@ -57,9 +57,12 @@ template <int GID> struct MsmCfg;
 #define G753_TP3A 4
 #define G753_TP3 8
 #endif
+#ifndef G753_NC_ACC1
+#define G753_NC_ACC1 128  // columns per block of the prime-field accumulation kernel
+#endif
 template <> struct MsmCfg<0> {
   static constexpr bool AFFINE = true;
-  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = 128, NC_RED = 96;
+  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = G753_NC_ACC1, NC_RED = 96;
   template <int NC, int LANES = 1> using SC = SCurveM4G1<Lay<NC, LANES>>;
 };
 template <> struct MsmCfg<1> {
@@ -69,7 +72,7 @@ template <> struct MsmCfg<1> {
 };
 template <> struct MsmCfg<2> {
   static constexpr bool AFFINE = true;
-  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = 128, NC_RED = 96;
+  static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = G753_NC_ACC1, NC_RED = 96;
   template <int NC, int LANES = 1> using SC = SCurveM6G1<Lay<NC, LANES>>;
 };
 template <> struct MsmCfg<3> {

@@ -21,6 +21,12 @@
 #include "device.cuh"
 #include "fq.cuh"
 
+// Fq2 products of the two-lane accumulation tower: 0 = two rounds of plain products, 1 = one
+// two-product call per lane (lazy reduction), 2 = squarings through the same body as well
+#ifndef G753_FQ2_LAZY
+#define G753_FQ2_LAZY 1
+#endif
+
 namespace g753 {
 
 #if defined(G753_HOST_EMUL)
@@ -203,53 +209,106 @@ G753_D void s_stg(Fq* g, int a) {
   for (int k = 0; k < SLOT_CHUNKS; k++) p[k] = q[k * T::NC];
 }
 
-// ---- fused forms for the six-slot mixed addition of the prime-field curves (EcS::madd6_g) ----
-// A product reads two slots and writes one; the formulas of a mixed addition reuse PP and PPP as a
-// factor of three / two products, so keeping that factor in registers across the products removes
-// its slot (and its reloads), and folding the subtraction that follows a product into the same
-// call removes a round trip through shared memory.  Six slots per thread instead of eight puts
-// three 128-thread blocks (12 warps) on an SM instead of two.
-// d = +-(g * b) - c with g in global memory; returns d == 0
+// ---- the six-slot mixed addition of the prime-field curves (EcS::madd6_g) -----------------------
+// madd-2008-s on a point in slots X, Y, ZZ, ZZZ = P .. P + 3 with only two temporaries t0, t1 = W, W + 1
+// (six slots per thread instead of eight: three 128-thread blocks = 12 warps per SM instead of 8).
+// Two things make that possible: PP = P^2 never gets a slot - it stays in registers as the common
+// factor of the three products that use it - and the subtraction that follows a product is folded
+// into the same step.  The whole addition is a short micro-program run by ONE function with ONE
+// inlined product and ONE inlined squaring: a B200 fetches instructions fast enough only while the
+// hot code of an SM stays around 100 KB (measured: the same formulas spread over five fused
+// functions, each with its own 45 KB multiplier body, ran at 63 % instead of 85 % pipe utilisation
+// with 6 stall cycles per issue waiting for instructions, profiles/r01_bucket_acc_2p22_v19).
+//
+//   phase 0:  t0 = x2 ZZ - X (P),  t1 = +-(y2 ZZZ) - Y (R);  returns bit 0 = (P == 0), bit 1 = (R == 0)
+//   phase 1:  f = t0^2 (PP);  X *= f (Q);  ZZ *= f;  t0 *= f (PPP);  ZZZ *= t0;  Y *= t0;
+//             t0 = t1^2 - t0;  X = t0 - 2X (X3), t0 = Q - X3;  Y = t1 t0 - Y (Y3)
 template <int FID, class T>
-G753_NI bool s_gmul_sub(int d, const Fq* g, int b, int c, bool negate) {
-  Fq r = fq_mul<FID>(g_ld(g), s_ld<T>(b));
-  const Fq cc = s_ld<T>(c);
-  r = negate ? fq_neg<FID>(fq_add<FID>(r, cc)) : fq_sub<FID>(r, cc);
-  s_st<T>(d, r);
-  uint32_t t = 0;
+G753_NI unsigned s_madd6(int P, int W, const Fq* q, bool negq, int phase) {
+  enum { AG = 1, SQR = 2, KEEP = 4, TOF = 8, SUBC = 16, NEGADD = 32, XPOST = 64 };
+  const int X = P, Y = P + 1, ZZ = P + 2, ZZZ = P + 3, t0 = W, t1 = W + 1;
+  Fq f;  // retained factor
 #pragma unroll
-  for (int i = 0; i < NL; i++) t |= r.l[i];
-  return t == 0;
-}
-// f = slot[fsrc] (squared first when `square`); slot[d_i] *= f for the nd slots packed 8 bits each
-// in dpack.  f is read before any destination is written, so fsrc may be one of them.
-template <int FID, class T>
-G753_NI void s_mul_many(int fsrc, bool square, unsigned dpack, int nd) {
-  Fq f = s_ld<T>(fsrc);
-  if (square) f = fq_sqr<FID>(f);
+  for (int i = 0; i < NL; i++) f.l[i] = 0;
+  unsigned zero = 0;
+  const int first = phase == 0 ? 0 : 2, last = phase == 0 ? 2 : 10;
 #pragma unroll 1
-  for (int i = 0; i < nd; i++) {
-    const int d = (int)((dpack >> (8 * i)) & 0xffu);
-    s_st<T>(d, fq_mul<FID>(s_ld<T>(d), f));
+  for (int s = first; s < last; s++) {
+    int d = 0, a = 0, b = 0, c = 0;
+    unsigned fl = 0;
+    switch (s) {
+      case 0: d = t0; b = ZZ; c = X; fl = AG | SUBC; break;
+      case 1: d = t1; b = ZZZ; c = Y; fl = AG | (negq ? NEGADD : SUBC); break;
+      case 2: a = t0; fl = SQR | TOF; break;
+      case 3: d = X; a = X; fl = KEEP; break;
+      case 4: d = ZZ; a = ZZ; fl = KEEP; break;
+      case 5: d = t0; a = t0; fl = KEEP; break;
+      case 6: d = ZZZ; a = ZZZ; b = t0; break;
+      case 7: d = Y; a = Y; b = t0; break;
+      case 8: d = t0; a = t1; c = t0; fl = SQR | SUBC | XPOST; break;
+      default: d = Y; a = t1; b = t0; c = Y; fl = SUBC; break;
+    }
+    const Fq A = (fl & AG) ? g_ld(q + s) : s_ld<T>(a);
+    Fq r;
+    if (fl & SQR) {
+      r = fq_sqr<FID>(A);
+    } else {
+      if (!(fl & KEEP)) f = s_ld<T>(b);
+      r = fq_mul<FID>(A, f);
+    }
+    if (fl & TOF) {
+      f = r;
+      continue;
+    }
+    if (fl & (SUBC | NEGADD)) {
+      const Fq cc = s_ld<T>(c);
+      r = (fl & NEGADD) ? fq_neg<FID>(fq_add<FID>(r, cc)) : fq_sub<FID>(r, cc);
+    }
+    if (fl & XPOST) {  // r = R^2 - PPP: X3 = r - 2Q into X, Q - X3 into d
+      const Fq qq = s_ld<T>(X);
+      r = fq_sub<FID>(fq_sub<FID>(r, qq), qq);
+      s_st<T>(X, r);
+      r = fq_sub<FID>(qq, r);
+    }
+    s_st<T>(d, r);
+    if (s < 2 && fq_is_zero(r)) zero |= 1u << s;
   }
+  return zero;
 }
-// d = a^2 - c
+
+// ---- two products under one reduction on slots ---------------------------------------------------
+// returns a * slot[b] + c * slot[e] (fq_mul2).  a and c are in registers; the multipliers are
+// streamed from their slots, one 16-byte chunk every four steps.
 template <int FID, class T>
-G753_NI void s_sqr_sub(int d, int a, int c) {
-  s_st<T>(d, fq_sub<FID>(fq_sqr<FID>(s_ld<T>(a)), s_ld<T>(c)));
+G753_D Fq s_mul2_stream(const Fq& a, int b, const Fq& c, int e) {
+  const uint4* pb = slot_ptr<T>(b);
+  const uint4* pe = slot_ptr<T>(e);
+  uint32_t even[NL], odd[NL];
+#pragma unroll
+  for (int k = 0; k < SLOT_CHUNKS; k++) {
+    const uint4 vb = pb[k * T::NC], ve = pe[k * T::NC];
+    const uint32_t bb[4] = {vb.x, vb.y, vb.z, vb.w}, ee[4] = {ve.x, ve.y, ve.z, ve.w};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (k == 0 && u == 0) mont2_step<FID, true>(even, odd, a.l, bb[0], c.l, ee[0]);
+      else if (u & 1) mont2_step<FID, false>(odd, even, a.l, bb[u], c.l, ee[u]);
+      else mont2_step<FID, false>(even, odd, a.l, bb[u], c.l, ee[u]);
+    }
+  }
+  return mont_finish<FID>(even, odd);
 }
-// d = a * b - c
-template <int FID, class T>
-G753_NI void s_mul_sub(int d, int a, int b, int c) {
-  s_st<T>(d, fq_sub<FID>(fq_mul<FID>(s_ld<T>(a), s_ld<T>(b)), s_ld<T>(c)));
-}
-// (x, u) <- (u - 2x, x - (u - 2x)): X3 = (R^2 - PPP) - 2Q and Q - X3 from x = Q, u = R^2 - PPP
-template <int FID, class T>
-G753_NI void s_x3(int x, int u) {
-  const Fq q = s_ld<T>(x);
-  const Fq x3 = fq_sub<FID>(fq_sub<FID>(s_ld<T>(u), q), q);
-  s_st<T>(x, x3);
-  s_st<T>(u, fq_sub<FID>(q, x3));
+// d = slot[a] * slot[b] + f(slot[c]) * slot[e], f by `mode`: 0 identity, 1 negation, 2 times NR (the
+// non-residue of an Fq2 product).  The lanes of a column reconverge before d is written (d may be an
+// operand of the other lanes' products) and after.
+template <int FID, class T, unsigned NR>
+G753_NI void s_mul2(int d, int a, int b, int c, int e, int mode) {
+  Fq cc = s_ld<T>(c);
+  if (mode == 1) cc = fq_neg<FID>(cc);
+  if (mode == 2) cc = fq_mul_small<FID, NR>(cc);
+  const Fq r = s_mul2_stream<FID, T>(s_ld<T>(a), b, cc, e);
+  T::sync();
+  s_st<T>(d, r);
+  T::sync();
 }
 
 // ---- towers: an element is K consecutive slots; `t` is the first of NTMP scratch slots ----
@@ -477,6 +536,11 @@ struct Tw2C {
   static G753_NI void mul(int d, int a, int b, int t) {
     const int r = L::role();
     if (L::TP == 2) {
+#if G753_FQ2_LAZY
+      // one lane per coefficient, each a sum of two products under one reduction (s_mul2):
+      // a0 b0 + (NR a1) b1 | a0 b1 + a1 b0 - 1752 limb-MACs of lane time instead of 2 x 1176
+      s_mul2<FID, L, NR>(d + r, a, b + r, a + 1, b + 1 - r, r == 0 ? 2 : 0);
+#else
       s_mul<FID, L>(t + r, a + r, b + r);              // a0 b0 | a1 b1
       s_mul<FID, L>(t + 2 + r, a + r, b + 1 - r);      // a0 b1 | a1 b0
       L::sync();
@@ -487,6 +551,7 @@ struct Tw2C {
         s_add<FID, L>(d + 1, t + 2, t + 3);
       }
       L::sync();
+#endif
       return;
     }
     if (r == 2 || r == 3) s_add<FID, L>(t + r, r == 2 ? a : b, r == 2 ? a + 1 : b + 1);
@@ -505,6 +570,14 @@ struct Tw2C {
   // complex squaring (fp2.rs:128-144): a0 a1 and (a0 + a1)(a0 + NR a1) on lanes 0, 1
   static G753_NI void sqr(int d, int a, int t) {
     const int r = L::role();
+#if G753_FQ2_LAZY >= 2
+    if (L::TP == 2) {
+      // through the same two-product body as mul (one multiplier body in the accumulation kernel's
+      // hot code): a0^2 + (NR a1) a1 | a0 a1 + a1 a0
+      s_mul2<FID, L, NR>(d + r, a, a + r, a + 1, a + 1 - r, r == 0 ? 2 : 0);
+      return;
+    }
+#endif
     if (r == 0) s_add<FID, L>(t + 1, a, a + 1);
     if (r == 1) {
       s_mul_small<FID, L, NR>(t + 2, a + 1);

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(HERE, "libg753.so")
+# G753_LIB: a differently built libg753.so (development A/B runs); the in-tree library otherwise
+DEFAULT_LIB = os.environ.get("G753_LIB") or os.path.join(HERE, "libg753.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_DOMAIN, ERR_NO_DEVICE = range(6)
 

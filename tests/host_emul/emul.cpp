@@ -86,6 +86,10 @@ static void curve_op(int op, const uint32_t* acc_in, const uint32_t* other, uint
     memcpy(gbuf, other, 96 * 2 * K);
     E::madd_g(P, gbuf, op == 6, S);
     get(out, P, 4 * K);
+  } else if (op == 7 || op == 8) {  // the accumulation kernel's form (six slots on the prime-field curves)
+    memcpy(gbuf, other, 96 * 2 * K);
+    E::madd_acc_g(P, gbuf, op == 8, S);
+    get(out, P, 4 * K);
   } else if (op == 1) {
     put(Q, other, 4 * K);
     E::add(P, Q, S);
@@ -107,6 +111,26 @@ extern "C" {
 void emul_field_op(int fid, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   if (fid == 0) field_op<0>(op, a, b, out);
   else field_op<1>(op, a, b, out);
+}
+// (a b + c d) / R under one reduction: fq_mul2 (registers) and s_mul2 (multipliers streamed from slots,
+// c optionally negated / times 13)
+void emul_field_mul2(int fid, int mode, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d,
+                     uint32_t* out) {
+  threadIdx.x = 0;
+  Fq x[4], r;
+  memcpy(x[0].l, a, 96);
+  memcpy(x[1].l, b, 96);
+  memcpy(x[2].l, c, 96);
+  memcpy(x[3].l, d, 96);
+  if (mode < 0) {
+    r = fid == 0 ? fq_mul2<0>(x[0], x[1], x[2], x[3]) : fq_mul2<1>(x[0], x[1], x[2], x[3]);
+  } else {
+    for (int i = 0; i < 4; i++) s_st<T>(i, x[i]);
+    if (fid == 0) s_mul2<0, T, 13>(0, 0, 1, 2, 3, mode);  // d aliases a
+    else s_mul2<1, T, 13>(0, 0, 1, 2, 3, mode);
+    r = s_ld<T>(0);
+  }
+  memcpy(out, r.l, 96);
 }
 // ext 2 = Fq2 over field 0 (MNT4 G2 base field); ext 3 = Fq3 over field 1 (MNT6 G2 base field)
 void emul_ext_op(int ext, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {

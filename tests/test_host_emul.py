@@ -80,6 +80,28 @@ def test_field_ops(emul, fid, F):
             assert run(5, a) == F.to_mont(F.inv(x))
 
 
+@pytest.mark.parametrize("fid,F", FIELDS)
+def test_two_products_one_reduction(emul, fid, F):
+    """fq_mul2 / s_mul2: (a b + c d) / R mod p with a single Montgomery reduction, canonical output"""
+    rng = O.SplitMix64(0x2B0D + fid)
+    p = F.p
+    edge = [0, 1, p - 1, p - 2, (1 << 752), F.R, (1 << 752) - 1, p - (1 << 32)]
+    quads = [(a, b, c, d) for a in edge[:4] for b in edge[2:6] for c in edge[1:5] for d in edge[3:]]
+    quads += [(p - 1, p - 1, p - 1, p - 1), (0, 0, 0, 0), (p - 1, p - 1, 0, 5), (0, 7, p - 1, p - 1)]
+    quads += [tuple(O.random_field_element(rng, F) for _ in range(4)) for _ in range(100)]
+    out = U32x24()
+    for a, b, c, d in quads:
+        want = (F.mont_mul(a, b) + F.mont_mul(c, d)) % p
+        emul.emul_field_mul2(fid, -1, to_buf([a]), to_buf([b]), to_buf([c]), to_buf([d]), out)
+        assert from_buf(out, 1)[0] == want
+        emul.emul_field_mul2(fid, 0, to_buf([a]), to_buf([b]), to_buf([c]), to_buf([d]), out)
+        assert from_buf(out, 1)[0] == want
+        emul.emul_field_mul2(fid, 1, to_buf([a]), to_buf([b]), to_buf([c]), to_buf([d]), out)
+        assert from_buf(out, 1)[0] == (F.mont_mul(a, b) - F.mont_mul(c, d)) % p
+        emul.emul_field_mul2(fid, 2, to_buf([a]), to_buf([b]), to_buf([c]), to_buf([d]), out)
+        assert from_buf(out, 1)[0] == (F.mont_mul(a, b) + 13 * F.mont_mul(c, d)) % p
+
+
 def test_reference_mul_kat_through_device_code(emul):
     """The reference's raw-limb multiplication KAT (fields/mnt4753/tests.rs:605-650,
     fields/mnt6753/tests.rs:811) through the device multiplier source."""
@@ -189,6 +211,11 @@ def test_curve_ops(emul, cid, C):
                 emul.emul_curve_op(cid, 0, to_buf(enc_xyzz(A, sc)), to_buf(enc_aff(B)), out)
                 assert dec_xyzz() == C.add(A, B)
                 emul.emul_curve_op(cid, 6, to_buf(enc_xyzz(A, sc)), to_buf(enc_aff(B)), out)
+                assert dec_xyzz() == C.add(A, C.neg(B))
+                # the accumulation kernel's form (six slots, fused products on the prime-field curves)
+                emul.emul_curve_op(cid, 7, to_buf(enc_xyzz(A, sc)), to_buf(enc_aff(B)), out)
+                assert dec_xyzz() == C.add(A, B)
+                emul.emul_curve_op(cid, 8, to_buf(enc_xyzz(A, sc)), to_buf(enc_aff(B)), out)
                 assert dec_xyzz() == C.add(A, C.neg(B))
             emul.emul_curve_op(cid, 1, to_buf(enc_xyzz(A, sc)), to_buf(enc_xyzz(B, scale)), out)
             assert dec_xyzz() == C.add(A, B)
