@@ -83,6 +83,9 @@ static inline int launch_check(const char*) { return G753_OK; }
 #else
 // ---------------------------------------------------------------- real device
 #include <cuda_runtime.h>
+#ifndef G753_SMEM_CARVEOUT
+#define G753_SMEM_CARVEOUT 1
+#endif
 #define G753_LAUNCH(kernel, grid, block, stream, ...) \
   kernel<<<(unsigned)(grid), (unsigned)(block), 0, (stream)>>>(__VA_ARGS__)
 // launch with `smem` bytes of dynamic shared memory (opt-in above 48 KB); the slot kernels are
@@ -90,8 +93,9 @@ static inline int launch_check(const char*) { return G753_OK; }
 #define G753_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...)                                        \
   do {                                                                                                  \
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));             \
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,                        \
-                         (int)cudaSharedmemCarveoutMaxShared);                                          \
+    if (G753_SMEM_CARVEOUT)                                                                             \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,                      \
+                           (int)cudaSharedmemCarveoutMaxShared);                                        \
     kernel<<<(unsigned)(grid), (unsigned)(block), (size_t)(smem), (stream)>>>(__VA_ARGS__);             \
   } while (0)
 namespace g753 {

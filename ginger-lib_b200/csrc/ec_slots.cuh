@@ -15,6 +15,14 @@
 #pragma once
 #include "slots.cuh"
 
+// Mixed addition of the prime-field accumulation kernel: 0 = madd_g on eight slots (two 128-thread
+// blocks per SM), 1 = madd6_g on six (three blocks).  Measured on a B200 at 2^22 points: 224 ms
+// against 266 ms - with 12 warps per SM walking a ~95 KB multiplier body the SM waits for
+// instructions, so the eight-slot form stays the default.
+#ifndef G753_ACC6
+#define G753_ACC6 0
+#endif
+
 namespace g753 {
 
 // curve descriptors on slots: tower type + multiplication by the curve coefficient a.
@@ -89,7 +97,7 @@ struct EcS {
   static constexpr int MADD_SCRATCH = (K == 1 ? 4 : 3) * K + M::NTMP;  // scratch slots of madd_g / mdbl_g
   static constexpr int ADD_SCRATCH = 4 * K + M::NTMP;   // scratch slots of add / add_g / dbl
   // scratch slots of madd_acc_g, the mixed addition of the accumulation kernel: two on the prime-field curves
-  static constexpr int ACC_SCRATCH = K == 1 ? 2 : MADD_SCRATCH;
+  static constexpr int ACC_SCRATCH = (K == 1 && G753_ACC6) ? 2 : MADD_SCRATCH;
 
   static G753_D bool is_inf(int P) { return M::is_zero(P + 2 * K); }
   static G753_D void set_inf(int P) {
@@ -256,7 +264,7 @@ struct EcS {
   }
   // the accumulation kernel's mixed addition: needs ACC_SCRATCH slots at W
   static G753_D void madd_acc_g(int P, const Fq* q, bool negq, int W) {
-    if constexpr (K == 1) madd6_g(P, q, negq, W);
+    if constexpr (K == 1 && G753_ACC6) madd6_g(P, q, negq, W);
     else madd_g(P, q, negq, W);
   }
 

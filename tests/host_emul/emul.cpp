@@ -88,7 +88,8 @@ static void curve_op(int op, const uint32_t* acc_in, const uint32_t* other, uint
     get(out, P, 4 * K);
   } else if (op == 7 || op == 8) {  // the accumulation kernel's form (six slots on the prime-field curves)
     memcpy(gbuf, other, 96 * 2 * K);
-    E::madd_acc_g(P, gbuf, op == 8, S);
+    if constexpr (E::K == 1) E::madd6_g(P, gbuf, op == 8, S);  // six-slot form (opt-in on the device: G753_ACC6)
+    else E::madd_acc_g(P, gbuf, op == 8, S);
     get(out, P, 4 * K);
   } else if (op == 1) {
     put(Q, other, 4 * K);

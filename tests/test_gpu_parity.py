@@ -153,8 +153,8 @@ def test_msm_small_vs_oracle(ctx, group):
 
 @pytest.mark.parametrize("group", [ffi.MNT4_G1, ffi.MNT6_G1])
 def test_msm_accumulate_exceptions(ctx, group):
-    """the branches of the six-slot mixed addition (EcS::madd6_g): acc + (-acc) -> infinity and on from
-    there, acc + acc -> doubling (also of a negated base), in one bucket each"""
+    """the branches of the accumulation kernel's mixed addition (EcS::madd_acc_g): acc + (-acc) -> infinity
+    and on from there, acc + acc -> doubling (also of a negated base), in one bucket each"""
     C = GROUPS[group]
     P, Q, R = sample_points(C, 3, 0xE0 + group)
     s, t = sample_scalars(C, 2, 0xE8 + group)
