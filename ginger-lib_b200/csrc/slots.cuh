@@ -26,11 +26,6 @@
 #ifndef G753_FQ2_LAZY
 #define G753_FQ2_LAZY 2
 #endif
-// squarings on slots through the product body (A/B switch: one multiplier body instead of two in the
-// hot code of the slot kernels, 1176 instead of 876 limb-MACs per squaring)
-#ifndef G753_SQR_VIA_MUL
-#define G753_SQR_VIA_MUL 0
-#endif
 
 namespace g753 {
 
@@ -142,12 +137,7 @@ G753_NI void s_mul(int d, int a, int b) {
 }
 template <int FID, class T>
 G753_NI void s_sqr(int d, int a) {
-#if G753_SQR_VIA_MUL
-  const Fq x = s_ld<T>(a);
-  s_st<T>(d, fq_mul<FID>(x, x));
-#else
   s_st<T>(d, fq_sqr<FID>(s_ld<T>(a)));
-#endif
 }
 template <int FID, class T>
 G753_NI void s_add(int d, int a, int b) {
