@@ -578,7 +578,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=22, help="log2 of the total number of points")
     ap.add_argument("--fft-log-n", type=int, default=22)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--cpu-log-n", type=int, default=16, help="log2 of the CPU baseline's bounded sample")
+    ap.add_argument("--cpu-log-n", type=int, default=20, help="log2 of the CPU baseline's bounded sample (~10 s on 16 threads)")
     ap.add_argument("--copies", type=int, default=0,
                     help="precomputed shifted copies of the resident key (0 = auto by memory budget, 1 = plain key)")
     ap.add_argument("--no-cpu", action="store_true")
