@@ -4,5 +4,5 @@ behind the C ABI of include/g753.h; this package is the host-side mirror of the 
 operator interface.  Importing the compute classes requires the built library - there is no
 CPU fallback."""
 from . import ffi  # noqa: F401
-from .algebra import (Bases, Context, DeviceVector, EvaluationDomain, FixedBaseMSM, MixedRadixDomain, VariableBaseMSM,  # noqa: F401
+from .algebra import (Bases, Context, DensePolynomial, DeviceVector, EvaluationDomain, FixedBaseMSM, MixedRadixDomain, VariableBaseMSM,  # noqa: F401
                       default_context)  # noqa: F401

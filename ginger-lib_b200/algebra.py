@@ -365,6 +365,48 @@ class MixedRadixDomain:
         return self._run(evals, ffi.COSET_IFFT)
 
 
+class DensePolynomial:
+    """`DensePolynomial<F>` for the two 753-bit scalar fields as far as the transforms carry it
+    (algebra/src/fft/polynomial/dense.rs): coefficient vector (n, 12) Montgomery, lowest degree first,
+    no trailing zeros (`from_coefficients_vec`, dense.rs:64-74)."""
+
+    def __init__(self, field, coeffs, ctx=None):
+        c = ffi.as_u64(coeffs).reshape(-1, LIMBS)
+        nz = np.flatnonzero(c.any(axis=1))
+        self.field, self.ctx = field, ctx or default_context()
+        self.coeffs = c[:nz[-1] + 1].copy() if nz.size else c[:0].copy()
+
+    def is_zero(self):
+        return self.coeffs.shape[0] == 0
+
+    def degree(self):
+        return max(self.coeffs.shape[0] - 1, 0)
+
+    def evaluate_over_domain(self, domain):
+        """dense.rs:237-248: the evaluations over the whole domain (zero-padded fft)"""
+        return domain.fft(self.coeffs)
+
+    def __mul__(self, other):
+        """`Mul for &DensePolynomial` (dense.rs:342-357): evaluate both over a domain of
+        len(a) + len(b) points, multiply point-wise, interpolate - chained on the device."""
+        if self.is_zero() or other.is_zero():
+            return DensePolynomial(self.field, np.zeros((0, LIMBS), dtype=np.uint64), self.ctx)
+        domain = EvaluationDomain.new(self.field, self.coeffs.shape[0] + other.coeffs.shape[0], ctx=self.ctx)
+        if domain is None:
+            raise ValueError("field is not smooth enough to construct domain")
+        a = DeviceVector(self.ctx, self.field, domain.size(), domain._resized(self.coeffs))
+        b = DeviceVector(self.ctx, self.field, domain.size(), domain._resized(other.coeffs))
+        try:
+            a.ntt(ffi.FFT)
+            b.ntt(ffi.FFT)
+            a.op(ffi.OP_MUL, b)
+            a.ntt(ffi.IFFT)
+            return DensePolynomial(self.field, a.download(), self.ctx)
+        finally:
+            a.free()
+            b.free()
+
+
 class DeviceVector:
     """A vector of field elements resident in HBM, for chaining transforms the way
     R1CStoQAP::witness_map does (r1cs_to_qap.rs:121-161) without host round trips."""

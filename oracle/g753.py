@@ -589,3 +589,76 @@ def groth16_create_proof(key, num_inputs, full_assignment, h, r, s, msm=msm_naiv
     g_c = acc(g1, g1.mul(g_a, s), g1.mul(g1_b, r), g1.neg(rs_delta), msm(g1, key.l_query, aux),
               msm(g1, key.h_query[:num_inputs], h_in), msm(g1, key.h_query[num_inputs:], h_aux))  # :318-337
     return g_a, g2_b, g_c
+
+
+# --------------------------------------------------------------------------------------
+# GM17 prover (proof-systems/src/gm17): the SAP witness map and create_proof, restated
+# --------------------------------------------------------------------------------------
+
+def sap_witness_map(field, a_evals, c_evals, d1, d2):
+    """R1CStoSAP::witness_map from the evaluated constraints onwards (gm17/r1cs_to_sap.rs:191-245).
+    a_evals / c_evals are the domain_size vectors the reference fills at :163-186 and :205-232
+    (padding included).  Returns h, domain_size + 1 canonical integers."""
+    p = field.p
+    n = len(a_evals)
+    assert len(c_evals) == n
+    dom = EvaluationDomain(field, n)
+    assert dom.size == n
+    a = dom.ifft(a_evals)                                    # :191
+    d1_double = 2 * d1 % p                                   # :193
+    h = [d1_double * ai % p for ai in a]                     # :194-195
+    d1d1 = d1 * d1 % p
+    h[0] = (h[0] - d2) % p                                   # :196
+    h[0] = (h[0] - d1d1) % p                                 # :198
+    h.append(d1d1)                                           # :199
+    a = dom.coset_fft(a)                                     # :201
+    aa = [x * x % p for x in a]                              # :203
+    c = dom.coset_fft(dom.ifft(c_evals))                     # :234-235
+    aa = [(x - y) % p for x, y in zip(aa, c)]                # :237
+    z_inv = pow((pow(dom.generator, n, p) - 1) % p, -1, p)   # :239, domain.rs:245-256
+    aa = dom.coset_ifft([x * z_inv % p for x in aa])         # :240
+    for i in range(n - 1):                                   # :242-245 (h[..domain_size - 1])
+        h[i] = (h[i] + aa[i]) % p
+    return h
+
+
+class GM17Key:
+    """The fields of gm17::Parameters the prover reads (gm17/mod.rs:138-149), as affine oracle points
+    (None = infinity)."""
+
+    def __init__(self, g1, g2, a_query, b_query, c_query_1, c_query_2, g_gamma_z, h_gamma_z, g_ab_gamma_z,
+                 g_gamma2_z2, g_gamma2_z_t):
+        self.g1, self.g2 = g1, g2
+        self.a_query, self.b_query, self.c_query_1, self.c_query_2 = a_query, b_query, c_query_1, c_query_2
+        self.g_gamma_z, self.h_gamma_z, self.g_ab_gamma_z = g_gamma_z, h_gamma_z, g_ab_gamma_z
+        self.g_gamma2_z2, self.g_gamma2_z_t = g_gamma2_z2, g_gamma2_z_t
+
+
+def gm17_create_proof(key, num_inputs, full_assignment, h, d1, d2, r, fr, msm=msm_naive):
+    """gm17/prover.rs:235-354 from the witness map's outputs onwards.  full_assignment: the SAP
+    assignment (inputs, aux and the extra variables of r1cs_to_sap.rs:127-151), canonical ints;
+    h: canonical ints; fr: the scalar field (r^2, 2 d1 r are field products, :299-301)."""
+    g1, g2, p = key.g1, key.g2, fr.p
+    ni = num_inputs
+    inp, aux = full_assignment[1:ni], full_assignment[ni:]    # :235-247
+    h_in, h_aux = h[:ni], h[ni:]                              # :250-261
+
+    def acc(curve, *pts):
+        t = None
+        for q in pts:
+            t = curve.add(t, q)
+        return t
+
+    g_a = acc(g1, g1.mul(key.g_gamma_z, r), key.a_query[0], g1.mul(key.g_gamma_z, d1),
+              msm(g1, key.a_query[1:ni], inp), msm(g1, key.a_query[ni:], aux))            # :264-278
+    g_b = acc(g2, g2.mul(key.h_gamma_z, r), key.b_query[0], g2.mul(key.h_gamma_z, d1),
+              msm(g2, key.b_query[1:ni], inp), msm(g2, key.b_query[ni:], aux))            # :280-296
+    r_2, r2 = 2 * r % p, r * r % p                            # :299-301
+    d1_r_2 = d1 * r_2 % p
+    c1_acc = msm(g1, key.c_query_1, aux)                      # :303-306 (get_c_query_1(0))
+    c2_acc = g1.add(msm(g1, key.c_query_2[1:ni], inp), msm(g1, key.c_query_2[ni:], aux))  # :308-315
+    g_acc = g1.add(msm(g1, key.g_gamma2_z_t[:ni], h_in), msm(g1, key.g_gamma2_z_t[ni:], h_aux))  # :317-325
+    g_c = acc(g1, c1_acc, g1.mul(key.g_gamma2_z2, r2), g1.mul(key.g_ab_gamma_z, r), g1.mul(key.g_ab_gamma_z, d1),
+              g1.mul(key.c_query_2[0], r), g1.mul(key.g_gamma2_z2, d1_r_2), g1.mul(c2_acc, r),
+              g1.mul(key.g_gamma2_z_t[0], d2), g_acc)                                    # :327-344
+    return g_a, g_b, g_c

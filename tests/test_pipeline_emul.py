@@ -194,6 +194,26 @@ def test_domain_public_fields_and_pointwise(ctx, field):
     assert array_field(F, got) == [x * zinv % F.p for x in a]
 
 
+@pytest.mark.parametrize("field", sorted(FIELDS))
+def test_dense_polynomial_mul(ctx, field):
+    """`&DensePolynomial * &DensePolynomial` through the transforms (dense.rs:342-357) = schoolbook product"""
+    F = FIELDS[field]
+    rng = O.SplitMix64(0xDE + field)
+    for la, lb in ((1, 1), (3, 5), (8, 8), (17, 2)):
+        a = [O.random_field_element(rng, F) for _ in range(la)]
+        b = [O.random_field_element(rng, F) for _ in range(lb)]
+        want = [0] * (la + lb - 1)
+        for i, x in enumerate(a):
+            for j, y in enumerate(b):
+                want[i + j] = (want[i + j] + x * y) % F.p
+        pa = G.DensePolynomial(field, field_array(F, a + [0, 0]), ctx)     # trailing zeros are dropped
+        pb = G.DensePolynomial(field, field_array(F, b), ctx)
+        assert pa.degree() == la - 1
+        assert array_field(F, (pa * pb).coeffs) == want
+    zero = G.DensePolynomial(field, field_array(F, [0, 0]), ctx)
+    assert zero.is_zero() and (zero * pb).is_zero() and (pb * zero).is_zero()
+
+
 def test_device_vector_chain(ctx):
     """ifft -> coset_fft -> pointwise -> coset_ifft chained on 'device' memory"""
     F = O.MNT4_FR
