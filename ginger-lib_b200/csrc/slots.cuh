@@ -26,6 +26,12 @@
 #ifndef G753_FQ2_LAZY
 #define G753_FQ2_LAZY 2
 #endif
+// Products on slots through a ROLLED multiplier (fq_mul_rolled below): ~9 KB of code per product instead
+// of ~45 KB, so that more than 8 warps per SM stop out-running instruction fetch.
+// Opt-in until measured on a B200 (round 2); bit-exact either way (tests/test_pipeline_emul.py runs both).
+#ifndef G753_ROLLED
+#define G753_ROLLED 0
+#endif
 
 namespace g753 {
 
@@ -130,14 +136,47 @@ G753_D void g_st(Fq* g, const Fq& a) {
   }
 }
 
+// a * slot[b] with the 24 Montgomery steps as a loop of six iterations of four (one 16-byte chunk of
+// the multiplier per iteration, read from the slot when it is needed): the loop body is all the code
+// there is.  Same accumulators and step as fq_mul; the first step runs on zeroed accumulators
+// instead of the multiply-only form (same instruction count).
+template <int FID, class T>
+G753_D Fq fq_mul_rolled(const Fq& a, const uint4* pb) {
+  uint32_t even[NL], odd[NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++) even[i] = odd[i] = 0;
+#pragma unroll 1
+  for (int k = 0; k < SLOT_CHUNKS; k++) {
+    const uint4 vb = pb[k * T::NC];
+    mont_step<FID, false>(even, odd, a.l, vb.x);
+    mont_step<FID, false>(odd, even, a.l, vb.y);
+    mont_step<FID, false>(even, odd, a.l, vb.z);
+    mont_step<FID, false>(odd, even, a.l, vb.w);
+  }
+  return mont_finish<FID>(even, odd);
+}
+// slot[a] * slot[b] / slot[a]^2 by the build's multiplier
+template <int FID, class T>
+G753_D Fq s_prod(const Fq& a, int b) {
+#if G753_ROLLED
+  return fq_mul_rolled<FID, T>(a, slot_ptr<T>(b));
+#else
+  return fq_mul<FID>(a, s_ld<T>(b));
+#endif
+}
+
 // ---- Fq on slots (d may alias a or b everywhere: operands are read before d is written) ----
 template <int FID, class T>
 G753_NI void s_mul(int d, int a, int b) {
-  s_st<T>(d, fq_mul<FID>(s_ld<T>(a), s_ld<T>(b)));
+  s_st<T>(d, s_prod<FID, T>(s_ld<T>(a), b));
 }
 template <int FID, class T>
 G753_NI void s_sqr(int d, int a) {
+#if G753_ROLLED
+  s_st<T>(d, fq_mul_rolled<FID, T>(s_ld<T>(a), slot_ptr<T>(a)));  // one multiplier body in the hot code
+#else
   s_st<T>(d, fq_sqr<FID>(s_ld<T>(a)));
+#endif
 }
 template <int FID, class T>
 G753_NI void s_add(int d, int a, int b) {
@@ -248,14 +287,25 @@ G753_NI unsigned s_madd6(int P, int W, const Fq* q, bool negq, int phase) {
       case 8: d = t0; a = t1; c = t0; fl = SQR | SUBC | XPOST; break;
       default: d = Y; a = t1; b = t0; c = Y; fl = SUBC; break;
     }
-    const Fq A = (fl & AG) ? g_ld(q + s) : s_ld<T>(a);
     Fq r;
+#if G753_ROLLED
+    // every product has one operand in a slot: the rolled multiplier streams that one and keeps the
+    // other (the global operand, the retained factor f, or a copy of the slot) in registers
+    if (fl & KEEP) {
+      r = fq_mul_rolled<FID, T>(f, slot_ptr<T>(a));
+    } else {
+      const Fq A = (fl & AG) ? g_ld(q + s) : s_ld<T>(a);
+      r = fq_mul_rolled<FID, T>(A, slot_ptr<T>((fl & SQR) ? a : b));
+    }
+#else
+    const Fq A = (fl & AG) ? g_ld(q + s) : s_ld<T>(a);
     if (fl & SQR) {
       r = fq_sqr<FID>(A);
     } else {
       if (!(fl & KEEP)) f = s_ld<T>(b);
       r = fq_mul<FID>(A, f);
     }
+#endif
     if (fl & TOF) {
       f = r;
       continue;
@@ -284,6 +334,18 @@ G753_D Fq s_mul2_stream(const Fq& a, int b, const Fq& c, int e) {
   const uint4* pb = slot_ptr<T>(b);
   const uint4* pe = slot_ptr<T>(e);
   uint32_t even[NL], odd[NL];
+#if G753_ROLLED
+#pragma unroll
+  for (int i = 0; i < NL; i++) even[i] = odd[i] = 0;
+#pragma unroll 1
+  for (int k = 0; k < SLOT_CHUNKS; k++) {
+    const uint4 vb = pb[k * T::NC], ve = pe[k * T::NC];
+    mont2_step<FID, false>(even, odd, a.l, vb.x, c.l, ve.x);
+    mont2_step<FID, false>(odd, even, a.l, vb.y, c.l, ve.y);
+    mont2_step<FID, false>(even, odd, a.l, vb.z, c.l, ve.z);
+    mont2_step<FID, false>(odd, even, a.l, vb.w, c.l, ve.w);
+  }
+#else
 #pragma unroll
   for (int k = 0; k < SLOT_CHUNKS; k++) {
     const uint4 vb = pb[k * T::NC], ve = pe[k * T::NC];
@@ -295,6 +357,7 @@ G753_D Fq s_mul2_stream(const Fq& a, int b, const Fq& c, int e) {
       else mont2_step<FID, false>(even, odd, a.l, bb[u], c.l, ee[u]);
     }
   }
+#endif
   return mont_finish<FID>(even, odd);
 }
 // d = slot[a] * slot[b] + f(slot[c]) * slot[e], f by `mode`: 0 identity, 1 negation, 2 times NR (the

@@ -29,6 +29,15 @@ static void field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out
     case 10: r = fq_mul_small<FID, 26>(x); break;
     case 11: r = fq_mul_small<FID, 121>(x); break;
     case 12: r = fq_dbl<FID>(x); break;
+    case 13:  // the product / squaring as the slot kernels run them (rolled multiplier under -DG753_ROLLED=1)
+    case 14:
+      threadIdx.x = 0;
+      s_st<T>(0, x);
+      s_st<T>(1, y);
+      if (op == 13) s_mul<FID, T>(1, 0, 1);  // d aliases b
+      else s_sqr<FID, T>(1, 0);
+      r = s_ld<T>(1);
+      break;
     default: r = fq_zero<FID>();
   }
   memcpy(out, r.l, 96);

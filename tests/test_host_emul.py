@@ -19,12 +19,15 @@ LIB = os.path.join(HERE, "host_emul", "libemul.so")
 CSRC = os.path.join(HERE, "..", "ginger-lib_b200", "csrc")
 
 
-@pytest.fixture(scope="module")
-def emul():
+# the default build and the opt-in rolled multiplier (slots.cuh, G753_ROLLED): identical results
+@pytest.fixture(scope="module", params=["", "_rolled"])
+def emul(request):
+    lib = LIB.replace(".so", request.param + ".so")
+    flags = ["-DG753_ROLLED=1"] if request.param else []
     deps = [SRC] + [os.path.join(CSRC, f) for f in ("fq.cuh", "slots.cuh", "ec_slots.cuh", "device.cuh", "constants.inc")]
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC])
-    return ctypes.CDLL(LIB)
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC"] + flags + ["-o", lib, SRC])
+    return ctypes.CDLL(lib)
 
 
 U32x24 = ctypes.c_uint32 * 24
@@ -62,10 +65,12 @@ def test_field_ops(emul, fid, F):
 
     for a, b in pairs:
         assert run(0, a, b) == F.mont_mul(a, b), (hex(a), hex(b))
+        assert run(13, a, b) == F.mont_mul(a, b), (hex(a), hex(b))
         assert run(1, a, b) == (a + b) % p
         assert run(2, a, b) == (a - b) % p
     for a in vals:
         assert run(3, a) == F.mont_mul(a, a)
+        assert run(14, a) == F.mont_mul(a, a)
         assert run(4, a) == (-a) % p
         assert run(6, a) == F.to_mont(a)
         assert run(7, a) == F.from_mont(a)

@@ -81,6 +81,24 @@ def test_msm_accumulate_exceptions(ctx, group):
         assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
 
 
+@pytest.fixture(scope="module")
+def ctx_optin():
+    """the opt-in kernel forms (six-slot mixed addition, rolled multiplier) in their own emulation build"""
+    from util753 import build_emul
+    lib = ffi.Library(build_emul(("-DG753_ACC6=1", "-DG753_ROLLED=1"), "_acc6_rolled"))
+    c = G.Context(0, library=lib)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_msm_optin_forms(ctx_optin, group):
+    """-DG753_ACC6=1 -DG753_ROLLED=1: same results from the six-slot addition and the rolled multiplier"""
+    test_msm_small(ctx_optin, group)
+    if GROUPS[group].F.k == 1:
+        test_msm_accumulate_exceptions(ctx_optin, group)
+
+
 def test_msm_window_sizes(ctx, monkeypatch):
     """force several window widths through the same input (exercises multi-level reduction)"""
     C = O.MNT4_G1

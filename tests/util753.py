@@ -116,14 +116,16 @@ def array_field(field, a):
     return out
 
 
-def build_emul():
-    """(re)build the TEST-ONLY host-emulation library of the C ABI when it is missing or stale"""
+def build_emul(flags=(), tag=""):
+    """(re)build the TEST-ONLY host-emulation library of the C ABI when it is missing or stale;
+    `flags` / `tag`: a differently configured build (e.g. the opt-in kernel forms) under its own name"""
     import subprocess
     src = os.path.join(HERE, "host_emul", "capi_emul.cpp")
-    lib = os.path.join(HERE, "host_emul", "libg753_emul.so")
+    lib = os.path.join(HERE, "host_emul", "libg753_emul%s.so" % tag)
     csrc = os.path.join(HERE, "..", "ginger-lib_b200", "csrc")
     deps = [src, os.path.join(HERE, "..", "include", "g753.h")] + [
         os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".cu", ".inc"))]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", lib, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++"] + list(flags) +
+                              ["-o", lib, src])
     return lib
