@@ -248,84 +248,6 @@ G753_D void s_stg(Fq* g, int a) {
   for (int k = 0; k < SLOT_CHUNKS; k++) p[k] = q[k * T::NC];
 }
 
-// ---- the six-slot mixed addition of the prime-field curves (EcS::madd6_g) -----------------------
-// madd-2008-s on a point in slots X, Y, ZZ, ZZZ = P .. P + 3 with only two temporaries t0, t1 = W, W + 1
-// (six slots per thread instead of eight: three 128-thread blocks = 12 warps per SM instead of 8).
-// Two things make that possible: PP = P^2 never gets a slot - it stays in registers as the common
-// factor of the three products that use it - and the subtraction that follows a product is folded
-// into the same step.  The whole addition is a short micro-program run by ONE function with ONE
-// inlined product and ONE inlined squaring: a B200 fetches instructions fast enough only while the
-// hot code of an SM stays around 100 KB (measured: the same formulas spread over five fused
-// functions, each with its own 45 KB multiplier body, ran at 63 % instead of 85 % pipe utilisation
-// with 6 stall cycles per issue waiting for instructions, profiles/r01_bucket_acc_2p22_v19).
-//
-//   phase 0:  t0 = x2 ZZ - X (P),  t1 = +-(y2 ZZZ) - Y (R);  returns bit 0 = (P == 0), bit 1 = (R == 0)
-//   phase 1:  f = t0^2 (PP);  X *= f (Q);  ZZ *= f;  t0 *= f (PPP);  ZZZ *= t0;  Y *= t0;
-//             t0 = t1^2 - t0;  X = t0 - 2X (X3), t0 = Q - X3;  Y = t1 t0 - Y (Y3)
-template <int FID, class T>
-G753_NI unsigned s_madd6(int P, int W, const Fq* q, bool negq, int phase) {
-  enum { AG = 1, SQR = 2, KEEP = 4, TOF = 8, SUBC = 16, NEGADD = 32, XPOST = 64 };
-  const int X = P, Y = P + 1, ZZ = P + 2, ZZZ = P + 3, t0 = W, t1 = W + 1;
-  Fq f;  // retained factor
-#pragma unroll
-  for (int i = 0; i < NL; i++) f.l[i] = 0;
-  unsigned zero = 0;
-  const int first = phase == 0 ? 0 : 2, last = phase == 0 ? 2 : 10;
-#pragma unroll 1
-  for (int s = first; s < last; s++) {
-    int d = 0, a = 0, b = 0, c = 0;
-    unsigned fl = 0;
-    switch (s) {
-      case 0: d = t0; b = ZZ; c = X; fl = AG | SUBC; break;
-      case 1: d = t1; b = ZZZ; c = Y; fl = AG | (negq ? NEGADD : SUBC); break;
-      case 2: a = t0; fl = SQR | TOF; break;
-      case 3: d = X; a = X; fl = KEEP; break;
-      case 4: d = ZZ; a = ZZ; fl = KEEP; break;
-      case 5: d = t0; a = t0; fl = KEEP; break;
-      case 6: d = ZZZ; a = ZZZ; b = t0; break;
-      case 7: d = Y; a = Y; b = t0; break;
-      case 8: d = t0; a = t1; c = t0; fl = SQR | SUBC | XPOST; break;
-      default: d = Y; a = t1; b = t0; c = Y; fl = SUBC; break;
-    }
-    Fq r;
-#if G753_ROLLED
-    // every product has one operand in a slot: the rolled multiplier streams that one and keeps the
-    // other (the global operand, the retained factor f, or a copy of the slot) in registers
-    if (fl & KEEP) {
-      r = fq_mul_rolled<FID, T>(f, slot_ptr<T>(a));
-    } else {
-      const Fq A = (fl & AG) ? g_ld(q + s) : s_ld<T>(a);
-      r = fq_mul_rolled<FID, T>(A, slot_ptr<T>((fl & SQR) ? a : b));
-    }
-#else
-    const Fq A = (fl & AG) ? g_ld(q + s) : s_ld<T>(a);
-    if (fl & SQR) {
-      r = fq_sqr<FID>(A);
-    } else {
-      if (!(fl & KEEP)) f = s_ld<T>(b);
-      r = fq_mul<FID>(A, f);
-    }
-#endif
-    if (fl & TOF) {
-      f = r;
-      continue;
-    }
-    if (fl & (SUBC | NEGADD)) {
-      const Fq cc = s_ld<T>(c);
-      r = (fl & NEGADD) ? fq_neg<FID>(fq_add<FID>(r, cc)) : fq_sub<FID>(r, cc);
-    }
-    if (fl & XPOST) {  // r = R^2 - PPP: X3 = r - 2Q into X, Q - X3 into d
-      const Fq qq = s_ld<T>(X);
-      r = fq_sub<FID>(fq_sub<FID>(r, qq), qq);
-      s_st<T>(X, r);
-      r = fq_sub<FID>(qq, r);
-    }
-    s_st<T>(d, r);
-    if (s < 2 && fq_is_zero(r)) zero |= 1u << s;
-  }
-  return zero;
-}
-
 // ---- two products under one reduction on slots ---------------------------------------------------
 // returns a * slot[b] + c * slot[e] (fq_mul2).  a and c are in registers; the multipliers are
 // streamed from their slots, one 16-byte chunk every four steps.
@@ -360,6 +282,99 @@ G753_D Fq s_mul2_stream(const Fq& a, int b, const Fq& c, int e) {
 #endif
   return mont_finish<FID>(even, odd);
 }
+// ---- the six-slot mixed addition of the prime-field curves (EcS::madd6_g) -----------------------
+// madd-2008-s on a point in slots X, Y, ZZ, ZZZ = P .. P + 3 with only two temporaries t0, t1 = W, W + 1
+// (six slots per thread instead of eight: three 128-thread blocks = 12 warps per SM instead of 8).
+// Two things make that possible: PP = P^2 never gets a slot - it stays in registers as the common
+// factor of the three products that use it - and the subtraction that follows a product is folded
+// into the same step.  The whole addition is a short micro-program run by ONE function with ONE
+// inlined product and ONE inlined squaring: a B200 fetches instructions fast enough only while the
+// hot code of an SM stays around 100 KB (measured: the same formulas spread over five fused
+// functions, each with its own 45 KB multiplier body, ran at 63 % instead of 85 % pipe utilisation
+// with 6 stall cycles per issue waiting for instructions, profiles/r01_bucket_acc_2p22_v19).
+//
+//   phase 0:  t0 = x2 ZZ - X (P),  t1 = +-(y2 ZZZ) - Y (R);  returns bit 0 = (P == 0), bit 1 = (R == 0)
+//   phase 1:  f = t0^2 (PP);  X *= f (Q);  ZZ *= f;  t0 *= f (PPP);  ZZZ *= t0;  Y *= t0;
+//             t0 = t1^2 - t0;  X = t0 - 2X (X3), t0 = Q - X3;  Y = t1 t0 - Y (Y3)
+//   (G753_ROLLED: Y *= t0 is skipped and the last step is Y = t1 (Q - X3) + (-Y) t0, two products under one
+//   reduction: 600 limb-MACs saved, which pays for the two squarings that go through the product body)
+template <int FID, class T>
+G753_NI unsigned s_madd6(int P, int W, const Fq* q, bool negq, int phase) {
+  enum { AG = 1, SQR = 2, KEEP = 4, TOF = 8, SUBC = 16, NEGADD = 32, XPOST = 64 };
+  const int X = P, Y = P + 1, ZZ = P + 2, ZZZ = P + 3, t0 = W, t1 = W + 1;
+  Fq f;  // retained factor
+#pragma unroll
+  for (int i = 0; i < NL; i++) f.l[i] = 0;
+  unsigned zero = 0;
+  const int first = phase == 0 ? 0 : 2, last = phase == 0 ? 2 : 10;
+#pragma unroll 1
+  for (int s = first; s < last; s++) {
+    int d = 0, a = 0, b = 0, c = 0;
+    unsigned fl = 0;
+    switch (s) {
+      case 0: d = t0; b = ZZ; c = X; fl = AG | SUBC; break;
+      case 1: d = t1; b = ZZZ; c = Y; fl = AG | (negq ? NEGADD : SUBC); break;
+      case 2: a = t0; fl = SQR | TOF; break;
+      case 3: d = X; a = X; fl = KEEP; break;
+      case 4: d = ZZ; a = ZZ; fl = KEEP; break;
+      case 5: d = t0; a = t0; fl = KEEP; break;
+      case 6: d = ZZZ; a = ZZZ; b = t0; break;
+      case 7: d = Y; a = Y; b = t0; break;
+      case 8: d = t0; a = t1; c = t0; fl = SQR | SUBC | XPOST; break;
+      default: d = Y; a = t1; b = t0; c = Y; fl = SUBC; break;
+    }
+    Fq r;
+#if G753_ROLLED
+    // with the rolled bodies code size is no concern, so the last two products share one reduction:
+    // Y3 = R (Q - X3) + (-Y1) PPP (fq_mul2).  Y1 and PPP stay in their slots until then: step 7 is
+    // skipped, step 8 leaves Q - X3 in f instead of overwriting PPP.
+    if (s == 7) continue;
+    if (s == 9) {
+      s_st<T>(Y, s_mul2_stream<FID, T>(f, t1, fq_neg<FID>(s_ld<T>(Y)), t0));
+      continue;
+    }
+    // every product has one operand in a slot: the rolled multiplier streams that one and keeps the
+    // other (the global operand, the retained factor f, or a copy of the slot) in registers
+    if (fl & KEEP) {
+      r = fq_mul_rolled<FID, T>(f, slot_ptr<T>(a));
+    } else {
+      const Fq A = (fl & AG) ? g_ld(q + s) : s_ld<T>(a);
+      r = fq_mul_rolled<FID, T>(A, slot_ptr<T>((fl & SQR) ? a : b));
+    }
+#else
+    const Fq A = (fl & AG) ? g_ld(q + s) : s_ld<T>(a);
+    if (fl & SQR) {
+      r = fq_sqr<FID>(A);
+    } else {
+      if (!(fl & KEEP)) f = s_ld<T>(b);
+      r = fq_mul<FID>(A, f);
+    }
+#endif
+    if (fl & TOF) {
+      f = r;
+      continue;
+    }
+    if (fl & (SUBC | NEGADD)) {
+      const Fq cc = s_ld<T>(c);
+      r = (fl & NEGADD) ? fq_neg<FID>(fq_add<FID>(r, cc)) : fq_sub<FID>(r, cc);
+    }
+    if (fl & XPOST) {  // r = R^2 - PPP: X3 = r - 2Q into X, Q - X3 into d
+      const Fq qq = s_ld<T>(X);
+      r = fq_sub<FID>(fq_sub<FID>(r, qq), qq);
+      s_st<T>(X, r);
+      r = fq_sub<FID>(qq, r);
+#if G753_ROLLED
+      f = r;
+      continue;
+#endif
+    }
+    s_st<T>(d, r);
+    if (s < 2 && fq_is_zero(r)) zero |= 1u << s;
+  }
+  return zero;
+}
+
+// ---- two products under one reduction on slots: s_mul2 (s_mul2_stream is defined above s_madd6) ----
 // d = slot[a] * slot[b] + f(slot[c]) * slot[e], f by `mode`: 0 identity, 1 negation, 2 times NR (the
 // non-residue of an Fq2 product).  The lanes of a column reconverge before d is written (d may be an
 // operand of the other lanes' products) and after.
