@@ -270,6 +270,14 @@ def test_bad_arguments(ctx):
     z = np.zeros((1, 24), dtype=np.uint64)
     assert lib.bases_upload(ctx.handle, 9, ffi.ptr(z), None, 1, ctypes.byref(h)) == ffi.ERR_BAD_ARG
     assert b"unknown group" in lib.last_error()
+    out = np.zeros(12, dtype=np.uint64)
+    assert lib.domain_constant(ctx.handle, ffi.FIELD_MNT6_FR, 15, 0, ffi.ptr(out)) == ffi.ERR_DOMAIN   # `None`
+    assert lib.domain_constant(ctx.handle, ffi.FIELD_MNT6_FR, 3, 5, ffi.ptr(out)) == ffi.ERR_BAD_ARG
+    assert lib.domain_constant(ctx.handle, ffi.FIELD_MNT6_FR, 3, 0, None) == ffi.ERR_BAD_ARG
+    # a 2^29 domain's constants need no O(n) tables
+    assert lib.domain_constant(ctx.handle, ffi.FIELD_MNT4_FR, 29, 1, ffi.ptr(out)) == ffi.OK
+    F = O.MNT4_FR
+    assert array_field(F, out) == [O.EvaluationDomain(F, 1 << 29).group_gen]
 
 
 @pytest.mark.parametrize("group,c,copies", [(ffi.MNT4_G1, 7, 4), (ffi.MNT4_G1, 0, 8), (ffi.MNT6_G2, 9, 3)])
