@@ -18,7 +18,8 @@
 // Mixed addition of the prime-field accumulation kernel: 0 = madd_g on eight slots (two 128-thread
 // blocks per SM), 1 = madd6_g on six (three blocks).  Measured on a B200 at 2^22 points: 224 ms
 // against 266 ms - with 12 warps per SM walking a ~95 KB multiplier body the SM waits for
-// instructions, so the eight-slot form stays the default.
+// instructions - and against 229 ms with the rolled multiplier (G753_ROLLED); the eight-slot form stays
+// the default.
 #ifndef G753_ACC6
 #define G753_ACC6 0
 #endif

@@ -28,7 +28,8 @@
 #endif
 // Products on slots through a ROLLED multiplier (fq_mul_rolled below): ~9 KB of code per product instead
 // of ~45 KB, so that more than 8 warps per SM stop out-running instruction fetch.
-// Opt-in until measured on a B200 (round 2); bit-exact either way (tests/test_pipeline_emul.py runs both).
+// Opt-in: measured on a B200 it removes the fetch stalls but is ~2 % slower than the default at equal work
+// (229.1 against 224.3 ms at 2^22); bit-exact either way (tests/test_pipeline_emul.py runs both).
 #ifndef G753_ROLLED
 #define G753_ROLLED 0
 #endif

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round-2 starting point: A/B of the opt-in kernel forms against the default build on one B200.
+# A/B of the opt-in kernel forms against the default build on one B200 (round-1 result for G1 at 2^22:
+# default 224.3 ms, rolled6 229.1 ms, rolled 246.3 ms - profiles/r01_ab45_rolled.jsonl; G2 not yet measured).
 #   here (CPU):   tools/dev/build_variant.sh rolled  -DG753_ROLLED=1
 #                 tools/dev/build_variant.sh rolled6 -DG753_ROLLED=1 -DG753_ACC6=1
 #   then:         gpurun --timeout 600 -- bash tools/dev/r2_ab_rolled.sh
