@@ -146,9 +146,11 @@ G753_D Fq fq_mul_rolled(const Fq& a, const uint4* pb) {
   uint32_t even[NL], odd[NL];
 #pragma unroll
   for (int i = 0; i < NL; i++) even[i] = odd[i] = 0;
+  uint4 nb = pb[0];
 #pragma unroll 1
   for (int k = 0; k < SLOT_CHUNKS; k++) {
-    const uint4 vb = pb[k * T::NC];
+    const uint4 vb = nb;
+    if (k + 1 < SLOT_CHUNKS) nb = pb[(k + 1) * T::NC];  // the next chunk arrives during these four steps
     mont_step<FID, false>(even, odd, a.l, vb.x);
     mont_step<FID, false>(odd, even, a.l, vb.y);
     mont_step<FID, false>(even, odd, a.l, vb.z);
@@ -260,9 +262,14 @@ G753_D Fq s_mul2_stream(const Fq& a, int b, const Fq& c, int e) {
 #if G753_ROLLED
 #pragma unroll
   for (int i = 0; i < NL; i++) even[i] = odd[i] = 0;
+  uint4 nb = pb[0], ne = pe[0];
 #pragma unroll 1
   for (int k = 0; k < SLOT_CHUNKS; k++) {
-    const uint4 vb = pb[k * T::NC], ve = pe[k * T::NC];
+    const uint4 vb = nb, ve = ne;
+    if (k + 1 < SLOT_CHUNKS) {
+      nb = pb[(k + 1) * T::NC];
+      ne = pe[(k + 1) * T::NC];
+    }
     mont2_step<FID, false>(even, odd, a.l, vb.x, c.l, ve.x);
     mont2_step<FID, false>(odd, even, a.l, vb.y, c.l, ve.y);
     mont2_step<FID, false>(even, odd, a.l, vb.z, c.l, ve.z);
