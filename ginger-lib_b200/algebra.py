@@ -316,6 +316,84 @@ class EvaluationDomain:
         finally:
             d.free()
 
+    # ---- the rest of the struct's methods (domain.rs:183-287); field arithmetic on the device ----
+    def _fop(self, op, a, b=None):
+        out = np.zeros((1, LIMBS), dtype=np.uint64)
+        a = np.ascontiguousarray(ffi.as_u64(a).reshape(1, LIMBS))
+        b = np.ascontiguousarray(ffi.as_u64(b).reshape(1, LIMBS)) if b is not None else None
+        self.ctx.lib.check(self.ctx.lib.field_op(self.ctx.handle, self.field, op, ffi.ptr(a), ffi.ptr(b), ffi.ptr(out), 1))
+        return out
+
+    def _one(self):
+        one = np.zeros((1, LIMBS), dtype=np.uint64)
+        one[0, 0] = 1
+        return self._fop(ffi.OP_TO_MONT, one)
+
+    def _pow_size(self, tau):
+        """tau^size by log2(size) squarings (`tau.pow(&[self.size])`)"""
+        t = ffi.as_u64(tau).reshape(1, LIMBS)
+        for _ in range(self.log_size_of_group):
+            t = self._fop(ffi.OP_SQR, t)
+        return t
+
+    def elements(self):
+        """the domain's elements 1, g, g^2, ... (domain.rs:234-240, 419-441) as an (n, 12) Montgomery
+        array: the transform of the unit vector e_1"""
+        if self.size_ == 1:
+            return self._one()
+        e1 = np.zeros((self.size_, LIMBS), dtype=np.uint64)
+        e1[1] = self._one()[0]
+        return self.fft(e1)
+
+    def evaluate_vanishing_polynomial(self, tau):
+        """z(tau) = tau^size - 1 (domain.rs:229-231); tau: 12 Montgomery limbs"""
+        return self._fop(ffi.OP_SUB, self._pow_size(tau), self._one()).reshape(LIMBS)
+
+    def vanishing_polynomial(self):
+        """the sparse polynomial X^size - 1 as [(degree, coefficient)] (domain.rs:222-225)"""
+        one = self._one()
+        zero = np.zeros((1, LIMBS), dtype=np.uint64)
+        return [(0, self._fop(ffi.OP_SUB, zero, one).reshape(LIMBS)), (self.size_, one.reshape(LIMBS))]
+
+    def evaluate_all_lagrange_coefficients(self, tau):
+        """L_i(tau) for every i (domain.rs:183-220): the indicator of tau's position when tau lies in the
+        domain, else (tau^n - 1) / n * g^i / (tau - g^i) - one element-wise inversion pass on the device
+        instead of the reference's batch_inversion (the inverses are the same numbers)."""
+        tau = np.ascontiguousarray(ffi.as_u64(tau).reshape(1, LIMBS))
+        n = self.size_
+        one = self._one()
+        t_size = self._pow_size(tau)
+        elems = self.elements().reshape(n, LIMBS)
+        if np.array_equal(t_size, one):
+            u = np.zeros((n, LIMBS), dtype=np.uint64)
+            hit = np.flatnonzero((elems == tau).all(axis=1))
+            if hit.size:
+                u[hit[0]] = one[0]
+            return u
+        l0 = self._fop(ffi.OP_MUL, self._fop(ffi.OP_SUB, t_size, one), self.size_inv)
+        u = DeviceVector(self.ctx, self.field, n, np.repeat(tau, n, axis=0))
+        e = DeviceVector(self.ctx, self.field, n, elems)
+        try:
+            u.op(ffi.OP_SUB, e)          # tau - g^i
+            u.op(ffi.OP_INV)
+            u.op(ffi.OP_MUL, e)
+            u.scale(l0)                  # * (tau^n - 1) / n
+            return u.download()
+        finally:
+            u.free()
+            e.free()
+
+    def reindex_by_subdomain(self, other, index):
+        """index of the `index`-th element in the ordering that lists the subdomain `other` first
+        (domain.rs:261-284)"""
+        assert self.size_ >= other.size_
+        period = self.size_ // other.size_
+        if index < other.size_:
+            return index * period
+        i = index - other.size_
+        x = period - 1
+        return i + (i // x) + 1
+
     # numpy arrays cannot be resized in place; the *_in_place forms return the resized vector
     fft_in_place = fft
     ifft_in_place = ifft

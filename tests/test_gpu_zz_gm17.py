@@ -70,3 +70,11 @@ def test_dense_polynomial_mul(ctx, field):
         pa = G.DensePolynomial(field, field_array(F, a + [0]), ctx)
         pb = G.DensePolynomial(field, field_array(F, b), ctx)
         assert array_field(F, (pa * pb).coeffs) == want
+
+
+@pytest.mark.parametrize("field", sorted(FIELDS))
+def test_domain_elements_vanishing_lagrange(ctx, field):
+    """EvaluationDomain::{elements, evaluate_vanishing_polynomial, evaluate_all_lagrange_coefficients,
+    reindex_by_subdomain} (domain.rs:183-284) on the device"""
+    from test_pipeline_emul import check_domain_methods
+    check_domain_methods(ctx, field, (1, 2, 64, 1 << 10))

@@ -232,6 +232,41 @@ def test_dense_polynomial_mul(ctx, field):
     assert zero.is_zero() and (zero * pb).is_zero() and (pb * zero).is_zero()
 
 
+@pytest.mark.parametrize("field", sorted(FIELDS))
+def test_domain_elements_vanishing_lagrange(ctx, field):
+    """elements, evaluate_vanishing_polynomial, evaluate_all_lagrange_coefficients, reindex_by_subdomain
+    (domain.rs:183-284) against their definitions"""
+    check_domain_methods(ctx, field, (1, 2, 8, 32))
+
+
+def check_domain_methods(cx, field, sizes):
+    F = FIELDS[field]
+    p = F.p
+    rng = O.SplitMix64(0xE1 + field)
+    for n in sizes:
+        dom = G.EvaluationDomain.new(field, n, ctx=cx)
+        ref = O.EvaluationDomain(F, n)
+        el = [pow(ref.group_gen, i, p) for i in range(n)]
+        assert array_field(F, dom.elements()) == el
+        tau = O.random_field_element(rng, F)
+        assert array_field(F, dom.evaluate_vanishing_polynomial(field_array(F, [tau]))) == [(pow(tau, n, p) - 1) % p]
+        (d0, c0), (d1, c1) = dom.vanishing_polynomial()
+        assert (d0, d1) == (0, n) and array_field(F, c0) == [p - 1] and array_field(F, c1) == [1]
+        # tau outside the domain: the Lagrange basis evaluated at tau (sums to 1, interpolates)
+        z = (pow(tau, n, p) - 1) * ref.size_inv % p
+        want = [z * w * pow((tau - w) % p, -1, p) % p for w in el]
+        got = array_field(F, dom.evaluate_all_lagrange_coefficients(field_array(F, [tau])))
+        assert got == want and sum(got) % p == 1
+        # tau inside the domain: an indicator vector
+        k = n // 2
+        got = array_field(F, dom.evaluate_all_lagrange_coefficients(field_array(F, [el[k]])))
+        assert got == [1 if i == k else 0 for i in range(n)]
+    big, small = G.EvaluationDomain.new(field, 16, ctx=cx), G.EvaluationDomain.new(field, 4, ctx=cx)
+    idx = [big.reindex_by_subdomain(small, i) for i in range(16)]
+    assert idx[:4] == [0, 4, 8, 12] and sorted(idx) == list(range(16))
+    assert idx[4:] == [1, 2, 3, 5, 6, 7, 9, 10, 11, 13, 14, 15]
+
+
 def test_device_vector_chain(ctx):
     """ifft -> coset_fft -> pointwise -> coset_ifft chained on 'device' memory"""
     F = O.MNT4_FR
