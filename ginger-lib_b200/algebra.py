@@ -59,6 +59,12 @@ class Context:
     def launches(self):
         return int(self.lib.launch_count(self.handle))
 
+    def last_msm_plan(self):
+        """window bits, windows, bucket rows and key copies of the last MSM on this context"""
+        buf = (ctypes.c_uint * 4)()
+        self.lib.check(self.lib.last_msm_plan(self.handle, buf))
+        return {"c": int(buf[0]), "windows": int(buf[1]), "rows": int(buf[2]), "copies": int(buf[3])}
+
     def last_msm_phases(self):
         buf = (ctypes.c_float * 8)()
         k = self.lib.last_msm_phases(self.handle, buf, 8)

@@ -1190,4 +1190,10 @@ int g753_last_msm_phases(g753_ctx* ctx, float* ms, int cap) {
   return k;
 }
 
+int g753_last_msm_plan(const g753_ctx* ctx, unsigned* plan4) {
+  if (!ctx || !plan4) return G753_ERR_BAD_ARG;
+  for (int i = 0; i < 4; i++) plan4[i] = ctx->last_plan[i];
+  return G753_OK;
+}
+
 }  // extern "C"

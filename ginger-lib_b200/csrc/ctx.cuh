@@ -33,6 +33,7 @@ struct g753_ctx {
   std::map<uint64_t, MixedTables> mixed[2]; // per field, keyed by the mixed-radix size N
   uint64_t launches = 0;
   float phase_ms[MSM_PHASES] = {0, 0, 0, 0, 0};
+  unsigned last_plan[4] = {0, 0, 0, 0};  // window bits, windows, bucket rows, key copies of the last MSM
   int forced_c = 0;
   int forced_affine = -1;  // G753_MSM_AFFINE: 0 / 1 force the accumulation kernel, unset = by size
   std::mutex mu;

@@ -33,6 +33,13 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
     key.copies = 1;
     key.c = ctx->forced_c;
   }
+  if (count) {
+    const MsmPlan pl = msm_plan(count, key.copies, key.c, key.rows);
+    ctx->last_plan[0] = pl.c;
+    ctx->last_plan[1] = pl.W;
+    ctx->last_plan[2] = pl.rows;
+    ctx->last_plan[3] = pl.copies;
+  }
   return msm_run<GID>(ctx->scratch, ctx->stream, key, d_scalars, count, (Fq*)d_out, hooks);
 }
 

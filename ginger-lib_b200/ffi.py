@@ -78,6 +78,7 @@ SYMBOLS = [
     ("g753_debug_scratch", _i, [_vp, _vp, _sz, ctypes.POINTER(_sz)]),
     ("g753_launch_count", ctypes.c_uint64, [_vp]),
     ("g753_last_msm_phases", _i, [_vp, ctypes.POINTER(ctypes.c_float), _i]),
+    ("g753_last_msm_plan", _i, [_vp, ctypes.POINTER(ctypes.c_uint)]),
 ]
 
 

@@ -113,6 +113,9 @@ def test_msm_window_sizes(ctx, monkeypatch):
         bases = cx.upload_bases(ffi.MNT4_G1, coords, inf)
         got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
         assert projective_to_point(C, got) == want, c
+        # g753_last_msm_plan: W * c covers the 753 scalar bits + the sign carry; a plain key has one row per window
+        plan = cx.last_msm_plan()
+        assert plan == {"c": c, "windows": -(-754 // c), "rows": -(-754 // c), "copies": 1}
         bases.free()
         cx.close()
 
