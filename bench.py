@@ -313,7 +313,10 @@ def run_ours(args):
     gpu_launches = ctx.launches - launches0
     ms_total = ev0.elapsed_time(ev1)
     phases = ctx.last_msm_phases()            # CUDA events of the last timed step, on the same stream
-    plan = ctx.last_msm_plan()                # window bits / windows / bucket rows / key copies of that step
+    try:
+        plan = ctx.last_msm_plan()            # window bits / windows / bucket rows / key copies of that step
+    except Exception:                         # introspection only: never fail the measurement over it
+        plan = None
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -425,10 +428,11 @@ def run_ours(args):
             "kernel_ms": acc_ms,
             # what the kernel actually executes: n * W mixed additions (XYZZ, 8 products + 2 squarings
             # of 1176 / 876 limb-MACs) - the fraction of the integer pipe's measured ceiling it sustains
-            "executed": {"plan": plan, "mixed_additions": n_local * plan["windows"],
-                         "limb_macs": n_local * plan["windows"] * (8 * 1176 + 2 * 876),
-                         "frac": n_local * plan["windows"] * (8 * 1176 + 2 * 876) / (acc_ms * 1e-3) / peak_mac_per_s
-                         if acc_ms else None},
+            "executed": None if not plan else {
+                "plan": plan, "mixed_additions": n_local * plan["windows"],
+                "limb_macs": n_local * plan["windows"] * (8 * 1176 + 2 * 876),
+                "frac": n_local * plan["windows"] * (8 * 1176 + 2 * 876) / (acc_ms * 1e-3) / peak_mac_per_s
+                if acc_ms else None},
             "whole_msm_frac": canon_all * LIMB_MACS_PER_MUL / (ms_per_step * 1e-3) / peak_mac_per_s,
             "phases_ms": phases,
         }
