@@ -4,6 +4,7 @@ nvcc cross-compiles without a GPU.  Each translation unit (the C ABI + NTT, and 
 group for the MSM pipeline) is compiled in parallel and linked into one shared library.
 Entry: build_library(force=False).
 """
+import hashlib
 import os
 import subprocess
 import sys
@@ -27,11 +28,29 @@ def _deps():
     return out
 
 
-def _stale(target, deps):
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+def source_hash():
+    """sha256 over every source the library is built from (csrc/*, include/g753.h) and the compiler
+    flags.  It is compiled into the library (g753_source_hash()), so a loaded libg753.so can always be
+    matched against the tree it claims to come from."""
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for path in sorted(_deps()):
+        h.update(os.path.basename(path).encode() + b"\0")
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def built_hash():
+    """the source hash recorded by the build that produced the in-tree library (None: never built)"""
+    try:
+        return open(os.path.join(OBJ, "source_hash.txt")).read().strip()
+    except OSError:
+        return None
+
+
+def _stale(target, want_hash):
+    return not os.path.exists(target) or built_hash() != want_hash
 
 
 def _nvcc():
@@ -41,15 +60,16 @@ def _nvcc():
 
 def build_library(force=False, verbose=False):
     """Compile csrc/*.cu into ginger-lib_b200/libg753.so for sm_100a. Returns the path."""
-    deps = _deps()
-    if not force and not _stale(LIB, deps):
+    want = source_hash()
+    if not force and not _stale(LIB, want):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
+    define = ["-DG753_SOURCE_HASH=\"%s\"" % want]
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        cmd = [nvcc] + NVCC_FLAGS + define + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
         proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
         if verbose:
             with open(os.path.join(OBJ, src + ".ptxas.log"), "w") as fh:
@@ -64,6 +84,8 @@ def build_library(force=False, verbose=False):
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + proc.stdout + proc.stderr)
+    with open(os.path.join(OBJ, "source_hash.txt"), "w") as fh:
+        fh.write(want + "\n")
     return LIB
 
 

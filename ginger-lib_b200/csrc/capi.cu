@@ -39,10 +39,13 @@ __global__ void k_bases_sanitize(Fq* __restrict__ bases, const uint8_t* __restri
 // fields/models/fp_768.rs:784-789; bytes.rs:70-78), the flag one byte (bytes.rs:220-225).  One
 // thread per base-field element: gather the 96 unaligned bytes, convert to Montgomery form
 // (from_repr, fp_768.rs:627-635) and store into the resident layout.
+// Validation as the reference's readers do it: a coordinate >= the modulus is an error (Fp768::read,
+// fp_768.rs:791-803: "Attempt to deserialize a field element over the modulus") and so is a flag byte
+// other than 0 or 1 (bool::read, bytes.rs:227-237); either sets a bit of *err and the load is rejected.
 template <int FID>
 __global__ void __launch_bounds__(128)
 k_bases_from_wire(const uint8_t* __restrict__ wire, unsigned n, unsigned fq_per_point, Fq* __restrict__ out,
-                  uint8_t* __restrict__ inf) {
+                  uint8_t* __restrict__ inf, unsigned* __restrict__ err) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * fq_per_point) return;
   const unsigned i = (unsigned)(t / fq_per_point), e = (unsigned)(t % fq_per_point);
@@ -53,7 +56,18 @@ k_bases_from_wire(const uint8_t* __restrict__ wire, unsigned n, unsigned fq_per_
   for (int w = 0; w < NL; w++)
     v.l[w] = (uint32_t)src[4 * w] | ((uint32_t)src[4 * w + 1] << 8) | ((uint32_t)src[4 * w + 2] << 16) |
              ((uint32_t)src[4 * w + 3] << 24);
-  const bool is_inf = wire[(size_t)i * rec + rec - 1] != 0;
+  const uint8_t flag = wire[(size_t)i * rec + rec - 1];
+  const bool is_inf = flag != 0;
+  {
+    // v < p ?  (borrow out of v - p)
+    uint32_t t = sub_cc(v.l[0], G753_FC(FID).p[0]);
+#pragma unroll
+    for (int w = 1; w < NL; w++) t = subc_cc(v.l[w], G753_FC(FID).p[w]);
+    const uint32_t borrow = subc(0, 0);
+    (void)t;
+    if (!borrow) atomicOr(err, 1u);
+    if (flag > 1) atomicOr(err, 2u);
+  }
   if (is_inf) v = fq_zero<FID>();   // infinite bases are stored as (0, 0), see k_bases_sanitize
   else v = fq_to_mont<FID>(v);
   out[t] = v;
@@ -86,7 +100,7 @@ static int ntt_field(g753_ctx* ctx, Fq* d_data, Fq* d_tmp, unsigned log_n, int m
 // R1CStoQAP::witness_map after the constraint evaluation (r1cs_to_qap.rs:121-166), chained on
 // the device: 7 transforms + the element-wise steps, no host round trips.
 template <int FID>
-static int witness_map_field(g753_ctx* ctx, Fq* a, Fq* b, Fq* c, unsigned log_n, const Fq* d_d, Fq* h) {
+static int witness_map_field(g753_ctx* ctx, Fq* a, Fq* b, Fq* c, unsigned log_n, const Fq3& d_d, Fq* h) {
   const size_t n = (size_t)1 << log_n;
   G753_TRY(ctx->scratch_io.reserve(sizeof(Fq) * n + 1024));
   Fq* tmp = (Fq*)ctx->scratch_io.ptr;
@@ -381,7 +395,11 @@ __global__ void __launch_bounds__(256) k_mac_probe(const Fq* seed, Fq* sink, int
 extern "C" {
 
 const char* g753_last_error(void) { return g_last_error; }
-const char* g753_version(void) { return "g753 0.1 (sm_100a)"; }
+const char* g753_version(void) { return "g753 0.2 (sm_100a)"; }
+#ifndef G753_SOURCE_HASH
+#define G753_SOURCE_HASH "unrecorded"
+#endif
+const char* g753_source_hash(void) { return G753_SOURCE_HASH; }
 
 int g753_device_count(int* count) {
   if (!count) return fail(G753_ERR_BAD_ARG, "null count");
@@ -424,6 +442,8 @@ int g753_ctx_create(int device, g753_ctx** out) {
   ctx->copy_ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < g753_ctx::MAX_CHUNKS && ctx->copy_ok; i++)
     if (cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) != cudaSuccess) ctx->copy_ok = false;
+  if (ctx->copy_ok && cudaEventCreateWithFlags(&ctx->ready_ev, cudaEventDisableTiming) != cudaSuccess) ctx->copy_ok = false;
+  (void)cudaGetLastError();
 #endif
   const char* fc = getenv("G753_MSM_C");
   if (fc) ctx->forced_c = atoi(fc);
@@ -448,6 +468,7 @@ int g753_ctx_destroy(g753_ctx* ctx) {
     for (int i = 0; i <= MSM_PHASES; i++) cudaEventDestroy(ctx->ev[i]);
   if (ctx->copy_ok) {
     for (int i = 0; i < g753_ctx::MAX_CHUNKS; i++) cudaEventDestroy(ctx->chunk_ev[i]);
+    cudaEventDestroy(ctx->ready_ev);
     cudaStreamDestroy(ctx->copy_stream);
   }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -511,23 +532,33 @@ int g753_bases_upload_wire(g753_ctx* ctx, int group, const uint8_t* wire, size_t
   b->n = n;
   const size_t rec = (size_t)2 * k * 96 + 1;
   uint8_t* d_wire = nullptr;
+  unsigned* d_err = nullptr;
+  unsigned h_err = 0;
   int rc = dev_alloc(&b->d_points, (size_t)2 * k * 96 * n);
   if (rc == G753_OK) rc = dev_alloc((void**)&b->d_inf, n ? n : 1);
-  if (rc == G753_OK && n) rc = dev_alloc((void**)&d_wire, rec * n);
+  if (rc == G753_OK && n) rc = dev_alloc((void**)&d_wire, rec * n + 256);
+  if (rc == G753_OK && n) {
+    d_err = (unsigned*)(d_wire + ((rec * n + 15) & ~(size_t)15));
+    rc = dev_memset(d_err, 0, sizeof(unsigned), ctx->stream);
+  }
   if (rc == G753_OK && n) rc = h2d(d_wire, wire, rec * n, ctx->stream);
   if (rc == G753_OK && n) {
     const bool mnt4 = (group == G753_MNT4_G1 || group == G753_MNT4_G2);   // base field id = 0 for MNT4
     if (mnt4)
       G753_LAUNCH(k_bases_from_wire<0>, div_up(n * 2 * k, 128), 128, ctx->stream, d_wire, (unsigned)n, (unsigned)(2 * k),
-                  (Fq*)b->d_points, b->d_inf);
+                  (Fq*)b->d_points, b->d_inf, d_err);
     else
       G753_LAUNCH(k_bases_from_wire<1>, div_up(n * 2 * k, 128), 128, ctx->stream, d_wire, (unsigned)n, (unsigned)(2 * k),
-                  (Fq*)b->d_points, b->d_inf);
+                  (Fq*)b->d_points, b->d_inf, d_err);
     ctx->launches++;
     rc = launch_check("k_bases_from_wire");
+    if (rc == G753_OK) rc = d2h(&h_err, d_err, sizeof(unsigned), ctx->stream);
   }
   if (rc == G753_OK) rc = stream_sync(ctx->stream);
   dev_free(d_wire);
+  if (rc == G753_OK && h_err)
+    rc = fail(G753_ERR_BAD_ARG, (h_err & 1u) ? "wire data: a coordinate is not below the field modulus (Fp768::read rejects it)"
+                                              : "wire data: an infinity flag byte is neither 0 nor 1 (bool::read rejects it)");
   if (rc != G753_OK) {
     dev_free(b->d_points);
     dev_free(b->d_inf);
@@ -664,10 +695,11 @@ static int msm_check(g753_ctx* ctx, const g753_bases* b, size_t first, size_t co
 
 #if !defined(G753_HOST_EMUL)
 static void collect_phases(g753_ctx* ctx) {
-  if (!ctx->ev_ok) return;
+  if (!ctx->ev_ok || !ctx->phases_valid) return;   // no MSM with count > 0 has run on this context yet
   for (int i = 0; i < MSM_PHASES; i++) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->phase_ms[i] = ms;
+    else (void)cudaGetLastError();
   }
 }
 #endif
@@ -695,19 +727,26 @@ int g753_msm(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count, con
 #if !defined(G753_HOST_EMUL)
   // upload the scalars in pieces on the copy stream; the digit extraction of piece j waits for
   // piece j only, so the transfer overlaps the start of the pipeline
+  // Only for PINNED (page-locked / registered) caller memory: a cudaMemcpyAsync from pageable memory
+  // blocks the host until the piece is staged, so nothing would overlap and the plain path is used.
   unsigned chunks = 1;
-  if (ctx->copy_ok && count >= ((size_t)1 << 18)) chunks = g753_ctx::MAX_CHUNKS;
+  if (ctx->copy_ok && count >= ((size_t)1 << 18)) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, scalars) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+      chunks = g753_ctx::MAX_CHUNKS;
+    else
+      (void)cudaGetLastError();
+  }
   if (chunks > 1) {
-    cudaEvent_t ready;
-    if (cudaEventCreateWithFlags(&ready, cudaEventDisableTiming) == cudaSuccess) {
-      cudaEventRecord(ready, ctx->stream);              // the staging buffer is free once earlier work is done
-      cudaStreamWaitEvent(ctx->copy_stream, ready, 0);
-      cudaEventDestroy(ready);
-    }
+    // the staging buffer is free once the work queued so far on the main stream is done
+    cudaError_t e = cudaEventRecord(ctx->ready_ev, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ready_ev, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "g753_msm: ordering the scalar upload");
     for (unsigned j = 0; j < chunks; j++) {
       const size_t lo = count * j / chunks, hi = count * (j + 1) / chunks;
       G753_TRY(h2d((char*)d_scalars + lo * 96, (const char*)scalars + lo * 96, (hi - lo) * 96, ctx->copy_stream));
-      cudaEventRecord(ctx->chunk_ev[j], ctx->copy_stream);
+      e = cudaEventRecord(ctx->chunk_ev[j], ctx->copy_stream);
+      if (e != cudaSuccess) return cuda_fail(e, "g753_msm: cudaEventRecord");
     }
     ctx->scalar_chunks = chunks;
     int rc = msm_any(ctx, b, first, count, d_scalars, d_out);
@@ -829,16 +868,12 @@ int g753_witness_map_dev(g753_ctx* ctx, int field, void* d_a, void* d_b, void* d
   if (!d_a || !d_b || !d_c || !d123_mont || !d_h) return fail(G753_ERR_BAD_ARG, "null pointer");
   G753_TRY(g753_domain_check(field, log_n));
   std::lock_guard<std::mutex> lock(ctx->mu);
-  // d1, d2, d3 travel through a small dedicated device slot
-  Fq* d_d = nullptr;
-  G753_TRY(dev_alloc((void**)&d_d, sizeof(Fq) * 3));
-  int rc = h2d(d_d, d123_mont, sizeof(Fq) * 3, ctx->stream);
-  if (rc == G753_OK)
-    rc = field == 0 ? witness_map_field<0>(ctx, (Fq*)d_a, (Fq*)d_b, (Fq*)d_c, log_n, d_d, (Fq*)d_h)
-                    : witness_map_field<1>(ctx, (Fq*)d_a, (Fq*)d_b, (Fq*)d_c, log_n, d_d, (Fq*)d_h);
-  if (rc == G753_OK) rc = stream_sync(ctx->stream);
-  dev_free(d_d);
-  return rc;
+  // d1, d2, d3 ride along as a kernel argument: no allocation, copy or synchronisation here - the
+  // call only queues work on the context's stream
+  Fq3 d;
+  memcpy(&d, d123_mont, sizeof(d));
+  return field == 0 ? witness_map_field<0>(ctx, (Fq*)d_a, (Fq*)d_b, (Fq*)d_c, log_n, d, (Fq*)d_h)
+                    : witness_map_field<1>(ctx, (Fq*)d_a, (Fq*)d_b, (Fq*)d_c, log_n, d, (Fq*)d_h);
 }
 
 int g753_witness_map(g753_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, const uint64_t* c,
@@ -1032,22 +1067,15 @@ int g753_vec_scale_dev(g753_ctx* ctx, int field, void* d_a, const uint64_t* k_mo
   if (!d_a || !k_mont || (field != 0 && field != 1)) return fail(G753_ERR_BAD_ARG, "bad argument");
   if (n == 0) return G753_OK;
   std::lock_guard<std::mutex> lock(ctx->mu);
-  // the constant travels through a small dedicated device slot (kept out of the scratch
-  // buffers, which may hold the caller's chained data)
-  Fq* d_k = nullptr;
-  G753_TRY(dev_alloc((void**)&d_k, sizeof(Fq)));
-  int rc = h2d(d_k, k_mont, sizeof(Fq), ctx->stream);
-  if (rc == G753_OK) {
-    if (field == 0)
-      G753_LAUNCH(k_vec_scale<0>, div_up(n, 256), 256, ctx->stream, (Fq*)d_a, d_k, n);
-    else
-      G753_LAUNCH(k_vec_scale<1>, div_up(n, 256), 256, ctx->stream, (Fq*)d_a, d_k, n);
-    ctx->launches++;
-    rc = launch_check("k_vec_scale");
-  }
-  if (rc == G753_OK) rc = stream_sync(ctx->stream);
-  dev_free(d_k);
-  return rc;
+  // the factor is a kernel argument (96 bytes by value): nothing is allocated, copied or waited for
+  Fq k;
+  memcpy(&k, k_mont, sizeof(k));
+  if (field == 0)
+    G753_LAUNCH(k_vec_scale_val<0>, div_up(n, 256), 256, ctx->stream, (Fq*)d_a, k, n);
+  else
+    G753_LAUNCH(k_vec_scale_val<1>, div_up(n, 256), 256, ctx->stream, (Fq*)d_a, k, n);
+  ctx->launches++;
+  return launch_check("k_vec_scale");
 }
 
 // ---- plumbing ------------------------------------------------------------------------------
@@ -1129,6 +1157,22 @@ int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uin
   return fail(G753_ERR_BAD_ARG, "unknown group");
 }
 
+int g753_ext_op(g753_ctx* ctx, int group, int lanes, int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                size_t n) {
+  CHECK_CTX(ctx);
+  if (!a || !out || (lanes != 0 && lanes != 1)) return fail(G753_ERR_BAD_ARG, "bad argument");
+  if (n == 0) return G753_OK;
+  if (n > ((size_t)1 << 24)) return fail(G753_ERR_BAD_ARG, "too many elements");
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  switch (group) {
+    case G753_MNT4_G1: return ext_op_impl<0>(ctx, lanes, op, a, b, out, n);
+    case G753_MNT4_G2: return ext_op_impl<1>(ctx, lanes, op, a, b, out, n);
+    case G753_MNT6_G1: return ext_op_impl<2>(ctx, lanes, op, a, b, out, n);
+    case G753_MNT6_G2: return ext_op_impl<3>(ctx, lanes, op, a, b, out, n);
+  }
+  return fail(G753_ERR_BAD_ARG, "unknown group");
+}
+
 int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms) {
   CHECK_CTX(ctx);
   if (!ms || blocks <= 0 || threads <= 0 || threads > 256 || iters <= 0) return fail(G753_ERR_BAD_ARG, "bad argument");
@@ -1191,7 +1235,7 @@ int g753_last_msm_phases(g753_ctx* ctx, float* ms, int cap) {
 }
 
 int g753_last_msm_plan(const g753_ctx* ctx, unsigned* plan4) {
-  if (!ctx || !plan4) return G753_ERR_BAD_ARG;
+  if (!ctx || !plan4) return fail(G753_ERR_BAD_ARG, "null pointer");
   for (int i = 0; i < 4; i++) plan4[i] = ctx->last_plan[i];
   return G753_OK;
 }

@@ -9,16 +9,6 @@
 #include "ntt.cuh"
 #include "ntt_mixed.cuh"
 
-namespace g753 {
-#if defined(G753_HOST_EMUL)
-static thread_local char g_last_error[512] = "";
-#endif
-static inline int fail(int code, const char* msg) {
-  snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
-  return code;
-}
-}  // namespace g753
-
 using namespace g753;
 
 enum { MSM_PHASES = 5 };
@@ -33,6 +23,7 @@ struct g753_ctx {
   std::map<uint64_t, MixedTables> mixed[2]; // per field, keyed by the mixed-radix size N
   uint64_t launches = 0;
   float phase_ms[MSM_PHASES] = {0, 0, 0, 0, 0};
+  bool phases_valid = false;  // every phase event of the last MSM was recorded (count > 0, this context)
   unsigned last_plan[4] = {0, 0, 0, 0};  // window bits, windows, bucket rows, key copies of the last MSM
   int forced_c = 0;
   int forced_affine = -1;  // G753_MSM_AFFINE: 0 / 1 force the accumulation kernel, unset = by size
@@ -44,6 +35,7 @@ struct g753_ctx {
   enum { MAX_CHUNKS = 8 };
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t chunk_ev[MAX_CHUNKS];
+  cudaEvent_t ready_ev;
   bool copy_ok = false;
 #endif
 };
@@ -74,12 +66,22 @@ static inline int use_device(g753_ctx* ctx) {
 }
 static inline void phase_mark(void* user, int phase) {
   g753_ctx* ctx = (g753_ctx*)user;
-  if (ctx->ev_ok && phase <= MSM_PHASES) cudaEventRecord(ctx->ev[phase], ctx->stream);
+  if (!ctx->ev_ok || phase > MSM_PHASES) return;
+  if (phase == 0) ctx->phases_valid = false;
+  const bool ok = cudaEventRecord(ctx->ev[phase], ctx->stream) == cudaSuccess;
+  if (!ok) (void)cudaGetLastError();  // timing is best effort: never leaves a stale error behind
+  if (phase == MSM_PHASES) ctx->phases_valid = ok;
 }
 static inline void chunk_wait(void* user, int chunk) {
   g753_ctx* ctx = (g753_ctx*)user;
-  if (ctx->copy_ok && ctx->scalar_chunks > 1 && chunk < g753_ctx::MAX_CHUNKS)
-    cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[chunk], 0);
+  if (ctx->copy_ok && ctx->scalar_chunks > 1 && chunk < g753_ctx::MAX_CHUNKS) {
+    cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[chunk], 0);
+    if (e != cudaSuccess) {
+      // ordering is not optional: fall back to a full wait for the copy stream
+      (void)cudaGetLastError();
+      cudaStreamSynchronize(ctx->copy_stream);
+    }
+  }
 }
 #else
 static inline int use_device(g753_ctx*) { return G753_OK; }
@@ -98,6 +100,8 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
                  void* d_out);
 template <int GID>
 int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out);
+template <int GID>
+int ext_op_impl(g753_ctx* ctx, int lanes, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 template <int GID>
 void points_sum_launch(g753_ctx* ctx, const void* d_pts, size_t count, void* d_out);
 template <int GID>

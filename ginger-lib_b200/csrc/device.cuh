@@ -38,6 +38,12 @@ static inline T atomicAdd(T* p, T v) {
   *p = old + v;
   return old;
 }
+template <class T>
+static inline T atomicOr(T* p, T v) {
+  T old = *p;
+  *p = old | v;
+  return old;
+}
 static inline unsigned __brev(unsigned x) {
   unsigned r = 0;
   for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
@@ -56,6 +62,11 @@ static inline unsigned __brev(unsigned x) {
   } while (0)
 #define G753_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) G753_LAUNCH(kernel, grid, block, stream, __VA_ARGS__)
 namespace g753 {
+static thread_local char g_last_error[512] = "";
+static inline int fail(int code, const char* msg) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
+  return code;
+}
 static inline int dev_alloc(void** p, size_t bytes) {
   *p = malloc(bytes ? bytes : 1);
   return *p ? G753_OK : G753_ERR_OOM;
@@ -94,6 +105,10 @@ static inline int launch_check(const char*) { return G753_OK; }
   } while (0)
 namespace g753 {
 extern thread_local char g_last_error[512];
+static inline int fail(int code, const char* msg) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
+  return code;
+}
 static inline int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
   return e == cudaErrorMemoryAllocation ? G753_ERR_OOM : G753_ERR_CUDA;

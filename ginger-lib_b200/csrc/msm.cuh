@@ -768,15 +768,15 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
     G753_MSM_LAUNCH(hooks, k_write_infinity<SCR>, 1, 1, stream, d_out);
     return launch_check("k_write_infinity");
   }
-  if (count > 0x7fffffffull) return G753_ERR_BAD_ARG;
+  if (count > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "msm: more than 2^31 - 1 scalars");
   const unsigned n = (unsigned)count;
   const MsmPlan pl = msm_plan(n, key.copies, key.c, key.rows);
-  if (pl.c == 0) return G753_ERR_BAD_ARG;
+  if (pl.c == 0) return fail(G753_ERR_BAD_ARG, "msm: no window size satisfies the forced plan");
   const bool affine = Cfg::AFFINE && key.affine > 0;  // opt-in (G753_MSM_AFFINE=1): measured slower, see header
   const MsmWorkspace ws = msm_workspace<GID>(pl, n, affine);
   if ((uint64_t)pl.W * n >= 0xffffffffull || (uint64_t)pl.rows * ws.row_cap >= 0xffffffffull ||
       (uint64_t)(pl.copies - 1) * key.copy_stride + n > 0x7fffffffull)
-    return G753_ERR_BAD_ARG;
+    return fail(G753_ERR_BAD_ARG, "msm: windows x points exceed the 32-bit index space of the sort");
   G753_TRY(scratch.reserve(ws.total));
   Carver cv(scratch.ptr);
   const size_t len = (size_t)pl.B + 1;

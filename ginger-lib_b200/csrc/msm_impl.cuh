@@ -112,6 +112,64 @@ int point_op_impl(g753_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, u
   return stream_sync(ctx->stream);
 }
 
+// Tower-arithmetic test hook: the coordinate field of the group (Fq, Fq2 or Fq3) through the very
+// tower code the kernels run - on the device the lane-cooperative Tw2C / Tw3C (slots.cuh) in the lane
+// counts of the accumulation kernels (lanes = 0) or of the reduction kernels (lanes = 1).  One column
+// per element pair.  ops: 0 mul, 1 add, 2 sub, 3 sqr, 4 neg, 5 inv, 12 dbl, 20 / 21 mul with the
+// destination aliasing a / b, 23 sqr in place (the in-place forms the curve formulas rely on).
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_ext_op(int op, const Fq* __restrict__ a, const Fq* __restrict__ b, unsigned n, Fq* __restrict__ out) {
+  typedef typename SC::M M;
+  constexpr int K = M::K, A = 0, B = K, D = 2 * K, TMP = 3 * K;
+  unsigned i = M::T::item();
+  if (i >= n) return;
+  M::ldg(A, a + (size_t)i * K);
+  M::ldg(B, (b ? b : a) + (size_t)i * K);
+  int res = D;
+  switch (op) {
+    case 0: M::mul(D, A, B, TMP); break;
+    case 1: M::add(D, A, B); break;
+    case 2: M::sub(D, A, B); break;
+    case 3: M::sqr(D, A, TMP); break;
+    case 4: M::neg(D, A); break;
+    case 5: M::inv(D, A, TMP); break;
+    case 12: M::dbl(D, A); break;
+    case 20: M::mul(A, A, B, TMP); res = A; break;
+    case 21: M::mul(B, A, B, TMP); res = B; break;
+    case 23: M::sqr(A, A, TMP); res = A; break;
+    default: M::set_zero(D);
+  }
+  M::stg(out + (size_t)i * K, res);
+}
+
+template <int GID>
+int ext_op_impl(g753_ctx* ctx, int lanes, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  typedef MsmCfg<GID> Cfg;
+  constexpr int K = Cfg::K, T = 32;
+  const size_t bytes = sizeof(Fq) * K * n;
+  G753_TRY(ctx->scratch_io.reserve(3 * Carver::pad(bytes) + 1024));
+  Carver cv(ctx->scratch_io.ptr);
+  Fq* da = cv.take<Fq>(K * n);
+  Fq* db = cv.take<Fq>(K * n);
+  Fq* dout = cv.take<Fq>(K * n);
+  G753_TRY(h2d(da, a, bytes, ctx->stream));
+  if (b) G753_TRY(h2d(db, b, bytes, ctx->stream));
+  if (lanes == 0) {
+    typedef typename Cfg::template SC<T, Cfg::TPA> SC;
+    G753_LAUNCH_SMEM(k_ext_op<SC>, div_up(n, T), T * Cfg::TPA, (slot_bytes<EcS<SC>, T>(3 * K + SC::M::NTMP + 1)), ctx->stream, op, da,
+                     b ? db : (const Fq*)nullptr, (unsigned)n, dout);
+  } else {
+    typedef typename Cfg::template SC<T, Cfg::TP> SC;
+    G753_LAUNCH_SMEM(k_ext_op<SC>, div_up(n, T), T * Cfg::TP, (slot_bytes<EcS<SC>, T>(3 * K + SC::M::NTMP + 1)), ctx->stream, op, da,
+                     b ? db : (const Fq*)nullptr, (unsigned)n, dout);
+  }
+  ctx->launches++;
+  G753_TRY(launch_check("k_ext_op"));
+  G753_TRY(d2h(out, dout, bytes, ctx->stream));
+  return stream_sync(ctx->stream);
+}
+
 template <int GID>
 void points_sum_launch(g753_ctx* ctx, const void* d_pts, size_t count, void* d_out) {
   constexpr int T = 32;  // columns; only column 0 works
@@ -437,6 +495,7 @@ int fixed_base_impl(g753_ctx* ctx, const uint64_t* base_xy, const uint64_t* scal
 #define G753_INSTANTIATE_GROUP(GID)                                                                        \
   template int msm_dispatch<GID>(g753_ctx*, const g753_bases*, size_t, size_t, const uint32_t*, void*);   \
   template int point_op_impl<GID>(g753_ctx*, int, const uint64_t*, const uint64_t*, uint64_t*);            \
+  template int ext_op_impl<GID>(g753_ctx*, int, int, const uint64_t*, const uint64_t*, uint64_t*, size_t);  \
   template void points_sum_launch<GID>(g753_ctx*, const void*, size_t, void*);                               \
   template int bases_generate_impl<GID>(g753_ctx*, const uint64_t*, uint64_t, size_t, void*);                \
   template int bases_precompute_impl<GID>(g753_ctx*, g753_bases*, unsigned);                                 \

@@ -390,6 +390,17 @@ __global__ void __launch_bounds__(256) k_vec_scale(Fq* __restrict__ a, const Fq*
   if (i >= n) return;
   a[i] = fq_mul<FID>(a[i], *k);
 }
+// the same with the factor passed BY VALUE as a kernel argument (96 bytes): a host constant reaches the
+// kernel without a device allocation, a copy or a synchronisation on the caller's critical path
+template <int FID>
+__global__ void __launch_bounds__(256) k_vec_scale_val(Fq* __restrict__ a, const Fq k, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  a[i] = fq_mul<FID>(a[i], k);
+}
+struct Fq3 {
+  Fq v[3];
+};
 
 // R1CStoQAP::witness_map element-wise steps (proof-systems/src/groth16/r1cs_to_qap.rs:137-166):
 //   ab[i] = (a[i] * b[i] - c[i]) * (g^n - 1)^-1        mul_polynomials_in_evaluation_domain,
@@ -407,20 +418,20 @@ k_witness_combine(Fq* __restrict__ a, const Fq* __restrict__ b, const Fq* __rest
 // h has n + 1 entries (r1cs_to_qap.rs:125-132, 163-166).  The reference builds h as
 // `vec![zero; n]` and then MULTIPLIES each h_i by (d2 a_i + d1 b_i) (:127-130), which leaves the
 // zeros in place; so h = [-d3 - d1 d2, 0, ..., 0, d1 d2] before the quotient is added to
-// h[..n-1].  Reproduced as is: d[0] = d1, d[1] = d2, d[2] = d3 (device, Montgomery form).
+// h[..n-1].  Reproduced as is: d = d1, d2, d3 (Montgomery form, passed by value).
 template <int FID>
 __global__ void __launch_bounds__(256)
-k_witness_finish(const Fq* __restrict__ ab, const Fq* __restrict__ d, Fq* __restrict__ h, size_t n) {
+k_witness_finish(const Fq* __restrict__ ab, const Fq3 d, Fq* __restrict__ h, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   Fq v = fq_zero<FID>();
   if (i + 1 < n) v = ab[i];
   if (i == 0 || i == n) {
-    Fq d1d2 = fq_mul<FID>(d[0], d[1]);
+    Fq d1d2 = fq_mul<FID>(d.v[0], d.v[1]);
     if (i == n) {
       v = d1d2;
     } else {
-      Fq base = fq_sub<FID>(fq_sub<FID>(fq_zero<FID>(), d[2]), d1d2);  // h[0] -= d3; h[0] -= d1 d2
+      Fq base = fq_sub<FID>(fq_sub<FID>(fq_zero<FID>(), d.v[2]), d1d2);  // h[0] -= d3; h[0] -= d1 d2
       v = fq_add<FID>(base, v);
     }
   }
@@ -456,7 +467,7 @@ static int ntt_run(const NttTables& T, cudaStream_t stream, Fq* d_data, Fq* d_tm
   const unsigned log_n = T.log_n;
   const size_t n = (size_t)1 << log_n;
   if (call.batch == 0) return G753_OK;
-  if (call.batch > 65535) return G753_ERR_BAD_ARG;
+  if (call.batch > 65535) return fail(G753_ERR_BAD_ARG, "ntt: more than 65535 vectors in one batch");
   const Fq* tw = call.inverse ? T.tw_inv : T.tw_fwd;
   Fq* src = d_data;
   Fq* dst = d_tmp;

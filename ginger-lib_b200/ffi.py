@@ -31,6 +31,7 @@ SYMBOLS = [
     ("g753_ctx_set_stream", _i, [_vp, _vp]),
     ("g753_last_error", ctypes.c_char_p, []),
     ("g753_version", ctypes.c_char_p, []),
+    ("g753_source_hash", ctypes.c_char_p, []),
     ("g753_bases_upload", _i, [_vp, _i, _vp, _vp, _sz, _pvp]),
     ("g753_bases_upload_wire", _i, [_vp, _i, _vp, _sz, _pvp]),
     ("g753_bases_free", _i, [_vp, _vp]),
@@ -74,6 +75,7 @@ SYMBOLS = [
     ("g753_stream", _vp, [_vp]),
     ("g753_field_op", _i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     ("g753_point_op", _i, [_vp, _i, _i, _vp, _vp, _vp]),
+    ("g753_ext_op", _i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz]),
     ("g753_mac_probe", _i, [_vp, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float)]),
     ("g753_debug_scratch", _i, [_vp, _vp, _sz, ctypes.POINTER(_sz)]),
     ("g753_launch_count", ctypes.c_uint64, [_vp]),

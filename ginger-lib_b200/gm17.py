@@ -44,21 +44,26 @@ class Parameters:
             return b
 
         def small(group, q, pre, post, k):
-            """pre + query[1..ni] + post as one short resident key"""
+            """pre + query[1..ni] + post as one short resident key; an entry of pre / post is either
+            affine limbs or (limbs, infinity flag)"""
             coords = ffi.as_u64(q[0]).reshape(-1, 2 * k * LIMBS)
-            rows = [ffi.as_u64(e).reshape(1, 2 * k * LIMBS) for e in pre] + [coords[1:ni]] + \
-                   [ffi.as_u64(e).reshape(1, 2 * k * LIMBS) for e in post]
+            split = lambda e: e if isinstance(e, tuple) else (e, False)
+            rows = [ffi.as_u64(split(e)[0]).reshape(1, 2 * k * LIMBS) for e in pre] + [coords[1:ni]] + \
+                   [ffi.as_u64(split(e)[0]).reshape(1, 2 * k * LIMBS) for e in post]
             c = np.concatenate(rows)
             i = np.zeros(c.shape[0], dtype=np.uint8)
+            i[:len(pre)] = [split(e)[1] for e in pre]
+            if post:
+                i[-len(post):] = [split(e)[1] for e in post]
             if q[1] is not None:
                 i[len(pre):len(pre) + ni - 1] = np.asarray(q[1], dtype=np.uint8)[1:ni]
             return Bases(ctx, group, c, i)
 
         def head(q, k):
+            """query[0] with its infinity flag: the reference adds it whatever it is (prover.rs:268, 286,
+            333-336), and an infinite base contributes nothing to the short MSM it rides in"""
             coords = ffi.as_u64(q[0]).reshape(-1, 2 * k * LIMBS)
-            if q[1] is not None and np.asarray(q[1])[0]:
-                raise ValueError("query[0] is the point at infinity")
-            return coords[0]
+            return (coords[0], bool(q[1] is not None and np.asarray(q[1])[0]))
 
         # A: [g_gamma_z, g_gamma_z, a_query[0], a_query[1..ni]] . [r, d1, 1, inputs]  (prover.rs:264-278)
         self.a_small = small(g1, a_query, [g_gamma_z, g_gamma_z, head(a_query, 1)], [], 1)

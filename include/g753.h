@@ -83,6 +83,10 @@ int g753_ctx_destroy(g753_ctx* ctx);
 int g753_ctx_set_stream(g753_ctx* ctx, void* cuda_stream);
 const char* g753_last_error(void);
 const char* g753_version(void);
+/* hash of the sources (csrc/*, this header, compiler flags) the loaded library was built from; the
+ * build recipe (ginger-lib_b200/build.py) rebuilds when it differs from the tree's and bench.py prints
+ * both, so a stale prebuilt binary cannot be measured unnoticed */
+const char* g753_source_hash(void);
 
 /* ---- MSM: VariableBaseMSM::multi_scalar_mul (algebra/src/msm/variable_base.rs:85-90) -- */
 /* Upload n affine bases once per proving key (Parameters::{a,b_g1,b_g2,h,l}_query,
@@ -239,6 +243,14 @@ int g753_field_op(g753_ctx* ctx, int field, int op, const uint64_t* a, const uin
  * a, b affine (2*k*12 limbs, (0,0) = infinity), scalar 12 limbs canonical, out projective */
 int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uint64_t* b,
                   uint64_t* out_xyz);
+/* coordinate-field test hook: out[i] = a[i] op b[i] over n elements of the group's coordinate field
+ * (Fq, Fq2 = c0,c1 or Fq3 = c0,c1,c2; k*12 Montgomery limbs each) THROUGH THE TOWER CODE THE MSM KERNELS
+ * RUN (fields/models/fp2.rs, fp3.rs on the lane-cooperative device towers); lanes = 0: the lane split
+ * of the accumulation kernels, 1: that of the reduction / set-up kernels.
+ * op: 0 mul, 1 add, 2 sub, 3 square, 4 neg, 5 inverse, 12 double, 20 / 21 mul with the result
+ * aliasing a / b, 23 square in place.  The reference's Fq2 / Fq3 KATs are replayed through it. */
+int g753_ext_op(g753_ctx* ctx, int group, int lanes, int op, const uint64_t* a, const uint64_t* b,
+                uint64_t* out, size_t n);
 /* Run `iters` dependent Montgomery multiplications per thread on `blocks` x `threads`
  * threads and report the kernel time in ms (CUDA events): the integer-pipe roofline probe
  * of SURVEY.md 8d.  variant 0 = fq_mul, 1 = fq_sqr, 2 = raw independent IMAD.WIDE stream,

@@ -12,7 +12,7 @@ from util753 import G, array_field, ffi, field_array, points_to_arrays, sample_p
 gm17 = __import__("importlib").import_module("ginger-lib_b200.gm17")
 
 
-def tiny_instance(seed, n=8, ni=2, n_aux=3, nc=2, engine="mnt4"):
+def tiny_instance(seed, n=8, ni=2, n_aux=3, nc=2, engine="mnt4", inf_head=False):
     """a synthetic GM17 proving key + SAP witness of the shapes gm17/generator.rs:222-343 produces:
     a / b / c_2 queries over all SAP variables, c_query_1 over the non-input ones, g_gamma2_z_t of
     domain size; domain >= 2 nc + 2 (ni - 1) + 1 (r1cs_to_sap.rs:153-157)"""
@@ -28,6 +28,10 @@ def tiny_instance(seed, n=8, ni=2, n_aux=3, nc=2, engine="mnt4"):
                     next(it1), next(it2), next(it1), next(it1), take(it1, n))
     key.b_query[n_vars - 1] = None      # an infinity base inside a query
     key.c_query_2[ni] = None
+    if inf_head:                        # query[0] at infinity: the reference adds it like any other point
+        key.a_query[0] = None
+        key.c_query_2[0] = None
+        key.g_gamma2_z_t[0] = None
     z = [1] + [O.random_field_element(rng, F) for _ in range(n_vars - 1)]
     z[ni] = 0                           # zero / one / p-1 witness values
     z[ni + 1] = 1
@@ -47,9 +51,9 @@ def upload(cx, key, ni, engine="mnt4"):
                            one(C1, key.g_ab_gamma_z), one(C1, key.g_gamma2_z2), q(C1, key.g_gamma2_z_t), ni)
 
 
-def check_instance(cx, seed, n, ni, n_aux, nc, d1, d2, r, engine="mnt4"):
+def check_instance(cx, seed, n, ni, n_aux, nc, d1, d2, r, engine="mnt4", inf_head=False):
     C1, C2, F, _, _, field = ENGINES[engine]
-    key, z, a, c = tiny_instance(seed, n, ni, n_aux, nc, engine)
+    key, z, a, c = tiny_instance(seed, n, ni, n_aux, nc, engine, inf_head)
     h_ref = O.sap_witness_map(F, a, c, d1, d2)
     h = gm17.witness_map(cx, field, field_array(F, a), field_array(F, c), d1, d2)
     assert array_field(F, h) == h_ref
@@ -67,6 +71,7 @@ def test_sap_witness_map_and_proof_tiny(ctx):  # noqa: F811
     check_instance(ctx, 0x1707, 8, 2, 3, 2, 5, 7, 0x1234567 << 600)
     check_instance(ctx, 0x1708, 16, 3, 4, 4, 0, 0, F.p - 3)
     check_instance(ctx, 0x1709, 4, 1, 3, 1, F.p - 1, 3, 0)
+    check_instance(ctx, 0x170A, 8, 2, 3, 2, 5, 7, 11, inf_head=True)
 
 
 def test_proof_tiny_mnt6(ctx):  # noqa: F811

@@ -484,3 +484,21 @@ def test_fixed_base_msm(ctx, group):
     k = sum(int(a) * int(b) for a, b in zip(array_to_ints(s_arr), array_to_ints(t_arr))) % C.r
     assert projective_to_point(C, got) == C.mul(base, k)
     bases.free()
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_bases_from_wire_rejects_malformed(ctx, group):
+    import shared_checks
+    shared_checks.check_wire_rejects_malformed(ctx, group)
+
+
+@pytest.mark.parametrize("group", [ffi.MNT4_G2, ffi.MNT6_G2])
+@pytest.mark.parametrize("lanes", [0, 1])
+def test_reference_ext_kats_on_device_towers(ctx, group, lanes):
+    """the reference's Fq2 / Fq3 KATs (fields/mnt4753/tests.rs:1071-1867, fields/mnt6753/tests.rs:1277-2378)
+    and random elements through the LANE-COOPERATIVE towers Tw2C / Tw3C (slots.cuh) the G2 kernels run, in the
+    lane split of the accumulation kernels (lanes = 0: 2 / 4 lanes per element) and of the reduction
+    kernels (lanes = 1: 4 / 8 lanes)"""
+    import shared_checks
+    shared_checks.check_reference_ext_kats(ctx, group, lanes)
+    shared_checks.check_ext_ops_random(ctx, group, lanes)

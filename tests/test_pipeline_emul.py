@@ -472,3 +472,18 @@ def test_fixed_base_msm(ctx, group):
     want_c, want_inf = points_to_arrays(C, [C.mul(base, s) for s in sc])
     assert (inf == want_inf).all()
     assert (out == want_c).all()
+
+
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_bases_from_wire_rejects_malformed(ctx, group):
+    import shared_checks
+    shared_checks.check_wire_rejects_malformed(ctx, group)
+
+
+@pytest.mark.parametrize("group", [ffi.MNT4_G2, ffi.MNT6_G2])
+def test_ext_op_entry_point(ctx, group):
+    """g753_ext_op: the reference's Fq2 / Fq3 KATs + random elements through the C ABI (this tier runs the
+    one-thread towers; the GPU tier runs the lane-cooperative ones through the same entry point)"""
+    import shared_checks
+    shared_checks.check_reference_ext_kats(ctx, group, 0)
+    shared_checks.check_ext_ops_random(ctx, group, 1, count=12)

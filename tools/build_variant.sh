@@ -2,7 +2,7 @@
 # usage: build_variant.sh <name> [-Dflags...]: libg753 built with extra flags into ginger-lib_b200/variants/ (A/B runs)
 set -e
 name=$1; shift
-root=$(cd "$(dirname "$0")/../.." && pwd)
+root=$(cd "$(dirname "$0")/.." && pwd)
 out=$root/ginger-lib_b200/variants; obj=$out/obj_$name
 mkdir -p $obj
 cd $root/ginger-lib_b200/csrc
