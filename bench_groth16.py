@@ -32,6 +32,58 @@ def mont_random(n, seed):
 GOLDEN = 0x9E3779B97F4A7C15
 
 
+def benchmark_circuit(num_constraints, p):
+    """The reference's own benchmark circuit (proof-systems/src/groth16/examples/snark-scalability/
+    constraints.rs:19-91) evaluated the way the prover does (r1cs_to_qap.rs:84-119, 147-156): inputs
+    [one, a = 1, b = 1], then alternately c = a + b (constraint (a + b) * 1 = c) and c = a * b, every c a new
+    aux variable, and a last constraint (sum of all pushed values)^2 = c_val.  Returns canonical ints:
+    the full assignment (3 inputs + num_constraints aux) and the evaluation vectors a, b, c over the
+    num_constraints + 3 rows the witness map fills (the 3 trailing rows are the input-consistency rows,
+    a = [1, a, b], b = c = 0).  The first ~30 values are small (1, 1, 2, 2, 4, 8, 12, 96, ...), the rest
+    fill the whole field; b is 1 on every other row."""
+    a_val, b_val = 1, 1
+    inputs = [1, a_val, b_val]
+    aux, ea, eb, ec = [], [], [], []
+    total = 2 * a_val            # constraints.rs:27-31 pushes (a_val, a_var) twice
+    for i in range(num_constraints - 1):
+        if i % 2:
+            c_val = a_val * b_val % p
+            ea.append(a_val)
+            eb.append(b_val)
+        else:
+            c_val = (a_val + b_val) % p
+            ea.append(c_val)     # <a_var + b_var, z>
+            eb.append(1)
+        ec.append(c_val)
+        aux.append(c_val)
+        total += c_val
+        a_val, b_val = b_val, c_val
+    total %= p
+    c_val = total * total % p
+    aux.append(c_val)
+    ea.append(total)
+    eb.append(total)
+    ec.append(c_val)
+    ea += inputs                 # r1cs_to_qap.rs:115-117
+    eb += [0, 0, 0]
+    ec += [0, 0, 0]
+    return inputs + aux, ea, eb, ec
+
+
+def ints_to_limbs(vals):
+    """canonical ints -> (n, 12) uint64"""
+    buf = b"".join(int(v).to_bytes(96, "little") for v in vals)
+    return np.frombuffer(buf, dtype=np.uint64).reshape(-1, 12).copy()
+
+
+def to_mont(ctx, field, arr):
+    ffi = importlib.import_module("ginger-lib_b200").ffi
+    arr = np.ascontiguousarray(arr, dtype=np.uint64)
+    out = np.zeros_like(arr)
+    ctx.lib.check(ctx.lib.field_op(ctx.handle, field, ffi.OP_TO_MONT, ffi.ptr(arr), None, ffi.ptr(out), arr.shape[0]))
+    return out
+
+
 def gen_range(ctx, group, seed, first, count):
     """bases[first .. first+count) of the synthetic key `seed` (g753_bases_generate indexes from 0, so
     the offset goes into the seed: a_i = splitmix64(seed + (i + 1) * GOLDEN))"""

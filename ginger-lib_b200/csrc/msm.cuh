@@ -27,6 +27,7 @@
 #pragma once
 #include <type_traits>
 
+#include "coop.cuh"
 #include "device.cuh"
 #include "ec_slots.cuh"
 
@@ -620,6 +621,74 @@ k_window_combine(const Fq* __restrict__ sums, unsigned stride, unsigned W, unsig
   for (int i = 0; i < 3; i++) E::M::stg(out_xyz + i * E::K, i * E::K);
 }
 
+#if !defined(G753_HOST_EMUL)
+// ---- warp-cooperative forms of the latency-bound steps (coop.cuh): one WARP per point ---------------
+constexpr int COOP_WARPS = 4;                 // warps (points) per block
+constexpr unsigned COOP_MAX_ITEMS = 4096;     // above this many independent points one thread per point wins
+
+// Horner fold over the W window sums, then the reference's homogeneous projective layout: the serial
+// chain of (W - 1) c doublings of variable_base.rs:72-82 at ~3 us per doubling instead of ~40 us
+template <int GID>
+__global__ void __launch_bounds__(32)
+k_window_combine_coop(const Fq* __restrict__ sums, unsigned stride, unsigned W, unsigned c, Fq* __restrict__ out_xyz) {
+  constexpr int PT = 4 * CoopGroup<GID>::K;
+  CoopEc<GID> ec;
+  ec.init((uint32_t*)g_slots);
+  ec.set_inf();
+  for (int w = (int)W - 1; w >= 0; w--) {
+    if (w != (int)W - 1)
+      for (unsigned k = 0; k < c; k++) ec.dbl();
+    ec.add_g(sums + (size_t)w * stride * PT);
+  }
+  ec.store_projective(out_xyz);
+}
+// sum of `count` homogeneous projective points (the multi-GPU fold)
+template <int GID>
+__global__ void __launch_bounds__(32)
+k_points_sum_coop(const Fq* __restrict__ pts, unsigned count, Fq* __restrict__ out_xyz) {
+  constexpr int K = CoopGroup<GID>::K;
+  CoopEc<GID> ec;
+  ec.init((uint32_t*)g_slots);
+  ec.set_inf();
+  for (unsigned k = 0; k < count; k++) ec.add_projective_g(pts + (size_t)k * 3 * K);
+  ec.store_projective(out_xyz);
+}
+// k_pair_sum with one warp per output point
+template <int GID>
+__global__ void __launch_bounds__(32 * COOP_WARPS)
+k_pair_sum_coop(const Fq* __restrict__ in, unsigned groups, unsigned m_in, Fq* __restrict__ out) {
+  constexpr int PT = 4 * CoopGroup<GID>::K;
+  CoopEc<GID> ec;
+  ec.init((uint32_t*)g_slots);
+  const unsigned half = (m_in + 1) / 2;
+  const unsigned t = blockIdx.x * COOP_WARPS + (threadIdx.x >> 5);
+  if (t >= groups * half) return;
+  const unsigned p = t % half, g = t / half;
+  const Fq* x = in + (size_t)g * m_in * PT;
+  ec.set_inf();
+  ec.add_g(x + (size_t)(2 * p) * PT);
+  if (2 * p + 1 < m_in) ec.add_g(x + (size_t)(2 * p + 1) * PT);
+  ec.store_xyzz(out + (size_t)t * PT);
+}
+// k_tail_scale with one warp per plane
+template <int GID>
+__global__ void __launch_bounds__(32 * COOP_WARPS)
+k_tail_scale_coop(const Fq* __restrict__ S, unsigned nbits, unsigned rows, unsigned log2f, Fq* __restrict__ Z) {
+  constexpr int PT = 4 * CoopGroup<GID>::K;
+  CoopEc<GID> ec;
+  ec.init((uint32_t*)g_slots);
+  const unsigned P = nbits + 1;
+  const unsigned t = blockIdx.x * COOP_WARPS + (threadIdx.x >> 5);
+  if (t >= rows * P) return;
+  const unsigned plane = t % P;
+  ec.set_inf();
+  ec.add_g(S + (size_t)t * PT);
+  if (plane < nbits)
+    for (unsigned k = 0; k < plane + log2f; k++) ec.dbl();
+  ec.store_xyzz(Z + (size_t)t * PT);
+}
+#endif
+
 template <class SC>
 __global__ void k_write_infinity(Fq* __restrict__ out_xyz) {
   typedef EcS<SC> E;
@@ -747,6 +816,26 @@ static inline typename std::enable_if<MsmCfg<GID>::AFFINE>::type msm_launch_affi
 template <int GID>
 static inline typename std::enable_if<!MsmCfg<GID>::AFFINE>::type msm_launch_affine(
     MsmHooks&, cudaStream_t, unsigned, const Fq*, const uint32_t*, const MsmItem*, const uint32_t*, Fq*, uint4*) {}
+
+// out[g * ceil(m_in / 2) + p] = in[g * m_in + 2p] + in[g * m_in + 2p + 1]: one thread per output point while
+// there are many, one warp per point (coop.cuh) once the launch is latency-bound
+template <int GID>
+static inline void msm_pair_sum(MsmHooks& hooks, cudaStream_t stream, const Fq* in, unsigned groups, unsigned m_in, Fq* out) {
+  typedef MsmCfg<GID> Cfg;
+  constexpr int CR = Cfg::NC_RED, TR = CR * Cfg::TP;
+  typedef typename Cfg::template SC<CR, Cfg::TP> SCR;
+  typedef EcS<SCR> ER;
+  constexpr size_t SMEM_RED = slot_bytes<ER, CR>(2 * ER::PT + ER::ADD_SCRATCH);
+  const size_t items = (size_t)groups * div_up(m_in, 2);
+#if !defined(G753_HOST_EMUL)
+  if (items <= COOP_MAX_ITEMS) {
+    G753_MSM_LAUNCH_SMEM(hooks, k_pair_sum_coop<GID>, div_up(items, COOP_WARPS), 32 * COOP_WARPS,
+                         coop_smem_bytes<GID>(COOP_WARPS), stream, in, groups, m_in, out);
+    return;
+  }
+#endif
+  G753_MSM_LAUNCH_SMEM(hooks, k_pair_sum<SCR>, div_up(items, CR), TR, SMEM_RED, stream, in, groups, m_in, out);
+}
 
 // d_scalars: count x 24 u32 canonical (device); d_out: 3K Fq (device)
 template <int GID>
@@ -888,15 +977,19 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
                            nbits, R, tail_a);
       Fq *cur = tail_a, *oth = tail_b;
       while (m > 1) {
-        G753_MSM_LAUNCH_SMEM(hooks, k_pair_sum<SCR>, div_up((size_t)R * P * div_up(m, 2), CR), TR, SMEM_RED, stream, cur,
-                             R * P, m, oth);
+        msm_pair_sum<GID>(hooks, stream, cur, R * P, m, oth);
         m = div_up(m, 2);
         Fq* t2 = cur;
         cur = oth;
         oth = t2;
       }
+#if defined(G753_HOST_EMUL)
       G753_MSM_LAUNCH_SMEM(hooks, k_tail_scale<SCR>, div_up((size_t)R * P, CR), TR, SMEM_RED, stream, cur, nbits, R, log2f,
                            oth);
+#else
+      G753_MSM_LAUNCH_SMEM(hooks, k_tail_scale_coop<GID>, div_up((size_t)R * P, COOP_WARPS), 32 * COOP_WARPS,
+                           coop_smem_bytes<GID>(COOP_WARPS), stream, cur, nbits, R, log2f, oth);
+#endif
       {
         Fq* t2 = cur;
         cur = oth;
@@ -904,8 +997,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
       }
       m = P;
       while (m > 1) {
-        G753_MSM_LAUNCH_SMEM(hooks, k_pair_sum<SCR>, div_up((size_t)R * div_up(m, 2), CR), TR, SMEM_RED, stream, cur, R, m,
-                             oth);
+        msm_pair_sum<GID>(hooks, stream, cur, R, m, oth);
         m = div_up(m, 2);
         Fq* t2 = cur;
         cur = oth;
@@ -916,8 +1008,13 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
     }
   }
   if (hooks.mark) hooks.mark(hooks.user, 4);
+#if defined(G753_HOST_EMUL)
   G753_MSM_LAUNCH_SMEM(hooks, k_window_combine<SCR>, 1, TR, SMEM_RED, stream, window_sums, 1u, R, pl.c,
                        d_out);
+#else
+  G753_MSM_LAUNCH_SMEM(hooks, k_window_combine_coop<GID>, 1, 32, coop_smem_bytes<GID>(1), stream, window_sums, 1u, R, pl.c,
+                       d_out);
+#endif
   if (hooks.mark) hooks.mark(hooks.user, 5);
   return launch_check("msm_run");
 }

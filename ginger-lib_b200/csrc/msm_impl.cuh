@@ -172,11 +172,17 @@ int ext_op_impl(g753_ctx* ctx, int lanes, int op, const uint64_t* a, const uint6
 
 template <int GID>
 void points_sum_launch(g753_ctx* ctx, const void* d_pts, size_t count, void* d_out) {
+#if defined(G753_HOST_EMUL)
   constexpr int T = 32;  // columns; only column 0 works
   typedef typename MsmCfg<GID>::template SC<T> SC;
   typedef EcS<SC> E;
   G753_LAUNCH_SMEM(k_points_sum<SC>, 1, T * MsmCfg<GID>::TP, (slot_bytes<E, T>(2 * E::PT + E::ADD_SCRATCH)), ctx->stream,
                    (const Fq*)d_pts, (unsigned)count, (Fq*)d_out);
+#else
+  // one warp, four field products at a time (coop.cuh): the fold is a latency chain
+  G753_LAUNCH_SMEM(k_points_sum_coop<GID>, 1, 32, coop_smem_bytes<GID>(1), ctx->stream, (const Fq*)d_pts, (unsigned)count,
+                   (Fq*)d_out);
+#endif
 }
 
 

@@ -613,20 +613,16 @@ static unsigned ln_window(size_t n_scalars) {  // :14-18
   return (unsigned)__builtin_ceil(2.0 / 3.0 * l + 2.0);
 }
 
+// the per-window task of msm_inner (:30-70): windows [first, first + count) of the scalars, one task each
 template <class C>
-static ProjP<C> msm_inner(const AffineP<C>* bases, size_t n_bases, const Big* scalars, size_t n_scalars,
-                          unsigned nthreads) {
-  const unsigned c = ln_window(n_scalars);
-  const unsigned num_bits = 753;
+static void msm_window_sums(const AffineP<C>* bases, size_t n_bases, const Big* scalars, size_t n_scalars, unsigned c,
+                            size_t first, size_t count, ProjP<C>* window_sums, unsigned nthreads) {
   Big fr_one;
   memset(&fr_one, 0, sizeof(fr_one));
   fr_one.l[0] = 1;
   const size_t n = n_bases < n_scalars ? n_bases : n_scalars;  // zip
-  std::vector<unsigned> window_starts;
-  for (unsigned w = 0; w < num_bits; w += c) window_starts.push_back(w);
-  std::vector<ProjP<C>> window_sums(window_starts.size());
-  parallel_for(window_starts.size(), nthreads, [&](size_t wi) {
-    const unsigned w_start = window_starts[wi];
+  parallel_for(count, nthreads, [&](size_t k) {
+    const unsigned w_start = (unsigned)((first + k) * c);
     ProjP<C> res = ProjP<C>::zero();
     std::vector<ProjP<C>> buckets(((size_t)1 << c) - 1, ProjP<C>::zero());
     for (size_t i = 0; i < n; i++) {
@@ -645,8 +641,18 @@ static ProjP<C> msm_inner(const AffineP<C>* bases, size_t n_bases, const Big* sc
       running.add_assign_mixed(buckets[b].into_affine());
       res.add_assign(running);
     }
-    window_sums[wi] = res;
+    window_sums[k] = res;
   });
+}
+
+template <class C>
+static ProjP<C> msm_inner(const AffineP<C>* bases, size_t n_bases, const Big* scalars, size_t n_scalars,
+                          unsigned nthreads) {
+  const unsigned c = ln_window(n_scalars);
+  const unsigned num_bits = 753;
+  const size_t windows = (num_bits + c - 1) / c;   // (0..num_bits).step_by(c)
+  std::vector<ProjP<C>> window_sums(windows);
+  msm_window_sums<C>(bases, n_bases, scalars, n_scalars, c, 0, windows, window_sums.data(), nthreads);
   ProjP<C> total = ProjP<C>::zero();
   for (size_t wi = window_sums.size(); wi-- > 1;) {
     total.add_assign(window_sums[wi]);
@@ -801,6 +807,26 @@ static int msm_entry(const u64* coords, const uint8_t* inf, size_t n_bases, cons
   load_affine<C>(coords, inf, n, bases);
   ProjP<C> r = msm_inner<C>(bases.data(), n, (const Big*)scalars, n_scalars, nthreads);
   store_proj<C>(r, out_xyz);
+  return 0;
+}
+
+// A bounded SAMPLE of one MSM for the CPU baseline (bench.py): `count` of the reference's per-window
+// tasks, windows [first, first + count), with the window size c of the FULL input; out receives the
+// `count` window sums (projective).  Every window task costs the same (n mixed additions into 2^c - 1
+// buckets + the running-sum reduction), so count / windows of the MSM's time is measured exactly.
+template <class C>
+static int msm_windows_entry(const u64* coords, const uint8_t* inf, size_t n_bases, const u64* scalars,
+                             size_t n_scalars, unsigned first, unsigned count, u64* out_xyz, unsigned nthreads) {
+  typedef typename C::BF BF;
+  std::vector<AffineP<C>> bases;
+  size_t n = n_bases < n_scalars ? n_bases : n_scalars;
+  load_affine<C>(coords, inf, n, bases);
+  const unsigned c = ln_window(n_scalars);
+  const unsigned windows = (753 + c - 1) / c;
+  if (first + count > windows) return 1;
+  std::vector<ProjP<C>> sums(count);
+  msm_window_sums<C>(bases.data(), n, (const Big*)scalars, n_scalars, c, first, count, sums.data(), nthreads);
+  for (unsigned k = 0; k < count; k++) store_proj<C>(sums[k], out_xyz + (size_t)k * 3 * BF::K * N);
   return 0;
 }
 
@@ -971,6 +997,18 @@ int ref753_msm(int group, const u64* coords, const uint8_t* inf, size_t n_bases,
   }
   return 1;
 }
+// windows [first, first + count) of the same MSM: out = count GroupProjective window sums
+int ref753_msm_windows(int group, const u64* coords, const uint8_t* inf, size_t n_bases, const u64* scalars,
+                       size_t n_scalars, unsigned first, unsigned count, u64* out_xyz, unsigned nthreads) {
+  switch (group) {
+    case 0: return msm_windows_entry<M4G1>(coords, inf, n_bases, scalars, n_scalars, first, count, out_xyz, nthreads);
+    case 1: return msm_windows_entry<M4G2>(coords, inf, n_bases, scalars, n_scalars, first, count, out_xyz, nthreads);
+    case 2: return msm_windows_entry<M6G1>(coords, inf, n_bases, scalars, n_scalars, first, count, out_xyz, nthreads);
+    case 3: return msm_windows_entry<M6G2>(coords, inf, n_bases, scalars, n_scalars, first, count, out_xyz, nthreads);
+  }
+  return 1;
+}
+unsigned ref753_msm_window_bits(size_t n_scalars) { return ln_window(n_scalars); }
 int ref753_walk(int group, const u64* p0_xy, const u64* d_xy, size_t n, u64* out_coords, unsigned nthreads) {
   switch (group) {
     case 0: return walk_entry<M4G1>(p0_xy, d_xy, n, out_coords, nthreads);

@@ -28,6 +28,9 @@ def lib():
         L.ref753_ext_op.argtypes = [i, i, vp, vp, vp]
         L.ref753_point_op.argtypes = [i, i, vp, vp, vp]
         L.ref753_msm.argtypes = [i, vp, vp, sz, vp, sz, vp, u]
+        L.ref753_msm_windows.argtypes = [i, vp, vp, sz, vp, sz, u, u, vp, u]
+        L.ref753_msm_window_bits.argtypes = [sz]
+        L.ref753_msm_window_bits.restype = u
         L.ref753_walk.argtypes = [i, vp, vp, sz, vp, u]
         L.ref753_fft.argtypes = [i, vp, u, i, u]
         _lib = L
@@ -79,6 +82,26 @@ def msm(group, coords, infinity, scalars, nthreads=None):
     out = np.zeros((3, k * 12), dtype=np.uint64)
     nt = nthreads or hardware_threads()
     assert lib().ref753_msm(group, _p(coords), _p(inf), coords.shape[0], _p(scalars), scalars.shape[0], _p(out), nt) == 0
+    return out
+
+
+def msm_window_bits(n_scalars):
+    """c of variable_base.rs:14-18 for this many scalars; the MSM has ceil(753 / c) windows"""
+    return int(lib().ref753_msm_window_bits(n_scalars))
+
+
+def msm_windows(group, coords, infinity, scalars, first, count, nthreads=None):
+    """`count` of the per-window tasks of the same MSM (variable_base.rs:30-70), windows [first, first+count):
+    returns the window sums, (count, 3, k*12) GroupProjective limbs.  The bounded sample of bench.py's
+    CPU baseline; folded over all windows it IS multi_scalar_mul (tests/test_oracle_cpp.py)."""
+    k = GROUP_K[group]
+    coords = np.ascontiguousarray(coords, dtype=np.uint64).reshape(-1, 2 * k * 12)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 12)
+    inf = np.ascontiguousarray(infinity, dtype=np.uint8) if infinity is not None else None
+    out = np.zeros((count, 3, k * 12), dtype=np.uint64)
+    nt = nthreads or hardware_threads()
+    assert lib().ref753_msm_windows(group, _p(coords), _p(inf), coords.shape[0], _p(scalars), scalars.shape[0],
+                                    first, count, _p(out), nt) == 0
     return out
 
 

@@ -116,6 +116,29 @@ def test_msm_vs_python(group):
     assert got == O.msm_naive(C, pts[:5], sc)
 
 
+@pytest.mark.parametrize("group", [0, 3])
+def test_msm_window_sample(group):
+    """msm_windows (the bounded sample the CPU baseline times): the per-window sums, folded high to low with
+    c doublings in between (variable_base.rs:72-82), are multi_scalar_mul"""
+    C = GROUPS[group]
+    n = 40 if C.F.k == 1 else 33
+    pts = sample_points(C, n, 0xA7 + group)
+    sc = sample_scalars(C, n, 0xB7 + group)
+    sc[3] = 1
+    coords, inf = points_to_arrays(C, pts)
+    arr = ints_to_array(sc)
+    c = R.msm_window_bits(n)
+    windows = (753 + c - 1) // c
+    lo = [projective_to_point(C, w) for w in R.msm_windows(group, coords, inf, arr, 0, 5)]
+    hi = [projective_to_point(C, w) for w in R.msm_windows(group, coords, inf, arr, 5, windows - 5, nthreads=2)]
+    total = None
+    for w in reversed(lo + hi):
+        for _ in range(c):
+            total = C.double(total) if total is not None else None
+        total = C.add(total, w)
+    assert total == O.msm_naive(C, pts, sc)
+
+
 def test_walk_generator():
     for group in (0, 1):
         C = GROUPS[group]
