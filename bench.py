@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Headline benchmark: MNT4-753 G1 VariableBaseMSM::multi_scalar_mul at 2^22 points (BASELINE.json
-metric / config 3), plus the 2^22 radix-2 FFT as a secondary figure.
+metric / config 3), with the 2^22 radix-2 FFT, configs 1, 2, 4 and the Groth16 proof (config 5) beside it.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference algorithm
@@ -11,12 +11,20 @@ range (strong scaling, as config 3 states), every rank runs a complete local MSM
 points are all-gathered over NCCL and folded on the device.
 
 Timed regions
-  value  : K steps with bases AND scalars resident in HBM (g753_msm_dev), CUDA events on the
-           context's stream, barrier + synchronize on both sides, max over ranks.
-  e2e    : K steps through the host-buffer C-ABI call the reference-facing shim makes
-           (g753_msm: scalars in pinned host memory -> H2D -> MSM -> D2H of the 288-byte result),
-           bases resident as a proving key is (uploaded once per key).
+  value    : K steps with bases AND scalars resident in HBM (g753_msm_dev), CUDA events on the
+             context's stream, barrier + synchronize on both sides, max over ranks.
+  e2e      : K steps through the host-buffer C-ABI call the reference-facing shim makes
+             (g753_msm: scalars in pinned host memory -> H2D -> MSM -> D2H of the 288-byte result),
+             bases resident as a proving key is (uploaded once per key).
+  e2e_cold : the literal one-shot drop-in multi_scalar_mul(&bases, &scalars) = g753_msm_host: bases AND
+             scalars in (pageable) host memory, uploaded per call, plain key (no precomputed copies).
 Inputs (1.1 GiB at N=1) are far larger than the 126 MB L2, so no explicit flush is needed between steps.
+
+Every figure is checked before it is reported: the MSM against (sum s_i a_i mod r) * G at full size and,
+at N = 1, against the C++ restatement of the reference on the same 2^22 bases and scalars; the FFT every
+limb against the restated transform; the sharded FFT against the single-GPU one; the proof against its
+discrete-log prediction.  The CPU restatement (oracle/ref753.cpp, kind "port") is the checker and the
+timed CPU baseline - it is never part of the measured GPU path.
 """
 import argparse
 import ctypes
@@ -36,7 +44,29 @@ if ROOT not in sys.path:
 
 GROUP = 0                     # G753_MNT4_G1
 LIMB_MACS_PER_MUL = 1176      # 2 * 24^2 + 24
+LIMB_MACS_PER_SQR = 876       # dedicated squaring (fq.cuh fq_sqr)
+LIMB_MACS_MUL2 = 1752         # two products under one reduction (fq.cuh fq_mul2)
 SEED = 0x5EED0001
+METRIC = "mnt4753_g1_msm_throughput"
+
+# limb-MACs one mixed addition of the accumulation kernel EXECUTES (ec_slots.cuh madd_g: 8 products + 2
+# squarings of the coordinate field):
+#   G1:        8 x 1176 + 2 x 876
+#   G2 / Fq2:  10 tower products, each two lanes x one two-product body (slots.cuh Tw2C, G753_FQ2_LAZY = 2)
+#   G2 / Fq3:  8 Karatsuba products (6 base products) + 2 Chung-Hasan squarings (5 base products)
+EXECUTED_MACS_PER_MADD = {0: 8 * 1176 + 2 * 876, 2: 8 * 1176 + 2 * 876, 1: 10 * 2 * 1752, 3: (8 * 6 + 2 * 5) * 1176}
+
+
+def workload_config(log_n, world, scaling):
+    """the workload, as both arms of the comparison name it (nothing implementation-specific)"""
+    n = 1 << log_n
+    n_local = n // world if scaling == "strong" else n
+    return {"workload": "MNT4-753 G1 VariableBaseMSM::multi_scalar_mul, 2^%d points (BASELINE config 3)" % log_n,
+            "points_total": n_local * world, "points_per_step": n_local * world,
+            "scalars": "uniform 752-bit canonical",
+            "bases": "synthetic affine points of the prime-order subgroup",
+            "l2": "inputs (%.0f MiB per step and GPU) larger than the 126 MB L2: no flush between steps" %
+                  ((n_local * 288) / 2**20)}
 
 
 def ref_window_params(n):
@@ -59,6 +89,13 @@ def random_scalars(n, seed):
     sc = rng.integers(0, np.iinfo(np.uint64).max, size=(n, 12), dtype=np.uint64, endpoint=True)
     sc[:, 11] &= np.uint64((1 << 48) - 1)
     return sc
+
+
+def random_field_elements(n, seed):
+    """valid Montgomery representations (< 2^752 < p), (n, 12) uint64"""
+    raw = random_scalars(n, seed)
+    raw[:, 11] &= np.uint64(0xFFFF)
+    return raw
 
 
 def dot_mod(scalars, logs, r):
@@ -93,6 +130,20 @@ def affine_of(xyz, p):
         return None
     zi = pow(Z, -1, p)
     return (X * zi % p, Y * zi % p)
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def library_provenance(lib):
+    """which sources the loaded libg753.so was built from, against this tree's"""
+    build = importlib.import_module("ginger-lib_b200.build")
+    loaded, tree = lib.source_hash().decode(), build.source_hash()
+    return {"version": lib.version().decode(), "source_hash": loaded, "tree_hash": tree, "matches_tree": loaded == tree}
 
 
 class ClockSampler:
@@ -148,48 +199,115 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm: the CPU restatement of the reference's algorithm (oracle/ref753.cpp), all host threads
+# CPU legs: the C++ restatement of the reference's algorithms (oracle/ref753.cpp) on all host threads.
+# These functions are the only places bench.py executes oracle/ code.
 # ---------------------------------------------------------------------------------------------
-def cpu_msm_rate(log_n, repeats, warmup, coords=None, scalars=None):
-    """times oracle.ref753.msm (variable_base.rs:10-83 restated, one task per window) on 2^log_n
-    points; returns (Mpts/s best, per-step seconds list, threads, result)"""
-    from oracle import ref753                      # the one place bench.py executes oracle/ code
+def cpu_walk_bases(group, n):
+    """P_i = (i + 1) * G, affine Montgomery limbs (oracle-side generator for the CPU arm)"""
+    from oracle import ref753
     params = importlib.import_module("ginger-lib_b200.params")
-    n = 1 << log_n
-    if coords is None:
-        g = np.stack([int_to_limbs(v) for v in params.GENERATOR_MONT[GROUP]])
-        coords = ref753.walk(GROUP, g, g, n)       # P_i = (i + 1) * G, affine
-        scalars = random_scalars(n, SEED + 7)
+    k = ref753.GROUP_K[group]
+    g = np.stack([int_to_limbs(v) for v in params.GENERATOR_MONT[group]]).reshape(2, k * 12)
+    return ref753.walk(group, g, g, n)
+
+
+def cpu_msm_full(group, coords, scalars):
+    """one whole multi_scalar_mul (variable_base.rs:10-83 restated, one task per window); (seconds, result, threads)"""
+    from oracle import ref753
     threads = ref753.hardware_threads()
-    times, out = [], None
-    for it in range(warmup + repeats):
-        t0 = time.perf_counter()
-        out = ref753.msm(GROUP, coords, None, scalars, threads)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    return n / min(times) / 1e6, times, threads, out
+    t0 = time.perf_counter()
+    out = ref753.msm(group, coords, None, scalars, threads)
+    return time.perf_counter() - t0, out, threads
+
+
+def cpu_fft(field, raw, mode):
+    from oracle import ref753
+    threads = ref753.hardware_threads()
+    t0 = time.perf_counter()
+    out = ref753.fft(field, raw, mode, threads)
+    return time.perf_counter() - t0, out, threads
+
+
+def cpu_groth16(log_n):
+    """create_proof's hot path (prover.rs:241-337 + r1cs_to_qap.rs:121-166) restated on the CPU port at a
+    2^log_n domain: seven transforms with the element-wise steps, into_repr, five long MSMs.  Wall seconds
+    per phase."""
+    from oracle import ref753
+    ffi = importlib.import_module("ginger-lib_b200").ffi
+    field, g1, g2 = ffi.FIELD_MNT4_FR, ffi.MNT4_G1, ffi.MNT4_G2
+    n = 1 << log_n
+    threads = ref753.hardware_threads()
+    a, b, c = (random_field_elements(n, 0x91 + i) for i in range(3))
+    z = random_field_elements(n, 0x94)
+    q_g1 = cpu_walk_bases(g1, n)
+    q_g2 = cpu_walk_bases(g2, n)
+    zinv = random_field_elements(1, 0x95)
+    t = {}
+    t0 = time.perf_counter()
+    fa = ref753.fft(field, ref753.fft(field, a, ffi.IFFT, threads), ffi.COSET_FFT, threads)
+    fb = ref753.fft(field, ref753.fft(field, b, ffi.IFFT, threads), ffi.COSET_FFT, threads)
+    fc = ref753.fft(field, ref753.fft(field, c, ffi.IFFT, threads), ffi.COSET_FFT, threads)
+    ab = ref753.field_op(field, 2, ref753.field_op(field, 0, fa, fb), fc)
+    ab = ref753.field_op(field, 0, ab, np.tile(zinv, (n, 1)))
+    h = ref753.fft(field, ab, ffi.COSET_IFFT, threads)
+    t["witness_map"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    hr = ref753.field_op(field, 7, h)            # into_repr (prover.rs:241-267)
+    zr = ref753.field_op(field, 7, z)
+    t["into_repr"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(3):                            # A, B1, L over the assignment
+        ref753.msm(g1, q_g1, None, zr, threads)
+    ref753.msm(g1, q_g1, None, hr, threads)       # H
+    t["msm_g1_x4"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref753.msm(g2, q_g2, None, zr, threads)       # B2
+    t["msm_g2"] = time.perf_counter() - t0
+    return t, threads
 
 
 def run_reference(args):
+    """the reference arm: the restated CPU algorithm on the SAME workload (2^log_n points, same window
+    size c and window count as the reference picks for that input).  A step is a bounded sample of one
+    MSM: `threads` of its ceil(753 / c) independent per-window tasks (variable_base.rs:30-70: one rayon
+    task per window, every window the same work: n mixed additions into 2^c - 1 buckets + the
+    running-sum reduction), i.e. one full wave of the thread pool; value = points x (windows timed /
+    windows) / step time.  The Horner fold of the window sums (:72-82, ~750 doublings, < 1 ms) is not in
+    the sample.  Warm-up steps run the same tasks on a 2^16-point prefix."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    log_n = args.cpu_log_n
-    rate, times, threads, _ = cpu_msm_rate(log_n, args.steps, args.warmup)
+    from oracle import ref753
+    log_n = args.log_n
     n = 1 << log_n
+    threads = ref753.hardware_threads()
+    coords = cpu_walk_bases(GROUP, n)
+    scalars = random_scalars(n, SEED + 7)
+    c, W = ref_window_params(n)
+    assert c == ref753.msm_window_bits(n)
+    per_step = min(W, threads)
+    small = min(n, 1 << 16)
+    for _ in range(args.warmup):
+        ref753.msm_windows(GROUP, coords[:small], None, scalars[:small], 0, min(per_step, ref_window_params(small)[1]), threads)
+    times = []
+    for it in range(args.steps):
+        first = (it * per_step) % max(1, W - per_step)      # the last (partial) window is never the only one
+        t0 = time.perf_counter()
+        ref753.msm_windows(GROUP, coords, None, scalars, first, per_step, threads)
+        times.append(time.perf_counter() - t0)
     mean = float(np.mean(times))
-    value = n / mean / 1e6
+    value = n * (per_step / W) / mean / 1e6
+    sample = ("%d of the %d per-window tasks (c = %d) of the 2^%d-point MSM per step = one wave of the %d-thread pool, "
+              "C++ restatement of variable_base.rs:10-83; full-MSM equivalent %.1f s"
+              % (per_step, W, c, log_n, threads, mean * W / per_step))
     line = {
-        "impl": "reference", "metric": "mnt4753_g1_msm_throughput", "value": value, "unit": "Mpts/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64x12 (753-bit Montgomery)",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64x12 (753-bit Montgomery)",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": "MNT4-753 G1 VariableBaseMSM::multi_scalar_mul, 2^22 points (BASELINE config 3)",
-                   "sample": "2^%d points per step (bounded CPU sample of the same workload)" % log_n},
-        "cpu_baseline": {"value": value, "unit": "Mpts/s", "cores": threads, "kind": "port",
-                         "sample": "2^%d-point MNT4-753 G1 MSM, C++ restatement of variable_base.rs:10-83 "
-                                   "(one task per window), %d threads" % (log_n, threads)},
+        "config": workload_config(log_n, args.gpus, args.scaling),
+        "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "Mpts/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -198,6 +316,21 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------
+def device_time(stream, fn, reps, warm=1):
+    """mean ms of fn() over reps, CUDA events on `stream`"""
+    import torch
+    for _ in range(warm):
+        fn()
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    stream.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -217,6 +350,10 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     ctx = G.Context(local_rank, stream=stream.cuda_stream)
     lib = ctx.lib
+    provenance = library_provenance(lib)
+    if not provenance["matches_tree"]:
+        raise SystemExit("libg753.so was built from other sources (%s) than this tree (%s): rebuild with "
+                         "__graft_entry__.build()" % (provenance["source_hash"], provenance["tree_hash"]))
 
     n_total = 1 << args.log_n
     n_local = n_total // world if args.scaling == "strong" else n_total
@@ -233,11 +370,6 @@ def run_ours(args):
     # ---- synthetic key and scalars ---------------------------------------------------------
     t_setup = time.perf_counter()
     bases = ctx.generate_bases(GROUP, n_local, seed)           # bases[i] = a_i * G, resident
-    t_pre = time.perf_counter()
-    if args.copies != 1:
-        bases.precompute(args.copies)                          # once per key: shifted copies 2^(j*rows*c) * P_i
-        ctx.sync()
-    precompute_s = time.perf_counter() - t_pre
     sc_np = random_scalars(n_local, seed + 1)
     sc_pinned = torch.from_numpy(sc_np.view(np.int64)).pin_memory()
     sc_host = sc_pinned.numpy().view(np.uint64)
@@ -248,6 +380,7 @@ def run_ours(args):
         d_final = torch.zeros(36, dtype=torch.int64, device="cuda")
     stream.synchronize()
     out_host = np.zeros((3, 12), dtype=np.uint64)
+    gen = np.stack([int_to_limbs(v) for v in params.GENERATOR_MONT[GROUP]])
 
     def step_resident():
         """one MSM, inputs resident; N > 1: all-gather of the partial points + device fold"""
@@ -268,12 +401,7 @@ def run_ours(args):
         step_resident()
         lib.check(lib.d2h(ctx.handle, ffi.ptr(out_host), ctypes.c_void_p(d_final.data_ptr()), 288))
 
-    # ---- correctness first: (sum s_i a_i mod r) * G, checked at full size ------------------
-    launches0 = ctx.launches
-    step_resident()
-    stream.synchronize()
-    launches_per_step = ctx.launches - launches0
-    res = (d_final if world > 1 else d_out).cpu().numpy().view(np.uint64).reshape(3, 12)
+    # the discrete-log prediction of the result: (sum s_i a_i mod r) * G
     k_local = dot_mod(sc_np, G.Bases.generated_logs(n_local, seed), r)
     if world > 1:
         ks = [None] * world
@@ -281,12 +409,64 @@ def run_ours(args):
         k_total = sum(ks) % r
     else:
         k_total = k_local
-    gen = np.stack([int_to_limbs(v) for v in params.GENERATOR_MONT[GROUP]])
     expect = np.zeros((3, 12), dtype=np.uint64)
     lib.check(lib.point_op(ctx.handle, GROUP, 2, ffi.ptr(gen), ffi.ptr(int_to_limbs(k_total)), ffi.ptr(expect)))
-    ok = affine_of(res, p) == affine_of(expect, p)
-    if not ok:
-        raise SystemExit("rank %d: MSM result differs from (sum s_i a_i) * G - refusing to report a number" % rank)
+    expect_affine = affine_of(expect, p)
+
+    def check_result(what):
+        res = (d_final if world > 1 else d_out).cpu().numpy().view(np.uint64).reshape(3, 12)
+        if affine_of(res, p) != expect_affine:
+            raise SystemExit("rank %d: %s differs from (sum s_i a_i) * G - refusing to report a number" % (rank, what))
+
+    # ---- the plain key first: correctness + its timing (the cold / one-shot path uses it) ---
+    step_resident()
+    stream.synchronize()
+    check_result("MSM on the plain key")
+    plain_ms = device_time(stream, step_resident, 2, warm=1)
+    plain_phases = ctx.last_msm_phases()
+    plain_plan = ctx.last_msm_plan()
+
+    # ---- CPU baseline and full-size parity (rank 0, N = 1): the restated reference on the SAME 2^22 bases
+    # and scalars, one whole multi_scalar_mul; its result must be the CUDA path's -------------------
+    cpu = None
+    cold = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        coords = bases.download()
+        cpu_s, cpu_out, threads = cpu_msm_full(GROUP, coords, sc_np)
+        if affine_of(cpu_out, p) != expect_affine:
+            raise SystemExit("the CPU restatement and the CUDA MSM disagree at full size")
+        c_ref, w_ref = ref_window_params(n_local)
+        cpu = {"value": n_local / cpu_s / 1e6, "unit": "Mpts/s", "cores": threads, "kind": "port",
+               "sample": "one whole 2^%d-point MSM on the benchmark's own bases and scalars (c = %d, %d window tasks), "
+                         "C++ restatement of variable_base.rs:10-83, %d threads, %.1f s; its result equals the CUDA "
+                         "path's (affine, every limb)" % (args.log_n, c_ref, w_ref, threads, cpu_s)}
+        # the literal one-shot drop-in: host bases + host scalars per call (pageable memory, plain key)
+        cold_out = np.zeros((3, 12), dtype=np.uint64)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            lib.check(lib.msm_host(ctx.handle, GROUP, ffi.ptr(coords), None, n_local, ffi.ptr(sc_np), n_local, ffi.ptr(cold_out)))
+            ts.append(time.perf_counter() - t0)
+        if affine_of(cold_out, p) != expect_affine:
+            raise SystemExit("g753_msm_host result differs")
+        cold = {"value": n_local / min(ts) / 1e6, "unit": "Mpts/s", "ms": min(ts) * 1e3,
+                "h2d_bytes_per_step": n_local * (192 + 96), "d2h_bytes_per_step": 288,
+                "path": "g753_msm_host: multi_scalar_mul(&bases, &scalars) with bases AND scalars in pageable host memory, "
+                        "uploaded per call; plain key, no precomputed copies",
+                "device_ms_plain_key": plain_ms, "phases_ms_plain_key": plain_phases, "plan_plain_key": plain_plan}
+        del coords
+
+    # ---- resident key with precomputed copies (once per key) ---------------------------------------
+    t_pre = time.perf_counter()
+    if args.copies != 1:
+        bases.precompute(args.copies)                          # shifted copies 2^(j*rows*c) * P_i
+        ctx.sync()
+    precompute_s = time.perf_counter() - t_pre
+    launches0 = ctx.launches
+    step_resident()
+    stream.synchronize()
+    launches_per_step = ctx.launches - launches0
+    check_result("MSM on the key with precomputed copies")
     setup_s = time.perf_counter() - t_setup
 
     # ---- integer-MAC roofline probe (live) -------------------------------------------------
@@ -322,6 +502,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = n_global / (ms_per_step * 1e-3) / 1e6
+    check_result("MSM after the timed steps")
 
     # ---- timed: end to end through the host-buffer call -----------------------------------
     for _ in range(2):
@@ -336,172 +517,211 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = n_global / (float(t.item()) / args.steps) / 1e6
-    res2 = out_host.copy()
-    if affine_of(res2, p) != affine_of(expect, p):
+    if affine_of(out_host.copy(), p) != expect_affine:
         raise SystemExit("rank %d: e2e result differs from the resident-path result" % rank)
+    bases.free()
+    del d_scalars
 
-    # ---- secondary: 2^log_n radix-2 FFT on mnt4753::Fr (rank 0 figure, per GPU) -------------
+    # ---- the 2^log_n FFT, configs 1 / 2 / 4, Groth16 --------------------------------------------------
     fft = None
     if not args.no_fft:
-        nf = 1 << args.fft_log_n
-        raw = random_scalars(nf, 99)
-        raw[:, 11] &= np.uint64(0xFFFF)        # < p: a valid Montgomery representation
-        vec = G.DeviceVector(ctx, ffi.FIELD_MNT4_FR, nf, raw)
-        for _ in range(3):
-            vec.ntt(ffi.FFT)
-        stream.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(args.steps, 5)
-        e0.record(stream)
-        for _ in range(reps):
-            vec.ntt(ffi.FFT)
-        e1.record(stream)
-        stream.synchronize()
-        fft_ms = e0.elapsed_time(e1) / reps
-        hbm_peak = 6543.4
-        try:
-            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-            peak_src = "measured (MEASURED_PEAKS.json)"
-        except (OSError, KeyError, ValueError):
-            hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        muls = (nf // 2) * args.fft_log_n
-        fft = {"metric": "mnt4753_fr_fft_throughput", "log_n": args.fft_log_n, "value": nf / (fft_ms * 1e-3),
-               "unit": "elements/s", "ms": fft_ms,
-               "roofline_hbm": {"bound": "hbm", "achieved": 192.0 * nf / (fft_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                                "unit": "GB/s", "frac": 192.0 * nf / (fft_ms * 1e-3) / 1e9 / hbm_peak,
-                                "peak_source": peak_src, "algorithmic_bytes": 192 * nf},
-               "roofline_int": {"bound": "int32-mac", "achieved": muls * LIMB_MACS_PER_MUL / (fft_ms * 1e-3) / 1e12,
-                                "peak": peak_mac_per_s / 1e12, "unit": "Tlimb-MAC/s",
-                                "frac": muls * LIMB_MACS_PER_MUL / (fft_ms * 1e-3) / peak_mac_per_s}}
-        vec.free()
-        if world > 1:
-            fft["sharded"] = sharded_fft(ctx, stream, ffi, args.fft_log_n, world, max(args.steps, 5))
-
-    # ---- CPU baseline beside it (rank 0, N = 1): same bases / scalars, bounded sample ------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        m = 1 << args.cpu_log_n
-        m = min(m, n_local)
-        coords = bases.download(0, m)
-        rate, times, threads, cpu_out = cpu_msm_rate(args.cpu_log_n, 1, 0, coords, sc_np[:m])
-        got = G.VariableBaseMSM.multi_scalar_mul(bases, sc_np[:m])
-        if affine_of(got, p) != affine_of(cpu_out, p):
-            raise SystemExit("CUDA MSM and the CPU restatement disagree on the %d-point sample" % m)
-        cpu = {"value": rate, "unit": "Mpts/s", "cores": threads, "kind": "port",
-               "sample": "first 2^%d of the benchmark's own bases/scalars, C++ restatement of "
-                         "variable_base.rs:10-83, 1 run of %.1f s; result equal to the CUDA path's" %
-                         (args.cpu_log_n, times[0])}
-
-    # ---- config 4: MNT6-753 G2 (Fq3) MSM at 2^20 + a mixed-radix transform (rank 0, N = 1) ----
-    cfg4 = None
-    if rank == 0 and world == 1 and not args.no_config4:
-        bases.free()
-        cfg4 = run_config4(ctx, G, ffi, params, args)
-
-    # ---- config 5: end-to-end Groth16 proof; N > 1: the long MSMs sharded by point range -------
+        fft = bench_fft(ctx, stream, G, args, rank, world, peak_mac_per_s)
+    cfg1 = cfg2 = cfg4 = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        cfg1 = run_config1(ctx, stream, G, params, args)
+        cfg2 = run_config2(ctx, stream, G, args)
+        cfg4 = run_config4(ctx, stream, G, ffi, params, args, peak_mac_per_s)
     g16 = None
     if not args.no_groth16:
         import bench_groth16
-        bases.free()
         g16 = bench_groth16.run(ctx, args.groth16_log_n, steps=max(2, min(args.steps, 3)), warmup=1, copies=args.copies,
-                                rank=rank, world=world, barrier=barrier if world > 1 else None)
+                                rank=rank, world=world, barrier=barrier if world > 1 else None,
+                                peak_mac_per_s=peak_mac_per_s)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            tcpu, threads = cpu_groth16(args.cpu_groth16_log_n)
+            total = sum(tcpu.values())
+            scale = 1 << (args.groth16_log_n - args.cpu_groth16_log_n)
+            g16["cpu_baseline"] = {
+                "value": total * 1e3, "unit": "ms", "cores": threads, "kind": "port",
+                "sample": "the prover's hot path restated on the CPU port at a 2^%d domain (7 transforms + element-wise "
+                          "steps, into_repr, A / B1 / L / H in G1 and B2 in G2 through the restated Pippenger); the 2^%d "
+                          "proof is >= %d x this (MSM cost per point falls slowly with n)"
+                          % (args.cpu_groth16_log_n, args.groth16_log_n, scale),
+                "phases_s": tcpu, "extrapolated_ms_at_bench_size": total * 1e3 * scale}
 
     if rank == 0:
         canon_all, canon_acc = canonical_field_muls(n_local)
         acc_ms = phases.get("accumulate", 0.0)
+        executed = None
+        if plan and acc_ms:
+            macs = n_local * plan["windows"] * EXECUTED_MACS_PER_MADD[GROUP]
+            executed = {"plan": plan, "mixed_additions": n_local * plan["windows"], "limb_macs": macs,
+                        "frac": macs / (acc_ms * 1e-3) / peak_mac_per_s}
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_bucket_acc_bytes_2p22")
-        except (OSError, ValueError):
-            pass
+        if world == 1 and args.log_n == 22:
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_bucket_acc_bytes_2p22")
+            except (OSError, ValueError):
+                pass
         roofline = {
             "bound": "int32-mac",
             "kernel": "k_bucket_acc",
-            "achieved": canon_acc * LIMB_MACS_PER_MUL / (acc_ms * 1e-3) / 1e12 if acc_ms else None,
+            # the fraction of the integer pipe's measured ceiling the kernel sustains on the work it EXECUTES
+            # (n x W signed-digit windows x one XYZZ mixed addition of 8 products + 2 squarings)
+            "achieved": executed["limb_macs"] / (acc_ms * 1e-3) / 1e12 if executed else None,
             "peak": peak_mac_per_s / 1e12,
             "unit": "Tlimb-MAC/s",
-            "frac": canon_acc * LIMB_MACS_PER_MUL / (acc_ms * 1e-3) / peak_mac_per_s if acc_ms else None,
+            "frac": executed["frac"] if executed else None,
             "traffic": traffic,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at "
+                              "2^22 on one GPU (profiles/); not measured per run, null for other shapes",
             "peak_source": "measured live: dependent fq_mul stream on 592x256 threads (g753_mac_probe), 1176 limb-MACs per product",
-            "algorithmic": "reference op count of the bucket accumulation: n*W*11 field muls * 1176 limb-MACs "
-                           "(SURVEY.md 8d), n=%d per GPU" % n_local,
             "kernel_ms": acc_ms,
-            # what the kernel actually executes: n * W mixed additions (XYZZ, 8 products + 2 squarings
-            # of 1176 / 876 limb-MACs) - the fraction of the integer pipe's measured ceiling it sustains
-            "executed": None if not plan else {
-                "plan": plan, "mixed_additions": n_local * plan["windows"],
-                "limb_macs": n_local * plan["windows"] * (8 * 1176 + 2 * 876),
-                "frac": n_local * plan["windows"] * (8 * 1176 + 2 * 876) / (acc_ms * 1e-3) / peak_mac_per_s
-                if acc_ms else None},
-            "whole_msm_frac": canon_all * LIMB_MACS_PER_MUL / (ms_per_step * 1e-3) / peak_mac_per_s,
+            "executed": executed,
+            # the same kernel time scored on the REFERENCE algorithm's operation count (n x W_ref
+            # unsigned windows x 11 products): above 1 because the executed algorithm does less work
+            "reference_count": {"limb_macs": canon_acc * LIMB_MACS_PER_MUL,
+                                "frac": canon_acc * LIMB_MACS_PER_MUL / (acc_ms * 1e-3) / peak_mac_per_s if acc_ms else None,
+                                "whole_msm_frac": canon_all * LIMB_MACS_PER_MUL / (ms_per_step * 1e-3) / peak_mac_per_s},
             "phases_ms": phases,
         }
+        config = workload_config(args.log_n, world, args.scaling)
         line = {
-            "metric": "mnt4753_g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "Mpts/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32x24 (753-bit Montgomery, integer)", "data": "synthetic",
-            "config": {"workload": "MNT4-753 G1 VariableBaseMSM::multi_scalar_mul, 2^%d points (BASELINE config 3)"
-                                   % args.log_n,
-                       "points_total": n_global, "points_per_gpu": n_local,
-                       "bases": "a_i*G, a_i = splitmix64 (g753_bases_generate), resident in HBM" +
-                                (" with precomputed shifted copies (g753_bases_precompute, %s, %.1f s once per key)"
-                                 % ("%d copies" % args.copies if args.copies else "as many as fit 6 GiB", precompute_s)
-                                 if args.copies != 1 else ""),
-                       "scalars": "uniform 752-bit canonical", "l2": "inputs (%.0f MiB/GPU) larger than L2" %
-                       ((n_local * 288) / 2**20),
-                       "parallelism": "point-range shards x%d, NCCL all-gather of partial points + device fold" % world
-                       if world > 1 else "single GPU",
-                       "verified": "result == (sum s_i a_i mod r)*G at full size"},
+            "config": config,
+            "run": {"points_per_gpu": n_local,
+                    "bases": "a_i*G, a_i = splitmix64 (g753_bases_generate), resident in HBM" +
+                             (" with precomputed shifted copies (g753_bases_precompute, %s, %.1f s once per key)"
+                              % ("%d copies" % args.copies if args.copies else "as many as fit 6 GiB", precompute_s)
+                              if args.copies != 1 else ""),
+                    "parallelism": "point-range shards x%d, NCCL all-gather of partial points + device fold" % world
+                    if world > 1 else "single GPU",
+                    "verified": "result == (sum s_i a_i mod r)*G at full size, plain key and precomputed key, before and "
+                                "after the timed steps" + ("; == the CPU restatement's result at full size" if cpu else "")},
             "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": n_local * 96,
                     "d2h_bytes_per_step": 288,
                     "path": "g753_msm: pinned host scalars -> H2D -> MSM -> D2H result; bases resident (proving key)"},
+            "e2e_cold": cold,
             "gpu_launches": gpu_launches, "launches_per_step": launches_per_step,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "fft": fft, "config4": cfg4, "groth16": g16,
-            "setup_s": setup_s, "key_precompute_s": precompute_s,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "fft": fft,
+            "config1": cfg1, "config2": cfg2, "config4": cfg4, "groth16": g16,
+            "setup_s": setup_s, "key_precompute_s": precompute_s, "library": provenance,
         }
         print(json.dumps(line), flush=True)
-    bases.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def sharded_fft(ctx, stream, ffi, log_n, world, reps):
+def bench_fft(ctx, stream, G, args, rank, world, peak_mac_per_s):
+    """the 2^fft_log_n radix-2 transform on mnt4753::Fr: verified, then device-timed (value), timed through
+    the host-buffer call (e2e), timed on the CPU port (cpu_baseline); N > 1: the sharded transform as well"""
+    import torch
+    ffi = G.ffi
+    field = ffi.FIELD_MNT4_FR
+    log_n = args.fft_log_n
+    nf = 1 << log_n
+    raw = random_field_elements(nf, 99)
+    vec = G.DeviceVector(ctx, field, nf, raw)
+    vec.ntt(ffi.FFT)
+    got = vec.download()
+    cpu = None
+    verified = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_s, want, threads = cpu_fft(field, raw, ffi.FFT)
+        if not np.array_equal(got, want):
+            raise SystemExit("2^%d FFT differs from the CPU restatement - refusing to report a number" % log_n)
+        verified = "every limb of the 2^%d outputs equals the C++ restatement of domain.rs:120-123 / 305-416" % log_n
+        cpu = {"value": nf / cpu_s, "unit": "elements/s", "cores": threads, "kind": "port",
+               "sample": "one whole 2^%d fft_in_place (best_fft) on the same input, %d threads, %.2f s" % (log_n, threads, cpu_s)}
+    else:
+        vec.ntt(ffi.IFFT)
+        if not np.array_equal(vec.download(), raw):
+            raise SystemExit("2^%d FFT: ifft(fft(x)) != x" % log_n)
+        verified = "ifft(fft(x)) == x at full size (the every-limb comparison with the CPU restatement runs at N = 1)"
+    vec.upload(raw)
+    reps = max(args.steps, 5)
+    fft_ms = device_time(stream, lambda: vec.ntt(ffi.FFT), reps, warm=3)
+    # end to end through g753_ntt: pinned host buffer in and out
+    pinned = torch.from_numpy(raw.view(np.int64).copy()).pin_memory()
+    host = pinned.numpy().view(np.uint64)
+    lib = ctx.lib
+    for _ in range(2):
+        lib.check(lib.ntt(ctx.handle, field, ffi.ptr(host), log_n, ffi.FFT))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        lib.check(lib.ntt(ctx.handle, field, ffi.ptr(host), log_n, ffi.FFT))
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    peak, peak_src = hbm_peak()
+    muls = (nf // 2) * log_n
+    res = {"metric": "mnt4753_fr_fft_throughput", "log_n": log_n, "value": nf / (fft_ms * 1e-3),
+           "unit": "elements/s", "ms": fft_ms, "verified": verified,
+           "e2e": {"value": nf / (e2e_ms * 1e-3), "unit": "elements/s", "ms": e2e_ms, "h2d_bytes_per_step": nf * 96,
+                   "d2h_bytes_per_step": nf * 96, "path": "g753_ntt: pinned host vector -> H2D -> transform -> D2H"},
+           "cpu_baseline": cpu,
+           "roofline_hbm": {"bound": "hbm", "achieved": 192.0 * nf / (fft_ms * 1e-3) / 1e9, "peak": peak,
+                            "unit": "GB/s", "frac": 192.0 * nf / (fft_ms * 1e-3) / 1e9 / peak,
+                            "peak_source": peak_src, "algorithmic_bytes": 192 * nf},
+           "roofline_int": {"bound": "int32-mac", "achieved": muls * LIMB_MACS_PER_MUL / (fft_ms * 1e-3) / 1e12,
+                            "peak": peak_mac_per_s / 1e12, "unit": "Tlimb-MAC/s",
+                            "frac": muls * LIMB_MACS_PER_MUL / (fft_ms * 1e-3) / peak_mac_per_s,
+                            "algorithmic": "(n / 2) log2 n butterflies x one 1176-limb-MAC product"}}
+    single = got if world > 1 else None
+    vec.free()
+    if world > 1:
+        res["sharded"] = sharded_fft(ctx, stream, G.ffi, log_n, world, reps, raw, single, rank)
+    return res
+
+
+def sharded_fft(ctx, stream, ffi, log_n, world, reps, raw_full, single_gpu_result, rank):
     """the 2^log_n transform sharded over all ranks (four-step): exchange fused into the
     last butterfly pass over peer memory when symmetric memory is available, else NCCL all-to-all.
-    Device-timed, max over ranks."""
+    The gathered output is compared, every limb, with the single-GPU transform of the same vector;
+    then device-timed, max over ranks."""
     import torch
     import torch.distributed as dist
     D = importlib.import_module("ginger-lib_b200.distributed")
     field = ffi.FIELD_MNT4_FR
     n = 1 << log_n
     dom = D.ShardedEvaluationDomain(ctx, field, log_n)
-    raw = random_scalars(dom.local, 123)
-    raw[:, 11] &= np.uint64(0xFFFF)
+    shard = dom.scatter(raw_full)
     dev = torch.device("cuda", ctx.device)
     path = "fused: last butterfly pass stores into peer memory (symmetric memory over NVLink), one barrier"
+    fused = None
     try:
-        # measured (profiles/r01_ntt_sharded_fused_n{2,4,8}.json): the fused exchange wins on 2 GPUs (3.36 vs
-        # 3.79 ms), ties on 4 and loses 5 % on 8, where its 96-byte remote stores cost more than NCCL's bulk
-        # copies save
-        if world > 4:
-            raise RuntimeError("NCCL preferred above 4 ranks")
+        if world > args_fused_max():
+            raise RuntimeError("NCCL preferred above %d ranks" % args_fused_max())
         fused = D.FusedShardedNTT(dom, stream)
-        fused.load(raw)
+        fused.load(shard)
         one = lambda: fused.transform(ffi.FFT)
+        fetch = fused.store
     except Exception as ex:                                   # no symmetric memory on this box / build
         path = "NCCL all_to_all_single between the column and row passes (%s)" % str(ex)[:60]
         with torch.cuda.stream(stream):
-            t_data = torch.from_numpy(raw.view(np.int64).reshape(-1).copy()).to(dev)
+            t_data = torch.from_numpy(shard.view(np.int64).reshape(-1).copy()).to(dev)
             t_send, t_recv = torch.empty_like(t_data), torch.empty_like(t_data)
         stream.synchronize()
-        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        pp = lambda t: ctypes.c_void_p(t.data_ptr())
 
         def exchange():
             with torch.cuda.stream(stream):
                 dist.all_to_all_single(t_recv, t_send)
-        one = lambda: dom.transform_dev(p(t_data), p(t_send), p(t_recv), ffi.FFT, exchange)
+        one = lambda: dom.transform_dev(pp(t_data), pp(t_send), pp(t_recv), ffi.FFT, exchange)
+
+        def fetch():
+            stream.synchronize()
+            return t_data.cpu().numpy().view(np.uint64).reshape(dom.local, 12)
+    # ---- correctness: one transform of the scattered input, gathered, against the single-GPU result ----
+    one()
+    full = dom.gather(fetch())
+    ok = bool(np.array_equal(full, single_gpu_result))
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if not all(flags):
+        raise SystemExit("sharded FFT differs from the single-GPU transform - refusing to report a number")
     for _ in range(3):
         one()
     stream.synchronize()
@@ -516,14 +736,95 @@ def sharded_fft(ctx, stream, ffi, log_n, world, reps):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     return {"n_gpus": world, "log_n": log_n, "ms": ms, "value": n / (ms * 1e-3), "unit": "elements/s", "exchange": path,
-            "exchange_bytes_per_rank": (n // world) * 96 * (world - 1) // world}
+            "exchange_bytes_per_rank": (n // world) * 96 * (world - 1) // world,
+            "verified": "gathered output == the single-GPU transform of the same vector, every limb"}
 
 
-def run_config4(ctx, G, ffi, params, args):
+def args_fused_max():
+    """largest world size the peer-memory exchange is used at (G753_FUSED_MAX_RANKS overrides)"""
+    return int(os.environ.get("G753_FUSED_MAX_RANKS", "4"))
+
+
+def run_config1(ctx, stream, G, params, args):
+    """BASELINE config 1: MNT4-753 G1 multi_scalar_mul at 2^16 points ('CPU reference runs today'), checked
+    against the C++ restatement; resident key with copies, resident plain key, one-shot host call"""
+    ffi = G.ffi
+    group, log_n = ffi.MNT4_G1, 16
+    n = 1 << log_n
+    p = params.GROUP_BASE_MODULUS[group]
+    bases = ctx.generate_bases(group, n, 0xC1)
+    coords = bases.download()
+    sc = random_scalars(n, 0xC11)
+    cpu_s, want, threads = cpu_msm_full(group, coords, sc) if not args.no_cpu else (None, None, None)
+    lib = ctx.lib
+    d_sc, d_out = G.DeviceVector(ctx, 0, n, sc), G.DeviceVector(ctx, 0, 3)
+    run = lambda: lib.check(lib.msm_dev(ctx.handle, bases.handle, 0, n, d_sc.ptr, d_out.ptr))
+    res = {"workload": "MNT4-753 G1 MSM, 2^16 points (BASELINE config 1)"}
+    out = np.zeros((3, 12), dtype=np.uint64)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        lib.check(lib.msm_host(ctx.handle, group, ffi.ptr(coords), None, n, ffi.ptr(sc), n, ffi.ptr(out)))
+        ts.append(time.perf_counter() - t0)
+    if want is not None and affine_of(out, p) != affine_of(want, p):
+        raise SystemExit("config 1: one-shot MSM differs from the CPU restatement")
+    res["one_shot_host_ms"] = min(ts) * 1e3
+    res["plain_key_device_ms"] = device_time(stream, run, 5)
+    res["plain_key_phases_ms"] = ctx.last_msm_phases()
+    res["plain_key_plan"] = ctx.last_msm_plan()
+    bases.precompute(args.copies)
+    ctx.sync()
+    res["precomputed_key_device_ms"] = device_time(stream, run, 5)
+    res["precomputed_key_phases_ms"] = ctx.last_msm_phases()
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, sc)
+    if want is not None:
+        if affine_of(got, p) != affine_of(want, p):
+            raise SystemExit("config 1: MSM differs from the CPU restatement")
+        res["verified"] = "one-shot and resident results == the C++ restatement of variable_base.rs:10-83 (affine, every limb)"
+        res["cpu_baseline"] = {"value": cpu_s * 1e3, "unit": "ms", "cores": threads, "kind": "port",
+                               "sample": "the same 2^16-point MSM, whole"}
+    d_sc.free()
+    d_out.free()
+    bases.free()
+    return res
+
+
+def run_config2(ctx, stream, G, args):
+    """BASELINE config 2: the four radix-2 transforms at 2^20 (mnt4753::Fr; mnt6753::Fr tops out at 2^14 -
+    SURVEY.md F2 - and is timed at that size).  Round trips checked here; the every-limb comparison of all
+    four modes with the CPU restatement is tests/test_gpu_parity.py::test_ntt_config2_vs_cpp_restatement."""
+    ffi = G.ffi
+    out = {"workload": "radix-2 fft / ifft / coset_fft / coset_ifft, 2^20 on mnt4753::Fr and 2^14 (the maximum) on "
+                       "mnt6753::Fr (BASELINE config 2)"}
+    names = {ffi.FFT: "fft", ffi.IFFT: "ifft", ffi.COSET_FFT: "coset_fft", ffi.COSET_IFFT: "coset_ifft"}
+    for tag, field, log_n in (("mnt4753_fr_2e20", ffi.FIELD_MNT4_FR, 20), ("mnt6753_fr_2e14", ffi.FIELD_MNT6_FR, 14)):
+        n = 1 << log_n
+        raw = random_field_elements(n, 0xC2 + log_n)
+        vec = G.DeviceVector(ctx, field, n, raw)
+        for fwd, inv in ((ffi.FFT, ffi.IFFT), (ffi.COSET_FFT, ffi.COSET_IFFT)):
+            vec.ntt(fwd)
+            vec.ntt(inv)
+            if not np.array_equal(vec.download(), raw):
+                raise SystemExit("config 2: round trip failed (%s)" % tag)
+        ms = {names[m]: device_time(stream, lambda m=m: vec.ntt(m), 10, warm=2) for m in names}
+        cpu = None
+        if not args.no_cpu:
+            cpu_s, want, threads = cpu_fft(field, raw, ffi.COSET_FFT)
+            vec.upload(raw)
+            vec.ntt(ffi.COSET_FFT)
+            if not np.array_equal(vec.download(), want):
+                raise SystemExit("config 2: coset_fft differs from the CPU restatement (%s)" % tag)
+            cpu = {"value": cpu_s * 1e3, "unit": "ms", "cores": threads, "kind": "port", "sample": "one coset_fft_in_place, same input"}
+        out[tag] = {"device_ms": ms, "cpu_baseline": cpu,
+                    "verified": "ifft(fft(x)) == x, coset_ifft(coset_fft(x)) == x" + ("; coset_fft == the C++ restatement, every limb" if cpu else "")}
+        vec.free()
+    return out
+
+
+def run_config4(ctx, stream, G, ffi, params, args, peak_mac_per_s):
     """BASELINE config 4: MNT6-753 G2 (over Fq3) MSM at 2^20 points on a resident synthetic key, verified
     by its discrete logs, and the mixed-radix transform at 2^15 * 25 = 819 200 points on mnt6753::Fr
     (round trip checked; parity unpinned - the reference has no mixed-radix domain)"""
-    import torch
     group, log_n = ffi.MNT6_G2, 20
     n = 1 << log_n
     t0 = time.perf_counter()
@@ -533,7 +834,6 @@ def run_config4(ctx, G, ffi, params, args):
     key_s = time.perf_counter() - t0
     sc = random_scalars(n, 0xC5)
     r = params.GROUP_ORDER[group]
-    p = params.GROUP_BASE_MODULUS[group]
     out = None
     times = []
     for it in range(3):
@@ -541,6 +841,7 @@ def run_config4(ctx, G, ffi, params, args):
         out = G.VariableBaseMSM.multi_scalar_mul(bases, sc)        # host scalars in, host point out
         times.append(time.perf_counter() - t1)
     phases = ctx.last_msm_phases()
+    plan = ctx.last_msm_plan()
     k = dot_mod(sc, G.Bases.generated_logs(n, 0xC4), r)
     gen = np.stack([int_to_limbs(v) for v in params.GENERATOR_MONT[group]]).reshape(-1)
     expect = np.zeros((3, 36), dtype=np.uint64)
@@ -552,28 +853,26 @@ def run_config4(ctx, G, ffi, params, args):
     if not (xy[0] == xy[1]).all():
         raise SystemExit("config 4: MNT6 G2 MSM differs from (sum s_i a_i) * G")
     bases.free()
+    macs = n * plan["windows"] * EXECUTED_MACS_PER_MADD[group]
+    acc_ms = phases.get("accumulate", 0.0)
     # mixed-radix transform
     N = (1 << 15) * 25
     field = ffi.FIELD_MNT6_FR
-    raw = random_scalars(N, 0xC6)
-    raw[:, 11] &= np.uint64(0xFFFF)
+    raw = random_field_elements(N, 0xC6)
     vec = G.DeviceVector(ctx, field, N, raw)
     lib = ctx.lib
     for mode in (ffi.FFT, ffi.IFFT):
         lib.check(lib.ntt_mixed_dev(ctx.handle, field, vec.ptr, N, mode))
     if not (vec.download() == raw).all():
         raise SystemExit("config 4: mixed-radix ifft(fft(x)) != x")
-    ctx.sync()
-    t1 = time.perf_counter()
-    reps = 5
-    for _ in range(reps):
-        lib.check(lib.ntt_mixed_dev(ctx.handle, field, vec.ptr, N, ffi.FFT))
-    ctx.sync()
-    mixed_ms = (time.perf_counter() - t1) / reps * 1e3
+    mixed_ms = device_time(stream, lambda: lib.check(lib.ntt_mixed_dev(ctx.handle, field, vec.ptr, N, ffi.FFT)), 5)
     vec.free()
     return {"msm": {"workload": "MNT6-753 G2 (Fq3) MSM, 2^20 points, resident key with precomputed copies (built in %.1f s)"
                                 % key_s,
-                    "ms": min(times) * 1e3, "mpts_per_s": n / min(times) / 1e6, "phases_ms": phases,
+                    "ms": min(times) * 1e3, "mpts_per_s": n / min(times) / 1e6, "phases_ms": phases, "plan": plan,
+                    "roofline": {"bound": "int32-mac", "kernel": "k_bucket_acc (Fq3 towers on 4 lanes)", "kernel_ms": acc_ms,
+                                 "executed_limb_macs": macs, "peak": peak_mac_per_s / 1e12, "unit": "Tlimb-MAC/s",
+                                 "frac": macs / (acc_ms * 1e-3) / peak_mac_per_s if acc_ms else None},
                     "verified": "result == (sum s_i a_i mod r) * G2 generator"},
             "mixed_radix_fft": {"field": "mnt6753::Fr", "n": N, "factorisation": "2^15 * 5^2", "ms": mixed_ms,
                                 "elements_per_s": N / (mixed_ms * 1e-3), "verified": "ifft(fft(x)) == x",
@@ -589,13 +888,13 @@ def main():
     ap.add_argument("--log-n", type=int, default=22, help="log2 of the total number of points")
     ap.add_argument("--fft-log-n", type=int, default=22)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--cpu-log-n", type=int, default=20, help="log2 of the CPU baseline's bounded sample (~10 s on 16 threads)")
+    ap.add_argument("--cpu-groth16-log-n", type=int, default=16, help="domain of the CPU port's bounded create_proof sample")
     ap.add_argument("--copies", type=int, default=0,
                     help="precomputed shifted copies of the resident key (0 = auto by memory budget, 1 = plain key)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fft", action="store_true")
     ap.add_argument("--no-groth16", action="store_true")
-    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip configs 1, 2 and 4")
     ap.add_argument("--groth16-log-n", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -243,7 +243,7 @@ def witness_map(ctx, field, a, b, c, d1, d2, d3):
     return h
 
 
-def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=None):
+def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=None, profile=None):
     """prover.rs:201-345 after constraint synthesis.
 
     full_assignment: (num_inputs + num_aux, 12) Montgomery, inputs first, index 0 = the constant one;
@@ -252,7 +252,11 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
 
     Scheduling: the large (throughput-bound) MSMs are queued on the main context's stream; the one MSM
     over per-proof bases (s*g_a + r*g1_b - rs*delta, a 753-doubling latency chain) runs on a second
-    context of the same device as soon as g_a and g1_b exist, overlapping the remaining large MSMs."""
+    context of the same device as soon as g_a and g1_b exist, overlapping the remaining large MSMs.
+
+    profile: optional dict; when given, the stream is drained after each of the five long MSMs and its
+    device phase times (digits / sort / accumulate / reduce / combine, ms) and plan are stored under the
+    MSM's name - a diagnostic pass (the extra synchronisations cost overlap), never the timed one."""
     import time
     ctx, ctx2, lib, field = params.ctx, params.ctx2, params.ctx.lib, params.field
     g1, g2, ni = params.g1, params.g2, params.num_inputs
@@ -317,6 +321,10 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
             """one of the five long MSMs (or this rank's shard of it, see ShardedParameters)"""
             bases, first, off = params.aux[name]
             msm(ctx, bases, first, max(0, total - off), d_vec.at(base_index + off), d_out)
+            if profile is not None:
+                ctx.sync()
+                profile[name] = dict(ctx.last_msm_phases(), points=max(0, min(total - off, len(bases) - first)),
+                                     plan=ctx.last_msm_plan())
 
         sharder = params.sharder
         # A (prover.rs:270-283) -> slots 0, 1; B in G1 (:286-299) -> slots 2, 3; g_a, g1_b -> slots 8, 9

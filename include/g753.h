@@ -83,7 +83,7 @@ int g753_ctx_destroy(g753_ctx* ctx);
 int g753_ctx_set_stream(g753_ctx* ctx, void* cuda_stream);
 const char* g753_last_error(void);
 const char* g753_version(void);
-/* hash of the sources (csrc/*, this header, compiler flags) the loaded library was built from; the
+/* hash of the sources (every file under csrc, this header, compiler flags) the loaded library was built from; the
  * build recipe (ginger-lib_b200/build.py) rebuilds when it differs from the tree's and bench.py prints
  * both, so a stale prebuilt binary cannot be measured unnoticed */
 const char* g753_source_hash(void);
