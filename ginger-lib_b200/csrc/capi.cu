@@ -99,6 +99,23 @@ static int ntt_field(g753_ctx* ctx, Fq* d_data, Fq* d_tmp, unsigned log_n, int m
 
 // R1CStoQAP::witness_map after the constraint evaluation (r1cs_to_qap.rs:121-166), chained on
 // the device: 7 transforms + the element-wise steps, no host round trips.
+// second half of the witness map: a, b, c hold the coset evaluations (ifft then coset_fft of the
+// constraint evaluations); h = coset_ifft((a b - c) / Z) with the d1, d2, d3 terms (r1cs_to_qap.rs:137-166)
+template <int FID>
+static int witness_map_tail_field(g753_ctx* ctx, Fq* a, const Fq* b, const Fq* c, unsigned log_n, const Fq3& d_d, Fq* h) {
+  const size_t n = (size_t)1 << log_n;
+  G753_TRY(ctx->scratch_io.reserve(sizeof(Fq) * n + 1024));
+  Fq* tmp = (Fq*)ctx->scratch_io.ptr;
+  const NttTables* T = nullptr;
+  G753_TRY(ntt_tables_get<FID>(ctx, log_n, &T));
+  const unsigned L = log_n ? log_n : 1;
+  G753_LAUNCH(k_witness_combine<FID>, div_up(n, 256), 256, ctx->stream, a, b, c, T->consts + 1 + 4 * L, n);
+  ctx->launches++;
+  G753_TRY(ntt_field<FID>(ctx, a, tmp, log_n, G753_COSET_IFFT));
+  G753_LAUNCH(k_witness_finish<FID>, div_up(n + 1, 256), 256, ctx->stream, a, d_d, h, n);
+  ctx->launches++;
+  return launch_check("witness_map");
+}
 template <int FID>
 static int witness_map_field(g753_ctx* ctx, Fq* a, Fq* b, Fq* c, unsigned log_n, const Fq3& d_d, Fq* h) {
   const size_t n = (size_t)1 << log_n;
@@ -110,14 +127,7 @@ static int witness_map_field(g753_ctx* ctx, Fq* a, Fq* b, Fq* c, unsigned log_n,
   G753_TRY(ntt_field<FID>(ctx, b, tmp, log_n, G753_COSET_FFT));
   G753_TRY(ntt_field<FID>(ctx, c, tmp, log_n, G753_IFFT));
   G753_TRY(ntt_field<FID>(ctx, c, tmp, log_n, G753_COSET_FFT));
-  const NttTables& T = ctx->tables[FID].find(log_n)->second;
-  const unsigned L = log_n ? log_n : 1;
-  G753_LAUNCH(k_witness_combine<FID>, div_up(n, 256), 256, ctx->stream, a, b, c, T.consts + 1 + 4 * L, n);
-  ctx->launches++;
-  G753_TRY(ntt_field<FID>(ctx, a, tmp, log_n, G753_COSET_IFFT));
-  G753_LAUNCH(k_witness_finish<FID>, div_up(n + 1, 256), 256, ctx->stream, a, d_d, h, n);
-  ctx->launches++;
-  return launch_check("witness_map");
+  return witness_map_tail_field<FID>(ctx, a, b, c, log_n, d_d, h);
 }
 
 // ---- sharded four-step NTT (ntt_dist.cuh) ----------------------------------------------------
@@ -874,6 +884,18 @@ int g753_witness_map_dev(g753_ctx* ctx, int field, void* d_a, void* d_b, void* d
   memcpy(&d, d123_mont, sizeof(d));
   return field == 0 ? witness_map_field<0>(ctx, (Fq*)d_a, (Fq*)d_b, (Fq*)d_c, log_n, d, (Fq*)d_h)
                     : witness_map_field<1>(ctx, (Fq*)d_a, (Fq*)d_b, (Fq*)d_c, log_n, d, (Fq*)d_h);
+}
+
+int g753_witness_map_tail_dev(g753_ctx* ctx, int field, void* d_a, const void* d_b, const void* d_c, unsigned log_n,
+                              const uint64_t* d123_mont, void* d_h) {
+  CHECK_CTX(ctx);
+  if (!d_a || !d_b || !d_c || !d123_mont || !d_h) return fail(G753_ERR_BAD_ARG, "null pointer");
+  G753_TRY(g753_domain_check(field, log_n));
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  Fq3 d;
+  memcpy(&d, d123_mont, sizeof(d));
+  return field == 0 ? witness_map_tail_field<0>(ctx, (Fq*)d_a, (const Fq*)d_b, (const Fq*)d_c, log_n, d, (Fq*)d_h)
+                    : witness_map_tail_field<1>(ctx, (Fq*)d_a, (const Fq*)d_b, (const Fq*)d_c, log_n, d, (Fq*)d_h);
 }
 
 int g753_witness_map(g753_ctx* ctx, int field, const uint64_t* a, const uint64_t* b, const uint64_t* c,

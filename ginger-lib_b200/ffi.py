@@ -65,6 +65,7 @@ SYMBOLS = [
     ("g753_vec_scale_dev", _i, [_vp, _i, _vp, _vp, _sz]),
     ("g753_witness_map", _i, [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp]),
     ("g753_witness_map_dev", _i, [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp]),
+    ("g753_witness_map_tail_dev", _i, [_vp, _i, _vp, _vp, _vp, _u, _vp, _vp]),
     ("g753_dev_alloc", _i, [_vp, _sz, _pvp]),
     ("g753_dev_free", _i, [_vp, _vp]),
     ("g753_h2d", _i, [_vp, _vp, _vp, _sz]),

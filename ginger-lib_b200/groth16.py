@@ -258,6 +258,9 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
     device phase times (digits / sort / accumulate / reduce / combine, ms) and plan are stored under the
     MSM's name - a diagnostic pass (the extra synchronisations cost overlap), never the timed one."""
     import time
+    if getattr(params, "plan", None) is not None:      # cost-weighted placement over several GPUs
+        from .groth16_placed import create_proof_placed
+        return create_proof_placed(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=timings, profile=profile)
     ctx, ctx2, lib, field = params.ctx, params.ctx2, params.ctx.lib, params.field
     g1, g2, ni = params.g1, params.g2, params.num_inputs
     k2 = ffi.GROUP_K[g2]

@@ -219,6 +219,12 @@ int g753_witness_map(g753_ctx* ctx, int field, const uint64_t* a, const uint64_t
                      unsigned log_n, const uint64_t* d123_mont, uint64_t* h);
 int g753_witness_map_dev(g753_ctx* ctx, int field, void* d_a, void* d_b, void* d_c, unsigned log_n,
                          const uint64_t* d123_mont, void* d_h);
+/* the second half alone, for provers that run the three independent chains ifft -> coset_fft of a, b, c
+ * (g753_ntt_dev) on different GPUs: d_a, d_b, d_c hold the COSET EVALUATIONS; d_h receives
+ * coset_ifft((a b - c) / Z) with the d1, d2, d3 terms (r1cs_to_qap.rs:137-166); d_a is clobbered.
+ * Both _dev forms only queue work on the context's stream. */
+int g753_witness_map_tail_dev(g753_ctx* ctx, int field, void* d_a, const void* d_b, const void* d_c, unsigned log_n,
+                              const uint64_t* d123_mont, void* d_h);
 
 /* ---- device memory / stream plumbing (so callers can chain without a CUDA toolchain) --- */
 int g753_dev_alloc(g753_ctx* ctx, size_t bytes, void** d_ptr);

@@ -100,6 +100,8 @@ extern "C" {
                             log_n: c_uint, d123_mont: *const u64, h: *mut u64) -> c_int;
     pub fn g753_witness_map_dev(ctx: *mut G753Ctx, field: c_int, d_a: *mut c_void, d_b: *mut c_void, d_c: *mut c_void,
                                 log_n: c_uint, d123_mont: *const u64, d_h: *mut c_void) -> c_int;
+    pub fn g753_witness_map_tail_dev(ctx: *mut G753Ctx, field: c_int, d_a: *mut c_void, d_b: *const c_void,
+                                     d_c: *const c_void, log_n: c_uint, d123_mont: *const u64, d_h: *mut c_void) -> c_int;
     pub fn g753_dev_alloc(ctx: *mut G753Ctx, bytes: usize, d_ptr: *mut *mut c_void) -> c_int;
     pub fn g753_dev_free(ctx: *mut G753Ctx, d_ptr: *mut c_void) -> c_int;
     pub fn g753_h2d(ctx: *mut G753Ctx, d_dst: *mut c_void, h_src: *const c_void, bytes: usize) -> c_int;

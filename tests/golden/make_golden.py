@@ -104,6 +104,22 @@ def small_consts(path):
     return out
 
 
+def pairing_consts(path):
+    """the pairing parameters of curves/mnt{4,6}753/mod.rs that are not 768-bit literals: the Miller loop
+    count (&[u64]), its signed-digit form WNAF (&[i32]) and the sign flags"""
+    text = open(path).read()
+    out = {}
+    m = re.search(r"const\s+ATE_LOOP_COUNT\s*:[^=]*=\s*&\[(.*?)\];", text, re.S)
+    limbs = [int(t.strip(), 0) for t in m.group(1).split(",") if t.strip()]
+    out["ATE_LOOP_COUNT"] = hex(sum(l << (64 * i) for i, l in enumerate(limbs)))
+    m = re.search(r"const\s+WNAF\s*:[^=]*=\s*&\[(.*?)\];", text, re.S)
+    out["WNAF"] = [int(t.strip()) for t in m.group(1).split(",") if t.strip()]
+    for name in ("ATE_IS_LOOP_COUNT_NEG", "FINAL_EXPONENT_LAST_CHUNK_W0_IS_NEG"):
+        m = re.search(r"const\s+%s\s*:\s*bool\s*=\s*(true|false)\s*;" % name, text)
+        out[name] = m.group(1) == "true"
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference tree not present; fixtures are already committed")
@@ -131,6 +147,10 @@ def main():
         json.dump(kat, f, indent=0, sort_keys=True)
     with open(os.path.join(HERE, "reference_params.json"), "w") as f:
         json.dump(params, f, indent=0, sort_keys=True)
+    pairing = {key: dict(pairing_consts(os.path.join(REF, FILES[key])), source="algebra/src/" + FILES[key])
+               for key in ("curves_mnt4753_mod", "curves_mnt6753_mod")}
+    with open(os.path.join(HERE, "reference_pairing.json"), "w") as f:
+        json.dump(pairing, f, indent=0, sort_keys=True)
     # the 96-byte serialisation fixtures (fields/mnt{4,6}753/test_vec/*_tobyte)
     for name in ("mnt4753", "mnt6753"):
         p = os.path.join(REF, "fields", name, "test_vec", name + "_tobyte")

@@ -128,3 +128,29 @@ def check_wire_rejects_malformed(ctx, group):
     w = bytearray(good)
     w[0:96] = (p - 1).to_bytes(96, "little")
     G.Bases.from_wire(ctx, group, bytes(w)).free()
+
+
+def check_proof_verifies_with_pairing(ctx, name, precompute=1):
+    """the reference's acceptance test (proof-systems/src/groth16/test.rs:216-301): a CRS generated for the
+    reference's benchmark circuit (generator.rs restated in oracle/pairing753.py), the proof made by THIS
+    library, accepted by the pairing check of verifier.rs:18-44 - an arbiter that shares no code with the
+    prover - and rejected for another public input"""
+    import importlib
+    import test_groth16_emul as T16
+    import test_oracle_pairing as TP
+    from oracle import pairing753 as PR
+    from util753 import field_array
+    groth16 = importlib.import_module("ginger-lib_b200.groth16")
+    eng, key, vk, ni, z, a, b, c = TP.tiny_groth16(name, num_constraints=5, seed=0x7e58)
+    C1, C2, F = T16.ENGINES[name][:3]
+    rng = O.SplitMix64(0x52)
+    r, s = O.random_field_element(rng, F), O.random_field_element(rng, F)
+    params = T16.upload(ctx, key, ni, precompute=precompute, engine=name)
+    proof = groth16.create_proof(params, field_array(F, z), field_array(F, a), field_array(F, b), field_array(F, c),
+                                 0, 0, 0, r, s)
+    got = (T16.affine_of(C1, proof.a, proof.infinity[0]), T16.affine_of(C2, proof.b, proof.infinity[1]),
+           T16.affine_of(C1, proof.c, proof.infinity[2]))
+    params.free()
+    assert PR.verify_proof(eng, vk, got, z[1:ni])
+    assert not PR.verify_proof(eng, vk, got, [z[1], (z[2] + 1) % F.p])
+    assert got == O.groth16_create_proof(key, ni, z, O.witness_map(F, a, b, c, 0, 0, 0), r, s)

@@ -42,6 +42,8 @@ assert [D.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (
 # sharded four-step NTT: scatter -> step1 -> all-to-all -> step2 -> gather == the oracle's transform
 from util753 import FIELDS, array_field, field_array
 for field, log_n in ((ffi.FIELD_MNT4_FR, 4), (ffi.FIELD_MNT6_FR, 5), (ffi.FIELD_MNT4_FR, 2)):
+    if world & (world - 1):
+        break                  # the four-step transform shards over a power-of-two number of ranks
     F = FIELDS[field]
     n = 1 << log_n
     rng = O.SplitMix64(0x800 + log_n)
@@ -82,22 +84,70 @@ got = (T16.affine_of(O.MNT4_G1, proof.a, proof.infinity[0]), T16.affine_of(O.MNT
        T16.affine_of(O.MNT4_G1, proof.c, proof.infinity[2]))
 assert got == want, (rank, "sharded groth16")
 P.free()
+# the same proof with cost-weighted PLACEMENT: whole MSMs / witness-map chains on different ranks,
+# point-to-point exchange of the chains and of h, all-gather of the partial sums
+placed = importlib.import_module("ginger-lib_b200.groth16_placed")
+totals = {{"a": n_aux, "b1": n_aux, "b2": n_aux, "h": n - 1 - ni, "l": n_aux}}
+plan = placed.ProofPlan(world, totals, k2=2, domain=n)
+full = {{"a": (O.MNT4_G1, ffi.MNT4_G1, key.a_query[ni:]), "b1": (O.MNT4_G1, ffi.MNT4_G1, key.b_g1_query[ni:]),
+        "b2": (O.MNT4_G2, ffi.MNT4_G2, key.b_g2_query[ni:]), "h": (O.MNT4_G1, ffi.MNT4_G1, key.h_query[ni:]),
+        "l": (O.MNT4_G1, ffi.MNT4_G1, key.l_query)}}
+mine = {{}}
+for name, (lo, hi) in plan.shards_of(rank).items():
+    C, grp, pts = full[name]
+    co, inf = points_to_arrays(C, pts[lo:hi])
+    mine[name] = ctx.upload_bases(grp, co, inf)
+P = placed.PlacedParameters(ctx, ffi.MNT4_G1, ffi.MNT4_G2, ffi.FIELD_MNT4_FR, one(O.MNT4_G1, key.alpha_g1),
+                            one(O.MNT4_G1, key.beta_g1), one(O.MNT4_G2, key.beta_g2), one(O.MNT4_G1, key.delta_g1),
+                            one(O.MNT4_G2, key.delta_g2), heads, mine, ni, plan)
+for _ in range(2):      # the second proof reuses the placed workspace
+    proof = groth16.create_proof(P, field_array(F, z), field_array(F, a), field_array(F, b), field_array(F, c), 1, 2, 3, r_, s_)
+    got = (T16.affine_of(O.MNT4_G1, proof.a, proof.infinity[0]), T16.affine_of(O.MNT4_G2, proof.b, proof.infinity[1]),
+           T16.affine_of(O.MNT4_G1, proof.c, proof.infinity[2]))
+    assert got == want, (rank, "placed groth16", plan.describe())
+P.free()
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
 
 
-def test_sharded_msm_two_ranks_gloo(tmp_path):
+def test_proof_plan_tiles_every_msm():
+    """the placement gives every point of every MSM to exactly one rank, at most one shard of an MSM per
+    rank, and spreads the load: on 8 ranks B2 (Fq2) runs on four of them and A, B1, L on one each, H on one
+    or two"""
+    placed = importlib.import_module("ginger-lib_b200.groth16_placed")
+    for world in (1, 2, 3, 4, 5, 8):
+        for n_aux, n_h, k2 in ((1 << 20, (1 << 20) - 4, 2), (7, 4, 2), (1000, 1020, 3), (3, 0, 2)):
+            totals = {"a": n_aux, "b1": n_aux, "b2": n_aux, "h": n_h, "l": n_aux}
+            plan = placed.ProofPlan(world, totals, k2=k2)
+            for nm, parts in plan.shards.items():
+                assert parts[0][1] == 0 and parts[-1][2] == totals[nm]
+                assert all(parts[i][2] == parts[i + 1][1] for i in range(len(parts) - 1))
+                assert len({r for r, _, _ in parts}) == len(parts)
+            covered = set()
+            for r in range(world):
+                covered |= set(plan.shards_of(r))
+            assert covered == set(totals)
+            assert 0 <= plan.finisher < world and set(plan.chain_owner) == {"a", "b", "c"}
+    plan = placed.ProofPlan(8, {"a": 1 << 20, "b1": 1 << 20, "b2": 1 << 20, "h": 1 << 20, "l": 1 << 20}, k2=2)
+    assert len(plan.shards["b2"]) == 4 and all(len(plan.shards[nm]) == 1 for nm in ("a", "b1", "l"))
+    # H waits for the witness map: its tail may move to the least loaded rank
+    assert len(plan.shards["h"]) <= 2 and plan.shards["h"][0][0] == plan.finisher
+    assert max(plan.load.values()) < 1.25 * sum(plan.load.values()) / 8
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_msm_ntt_and_provers_gloo(tmp_path, world):
     sys.path.insert(0, HERE)
     from util753 import build_emul
     build_emul()
     script = tmp_path / "worker.py"
-    port = 29500 + (os.getpid() % 2000)
-    script.write_text(WORKER.format(root=ROOT, here=HERE, port=port, world=2))
+    port = 29500 + (os.getpid() % 2000) + world
+    script.write_text(WORKER.format(root=ROOT, here=HERE, port=port, world=world))
     procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
-                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
-    outs = [p.communicate(timeout=600)[0] for p in procs]
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=900)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, o[-3000:])
         assert "rank %d ok" % r in o

@@ -127,3 +127,12 @@ def ctx_from_mont(ctx, field, arr):
     """into_repr on the host (independent of the library): Montgomery limbs -> canonical limbs"""
     F = O.MNT4_FR if field == ffi.FIELD_MNT4_FR else O.MNT6_FR
     return ints_to_array([F.from_mont(v) for v in array_to_ints(arr)])
+
+
+@pytest.mark.parametrize("engine", ["mnt4", "mnt6"])
+def test_proof_verifies_with_pairing(ctx, engine):
+    """generate (oracle) -> prove (this library, on the GPU) -> verify (pairing, oracle): the reference's
+    acceptance test groth16/test.rs:216-301 with an arbiter independent of the prover"""
+    import shared_checks
+    shared_checks.check_proof_verifies_with_pairing(ctx, engine)
+    shared_checks.check_proof_verifies_with_pairing(ctx, engine, precompute=0)

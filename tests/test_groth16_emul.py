@@ -91,3 +91,9 @@ def test_witness_map_and_proof_tiny(ctx):  # noqa: F811
 def test_proof_tiny_mnt6(ctx):  # noqa: F811
     """the other engine of the cycle: G2 over Fq3, scalar field of two-adicity 15"""
     check_instance(ctx, 0x6601, 4, 2, 3, 1, 2, 3, O.MNT6_FR.p - 5, 0x77 << 700, engine="mnt6")
+
+
+@pytest.mark.parametrize("engine", ["mnt4", "mnt6"])
+def test_proof_verifies_with_pairing(ctx, engine):  # noqa: F811
+    import shared_checks
+    shared_checks.check_proof_verifies_with_pairing(ctx, engine)
