@@ -3,6 +3,7 @@
 // Built two ways: nvcc for sm_100a (the product) and, with G753_HOST_EMUL, by g++ into a
 // test-only library that runs the barrier-free kernels sequentially on the host so that
 // indexing and orchestration can be checked without a GPU (tests/host_emul).
+#include "coop.cuh"
 #include "ctx.cuh"
 #include "ntt_dist.cuh"
 #include "ntt_mixed.cuh"
@@ -396,6 +397,60 @@ __global__ void __launch_bounds__(256) k_mac_probe(const Fq* seed, Fq* sink, int
     for (int i = 0; i < NL; i++) x.l[i] = (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32);
   }
   if (x.l[0] == 0x12345678u && x.l[5] == 0x9abcdef0u) sink[t & 255] = x;  // keep the chain live
+}
+#endif
+
+#if !defined(G753_HOST_EMUL)
+// test hook for the warp-cooperative field arithmetic (coop.cuh): four elements per warp pass, raw
+// (lazily reduced, not canonical) results so that they can be compared limb for limb with the Python model
+template <int FID>
+__global__ void __launch_bounds__(32)
+k_coop_op(int op, unsigned k, const Fq* __restrict__ a, const Fq* __restrict__ b, unsigned n, Fq* __restrict__ out) {
+  extern __shared__ uint4 coop_test_smem[];
+  CoopWarp<FID> w;
+  w.init((uint32_t*)coop_test_smem, 12);
+  const unsigned o = coop_octet(), l = coop_lane();
+  for (unsigned base = 0; base < n; base += 4) {
+    const unsigned cnt = n - base < 4 ? n - base : 4;
+    w.load(0, a + base, cnt);
+    w.load(4, b + base, cnt);
+    uint32_t A[3], B[3], R[3];
+    w.ld(A, o);
+    w.ld(B, 4 + o);
+    if (op == 0) {
+      coop_mul(R, A, B, w.n, w.np);
+    } else if (op == 1) {
+      uint32_t Z[3] = {0, 0, 0};
+      coop_add3(R, A, B, Z, 0);
+    } else if (op == 2) {
+      uint32_t Y[3] = {~B[0], ~B[1], ~B[2]};
+      const uint32_t* kpl = w.kp + k * 24 + 3 * l;
+      uint32_t Z[3] = {kpl[0], kpl[1], kpl[2]};
+      coop_add3(R, A, Y, Z, l == 0 ? 1u : 0u);
+    } else {
+      R[0] = A[0];
+      R[1] = A[1];
+      R[2] = A[2];
+    }
+    __syncwarp();
+    w.st(8 + o, R);
+    __syncwarp();
+    if (op == 3) w.canonicalize(8, cnt);
+    if (op == 4) {   // is_zero of a value below 2 p -> 0 / 1 in limb 0
+      bool z[4];
+      for (unsigned i = 0; i < 4; i++) z[i] = w.is_zero(8 + i);
+      uint32_t Zr[3] = {z[o] ? 1u : 0u, 0, 0};
+      __syncwarp();
+      if (l == 0) w.st(8 + o, Zr);
+      else {
+        uint32_t zero3[3] = {0, 0, 0};
+        w.st(8 + o, zero3);
+      }
+      __syncwarp();
+    }
+    w.store(out + base, 8, cnt);
+    __syncwarp();
+  }
 }
 #endif
 
@@ -1193,6 +1248,33 @@ int g753_ext_op(g753_ctx* ctx, int group, int lanes, int op, const uint64_t* a, 
     case G753_MNT6_G2: return ext_op_impl<3>(ctx, lanes, op, a, b, out, n);
   }
   return fail(G753_ERR_BAD_ARG, "unknown group");
+}
+
+int g753_coop_op(g753_ctx* ctx, int field, int op, unsigned k, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                 size_t n) {
+  CHECK_CTX(ctx);
+  if (!a || !b || !out || (field != 0 && field != 1) || op < 0 || op > 4 || k > 7) return fail(G753_ERR_BAD_ARG, "bad argument");
+  if (n == 0) return G753_OK;
+#if defined(G753_HOST_EMUL)
+  return fail(G753_ERR_NO_DEVICE, "the warp-cooperative arithmetic runs on a GPU only");
+#else
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t bytes = sizeof(Fq) * n;
+  G753_TRY(ctx->scratch_io.reserve(3 * Carver::pad(bytes) + 1024));
+  Carver cv(ctx->scratch_io.ptr);
+  Fq* da = cv.take<Fq>(n);
+  Fq* db = cv.take<Fq>(n);
+  Fq* dout = cv.take<Fq>(n);
+  G753_TRY(h2d(da, a, bytes, ctx->stream));
+  G753_TRY(h2d(db, b, bytes, ctx->stream));
+  const size_t smem = sizeof(uint32_t) * (COOP_CONST_WORDS + 12 * 24);
+  if (field == 0) k_coop_op<0><<<1, 32, smem, ctx->stream>>>(op, k, da, db, (unsigned)n, dout);
+  else k_coop_op<1><<<1, 32, smem, ctx->stream>>>(op, k, da, db, (unsigned)n, dout);
+  ctx->launches++;
+  G753_TRY(launch_check("k_coop_op"));
+  G753_TRY(d2h(out, dout, bytes, ctx->stream));
+  return stream_sync(ctx->stream);
+#endif
 }
 
 int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms) {

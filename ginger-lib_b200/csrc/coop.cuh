@@ -47,20 +47,6 @@ template <> struct CoopField<1> {
 G753_D unsigned coop_lane() { return threadIdx.x & 7u; }
 G753_D unsigned coop_octet() { return (threadIdx.x & 31u) >> 3; }
 
-// t[j..6] += a[0..2] * b  (7-word accumulator, two carry chains: limbs 0 and 2, then limb 1)
-G753_D void coop_mad_row(uint32_t* t, const int j, const uint32_t* a, uint32_t b) {
-  t[j] = mad_lo_cc(a[0], b, t[j]);
-  t[j + 1] = madc_hi_cc(a[0], b, t[j + 1]);
-  t[j + 2] = madc_lo_cc(a[2], b, t[j + 2]);
-  t[j + 3] = madc_hi_cc(a[2], b, t[j + 3]);
-#pragma unroll
-  for (int i = j + 4; i < 7; i++) t[i] = addc_cc(t[i], 0);
-  t[j + 1] = mad_lo_cc(a[1], b, t[j + 1]);
-  t[j + 2] = madc_hi_cc(a[1], b, t[j + 2]);
-#pragma unroll
-  for (int i = j + 3; i < 7; i++) t[i] = addc_cc(t[i], 0);
-}
-
 // Clean lanes of sum_l (r_l + cw_l 2^96) 2^(96 l) mod 2^768: every lane adds its lower neighbour's carry
 // word, then the 0 / 1 carries that remain ripple through one generate / propagate evaluation on the
 // octet's ballot.  Returns the carry out of the top lane (same value in all lanes of the octet).
@@ -85,48 +71,93 @@ G753_D uint32_t coop_resolve(uint32_t* r, uint32_t cw) {
   return ((sum >> 8) & 1u) + cw7;
 }
 
+// E, O += a[0..2] * b[0..2] (columns 0 .. 5, carries into column 6).  Two accumulators as in fq.cuh: the
+// partial products a_i b_j with i + j even land on the even-aligned column pairs of E, those with i + j odd
+// on the odd-aligned pairs of O, so every lo / hi pair is one IMAD.WIDE on an aligned register pair and no
+// partial product is ever re-aligned (with one accumulator half of the instructions ptxas emits are moves).
+// The value is sum_c (E[c] + O[c]) 2^(32 c); O[0] is unused.
+G753_D void coop_prod_acc(uint32_t* E, uint32_t* O, const uint32_t* a, const uint32_t* b) {
+  E[0] = mad_lo_cc(a[0], b[0], E[0]);
+  E[1] = madc_hi_cc(a[0], b[0], E[1]);
+  E[2] = madc_lo_cc(a[0], b[2], E[2]);
+  E[3] = madc_hi_cc(a[0], b[2], E[3]);
+  E[4] = madc_lo_cc(a[2], b[2], E[4]);
+  E[5] = madc_hi_cc(a[2], b[2], E[5]);
+  E[6] = addc(E[6], 0);
+  E[2] = mad_lo_cc(a[1], b[1], E[2]);
+  E[3] = madc_hi_cc(a[1], b[1], E[3]);
+  E[4] = addc_cc(E[4], 0);
+  E[5] = addc_cc(E[5], 0);
+  E[6] = addc(E[6], 0);
+  E[2] = mad_lo_cc(a[2], b[0], E[2]);
+  E[3] = madc_hi_cc(a[2], b[0], E[3]);
+  E[4] = addc_cc(E[4], 0);
+  E[5] = addc_cc(E[5], 0);
+  E[6] = addc(E[6], 0);
+  O[1] = mad_lo_cc(a[0], b[1], O[1]);
+  O[2] = madc_hi_cc(a[0], b[1], O[2]);
+  O[3] = madc_lo_cc(a[1], b[2], O[3]);
+  O[4] = madc_hi_cc(a[1], b[2], O[4]);
+  O[5] = addc_cc(O[5], 0);
+  O[6] = addc(O[6], 0);
+  O[1] = mad_lo_cc(a[1], b[0], O[1]);
+  O[2] = madc_hi_cc(a[1], b[0], O[2]);
+  O[3] = madc_lo_cc(a[2], b[1], O[3]);
+  O[4] = madc_hi_cc(a[2], b[1], O[4]);
+  O[5] = addc_cc(O[5], 0);
+  O[6] = addc(O[6], 0);
+}
+
 // out = a b / 2^768 mod p (lazily reduced: below (1 + x y / 2^15) p for inputs below x p, y p).
 // n: this lane's limbs of p; np: -p^-1 mod 2^96.  All 32 lanes call it (4 products per warp).
+// The warp runs alone on its scheduler: what counts is the number of instructions.
 G753_D void coop_mul(uint32_t* out, const uint32_t* a, const uint32_t* b, const uint32_t* n, const uint32_t* np) {
   const unsigned l = coop_lane();
-  uint32_t t[7];
+  uint32_t E[7], O[7];
 #pragma unroll
-  for (int i = 0; i < 7; i++) t[i] = 0;
+  for (int i = 0; i < 7; i++) E[i] = 0;
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    const uint32_t b0 = __shfl_sync(COOP_FULL, b[0], j, 8);
-    const uint32_t b1 = __shfl_sync(COOP_FULL, b[1], j, 8);
-    const uint32_t b2 = __shfl_sync(COOP_FULL, b[2], j, 8);
-    coop_mad_row(t, 0, a, b0);
-    coop_mad_row(t, 1, a, b1);
-    coop_mad_row(t, 2, a, b2);
-    // M = t[0..2] * np mod 2^96 (every lane computes it on its own t; lane 0's is the one that counts)
-    uint32_t m0 = t[0] * np[0];
-    const uint64_t s1 = (uint64_t)__umulhi(t[0], np[0]) + (uint64_t)(t[0] * np[1]) + (uint64_t)(t[1] * np[0]);
-    uint32_t m1 = (uint32_t)s1;
-    uint32_t m2 = (uint32_t)(s1 >> 32) + __umulhi(t[0], np[1]) + __umulhi(t[1], np[0]) + t[0] * np[2] + t[1] * np[1] +
-                  t[2] * np[0];
-    m0 = __shfl_sync(COOP_FULL, m0, 0, 8);
-    m1 = __shfl_sync(COOP_FULL, m1, 0, 8);
-    m2 = __shfl_sync(COOP_FULL, m2, 0, 8);
-    coop_mad_row(t, 0, n, m0);
-    coop_mad_row(t, 1, n, m1);
-    coop_mad_row(t, 2, n, m2);
+#pragma unroll
+    for (int i = 0; i < 7; i++) O[i] = 0;
+    uint32_t B[3];
+    B[0] = __shfl_sync(COOP_FULL, b[0], j, 8);
+    B[1] = __shfl_sync(COOP_FULL, b[1], j, 8);
+    B[2] = __shfl_sync(COOP_FULL, b[2], j, 8);
+    coop_prod_acc(E, O, a, B);
+    // the low digit t[0..2] of E + O, then M = t * np mod 2^96 (lane 0's is the one that counts)
+    const uint32_t t0 = E[0];
+    const uint32_t t1 = add_cc(E[1], O[1]);
+    const uint32_t t2 = addc(E[2], O[2]);
+    uint32_t M[3];
+    M[0] = t0 * np[0];
+    const uint64_t s1 = (uint64_t)__umulhi(t0, np[0]) + (uint64_t)(t0 * np[1]) + (uint64_t)(t1 * np[0]);
+    M[1] = (uint32_t)s1;
+    M[2] = (uint32_t)(s1 >> 32) + __umulhi(t0, np[1]) + __umulhi(t1, np[0]) + t0 * np[2] + t1 * np[1] + t2 * np[0];
+    M[0] = __shfl_sync(COOP_FULL, M[0], 0, 8);
+    M[1] = __shfl_sync(COOP_FULL, M[1], 0, 8);
+    M[2] = __shfl_sync(COOP_FULL, M[2], 0, 8);
+    coop_prod_acc(E, O, n, M);
+    // merge the accumulators: columns 0 .. 6 of this lane's total
+    E[1] = add_cc(E[1], O[1]);
+#pragma unroll
+    for (int i = 2; i < 6; i++) E[i] = addc_cc(E[i], O[i]);
+    E[6] = addc(E[6], O[6]);
     // divide by 2^96: lane l keeps its high half, receives the low half of lane l + 1
-    uint32_t r0 = __shfl_down_sync(COOP_FULL, t[0], 1, 8);
-    uint32_t r1 = __shfl_down_sync(COOP_FULL, t[1], 1, 8);
-    uint32_t r2 = __shfl_down_sync(COOP_FULL, t[2], 1, 8);
+    uint32_t r0 = __shfl_down_sync(COOP_FULL, E[0], 1, 8);
+    uint32_t r1 = __shfl_down_sync(COOP_FULL, E[1], 1, 8);
+    uint32_t r2 = __shfl_down_sync(COOP_FULL, E[2], 1, 8);
     if (l == 7) r0 = r1 = r2 = 0;
-    t[0] = add_cc(t[3], r0);
-    t[1] = addc_cc(t[4], r1);
-    t[2] = addc_cc(t[5], r2);
-    t[3] = addc(t[6], 0);
-    t[4] = t[5] = t[6] = 0;
+    E[0] = add_cc(E[3], r0);
+    E[1] = addc_cc(E[4], r1);
+    E[2] = addc_cc(E[5], r2);
+    E[3] = addc(E[6], 0);
+    E[4] = E[5] = E[6] = 0;
   }
-  out[0] = t[0];
-  out[1] = t[1];
-  out[2] = t[2];
-  coop_resolve(out, t[3]);
+  out[0] = E[0];
+  out[1] = E[1];
+  out[2] = E[2];
+  coop_resolve(out, E[3]);
 }
 
 // out = a + y + z + inc over the octet (three-operand lane sums, carries resolved); returns the carry

@@ -78,7 +78,8 @@ struct SCurveM4G2 {
 };
 template <class L>
 struct SCurveM6G2 {
-  typedef Tw3C<1, L, 11> M;
+  // three lanes: the lazy one-coefficient-per-lane tower (accumulation kernels); four / eight: Karatsuba
+  typedef typename SelectT<L::TP == 3, Tw3L<1, L, 11>, Tw3C<1, L, 11>>::type M;
   static constexpr int ID = 3;
   // twist a' = 11 u^2: (c0, c1, c2) -> (121 c1, 121 c2, 11 c0) (curves/mnt6753/g2.rs:148-155); d != a
   static G753_D void mul_by_a(int d, int a) {

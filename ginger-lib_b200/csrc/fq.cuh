@@ -365,6 +365,33 @@ G753_HD void mont2_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi
   row_mad(E, G753_FC(FID).p, m);
   O[NL - 1] = addc(O[NL - 1], 0);
 }
+// Three products under ONE reduction: (a b + c d + e f) / R mod p - one coefficient of an Fq3 product
+// (fp3.rs:433-478 computes c0 = a0 b0 + nr (a1 b2 + a2 b1) etc.).  3 x 576 + 600 limb-MACs.  The running
+// total stays below (a + c + e + p) 2^32 < 4 p 2^32 < 2^(32 (NL + 1)) like mont2_step's, and the result
+// (a b + c d + e f + M p) / R < p (1 + 3 p / R) < 2 p needs the same single conditional subtraction.
+template <int FID, bool FIRST>
+G753_HD void mont3_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, const uint32_t* c, uint32_t di,
+                        const uint32_t* e, uint32_t fi) {
+  if (FIRST) {
+    row_mul(O, a + 1, bi);
+    row_mul(E, a, bi);
+  } else {
+    E[0] = add_cc(E[0], O[1]);
+    row_mad_shift(O, a + 1, bi);
+    row_mad(E, a, bi);
+    O[NL - 1] = addc(O[NL - 1], 0);
+  }
+  row_mad(O, c + 1, di);
+  row_mad(E, c, di);
+  O[NL - 1] = addc(O[NL - 1], 0);
+  row_mad(O, e + 1, fi);
+  row_mad(E, e, fi);
+  O[NL - 1] = addc(O[NL - 1], 0);
+  uint32_t m = mul_lo(E[0], G753_FC(FID).inv32);
+  row_mad(O, G753_FC(FID).p + 1, m);
+  row_mad(E, G753_FC(FID).p, m);
+  O[NL - 1] = addc(O[NL - 1], 0);
+}
 // the accumulators after the last step -> canonical element (NL is even: `even` holds the columns)
 template <int FID>
 G753_HD Fq mont_finish(const uint32_t* even, const uint32_t* odd) {
@@ -384,6 +411,18 @@ G753_HD Fq fq_mul2(const Fq& a, const Fq& b, const Fq& c, const Fq& d) {
   for (int i = 1; i < NL; i += 2) {
     mont2_step<FID, false>(odd, even, a.l, b.l[i], c.l, d.l[i]);
     if (i + 1 < NL) mont2_step<FID, false>(even, odd, a.l, b.l[i + 1], c.l, d.l[i + 1]);
+  }
+  return mont_finish<FID>(even, odd);
+}
+
+template <int FID>
+G753_HD Fq fq_mul3(const Fq& a, const Fq& b, const Fq& c, const Fq& d, const Fq& e, const Fq& f) {
+  uint32_t even[NL], odd[NL];
+  mont3_step<FID, true>(even, odd, a.l, b.l[0], c.l, d.l[0], e.l, f.l[0]);
+#pragma unroll
+  for (int i = 1; i < NL; i += 2) {
+    mont3_step<FID, false>(odd, even, a.l, b.l[i], c.l, d.l[i], e.l, f.l[i]);
+    if (i + 1 < NL) mont3_step<FID, false>(even, odd, a.l, b.l[i + 1], c.l, d.l[i + 1], e.l, f.l[i + 1]);
   }
   return mont_finish<FID>(even, odd);
 }

@@ -55,7 +55,7 @@ template <int GID> struct MsmCfg;
 #else
 #define G753_TP2A 2
 #define G753_TP2 4
-#define G753_TP3A 4
+#define G753_TP3A 3
 #define G753_TP3 8
 #endif
 #ifndef G753_NC_ACC1
@@ -78,7 +78,7 @@ template <> struct MsmCfg<2> {
 };
 template <> struct MsmCfg<3> {
   static constexpr bool AFFINE = false;
-  static constexpr int K = 3, TP = G753_TP3, TPA = G753_TP3A, NC_ACC = 32, NC_RED = 16;
+  static constexpr int K = 3, TP = G753_TP3, TPA = G753_TP3A, NC_ACC = G753_TP3A == 3 ? 40 : 32, NC_RED = 16;
   template <int NC, int LANES = G753_TP3> using SC = SCurveM6G2<Lay<NC, LANES>>;
 };
 
@@ -91,13 +91,23 @@ struct MsmPlan {
   unsigned copies;  // key copies actually used = ceil(W / rows)
 };
 
-// Cost model in units of one field multiplication of the saturated accumulation kernel (7 G/s
-// measured): a mixed add is 10 (XYZZ); the reduction does 2 full adds (28) per bucket (its 13-slot
-// footprint caps it at ~5 warps per SM, so it runs at about half rate, but larger windows also
-// shorten the per-addition cost of the accumulation: 30 reproduces the measured optimum, c = 20 at
-// 2^21..2^22 with 8 copies); the final Horner fold is a serial chain of rows * c doublings on ONE
-// thread, each field multiplication of which takes ~2.8 us = ~20 000 units.
-static inline MsmPlan msm_plan(size_t n, unsigned copies = 1, int forced_c = 0, unsigned forced_rows = 0) {
+// Cost model in units of one base-field multiplication of the saturated accumulation kernel (7 G/s
+// measured).  Per point and window: one mixed addition (10 products of the coordinate field).  Per bucket:
+// the running-sum reduction, 2 full additions on a kernel that runs at about half rate - 50 reproduces
+// the measured reduce phases (2^22 points, 5 rows of 2^19 buckets: 17 ms; 2^19 points, one row: 4.9 ms).
+// Per bucket row: the Horner fold on ONE cooperating warp (coop.cuh), c doublings + one addition of the
+// window sum, a latency chain measured at ~3.5 us per G1 doubling = 25 000 units (Fq2: x 4, Fq3: x 8.7;
+// the one-thread fold it replaces cost 200 000 per doubling).
+struct MsmCost {
+  double madd, bucket, fold_dbl, fold_add;
+};
+template <int GID>
+static inline MsmCost msm_cost() {
+  const double tower = MsmCfg<GID>::K == 1 ? 1.0 : MsmCfg<GID>::K == 2 ? 3.4 : 9.5;   // coordinate-field cost ratio
+  const double fold = MsmCfg<GID>::K == 1 ? 1.0 : MsmCfg<GID>::K == 2 ? 4.0 : 8.7;
+  return MsmCost{10.0 * tower, 50.0 * tower, 25000.0 * fold, 45000.0 * fold};
+}
+static inline MsmPlan msm_plan(const MsmCost& k, size_t n, unsigned copies = 1, int forced_c = 0, unsigned forced_rows = 0) {
   MsmPlan best{0, 0, 0, 0, 0};
   double best_cost = 0;
   if (copies == 0) copies = 1;
@@ -106,7 +116,8 @@ static inline MsmPlan msm_plan(size_t n, unsigned copies = 1, int forced_c = 0, 
     unsigned W = (SCALAR_BITS + 1 + c - 1) / c;
     unsigned rows = forced_rows ? forced_rows : (W + copies - 1) / copies;
     double B = (double)(1u << (c - 1));
-    double cost = (double)W * 10.0 * (double)n + (double)rows * 30.0 * B + (double)rows * c * 10.0 * 20000.0;
+    double cost = (double)W * k.madd * (double)n + (double)rows * k.bucket * B +
+                  (double)rows * ((double)c * k.fold_dbl + k.fold_add);
     if (best.c == 0 || cost < best_cost) {
       best = MsmPlan{c, W, 1u << (c - 1), rows, (W + rows - 1) / rows};
       best_cost = cost;
@@ -286,6 +297,7 @@ k_bucket_acc(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const MsmItem* __restrict__ items, const uint32_t* __restrict__ item_total,
              Fq* __restrict__ points) {
   typedef EcS<SC> E;
+  if (E::M::T::idle()) return;
   unsigned pos = E::M::T::item();
   if (pos >= *item_total) return;
   const MsmItem it = items[pos];
@@ -481,6 +493,7 @@ k_bucket_fixup_level(const uint32_t* __restrict__ item_cnt, const uint32_t* __re
                      const uint32_t* __restrict__ part_bucket, const uint32_t* __restrict__ item_total, unsigned NB,
                      unsigned stride, Fq* __restrict__ points) {
   typedef EcS<SC> E;
+  if (E::M::T::idle()) return;
   unsigned q = E::M::T::item();
   if (q >= *item_total) return;
   const uint32_t t = part_bucket[q];
@@ -502,6 +515,7 @@ __global__ void __launch_bounds__(SC::M::T::THREADS)
 k_bucket_fixup(const uint32_t* __restrict__ item_cnt, const uint32_t* __restrict__ item_off,
                unsigned NB, Fq* __restrict__ points) {
   typedef EcS<SC> E;
+  if (E::M::T::idle()) return;
   unsigned t = E::M::T::item();
   if (t >= NB) return;
   if (item_cnt[t] < 2) return;
@@ -843,7 +857,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
                    size_t count, Fq* d_out, MsmHooks hooks) {
   typedef MsmCfg<GID> Cfg;
   constexpr int CA = Cfg::NC_ACC, CR = Cfg::NC_RED;        // columns (curve operations) per block
-  constexpr int TA = CA * Cfg::TPA, TR = CR * Cfg::TP;     // threads per block
+  constexpr int TA = Lay<CA, Cfg::TPA>::THREADS, TR = CR * Cfg::TP;     // threads per block (whole warps)
   typedef typename Cfg::template SC<CA, Cfg::TPA> SCA;
   typedef typename Cfg::template SC<CR, Cfg::TP> SCR;
   typedef EcS<SCA> EA;
@@ -859,7 +873,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   }
   if (count > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "msm: more than 2^31 - 1 scalars");
   const unsigned n = (unsigned)count;
-  const MsmPlan pl = msm_plan(n, key.copies, key.c, key.rows);
+  const MsmPlan pl = msm_plan(msm_cost<GID>(), n, key.copies, key.c, key.rows);
   if (pl.c == 0) return fail(G753_ERR_BAD_ARG, "msm: no window size satisfies the forced plan");
   const bool affine = Cfg::AFFINE && key.affine > 0;  // opt-in (G753_MSM_AFFINE=1): measured slower, see header
   const MsmWorkspace ws = msm_workspace<GID>(pl, n, affine);

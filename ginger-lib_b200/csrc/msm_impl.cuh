@@ -34,7 +34,7 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
     key.c = ctx->forced_c;
   }
   if (count) {
-    const MsmPlan pl = msm_plan(count, key.copies, key.c, key.rows);
+    const MsmPlan pl = msm_plan(msm_cost<GID>(), count, key.copies, key.c, key.rows);
     ctx->last_plan[0] = pl.c;
     ctx->last_plan[1] = pl.W;
     ctx->last_plan[2] = pl.rows;
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(SC::M::T::THREADS)
 k_ext_op(int op, const Fq* __restrict__ a, const Fq* __restrict__ b, unsigned n, Fq* __restrict__ out) {
   typedef typename SC::M M;
   constexpr int K = M::K, A = 0, B = K, D = 2 * K, TMP = 3 * K;
+  if (M::T::idle()) return;
   unsigned i = M::T::item();
   if (i >= n) return;
   M::ldg(A, a + (size_t)i * K);
@@ -156,9 +157,10 @@ int ext_op_impl(g753_ctx* ctx, int lanes, int op, const uint64_t* a, const uint6
   G753_TRY(h2d(da, a, bytes, ctx->stream));
   if (b) G753_TRY(h2d(db, b, bytes, ctx->stream));
   if (lanes == 0) {
-    typedef typename Cfg::template SC<T, Cfg::TPA> SC;
-    G753_LAUNCH_SMEM(k_ext_op<SC>, div_up(n, T), T * Cfg::TPA, (slot_bytes<EcS<SC>, T>(3 * K + SC::M::NTMP + 1)), ctx->stream, op, da,
-                     b ? db : (const Fq*)nullptr, (unsigned)n, dout);
+    constexpr int TA = Cfg::TPA == 3 ? 40 : T;      // three lanes per column: ten columns per warp
+    typedef typename Cfg::template SC<TA, Cfg::TPA> SC;
+    G753_LAUNCH_SMEM(k_ext_op<SC>, div_up(n, TA), (Lay<TA, Cfg::TPA>::THREADS), (slot_bytes<EcS<SC>, TA>(3 * K + SC::M::NTMP + 1)),
+                     ctx->stream, op, da, b ? db : (const Fq*)nullptr, (unsigned)n, dout);
   } else {
     typedef typename Cfg::template SC<T, Cfg::TP> SC;
     G753_LAUNCH_SMEM(k_ext_op<SC>, div_up(n, T), T * Cfg::TP, (slot_bytes<EcS<SC>, T>(3 * K + SC::M::NTMP + 1)), ctx->stream, op, da,
@@ -285,7 +287,7 @@ int bases_precompute_impl(g753_ctx* ctx, g753_bases* b, unsigned copies) {
   typedef typename MsmCfg<GID>::template SC<T> SC;
   typedef EcS<SC> E;
   const size_t n = b->n;
-  const MsmPlan pl = msm_plan(n, copies, ctx->forced_c);
+  const MsmPlan pl = msm_plan(msm_cost<GID>(), n, copies, ctx->forced_c);
   if (pl.copies <= 1 || n == 0) return G753_OK;
   if ((uint64_t)pl.copies * n > 0x7fffffffull) return fail(G753_ERR_BAD_ARG, "copies * n exceeds the 31-bit base index");
   const size_t pt_bytes = sizeof(Fq) * 2 * K;

@@ -53,17 +53,23 @@ constexpr int SLOT_CHUNKS = NL / 4;  // 6 x 16 bytes per Fq
 //   the slow index (lane = role * (32 / TP) + column-in-warp): a quarter-warp touches
 //   consecutive columns of one slot, keeping LDS.128 / STS.128 conflict-free.
 // A "slot type" T below is either a plain int-like column count (legacy spelling Lay<T, 1>) or Lay.
+//   TP = 3 (Fq3 accumulation): ten columns per warp on lanes 0 .. 29, one coefficient per lane; lanes 30
+//   and 31 are idle (role() == TP: kernels return at once for them, see idle()).
 template <int NC_, int TP_>
 struct Lay {
-  static constexpr int NC = NC_, TP = TP_, THREADS = NC_ * TP_, CPW = 32 / TP_;  // CPW: columns per warp
+  static constexpr int NC = NC_, TP = TP_, CPW = 32 / TP_;  // CPW: columns per warp
+  static constexpr int THREADS = NC_ / CPW * 32;             // whole warps (= NC * TP when TP divides 32)
+  static_assert(NC_ % CPW == 0, "columns per block must fill whole warps");
   static G753_D int col() {
     if (TP == 1) return (int)threadIdx.x;
-    return (int)(threadIdx.x >> 5) * CPW + (int)(threadIdx.x & (CPW - 1));
+    return (int)(threadIdx.x >> 5) * CPW + (int)((threadIdx.x & 31) % CPW);
   }
   static G753_D int role() {
     if (TP == 1) return 0;
     return (int)((threadIdx.x & 31) / CPW);
   }
+  // lanes that belong to no column (TP = 3: lanes 30, 31 of every warp)
+  static G753_D bool idle() { return (32 % TP) != 0 && role() >= TP; }
   // reconverge the lanes of this column and order their slot accesses
   static G753_D void sync() {
 #if defined(__CUDA_ARCH__)
@@ -71,7 +77,7 @@ struct Lay {
       unsigned m = 0;
 #pragma unroll
       for (int r = 0; r < TP; r++) m |= 1u << (r * CPW);
-      __syncwarp(m << (threadIdx.x & (CPW - 1)));
+      __syncwarp(m << ((threadIdx.x & 31) % CPW));
     }
 #endif
   }
@@ -395,6 +401,28 @@ G753_NI void s_mul2(int d, int a, int b, int c, int e, int mode) {
   T::sync();
   s_st<T>(d, r);
   T::sync();
+}
+
+// ---- three products under one reduction on slots: x0 * slot[y0] + x1 * slot[y1] + x2 * slot[y2] (fq_mul3);
+// the multiplicands are in registers, the multipliers are streamed from their slots 16 bytes at a time
+template <int FID, class T>
+G753_D Fq s_mul3_stream(const Fq& x0, int y0, const Fq& x1, int y1, const Fq& x2, int y2) {
+  const uint4* p0 = slot_ptr<T>(y0);
+  const uint4* p1 = slot_ptr<T>(y1);
+  const uint4* p2 = slot_ptr<T>(y2);
+  uint32_t even[NL], odd[NL];
+#pragma unroll
+  for (int k = 0; k < SLOT_CHUNKS; k++) {
+    const uint4 v0 = p0[k * T::NC], v1 = p1[k * T::NC], v2 = p2[k * T::NC];
+    const uint32_t b0[4] = {v0.x, v0.y, v0.z, v0.w}, b1[4] = {v1.x, v1.y, v1.z, v1.w}, b2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (k == 0 && u == 0) mont3_step<FID, true>(even, odd, x0.l, b0[0], x1.l, b1[0], x2.l, b2[0]);
+      else if (u & 1) mont3_step<FID, false>(odd, even, x0.l, b0[u], x1.l, b1[u], x2.l, b2[u]);
+      else mont3_step<FID, false>(even, odd, x0.l, b0[u], x1.l, b1[u], x2.l, b2[u]);
+    }
+  }
+  return mont_finish<FID>(even, odd);
 }
 
 // ---- towers: an element is K consecutive slots; `t` is the first of NTMP scratch slots ----
@@ -855,6 +883,88 @@ struct Tw3C {
   static G753_D void stg(Fq* g, int a) {
     const int r = L::role();
     if (r < K) s_stg<L>(g + r, a + r);
+  }
+};
+
+// Fq3 on THREE lanes, one coefficient per lane, schoolbook with lazy reduction (fp3.rs:433-478 gives the
+// same values): c0 = a0 b0 + nr (a1 b2 + a2 b1), c1 = a0 b1 + a1 b0 + nr a2 b2, c2 = a0 b2 + a1 b1 + a2 b0 -
+// every coefficient is ONE three-product body (s_mul3_stream: 3 x 576 + 600 limb-MACs), no lane idles during a
+// product and no temporaries are needed, so a warp carries ten columns (lanes 0 .. 29) instead of the eight of
+// the four-lane Karatsuba form whose second round leaves two (squaring: three) lanes idle.  The squaring goes
+// through the same body (one multiplier body in the accumulation kernel's hot code).  The scratch slots
+// (NTMP) serve inv only, which runs on lane 0 with the one-thread tower.
+template <int FID, class L, unsigned NR>
+struct Tw3L {
+  typedef L T;
+  static constexpr int K = 3, NTMP = 6, FIELD = FID;
+  static_assert(L::TP == 3, "one lane per coefficient");
+  static G753_NI void mul(int d, int a, int b, int) {
+    const int r = L::role();
+    // lane r:  x0 * b[r]  +  x1 * b[(r + 2) % 3]  +  x2 * b[(r + 1) % 3],  x_i = a_i times nr where the
+    // product wraps around u^3 = nr: (r = 0: a1, a2;  r = 1: a2)
+    const Fq x0 = s_ld<L>(a);
+    Fq x1 = s_ld<L>(a + 1), x2 = s_ld<L>(a + 2);
+    const Fq n1 = fq_mul_small<FID, NR>(x1), n2 = fq_mul_small<FID, NR>(x2);
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      x1.l[i] = r == 0 ? n1.l[i] : x1.l[i];
+      x2.l[i] = r <= 1 ? n2.l[i] : x2.l[i];
+    }
+    const int y0 = b + r, y1 = b + (r == 0 ? 2 : r - 1), y2 = b + (r == 2 ? 0 : r + 1);
+    const Fq res = s_mul3_stream<FID, L>(x0, y0, x1, y1, x2, y2);
+    L::sync();               // every lane has read a and b: d may alias either
+    s_st<L>(d + r, res);
+    L::sync();
+  }
+  static G753_D void sqr(int d, int a, int t) { mul(d, a, a, t); }
+  static G753_NI void inv(int d, int a, int t) {
+    if (L::role() == 0) Tw3<FID, L, NR>::inv(d, a, t);
+    L::sync();
+  }
+  static G753_D void add(int d, int a, int b) {
+    const int r = L::role();
+    s_add<FID, L>(d + r, a + r, b + r);
+    L::sync();
+  }
+  static G753_D void sub(int d, int a, int b) {
+    const int r = L::role();
+    s_sub<FID, L>(d + r, a + r, b + r);
+    L::sync();
+  }
+  static G753_D void dbl(int d, int a) {
+    const int r = L::role();
+    s_dbl<FID, L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D void neg(int d, int a) {
+    const int r = L::role();
+    s_neg<FID, L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D void copy(int d, int a) {
+    const int r = L::role();
+    s_copy<L>(d + r, a + r);
+    L::sync();
+  }
+  static G753_D bool is_zero(int a) { return s_is_zero<L>(a) && s_is_zero<L>(a + 1) && s_is_zero<L>(a + 2); }
+  static G753_D void set_zero(int d) {
+    s_set_zero<L>(d + L::role());
+    L::sync();
+  }
+  static G753_D void set_one(int d) {
+    const int r = L::role();
+    if (r == 0) s_set_one<FID, L>(d);
+    else s_set_zero<L>(d + r);
+    L::sync();
+  }
+  static G753_D void ldg(int d, const Fq* g) {
+    const int r = L::role();
+    s_ldg<L>(d + r, g + r);
+    L::sync();
+  }
+  static G753_D void stg(Fq* g, int a) {
+    const int r = L::role();
+    s_stg<L>(g + r, a + r);
   }
 };
 #endif

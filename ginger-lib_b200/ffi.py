@@ -77,6 +77,7 @@ SYMBOLS = [
     ("g753_field_op", _i, [_vp, _i, _i, _vp, _vp, _vp, _sz]),
     ("g753_point_op", _i, [_vp, _i, _i, _vp, _vp, _vp]),
     ("g753_ext_op", _i, [_vp, _i, _i, _i, _vp, _vp, _vp, _sz]),
+    ("g753_coop_op", _i, [_vp, _i, _i, _u, _vp, _vp, _vp, _sz]),
     ("g753_mac_probe", _i, [_vp, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float)]),
     ("g753_debug_scratch", _i, [_vp, _vp, _sz, ctypes.POINTER(_sz)]),
     ("g753_launch_count", ctypes.c_uint64, [_vp]),

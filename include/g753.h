@@ -257,6 +257,13 @@ int g753_point_op(g753_ctx* ctx, int group, int op, const uint64_t* a, const uin
  * aliasing a / b, 23 square in place.  The reference's Fq2 / Fq3 KATs are replayed through it. */
 int g753_ext_op(g753_ctx* ctx, int group, int lanes, int op, const uint64_t* a, const uint64_t* b,
                 uint64_t* out, size_t n);
+/* test hook of the warp-cooperative field arithmetic the latency-bound kernels use (window fold, point folds,
+ * reduction tail; csrc/coop.cuh): out[i] = op(a[i], b[i]) on 24-limb values of the BASE field of MNT4 (field 0) /
+ * MNT6 (field 1), raw results (lazily reduced, NOT canonical) so that they compare limb for limb with the model
+ * in tools/gen_coop.py.  op 0: Montgomery product a b / 2^768 (+ a multiple of p); 1: a + b; 2: a + 2^k p - b;
+ * 3: a -> a mod p for a < 2 p; 4: out = 1 if a in {0, p} else 0. */
+int g753_coop_op(g753_ctx* ctx, int field, int op, unsigned k, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                 size_t n);
 /* Run `iters` dependent Montgomery multiplications per thread on `blocks` x `threads`
  * threads and report the kernel time in ms (CUDA events): the integer-pipe roofline probe
  * of SURVEY.md 8d.  variant 0 = fq_mul, 1 = fq_sqr, 2 = raw independent IMAD.WIDE stream,

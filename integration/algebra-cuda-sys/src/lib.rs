@@ -116,6 +116,8 @@ extern "C" {
                          out_xyz: *mut u64) -> c_int;
     pub fn g753_ext_op(ctx: *mut G753Ctx, group: c_int, lanes: c_int, op: c_int, a: *const u64, b: *const u64,
                        out: *mut u64, n: usize) -> c_int;
+    pub fn g753_coop_op(ctx: *mut G753Ctx, field: c_int, op: c_int, k: c_uint, a: *const u64, b: *const u64, out: *mut u64,
+                        n: usize) -> c_int;
     pub fn g753_mac_probe(ctx: *mut G753Ctx, variant: c_int, blocks: c_int, threads: c_int, iters: c_int,
                           ms: *mut c_float) -> c_int;
     pub fn g753_debug_scratch(ctx: *mut G753Ctx, h_dst: *mut c_void, bytes: usize, cap: *mut usize) -> c_int;

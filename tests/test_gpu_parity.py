@@ -502,3 +502,63 @@ def test_reference_ext_kats_on_device_towers(ctx, group, lanes):
     import shared_checks
     shared_checks.check_reference_ext_kats(ctx, group, lanes)
     shared_checks.check_ext_ops_random(ctx, group, lanes)
+
+
+@pytest.mark.parametrize("fid", [0, 1])
+def test_coop_field_arithmetic_vs_model(ctx, fid):
+    """the warp-cooperative field arithmetic (csrc/coop.cuh: one product on 8 lanes, digit-serial Montgomery in
+    base 2^96, ballot-resolved carries) limb for limb against its Python model (tools/gen_coop.py), on edge
+    values (all-ones digits, values at the bounds, carries rippling across every lane) and random ones"""
+    import importlib.util
+    import random
+    spec = importlib.util.spec_from_file_location("gen_coop", os.path.join(HERE, "..", "tools", "gen_coop.py"))
+    GC = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(GC)
+    p = GC.field_moduli()[fid]
+    f = GC.Field(p)
+    rng = random.Random(0xC0F + fid)
+    M96 = (1 << 96) - 1
+    edge = [0, 1, p - 1, p, p + 1, 2 * p - 1, M96, M96 << 96, (1 << 753) - 1, 100 * p, (1 << 192) - 1,
+            sum(M96 << (192 * i) for i in range(4)), (1 << 767) - 1, sum(M96 << (96 * i) for i in range(7)),
+            (1 << 96), (1 << 672)]
+    vals = edge + [rng.randrange(0, 181 * p) for _ in range(80)]
+
+    def arr(xs):
+        return ints_to_array(xs)
+
+    def run(op, xs, ys, k=0):
+        a, b = arr(xs), arr(ys)
+        out = np.zeros_like(a)
+        ctx.lib.check(ctx.lib.coop_op(ctx.handle, fid, op, k, ffi.ptr(a), ffi.ptr(b), ffi.ptr(out), len(xs)))
+        return array_to_ints(out)
+
+    # products (input bounds x y <= 2^15)
+    xs, ys = [], []
+    for i, x in enumerate(vals):
+        for y in vals[i % 5::5]:
+            if (x // p + 1) * (y // p + 1) <= (1 << 15) and x < (1 << 768) and y < (1 << 768):
+                xs.append(x)
+                ys.append(y)
+    got = run(0, xs, ys)
+    want = [GC.join(f.mul(GC.split(x), GC.split(y))) for x, y in zip(xs, ys)]
+    assert got == want
+    # sums and differences
+    xs, ys = [], []
+    for x in vals:
+        for y in vals[::4]:
+            if x + y < (1 << 768):
+                xs.append(x)
+                ys.append(y)
+    assert run(1, xs, ys) == [x + y for x, y in zip(xs, ys)]
+    for k in range(GC.MAX_K_LOG + 1):
+        xs, ys = [], []
+        for x in vals:
+            for y in vals[::6]:
+                if y <= (p << k) and x + (p << k) - y < (1 << 768):
+                    xs.append(x)
+                    ys.append(y)
+        assert run(2, xs, ys, k) == [x + (p << k) - y for x, y in zip(xs, ys)]
+    # canonicalisation and the zero test of values below 2 p
+    xs = [0, 1, p - 1, p, p + 1, 2 * p - 1] + [rng.randrange(0, 2 * p) for _ in range(30)]
+    assert run(3, xs, xs) == [x % p for x in xs]
+    assert run(4, xs, xs) == [1 if x % p == 0 else 0 for x in xs]
