@@ -342,26 +342,38 @@ static int mixed_run(g753_ctx* ctx, Fq* d_data, Fq* d_tmp, uint64_t N, int mode)
   G753_TRY(ntt_tables_get<FID>(ctx, T->a, &T2));
   const bool inverse = (mode == G753_IFFT || mode == G753_COSET_IFFT);
   const size_t n2 = (size_t)1 << T->a;
-  // step 1: column DFTs (coset_fft: inputs scaled by g^i on the fly)
-  G753_LAUNCH(k_small_dft<FID>, div_up(N, 128), 128, ctx->stream, d_data, d_tmp, T->zeta + (inverse ? T->m : 0), T->m, n2,
-              mode == G753_COSET_FFT ? T->coset : (const Fq*)nullptr);
-  ctx->launches++;
+  // step 1: column DFTs of length m (coset_fft: inputs scaled by g^i on the fly), in two stages when m = q1 q2
+  const Fq* zt = T->zeta + (inverse ? T->m : 0);
+  const Fq* pre = mode == G753_COSET_FFT ? T->coset : (const Fq*)nullptr;
+  const unsigned q1 = mixed_q1(T->m), q2 = T->m / q1;
+  Fq *cols = d_tmp, *other = d_data;       // where the column DFTs end up / the free buffer
+  if (q1 > 1) {
+    G753_LAUNCH(k_small_dft_a<FID>, div_up(N, 128), 128, ctx->stream, d_data, d_tmp, zt, T->m, q1, q2, n2, pre);
+    G753_LAUNCH(k_small_dft_c<FID>, div_up(N, 128), 128, ctx->stream, d_tmp, d_data, zt, T->m, q1, q2, n2);
+    ctx->launches += 2;
+    cols = d_data;
+    other = d_tmp;
+  } else {
+    G753_LAUNCH(k_small_dft<FID>, div_up(N, 128), 128, ctx->stream, d_data, d_tmp, zt, T->m, n2, pre);
+    ctx->launches++;
+  }
   // steps 2 + 3: twiddles as the pre table of the m batched radix-2 transforms
   NttCall c;
   c.inverse = inverse;
   c.batch = T->m;
   c.pre = T->tw + (inverse ? N : 0);
   c.pre_stride = n2;
-  G753_TRY(ntt_run<FID>(*T2, ctx->stream, d_tmp, d_data, c, &ctx->launches));
+  G753_TRY(ntt_run<FID>(*T2, ctx->stream, cols, other, c, &ctx->launches));
   // step 4: Z[k1][k2] -> out[k1 + m k2]
-  G753_LAUNCH(k_permute3, div_up(N, 256), 256, ctx->stream, d_tmp, d_data, T->m, (unsigned)n2, 1u, (size_t)1,
+  G753_LAUNCH(k_permute3, div_up(N, 256), 256, ctx->stream, cols, other, T->m, (unsigned)n2, 1u, (size_t)1,
               (size_t)T->m, (size_t)0);
   ctx->launches++;
   if (mode == G753_IFFT)
-    G753_LAUNCH(k_vec_scale<FID>, div_up(N, 256), 256, ctx->stream, d_data, T->consts + 2, (size_t)N);
+    G753_LAUNCH(k_vec_scale<FID>, div_up(N, 256), 256, ctx->stream, other, T->consts + 2, (size_t)N);
   else if (mode == G753_COSET_IFFT)
-    G753_LAUNCH(k_vec_op<FID>, div_up(N, 256), 256, ctx->stream, d_data, T->coset_inv, G753_OP_MUL, (size_t)N);
+    G753_LAUNCH(k_vec_op<FID>, div_up(N, 256), 256, ctx->stream, other, T->coset_inv, G753_OP_MUL, (size_t)N);
   if (inverse) ctx->launches++;
+  if (other != d_data) G753_TRY(d2d(d_data, other, sizeof(Fq) * N, ctx->stream));
   return launch_check("mixed_run");
 }
 
@@ -397,6 +409,83 @@ __global__ void __launch_bounds__(256) k_mac_probe(const Fq* seed, Fq* sink, int
     for (int i = 0; i < NL; i++) x.l[i] = (uint32_t)acc[i] ^ (uint32_t)(acc[i] >> 32);
   }
   if (x.l[0] == 0x12345678u && x.l[5] == 0x9abcdef0u) sink[t & 255] = x;  // keep the chain live
+}
+
+// latency probes of the warp-cooperative arithmetic (one warp): 5 = dependent coop_mul chain, 6 = dependent
+// fused linear operations, 7 = the G1 doubling micro-program, 8 = the G1 addition (head + tail)
+__global__ void __launch_bounds__(32) k_coop_probe(int variant, const Fq* seed, Fq* sink, int iters) {
+  extern __shared__ uint4 coop_probe_smem[];
+  CoopEc<0> ec;
+  ec.init((uint32_t*)coop_probe_smem);
+  typedef CoopGroup<0> Gp;
+  ec.w.load(Gp::P, seed, 4);
+  ec.w.load(Gp::Q, seed + 4, 4);
+  if (variant == 5) {
+    uint32_t A[3], B[3];
+    ec.w.ld(A, Gp::P);
+    ec.w.ld(B, Gp::Q);
+    for (int k = 0; k < iters; k++) coop_mul(A, A, B, ec.w.n, ec.w.np);
+    ec.w.st(Gp::P, A);
+  } else if (variant == 6) {
+    uint32_t A[3], B[3], Z[3] = {0, 0, 0};
+    ec.w.ld(A, Gp::P);
+    ec.w.ld(B, Gp::Q);
+    for (int k = 0; k < iters; k++) coop_add3(A, A, B, Z, 0);
+    ec.w.st(Gp::P, A);
+  } else if (variant == 7) {
+    for (int k = 0; k < iters; k++) ec.dbl();
+  } else {
+    for (int k = 0; k < iters; k++) ec.add_q();
+  }
+  ec.w.store(sink, Gp::P, 4);
+}
+
+// The OTHER multiplier pipe (bounded experiment): the instruction mix of a 753-bit Montgomery
+// product on 15 limbs of 52 bits through the FP64 unit.  A 52 x 52 -> 104 bit limb product is two DFMAs in
+// round-to-zero (hi = fma(a, b, 2^104) keeps the top 52 bits in its mantissa, lo = fma(a, b, 2^104 + 2^52 - hi)
+// the low 52) and one DADD; the raw bit patterns are summed as 64-bit integers column by column.  One
+// iteration = the 15 x 15 limb products of a x b plus the 15 x 15 of the reduction M x p (M folded from the
+// low columns) = 450 limb products, the count of one Montgomery product; the columns feed the next
+// iteration, so the chain is dependent like the IMAD probe's.
+__global__ void __launch_bounds__(256) k_dfma_probe(const double* seed, double* sink, int iters) {
+  constexpr int L = 15;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  double a[L], b[L], p[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) {
+    a[i] = seed[(t + i) & 255];
+    b[i] = seed[(t + 31 * i + 7) & 255];
+    p[i] = seed[(17 * i + 3) & 255];
+  }
+  const double C1 = 0x1p104, C2 = 0x1p104 + 0x1p52;
+  for (int k = 0; k < iters; k++) {
+    long long col[2 * L];
+#pragma unroll
+    for (int c = 0; c < 2 * L; c++) col[c] = 0;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+      for (int i = 0; i < L; i++) {
+        // second pass: the multiplier limb is derived from the running low column (the "M" of the reduction)
+        const double x = pass == 0 ? a[i] : (double)(col[i] & 0xFFFFFFFFFFFFFll);
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+          const double y = pass == 0 ? b[j] : p[j];
+          const double hi = __fma_rz(x, y, C1);
+          const double lo = __fma_rz(x, y, C2 - hi);
+          col[i + j + 1] += __double_as_longlong(hi);
+          col[i + j] += __double_as_longlong(lo);
+        }
+      }
+    }
+    // fold the upper columns back into the operand (keeps the chain dependent; exact values do not matter)
+#pragma unroll
+    for (int i = 0; i < L; i++) a[i] = (double)((col[L + i] ^ col[i]) & 0xFFFFFFFFFFFFFll);
+  }
+  double acc = 0;
+#pragma unroll
+  for (int i = 0; i < L; i++) acc += a[i];
+  if (acc == 1234.5) sink[t & 255] = acc;
 }
 #endif
 
@@ -1253,7 +1342,7 @@ int g753_ext_op(g753_ctx* ctx, int group, int lanes, int op, const uint64_t* a, 
 int g753_coop_op(g753_ctx* ctx, int field, int op, unsigned k, const uint64_t* a, const uint64_t* b, uint64_t* out,
                  size_t n) {
   CHECK_CTX(ctx);
-  if (!a || !b || !out || (field != 0 && field != 1) || op < 0 || op > 4 || k > 7) return fail(G753_ERR_BAD_ARG, "bad argument");
+  if (!a || !b || !out || (field != 0 && field != 1) || op < 0 || op > 4 || k > 11) return fail(G753_ERR_BAD_ARG, "bad argument");
   if (n == 0) return G753_OK;
 #if defined(G753_HOST_EMUL)
   return fail(G753_ERR_NO_DEVICE, "the warp-cooperative arithmetic runs on a GPU only");
@@ -1300,7 +1389,17 @@ int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iter
   cudaEventCreate(&e1);
   if (rc == G753_OK) {
     cudaEventRecord(e0, ctx->stream);
-    if (variant == 0) k_mac_probe<0><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
+    if (variant >= 5 && variant <= 8) {
+      k_coop_probe<<<1, 32, coop_smem_bytes<0>(1), ctx->stream>>>(variant, d_seed, d_seed + 256, iters);
+    } else if (variant == 4) {
+      // 256 doubles below 2^52 (exact integers) over the same seed buffer
+      std::vector<double> hd(256);
+      for (int i = 0; i < 256; i++) hd[i] = (double)((((uint64_t)h[2 * i] << 32) | h[2 * i + 1]) & 0xFFFFFFFFFFFFFull);
+      rc = h2d(d_seed, hd.data(), hd.size() * sizeof(double), ctx->stream);
+      if (rc == G753_OK) rc = stream_sync(ctx->stream);
+      cudaEventRecord(e0, ctx->stream);
+      k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>((const double*)d_seed, (double*)(d_seed + 256), iters);
+    } else if (variant == 0) k_mac_probe<0><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
     else if (variant == 1) k_mac_probe<1><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
     else if (variant == 3) k_mac_probe<3><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);
     else k_mac_probe<2><<<blocks, threads, 0, ctx->stream>>>(d_seed, d_seed + 256, iters);

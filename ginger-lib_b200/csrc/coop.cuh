@@ -30,8 +30,8 @@ namespace g753 {
 
 constexpr unsigned COOP_FULL = 0xffffffffu;
 constexpr unsigned COOP_HAS_MUL = 1u << 28, COOP_HAS_LIN = 1u << 29;
-enum { COOP_NOP = 0, COOP_MUL = 1, COOP_ADD = 2, COOP_SUB = 3, COOP_CPY = 4 };
-constexpr int COOP_KP_ROWS = 8;                      // 2^0 .. 2^7 times p
+enum { COOP_NOP = 0, COOP_MUL = 1, COOP_LIN = 2 };
+constexpr int COOP_KP_ROWS = 12;                     // 2^0 .. 2^11 times p
 constexpr int COOP_CONST_WORDS = COOP_KP_ROWS * 24;  // shared-memory words in front of a block's slots
 
 template <int FID> struct CoopField;
@@ -235,44 +235,63 @@ struct CoopWarp {
     __syncwarp();
   }
 
-  // interpret a micro-program (rows x 4 words); uniform control flow, no divergence inside a row
-  G753_D void run(const uint32_t* __restrict__ prog, unsigned rows) {
+  // acc (3 limbs + carry word) += c * x
+  static G753_D void mac3(uint32_t* acc, uint32_t& cw, const uint32_t* x, uint32_t c) {
+    acc[0] = mad_lo_cc(x[0], c, acc[0]);
+    acc[1] = madc_lo_cc(x[1], c, acc[1]);
+    acc[2] = madc_lo_cc(x[2], c, acc[2]);
+    cw = addc(cw, 0);
+    acc[1] = mad_hi_cc(x[0], c, acc[1]);
+    acc[2] = madc_hi_cc(x[1], c, acc[2]);
+    cw = madc_hi(x[2], c, cw);
+  }
+
+  // interpret a micro-program (rows of 4 instructions x 2 words, __constant__ memory); uniform control flow:
+  // in a row of products every octet multiplies, in a linear row every octet evaluates
+  // ca a + cb b + cc c (+ 2^k p), idle octets on harmless operands.
+  template <class PROG>
+  G753_D void run() {
     const unsigned o = coop_octet(), l = coop_lane();
-    for (unsigned r = 0; r < rows; r++) {
-      const uint32_t w0 = __ldg(prog + 4 * r);
-      const uint32_t w = __ldg(prog + 4 * r + o);
-      const unsigned op = w & 7u, d = (w >> 3) & 127u, a = (w >> 10) & 127u, b = (w >> 17) & 127u, k = (w >> 24) & 15u;
+    uint32_t nf = PROG::w(0), n0 = PROG::w(2 * o), n1 = PROG::w(2 * o + 1);
+#pragma unroll 1
+    for (unsigned r = 0; r < PROG::ROWS; r++) {
+      const uint32_t flags = nf, w0 = n0, w1 = n1;
+      if (r + 1 < PROG::ROWS) {        // the next row's words arrive while this row executes
+        nf = PROG::w(8 * (r + 1));
+        n0 = PROG::w(8 * (r + 1) + 2 * o);
+        n1 = PROG::w(8 * (r + 1) + 2 * o + 1);
+      }
+      const unsigned op = w0 & 7u, d = (w0 >> 3) & 127u, a = (w0 >> 10) & 127u, b = (w0 >> 17) & 127u, k = (w0 >> 24) & 15u;
       uint32_t A[3], B[3], R[3];
       ld(A, a);
       ld(B, b);
-      R[0] = A[0];
-      R[1] = A[1];
-      R[2] = A[2];   // COOP_CPY
-      if (w0 & COOP_HAS_MUL) {
-        uint32_t M[3];
-        coop_mul(M, A, B, n, np);
-        if (op == COOP_MUL) {
-          R[0] = M[0];
-          R[1] = M[1];
-          R[2] = M[2];
-        }
-      }
-      if (w0 & COOP_HAS_LIN) {
-        // add: A + B;  sub: A + ~B + 1 + 2^k p;  others: A + 0 (result unused)
-        uint32_t Y[3], Z[3], S[3];
-        const bool is_add = op == COOP_ADD, is_sub = op == COOP_SUB;
+      if (flags & COOP_HAS_MUL) {
+        coop_mul(R, A, B, n, np);
+      } else {
+        uint32_t C[3];
+        ld(C, w1 & 127u);
+        const uint32_t ca = (w1 >> 7) & 15u, cb = (w1 >> 12) & 15u, cc = (w1 >> 17) & 15u;
+        const bool na = (w1 >> 11) & 1u, nb = (w1 >> 16) & 1u, nc = (w1 >> 21) & 1u;
+        const bool neg = na || nb || nc;
         const uint32_t* kpl = kp + k * 24 + 3 * l;
+        uint32_t cw = 0;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-          Y[i] = is_add ? B[i] : is_sub ? ~B[i] : 0u;
-          Z[i] = is_sub ? kpl[i] : 0u;
+          R[i] = neg ? kpl[i] : 0u;
+          A[i] = na ? ~A[i] : A[i];
+          B[i] = nb ? ~B[i] : B[i];
+          C[i] = nc ? ~C[i] : C[i];
         }
-        coop_add3(S, A, Y, Z, (is_sub && l == 0) ? 1u : 0u);
-        if (is_add || is_sub) {
-          R[0] = S[0];
-          R[1] = S[1];
-          R[2] = S[2];
-        }
+        mac3(R, cw, A, ca);
+        mac3(R, cw, B, cb);
+        mac3(R, cw, C, cc);
+        // the + 1 of every complemented term enters at the lowest lane
+        const uint32_t inc = l == 0 ? (na ? ca : 0u) + (nb ? cb : 0u) + (nc ? cc : 0u) : 0u;
+        R[0] = add_cc(R[0], inc);
+        R[1] = addc_cc(R[1], 0);
+        R[2] = addc_cc(R[2], 0);
+        cw = addc(cw, 0);
+        coop_resolve(R, cw);
       }
       __syncwarp();
       if (op != COOP_NOP) st(d, R);
@@ -319,12 +338,12 @@ template <int GID> struct CoopGroup;
 #define G753_COOP_GROUP(GID, NAME, KK, FIELD)                                                                     \
   template <> struct CoopGroup<GID> {                                                                             \
     static constexpr int K = KK, FID = FIELD, P = 0, Q = 4 * KK, ONE = 8 * KK, SLOTS = COOP_##NAME##_SLOTS;       \
-    static G753_D CoopProg dbl() { return CoopProg{COOP_##NAME##_DBL, sizeof(COOP_##NAME##_DBL) / 16, 0}; }        \
-    static G753_D CoopProg add_head() { return CoopProg{COOP_##NAME##_ADD_HEAD, sizeof(COOP_##NAME##_ADD_HEAD) / 16, 0}; } \
-    static G753_D CoopProg add_tail() { return CoopProg{COOP_##NAME##_ADD_TAIL, sizeof(COOP_##NAME##_ADD_TAIL) / 16, 0}; } \
-    static G753_D CoopProg reduce() { return CoopProg{COOP_##NAME##_REDUCE, sizeof(COOP_##NAME##_REDUCE) / 16, 0}; }     \
-    static G753_D CoopProg to_proj() { return CoopProg{COOP_##NAME##_TO_PROJ, sizeof(COOP_##NAME##_TO_PROJ) / 16, 0}; }   \
-    static G753_D CoopProg from_proj() { return CoopProg{COOP_##NAME##_FROM_PROJ, sizeof(COOP_##NAME##_FROM_PROJ) / 16, 0}; } \
+    typedef COOP_##NAME##_DBL_P Dbl;                                                                               \
+    typedef COOP_##NAME##_ADD_HEAD_P AddHead;                                                                      \
+    typedef COOP_##NAME##_ADD_TAIL_P AddTail;                                                                      \
+    typedef COOP_##NAME##_REDUCE_P Reduce;                                                                         \
+    typedef COOP_##NAME##_TO_PROJ_P ToProj;                                                                        \
+    typedef COOP_##NAME##_FROM_PROJ_P FromProj;                                                                    \
     static G753_D const unsigned char* add_tp() { return COOP_##NAME##_ADD_TP; }                                   \
     static G753_D const unsigned char* add_tr() { return COOP_##NAME##_ADD_TR; }                                   \
   };
@@ -345,10 +364,9 @@ struct CoopEc {
     w.init(smem, Gp::SLOTS);
     w.set_one(Gp::ONE);
   }
-  G753_D void run(const CoopProg& p) { w.run(p.words, p.rows); }
   G753_D void set_inf() { w.set_zero(Gp::P, 4 * K); }
   G753_D bool is_inf() const { return w.is_zero(Gp::P + 2 * K, K); }
-  G753_D void dbl() { run(Gp::dbl()); }
+  G753_D void dbl() { w.template run<typename Gp::Dbl>(); }
   // P += Q, Q an XYZZ point in the Q slots (zero ZZ = infinity)
   G753_D void add_q() {
     if (w.is_zero(Gp::Q + 2 * K, K)) return;
@@ -356,7 +374,7 @@ struct CoopEc {
       w.copy(Gp::P, Gp::Q, 4 * K);
       return;
     }
-    run(Gp::add_head());
+    w.template run<typename Gp::AddHead>();
     bool pz = true, rz = true;
     for (int i = 0; i < K; i++) {
       pz = w.is_zero(Gp::add_tp()[i]) && pz;
@@ -367,7 +385,7 @@ struct CoopEc {
       else set_inf();         // P == -Q
       return;
     }
-    run(Gp::add_tail());
+    w.template run<typename Gp::AddTail>();
   }
   G753_D void add_g(const Fq* q_xyzz) {
     w.load(Gp::Q, q_xyzz, 4 * K);
@@ -377,7 +395,7 @@ struct CoopEc {
   G753_D void add_projective_g(const Fq* q_xyz) {
     w.load(Gp::Q, q_xyz, 3 * K);
     if (w.is_zero(Gp::Q + 2 * K, K)) return;    // Z == 0: the point at infinity
-    run(Gp::from_proj());
+    w.template run<typename Gp::FromProj>();
     add_q();
   }
   // P -> the reference's homogeneous projective, canonical, (0 : 1 : 0) for infinity; written to out_xyz
@@ -386,7 +404,7 @@ struct CoopEc {
       w.set_zero(Gp::P, 3 * K);
       w.copy(Gp::P + K, Gp::ONE, 1);
     } else {
-      run(Gp::to_proj());
+      w.template run<typename Gp::ToProj>();
       w.canonicalize(Gp::P, 3 * K);
     }
     w.store(out_xyz, Gp::P, 3 * K);
@@ -396,7 +414,7 @@ struct CoopEc {
     if (is_inf()) {
       w.set_zero(Gp::P, 4 * K);    // all-zero limbs, the encoding of infinity the slot kernels use
     } else {
-      run(Gp::reduce());           // X, Y below 2 p (ZZ, ZZZ are); then one conditional subtraction each
+      w.template run<typename Gp::Reduce>();   // X, Y below 2 p (ZZ, ZZZ are); then one conditional subtraction each
       w.canonicalize(Gp::P, 4 * K);
     }
     w.store(out, Gp::P, 4 * K);

@@ -87,6 +87,63 @@ k_small_dft(const Fq* __restrict__ in, Fq* __restrict__ out, const Fq* __restric
   out[t] = acc;
 }
 
+// The same column DFT of length m = q1 q2 in two stages (Cooley-Tukey on the odd part: i1 = a q2 + b,
+// k1 = c + q1 d):
+//   stage A:  T[b][c] = zeta^(b c) * sum_a in[a q2 + b] (zeta^q2)^(a c)        q1 + 1 products per element
+//   stage C:  out[c + q1 d] = sum_b T[b][c] (zeta^q1)^(b d)                     q2 products per element
+// instead of m: 25 points = 5 x 5 cost ~10 products per element instead of 25 (trivial factors are skipped).
+template <int FID>
+__global__ void __launch_bounds__(128)
+k_small_dft_a(const Fq* __restrict__ in, Fq* __restrict__ tmp, const Fq* __restrict__ zt, unsigned m, unsigned q1,
+              unsigned q2, size_t n2, const Fq* __restrict__ pre) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)m * n2) return;
+  const size_t i2 = t % n2;
+  const unsigned bc = (unsigned)(t / n2), b = bc / q1, c = bc % q1;   // tmp layout [b][c][i2]
+  Fq acc = fq_zero<FID>();
+  const unsigned step = (q2 * c) % m;
+  unsigned e = 0;  // (a q2 c) mod m
+  for (unsigned a = 0; a < q1; a++) {
+    const size_t src = (size_t)(a * q2 + b) * n2 + i2;
+    Fq v = in[src];
+    if (pre != nullptr) v = fq_mul<FID>(v, pre[src]);
+    if (e != 0) v = fq_mul<FID>(v, zt[e]);
+    acc = fq_add<FID>(acc, v);
+    e += step;
+    if (e >= m) e -= m;
+  }
+  const unsigned tw = (b * c) % m;
+  if (tw != 0) acc = fq_mul<FID>(acc, zt[tw]);
+  tmp[t] = acc;
+}
+template <int FID>
+__global__ void __launch_bounds__(128)
+k_small_dft_c(const Fq* __restrict__ tmp, Fq* __restrict__ out, const Fq* __restrict__ zt, unsigned m, unsigned q1,
+              unsigned q2, size_t n2) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)m * n2) return;
+  const size_t i2 = t % n2;
+  const unsigned k1 = (unsigned)(t / n2), c = k1 % q1, d = k1 / q1;   // out row k1 = c + q1 d
+  Fq acc = fq_zero<FID>();
+  const unsigned step = (q1 * d) % m;
+  unsigned e = 0;  // (b q1 d) mod m
+  for (unsigned b = 0; b < q2; b++) {
+    Fq v = tmp[(size_t)(b * q1 + c) * n2 + i2];
+    if (e != 0) v = fq_mul<FID>(v, zt[e]);
+    acc = fq_add<FID>(acc, v);
+    e += step;
+    if (e >= m) e -= m;
+  }
+  out[t] = acc;
+}
+// m = q1 q2 with q1 the largest divisor of m not above sqrt(m) (1 for a prime: single stage)
+static inline unsigned mixed_q1(unsigned m) {
+  unsigned best = 1;
+  for (unsigned q = 2; q * q <= m; q++)
+    if (m % q == 0) best = q;
+  return best;
+}
+
 static inline bool div_small_768(const uint32_t* num, uint64_t d, uint32_t* quo) {
   // quo = num / d for a 768-bit num and d < 2^32; returns true when the division is exact
   uint64_t rem = 0;

@@ -58,8 +58,8 @@ constexpr int SLOT_CHUNKS = NL / 4;  // 6 x 16 bytes per Fq
 template <int NC_, int TP_>
 struct Lay {
   static constexpr int NC = NC_, TP = TP_, CPW = 32 / TP_;  // CPW: columns per warp
-  static constexpr int THREADS = NC_ / CPW * 32;             // whole warps (= NC * TP when TP divides 32)
-  static_assert(NC_ % CPW == 0, "columns per block must fill whole warps");
+  static constexpr int THREADS = TP_ == 1 ? NC_ : NC_ / CPW * 32;   // whole warps (= NC * TP when TP divides 32)
+  static_assert(TP_ == 1 || NC_ % CPW == 0, "columns per block must fill whole warps");
   static G753_D int col() {
     if (TP == 1) return (int)threadIdx.x;
     return (int)(threadIdx.x >> 5) * CPW + (int)((threadIdx.x & 31) % CPW);

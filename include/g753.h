@@ -267,7 +267,9 @@ int g753_coop_op(g753_ctx* ctx, int field, int op, unsigned k, const uint64_t* a
 /* Run `iters` dependent Montgomery multiplications per thread on `blocks` x `threads`
  * threads and report the kernel time in ms (CUDA events): the integer-pipe roofline probe
  * of SURVEY.md 8d.  variant 0 = fq_mul, 1 = fq_sqr, 2 = raw independent IMAD.WIDE stream,
- * 3 = fq_inv (safegcd) */
+ * 3 = fq_inv (safegcd), 4 = the instruction mix of one 753-bit Montgomery product on 15 x 52-bit limbs through the
+ * FP64 pipe (2 DFMA + 1 DADD + 2 integer adds per limb product; a measurement of the other multiplier pipe, not a
+ * multiplier) */
 int g753_mac_probe(g753_ctx* ctx, int variant, int blocks, int threads, int iters, float* ms);
 /* debugging aid: copy the first `bytes` of the MSM workspace to the host; *cap = its size */
 int g753_debug_scratch(g753_ctx* ctx, void* h_dst, size_t bytes, size_t* cap);

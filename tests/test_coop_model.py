@@ -56,6 +56,22 @@ def test_lane_arithmetic(fid):
             for k in range(GC.MAX_K_LOG + 1):
                 if b <= (p << k) and a + (p << k) - b < R:
                     assert GC.join(f.sub(GC.split(a), GC.split(b), k)) == a + (p << k) - b
+    # the fused linear operation ca a +- cb b +- cc c (+ 2^k p)
+    for _ in range(300):
+        terms, want, neg = [], 0, 0
+        for _ in range(rng.randrange(1, 4)):
+            x, c = rng.choice(vals), rng.randrange(1, GC.CMAX + 1) * rng.choice((1, -1))
+            terms.append((x, c))
+            want += c * x
+            neg += -c * x if c < 0 else 0
+        k = 0
+        while (p << k) < neg:
+            k += 1
+        if k > GC.MAX_K_LOG or not any(c < 0 for _, c in terms):
+            k = 0
+        want += (p << k) if any(c < 0 for _, c in terms) else 0
+        if 0 <= want < R:
+            assert GC.join(f.lin([(GC.split(x), c) for x, c in terms], k)) == want
     for a in [0, 1, p - 1, p, p + 1, 2 * p - 1] + [rng.randrange(0, 2 * p) for _ in range(40)]:
         assert GC.join(f.cond_sub_p(GC.split(a))) == a % p
         assert f.is_zero_mod_p(GC.split(a)) == (a % p == 0)

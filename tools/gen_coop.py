@@ -13,6 +13,10 @@ shared-memory slots) which csrc/coop.cuh interprets; this file is also their exa
   * Builder / Fk      formulas as a DAG over base-field operations (towers expanded: Karatsuba Fq2 /
                       Fq3 products, complex / Chung-Hasan squarings - fp2.rs:128-144, 387-401,
                       fp3.rs:165-185, 451-478; XYZZ dbl-2008-s-1 / add-2008-s / madd-2008-s)
+  * linear algebra    sums, differences and small multiples are kept as LINEAR EXPRESSIONS over the products and
+                      inputs and only materialised - as ONE fused operation of up to three terms,
+                      d = ca A +- cb B +- cc C (+ 2^k p) - where a product or an output needs them: chains like
+                      M = 3 X^2 + a ZZ^2, X3 = M^2 - 2 S, S - X3 = 3 S - M^2 collapse into single rows
   * schedule()        list scheduling into levels (linear operations first, then up to 4 products)
   * allocate()        slot allocation with in-place outputs
   * bounds            values are kept LAZILY reduced: a product of inputs < x p, y p is
@@ -30,13 +34,14 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-NOP, MUL, ADD, SUB, CPY = 0, 1, 2, 3, 4
-OPNAME = {NOP: "nop", MUL: "mul", ADD: "add", SUB: "sub", CPY: "cpy"}
+NOP, MUL, LIN = 0, 1, 2
+OPNAME = {NOP: "nop", MUL: "mul", LIN: "lin"}
+CMAX = 15                              # largest |coefficient| of a fused linear operation
 LANES, LPL = 8, 3                      # lanes per field element, limbs per lane
 MASK32 = 0xFFFFFFFF
 MASK96 = (1 << 96) - 1
 R_BITS = 768
-MAX_K_LOG = 7                          # K p tables for K = 2^0 .. 2^7
+MAX_K_LOG = 11                         # K p tables for K = 2^0 .. 2^11
 MUL_HEADROOM = 1 << 15                 # R / p >= 2^15 for both fields
 
 
@@ -44,92 +49,171 @@ MUL_HEADROOM = 1 << 15                 # R / p >= 2^15 for both fields
 # formula DAG
 # ---------------------------------------------------------------------------------------------
 class Node:
-    __slots__ = ("op", "a", "b", "bound", "k", "idx", "slot", "level", "name", "pin")
+    """op "in" (input slot), MUL (a, b) or LIN (terms = [(node, coef)], adds 2^k p when a coef is negative)"""
+    __slots__ = ("op", "a", "b", "terms", "bound", "k", "idx", "slot", "level", "name")
 
-    def __init__(self, op, a=None, b=None, bound=1.0, k=0, name=""):
-        self.op, self.a, self.b, self.bound, self.k, self.name = op, a, b, bound, k, name
+    def __init__(self, op, a=None, b=None, terms=None, bound=1.0, k=0, name=""):
+        self.op, self.a, self.b, self.terms, self.bound, self.k, self.name = op, a, b, terms, bound, k, name
         self.idx = -1
         self.slot = None
         self.level = -1
-        self.pin = None
+
+    def operands(self):
+        if self.op == MUL:
+            return [self.a, self.b]
+        if self.op == LIN:
+            return [n for n, _ in self.terms]
+        return []
 
 
 REDUCE_ABOVE = 181.0      # sqrt(2^15): any two values at or below it may be multiplied
 
 
+def _klog(x):
+    k = 0
+    while (1 << k) < x:
+        k += 1
+    return k
+
+
+class Val:
+    """a linear expression sum_i coef_i * node_i over inputs and products (never over other sums)"""
+    __slots__ = ("b", "e")
+
+    def __init__(self, bld, expr):
+        self.b = bld
+        self.e = {i: c for i, c in expr.items() if c}
+
+    @property
+    def bound(self):
+        nodes = self.b.nodes
+        pos = sum(c * nodes[i].bound for i, c in self.e.items() if c > 0)
+        neg = sum(-c * nodes[i].bound for i, c in self.e.items() if c < 0)
+        return pos + ((1 << _klog(neg)) if neg > 0 else 0.0)
+
+
 class Builder:
     def __init__(self, one_slot=None):
         self.nodes = []
-        self.inputs = []
         self.one_slot = one_slot
         self._one = None
         self._reduced = {}
-
-    def one(self):
-        if self._one is None:
-            self._one = self.inp(self.one_slot, 1.0, "one")
-        return self._one
-
-    def reduce(self, a):
-        """a -> a R R^-1 = a (mod p), below (1 + bound / 2^15) p: one Montgomery product by ONE"""
-        if a.idx not in self._reduced:
-            n = self._add(Node(MUL, a, self.one(), bound=1.0 + a.bound / MUL_HEADROOM))
-            self._reduced[a.idx] = n
-        return self._reduced[a.idx]
+        self._lin = {}
 
     def _add(self, n):
         n.idx = len(self.nodes)
         self.nodes.append(n)
         return n
 
+    def _val(self, node):
+        return Val(self, {node.idx: 1})
+
     def inp(self, slot, bound, name=""):
         n = self._add(Node("in", bound=float(bound), name=name))
         n.slot = slot
-        self.inputs.append(n)
-        return n
+        return self._val(n)
 
-    def mul(self, a, b):
-        # lazily reduced operands: bring the larger one down when the product would leave the headroom
-        while a.bound * b.bound > MUL_HEADROOM:
-            if a.bound >= b.bound:
-                assert a.bound > 2.0
-                a = self.reduce(a)
-                if a is b:
-                    b = a
-            else:
-                b = self.reduce(b)
-        xy = a.bound * b.bound
-        return self._add(Node(MUL, a, b, bound=1.0 + xy / MUL_HEADROOM))
+    def one(self):
+        if self._one is None:
+            self._one = self.inp(self.one_slot, 1.0, "one")
+        return self._one
 
+    # ---- linear algebra: no operations are emitted here -------------------------------------------------
     def add(self, a, b):
-        return self._add(Node(ADD, a, b, bound=a.bound + b.bound))
+        e = dict(a.e)
+        for i, c in b.e.items():
+            e[i] = e.get(i, 0) + c
+        return Val(self, e)
 
     def sub(self, a, b):
-        if b.bound > (1 << MAX_K_LOG):
-            b = self.reduce(b)
-        k = 0
-        while (1 << k) < b.bound:
-            k += 1
-        assert k <= MAX_K_LOG, "subtrahend bound too large"
-        return self._add(Node(SUB, a, b, bound=a.bound + (1 << k), k=k))
+        e = dict(a.e)
+        for i, c in b.e.items():
+            e[i] = e.get(i, 0) - c
+        return Val(self, e)
 
     def small(self, a, c):
-        """c * a for a small positive integer c by doubling and adding (the curve / non-residue constants
-        2, 11, 13, 26, 121 of SURVEY.md appendix A)"""
-        assert c >= 1
-        acc = None
-        pw = a
-        while c:
-            if c & 1:
-                acc = pw if acc is None else self.add(acc, pw)
-            c >>= 1
-            if c:
-                pw = self.add(pw, pw)
-        return acc
+        """c * a for a small positive integer c (the curve / non-residue constants 2, 11, 13, 26, 121 of
+        SURVEY.md appendix A)"""
+        return Val(self, {i: c * x for i, x in a.e.items()})
+
+    # ---- materialisation -----------------------------------------------------------------------------------
+    def _reduce_node(self, n):
+        """n -> n R R^-1 = n (mod p), below (1 + bound / 2^15) p: one Montgomery product by ONE"""
+        if n.idx not in self._reduced:
+            one = self.node_of(self.one())
+            self._reduced[n.idx] = self._add(Node(MUL, n, one, bound=1.0 + n.bound / MUL_HEADROOM))
+        return self._reduced[n.idx]
+
+    def reduce(self, a):
+        return self._val(self._reduce_node(self.node_of(a)))
+
+    def _lin_node(self, terms):
+        """one fused operation: terms = [(node, coef)], at most three, |coef| <= CMAX"""
+        assert 1 <= len(terms) <= 3 and all(0 < abs(c) <= CMAX for _, c in terms)
+        key = tuple(sorted((n.idx, c) for n, c in terms))
+        if key in self._lin:
+            return self._lin[key]
+        while True:
+            pos = sum(c * n.bound for n, c in terms if c > 0)
+            neg = sum(-c * n.bound for n, c in terms if c < 0)
+            k = _klog(neg) if neg > 0 else 0
+            if k <= MAX_K_LOG and pos + (1 << k) < (1 << 14):
+                break
+            # bring the largest operand down first
+            j = max(range(len(terms)), key=lambda t: abs(terms[t][1]) * terms[t][0].bound)
+            assert terms[j][0].bound > 2.0, "cannot bound a linear operation"
+            terms = [(self._reduce_node(n) if t == j else n, c) for t, (n, c) in enumerate(terms)]
+        node = self._add(Node(LIN, terms=list(terms), bound=pos + ((1 << k) if neg > 0 else 0.0), k=k))
+        self._lin[key] = node
+        return node
+
+    def node_of(self, v, force=False):
+        """the node holding v: an input / product itself, or fused linear operations computing it"""
+        nodes = self.nodes
+        terms = sorted(((nodes[i], c) for i, c in v.e.items()), key=lambda t: (-(abs(t[1]) * t[0].bound), t[0].idx))
+        assert terms, "the zero expression has no node"
+        if len(terms) == 1 and terms[0][1] == 1 and not force:
+            return terms[0][0]
+        # coefficients beyond CMAX: scale the operand in steps (121 = 11 * 11, 26 * 5 = 13 * 10 ...)
+        fixed = []
+        for n, c in terms:
+            while abs(c) > CMAX:
+                f = next((d for d in range(CMAX, 1, -1) if abs(c) % d == 0), None)
+                if f is None:                         # no small factor: c x = CMAX (q x) ... + r x handled as two terms
+                    q, r = divmod(abs(c), CMAX)
+                    t = self._lin_node([(n, CMAX)])
+                    sgn = 1 if c > 0 else -1
+                    if r:
+                        fixed.append((n, sgn * r))
+                    n, c = t, sgn * q
+                else:
+                    n = self._lin_node([(n, f)])
+                    c = c // f
+            fixed.append((n, c))
+        terms = fixed
+        # more than three terms: fold the three heaviest into a temporary first
+        while len(terms) > 3:
+            t = self._lin_node(terms[:3])
+            terms = [(t, 1)] + terms[3:]
+        return self._lin_node(terms)
+
+    def mul(self, a, b):
+        na, nb = self.node_of(a), self.node_of(b)
+        same = na is nb
+        # lazily reduced operands: bring the larger one down when the product would leave the headroom
+        while na.bound * nb.bound > MUL_HEADROOM:
+            if na.bound >= nb.bound:
+                assert na.bound > 2.0
+                na = self._reduce_node(na)
+                if same:
+                    nb = na
+            else:
+                nb = self._reduce_node(nb)
+        return self._val(self._add(Node(MUL, na, nb, bound=1.0 + na.bound * nb.bound / MUL_HEADROOM)))
 
 
 class Fk:
-    """element of Fq, Fq2 = Fq[u]/(u^2 - nr) or Fq3 = Fq[u]/(u^3 - nr) as a tuple of DAG nodes"""
+    """element of Fq, Fq2 = Fq[u]/(u^2 - nr) or Fq3 = Fq[u]/(u^3 - nr) as a tuple of linear expressions"""
 
     def __init__(self, bld, c, nr):
         self.b, self.c, self.nr = bld, tuple(c), nr
@@ -175,23 +259,17 @@ class Fk:
         B, nr = self.b, self.nr
         a = self.c
         if self.k == 1:
-            x = a[0]
-            while x.bound * x.bound > MUL_HEADROOM:
-                x = B.reduce(x)
-            return self._w([B.mul(x, x)])
+            return self._w([B.mul(a[0], a[0])])
         if self.k == 2:     # complex squaring, fp2.rs:128-144
             ab = B.mul(a[0], a[1])
             t = B.mul(B.add(a[0], a[1]), B.add(a[0], B.small(a[1], nr)))
             c0 = B.sub(B.sub(t, ab), B.small(ab, nr))
             return self._w([c0, B.add(ab, ab)])
         # Chung-Hasan SQR2, fp3.rs:165-185
-        a = [B.reduce(x) if x.bound > REDUCE_ABOVE else x for x in a]
         s0 = B.mul(a[0], a[0])
         ab = B.mul(a[0], a[1])
         s1 = B.add(ab, ab)
         t = B.add(B.sub(a[0], a[1]), a[2])
-        if t.bound > REDUCE_ABOVE:
-            t = B.reduce(t)
         s2 = B.mul(t, t)
         bc = B.mul(a[1], a[2])
         s3 = B.add(bc, bc)
@@ -288,8 +366,8 @@ def formula_add_head(g, mixed):
     Pd = X2 * ZZ1 - U1
     Rd = Y2 * ZZZ1 - S1
     k, nr = g["k"], g["nr"]
-    tP = Fk(bld, [bld.mul(c, one) for c in Pd.c], nr)
-    tR = Fk(bld, [bld.mul(c, one) for c in Rd.c], nr)
+    tP = Fk(bld, [bld.reduce(c) for c in Pd.c], nr)
+    tR = Fk(bld, [bld.reduce(c) for c in Rd.c], nr)
     return bld, lay, dict(U1=U1, S1=S1, Pd=Pd, Rd=Rd, tP=tP, tR=tR)
 
 
@@ -328,9 +406,8 @@ def formula_to_projective(g):
     lay = Layout(g["k"])
     bld = Builder(lay.ONE)
     X, Y, ZZ, ZZZ = _point(bld, g, lay.P, ACC_BOUND, "P")
-    outs = dict(X=X * ZZZ, Y=Y * ZZ, ZZ=ZZ * ZZZ)
-    # below 2 p, so that one conditional subtraction makes them canonical
-    return bld, lay, close_outputs(bld, outs, dict(X=2.0, Y=2.0, ZZ=2.0))
+    # (compiled with the limit 2 p, so that one conditional subtraction makes the coordinates canonical)
+    return bld, lay, dict(X=X * ZZZ, Y=Y * ZZ, ZZ=ZZ * ZZZ)
 
 
 def formula_reduce(g):
@@ -359,17 +436,30 @@ def formula_from_projective(g):
 # ---------------------------------------------------------------------------------------------
 # scheduling and slot allocation
 # ---------------------------------------------------------------------------------------------
-def live_nodes(bld, outputs):
+def output_nodes(bld, outputs, limit=None):
+    """materialise the output expressions; where a lazily reduced value would exceed the accumulator's
+    persistent bound it goes through a product by ONE.  name -> list of nodes (one per tower coefficient)"""
+    out = {}
+    for nm, v in outputs.items():
+        nodes = []
+        for x in v.c:
+            n = bld.node_of(x)
+            if limit is not None and nm in limit and n.bound > limit[nm]:
+                n = bld._reduce_node(n)
+            nodes.append(n)
+        out[nm] = nodes
+    return out
+
+
+def live_nodes(bld, out_nodes):
     keep = set()
-    stack = [n for v in outputs.values() for n in v.c]
+    stack = [n for ns in out_nodes.values() for n in ns]
     while stack:
         n = stack.pop()
         if n.idx in keep:
             continue
         keep.add(n.idx)
-        for x in (n.a, n.b):
-            if x is not None:
-                stack.append(x)
+        stack.extend(n.operands())
     return [n for n in bld.nodes if n.idx in keep]
 
 
@@ -379,27 +469,21 @@ def schedule(nodes):
     height = {}
     users = {n.idx: [] for n in nodes}
     for n in nodes:
-        for x in (n.a, n.b):
-            if x is not None:
-                users[x.idx].append(n)
+        for x in n.operands():
+            users[x.idx].append(n)
     for n in reversed(nodes):
         h = 0
         for u in users[n.idx]:
             h = max(h, height[u.idx])
-        height[n.idx] = h + (10 if n.op == MUL else 1 if n.op in (ADD, SUB) else 0)
+        height[n.idx] = h + (10 if n.op == MUL else 2 if n.op == LIN else 0)
     done = {n.idx for n in nodes if n.op == "in"}
     pending = [n for n in nodes if n.op != "in"]
     levels = []
     while pending:
-        ready = [n for n in pending if all(x is None or x.idx in done for x in (n.a, n.b))]
+        ready = [n for n in pending if all(x.idx in done for x in n.operands())]
         assert ready
-        lin = [n for n in ready if n.op in (ADD, SUB)]
-        if lin:
-            lin.sort(key=lambda n: -height[n.idx])
-            take = lin[:4]
-        else:
-            muls = sorted(ready, key=lambda n: -height[n.idx])
-            take = muls[:4]
+        lin = [n for n in ready if n.op == LIN]
+        take = sorted(lin if lin else ready, key=lambda n: -height[n.idx])[:4]
         for n in take:
             n.level = len(levels)
             done.add(n.idx)
@@ -408,42 +492,40 @@ def schedule(nodes):
     return levels
 
 
-def allocate(bld, nodes, levels, outputs, out_base, lay, n_slots_hint=0, extra_pinned=None):
+def allocate(nodes, levels, out_nodes, out_base, lay):
     """slots for every node.  Inputs sit in their fixed slots; output coordinate `name` is pinned to the
     accumulator slot out_base + index; everything else takes scratch slots.  Within a level all operands
-    are read before any result is written, so a slot whose last reader is in level t may be written in t."""
+    are read before any result is written, so a slot whose last reader is in level t may be written in t.
+    Returns the (slot, node) copies still to be made (pinned slot busy, or the output is an input) and the
+    number of slots used."""
     k = lay.k
     order = {"X": 0, "Y": 1, "ZZ": 2, "ZZZ": 3}
     pinned = {}
     if out_base is not None:
-        for name, v in outputs.items():
+        for name, ns in out_nodes.items():
             if name in order:
-                for j, n in enumerate(v.c):
+                for j, n in enumerate(ns):
                     pinned[n.idx] = out_base + order[name] * k + j
     last_use = {n.idx: -1 for n in nodes}
     for lv, ops in enumerate(levels):
         for n in ops:
-            for x in (n.a, n.b):
-                if x is not None:
-                    last_use[x.idx] = max(last_use[x.idx], lv)
-    out_nodes = {n.idx for v in outputs.values() for n in v.c}
+            for x in n.operands():
+                last_use[x.idx] = max(last_use[x.idx], lv)
     INF = 1 << 30
-    for i in out_nodes:
-        last_use[i] = INF
+    for ns in out_nodes.values():
+        for n in ns:
+            last_use[n.idx] = INF
     occupied = {}     # slot -> node idx
     for n in nodes:
         if n.op == "in":
             occupied[n.slot] = n.idx
-    # slots that hold caller state and are not inputs of this program must not be clobbered: the
-    # allocator only hands out scratch slots and the pinned output slots
     scratch_next = [max([lay.SCRATCH] + [n.slot + 1 for n in nodes if n.op == "in"])]
     free_scratch = []
     copies = []
-    byidx = {n.idx: n for n in nodes}
 
     def release(level):
         for s, i in list(occupied.items()):
-            if last_use[i] <= level and last_use[i] != INF:
+            if last_use[i] <= level:
                 del occupied[s]
                 if s >= lay.SCRATCH:
                     free_scratch.append(s)
@@ -467,35 +549,50 @@ def allocate(bld, nodes, levels, outputs, out_base, lay, n_slots_hint=0, extra_p
                 if want is not None:
                     copies.append((want, n))
             occupied[n.slot] = n.idx
-    # an output that IS an input node (e.g. U1 = X1 in the mixed addition) keeps its slot
+    for n in nodes:                      # an output that IS an input but belongs elsewhere
+        if n.op == "in" and n.idx in pinned and pinned[n.idx] != n.slot:
+            copies.append((pinned[n.idx], n))
     n_slots = max([scratch_next[0]] + [n.slot + 1 for n in nodes if n.slot is not None])
     return copies, n_slots
-
-
-def encode(op, d, a, b, k=0):
-    assert 0 <= d < 128 and 0 <= a < 128 and 0 <= b < 128 and 0 <= k < 16
-    return op | (d << 3) | (a << 10) | (b << 17) | (k << 24)
 
 
 HAS_MUL, HAS_LIN = 1 << 28, 1 << 29
 
 
+def encode(op, d=0, terms=(), k=0):
+    """two 32-bit words: op (3 bits) | dst << 3 | a << 10 | b << 17 | k << 24   and
+    c | (|ca| << 7) | (sign a << 11) | (|cb| << 12) | (sign b << 16) | (|cc| << 17) | (sign c << 21);
+    a product uses a and b only"""
+    slots = [t[0] for t in terms] + [0] * (3 - len(terms))
+    coefs = [t[1] for t in terms] + [0] * (3 - len(terms))
+    assert all(0 <= x < 128 for x in slots + [d]) and 0 <= k < 16 and all(abs(c) <= CMAX for c in coefs)
+    w0 = op | (d << 3) | (slots[0] << 10) | (slots[1] << 17) | (k << 24)
+    w1 = slots[2]
+    for j, c in enumerate(coefs):
+        w1 |= (abs(c) << (7 + 5 * j)) | ((1 if c < 0 else 0) << (11 + 5 * j))
+    return w0, w1
+
+
 def assemble(levels, copies):
-    words = []
+    """rows of 4 instructions (one per octet) of two words each; word 0 of a row carries its flags"""
+    rows = []
+
+    def row_of(instrs, flags):
+        instrs = instrs + [encode(NOP)] * (4 - len(instrs))
+        words = [w for ins in instrs for w in ins]
+        words[0] |= flags
+        return words
     for ops in levels:
-        row = []
+        instrs = []
         for n in ops:
-            row.append(encode(n.op, n.slot, n.a.slot, n.b.slot, n.k))
-        row += [encode(NOP, 0, 0, 0)] * (4 - len(row))
-        flags = (HAS_MUL if any(n.op == MUL for n in ops) else 0) | (HAS_LIN if any(n.op in (ADD, SUB) for n in ops) else 0)
-        row[0] |= flags
-        words.append(row)
+            if n.op == MUL:
+                instrs.append(encode(MUL, n.slot, [(n.a.slot, 1), (n.b.slot, 1)]))
+            else:
+                instrs.append(encode(LIN, n.slot, [(x.slot, c) for x, c in n.terms], n.k))
+        rows.append(row_of(instrs, HAS_MUL if ops[0].op == MUL else HAS_LIN))
     for i in range(0, len(copies), 4):
-        row = [encode(CPY, d, n.slot, 0) for d, n in copies[i:i + 4]]
-        row += [encode(NOP, 0, 0, 0)] * (4 - len(row))
-        row[0] |= HAS_LIN
-        words.append(row)
-    return words
+        rows.append(row_of([encode(LIN, d, [(n.slot, 1)]) for d, n in copies[i:i + 4]], HAS_LIN))
+    return rows
 
 
 class Program:
@@ -503,67 +600,51 @@ class Program:
         self.name, self.words, self.n_slots, self.info = name, words, n_slots, info
 
 
-def close_outputs(bld, outputs, limit):
-    """bring every output coordinate under the accumulator's persistent bound (a product by ONE where
-    the lazily reduced value would exceed it)"""
-    for nm, v in list(outputs.items()):
-        if nm in limit:
-            outputs[nm] = v._w([bld.reduce(n) if n.bound > limit[nm] else n for n in v.c])
-    return outputs
-
-
-def compile_formula(name, bld, lay, outputs, out_base, check_closed=True):
-    if check_closed:
-        outputs = close_outputs(bld, outputs, ACC_BOUND)
-    nodes = live_nodes(bld, outputs)
+def compile_formula(name, bld, lay, outputs, out_base, limit=None):
+    out_nodes = output_nodes(bld, outputs, limit)
+    nodes = live_nodes(bld, out_nodes)
     levels = schedule(nodes)
-    copies, n_slots = allocate(bld, nodes, levels, outputs, out_base, lay)
-    if check_closed:
-        for nm, v in outputs.items():
-            if nm in ACC_BOUND:
-                for n in v.c:
-                    assert n.bound <= ACC_BOUND[nm], "%s: output %s bound %g exceeds the accumulator's %g" % (
-                        name, nm, n.bound, ACC_BOUND[nm])
+    for ops in levels:
+        assert len({n.op for n in ops}) == 1
+    copies, n_slots = allocate(nodes, levels, out_nodes, out_base, lay)
+    if limit is not None:
+        for nm, ns in out_nodes.items():
+            if nm in limit:
+                for n in ns:
+                    assert n.bound <= limit[nm], "%s: output %s bound %g exceeds %g" % (name, nm, n.bound, limit[nm])
     for n in nodes:
         assert n.bound < (1 << 15), "value may exceed 2^768"
-    info = dict(levels=len(levels), mul_levels=sum(1 for ops in levels if any(n.op == MUL for n in ops)),
-                muls=sum(1 for n in nodes if n.op == MUL), lin=sum(1 for n in nodes if n.op in (ADD, SUB)),
-                copies=len(copies))
-    return Program(name, assemble(levels, copies), n_slots, info)
+    info = dict(rows=len(levels) + (len(copies) + 3) // 4, mul_rows=sum(1 for ops in levels if ops[0].op == MUL),
+                muls=sum(1 for n in nodes if n.op == MUL), lins=sum(1 for n in nodes if n.op == LIN), copies=len(copies))
+    prog = Program(name, assemble(levels, copies), n_slots, info)
+    prog.out_nodes = out_nodes
+    return prog
 
 
 def build_group(gid, with_mixed=True):
     g = GROUPS[gid]
     progs = {}
     bld, lay, outs = formula_dbl(g)
-    progs["dbl"] = compile_formula("dbl", bld, lay, outs, lay.P)
+    progs["dbl"] = compile_formula("dbl", bld, lay, outs, lay.P, ACC_BOUND)
     bld, lay, outs = formula_reduce(g)
-    progs["reduce"] = compile_formula("reduce", bld, lay, outs, lay.P, check_closed=False)
+    progs["reduce"] = compile_formula("reduce", bld, lay, outs, lay.P, dict(X=2.0, Y=2.0))
     for mixed in ((False, True) if with_mixed else (False,)):
         tag = "madd" if mixed else "add"
         bld, lay, outs = formula_add_head(g, mixed)
-        nodes = live_nodes(bld, outs)
-        levels = schedule(nodes)
         # the head's results stay in scratch for the tail: no pinned outputs
-        copies, n_slots = allocate(bld, nodes, levels, outs, None, lay)
-        assert not copies
-        head = Program(tag + "_head", assemble(levels, []), n_slots,
-                       dict(levels=len(levels), mul_levels=sum(1 for ops in levels if any(n.op == MUL for n in ops)),
-                            muls=sum(1 for n in nodes if n.op == MUL), lin=sum(1 for n in nodes if n.op in (ADD, SUB)),
-                            copies=0))
-        head.test_slots = dict(tP=[n.slot for n in outs["tP"].c], tR=[n.slot for n in outs["tR"].c])
-        hb = {nm: ([n.slot for n in v.c], [n.bound for n in v.c]) for nm, v in outs.items()}
+        head = compile_formula(tag + "_head", bld, lay, outs, None, dict(tP=2.0, tR=2.0))
+        assert head.info["copies"] == 0
+        on = head.out_nodes
+        head.test_slots = dict(tP=[n.slot for n in on["tP"]], tR=[n.slot for n in on["tR"]])
+        hb = {nm: ([n.slot for n in ns], [n.bound for n in ns]) for nm, ns in on.items()}
         progs[tag + "_head"] = head
         bld, lay, outs2 = formula_add_tail(g, mixed, hb)
-        # the tail must not reuse the head's live scratch slots before reading them: they are inputs of
-        # the tail DAG, which the allocator treats as occupied until their last use
-        tail = compile_formula(tag + "_tail", bld, lay, outs2, lay.P)
-        # scratch numbering of the tail starts above the head's slots
-        progs[tag + "_tail"] = tail
+        # the head's live scratch slots are inputs of the tail DAG: occupied until their last use
+        progs[tag + "_tail"] = compile_formula(tag + "_tail", bld, lay, outs2, lay.P, ACC_BOUND)
     bld, lay, outs = formula_to_projective(g)
-    progs["to_proj"] = compile_formula("to_proj", bld, lay, outs, lay.P, check_closed=False)
+    progs["to_proj"] = compile_formula("to_proj", bld, lay, outs, lay.P, dict(X=2.0, Y=2.0, ZZ=2.0))
     bld, lay, outs, base = formula_from_projective(g)
-    progs["from_proj"] = compile_formula("from_proj", bld, lay, outs, base, check_closed=False)
+    progs["from_proj"] = compile_formula("from_proj", bld, lay, outs, base)
     return progs
 
 
@@ -654,6 +735,25 @@ class Field:
         assert top == 1, "a + K p - b must not be negative"
         return [to3(x) for x in out]
 
+    def lin(self, terms, k):
+        """sum_i coef_i x_i (+ 2^k p when a coefficient is negative), as coop.cuh's fused linear operation:
+        every lane sums coef * limbs (complemented limbs for negative coefficients, whose +1s enter at lane
+        0) into a wide value, the carries are resolved once; the carries out of 2^768 cancel"""
+        has_neg = any(c < 0 for _, c in terms)
+        inc = sum(-c for _, c in terms if c < 0)
+        s = [0] * LANES
+        for x, c in terms:
+            for l in range(LANES):
+                v = lane96(x[l])
+                s[l] += abs(c) * ((MASK96 ^ v) if c < 0 else v)
+        if has_neg:
+            for l in range(LANES):
+                s[l] += lane96(self.kp[k][l])
+            s[0] += inc
+        assert all(x < (1 << 128) for x in s)
+        out, _ = resolve([x & MASK96 for x in s], [x >> 96 for x in s])
+        return [to3(x) for x in out]
+
     def cond_sub_p(self, a):
         """a in [0, 2p) -> a mod p"""
         s = [lane96(a[l]) + (MASK96 ^ lane96(self.pl[l])) + (1 if l == 0 else 0) for l in range(LANES)]
@@ -682,19 +782,23 @@ class Sim:
         f = self.f
         for row in prog.words:
             results = []
-            for w in row:
-                op, d, a, b, k = w & 7, (w >> 3) & 127, (w >> 10) & 127, (w >> 17) & 127, (w >> 24) & 15
+            for o in range(4):
+                w0, w1 = row[2 * o], row[2 * o + 1]
+                op, d, a, b, k = w0 & 7, (w0 >> 3) & 127, (w0 >> 10) & 127, (w0 >> 17) & 127, (w0 >> 24) & 15
                 if op == NOP:
                     continue
-                A, Bv = self.slots[a], self.slots[b]
                 if op == MUL:
-                    r = f.mul(A, Bv)
-                elif op == ADD:
-                    r = f.add(A, Bv)
-                elif op == SUB:
-                    r = f.sub(A, Bv, k)
+                    r = f.mul(self.slots[a], self.slots[b])
                 else:
-                    r = [list(x) for x in A]
+                    slots = (a, b, w1 & 127)
+                    terms = []
+                    for j in range(3):
+                        mag, neg = (w1 >> (7 + 5 * j)) & 15, (w1 >> (11 + 5 * j)) & 1
+                        if mag:
+                            terms.append((self.slots[slots[j]], -mag if neg else mag))
+                    r = f.lin(terms, k)
+                    want = sum(c * join(x) for x, c in terms) + ((self.f.p << k) if any(c < 0 for _, c in terms) else 0)
+                    assert 0 <= want < (1 << R_BITS) and join(r) == want, "linear operation out of range"
                 results.append((d, r))
             for d, r in results:
                 self.slots[d] = r
@@ -715,12 +819,15 @@ def emit(path):
     mods = field_moduli()
     out = []
     out.append("// GENERATED by tools/gen_coop.py - do not edit.  Micro-programs of the warp-cooperative group law")
-    out.append("// (csrc/coop.cuh): rows of four 32-bit instructions, one per octet of a warp:")
-    out.append("//   op (3 bits: 0 nop, 1 mul, 2 add, 3 sub, 4 copy) | dst << 3 | a << 10 | b << 17 | k << 24 (sub adds 2^k p);")
-    out.append("//   bit 28 / 29 of word 0: the row holds a product / a linear operation.")
+    out.append("// (csrc/coop.cuh): rows of four instructions, one per octet of a warp, two 32-bit words each:")
+    out.append("//   word 0: op (3 bits: 0 nop, 1 product a * b, 2 linear) | dst << 3 | a << 10 | b << 17 | k << 24;")
+    out.append("//   word 1: c | |ca| << 7 | sign a << 11 | |cb| << 12 | sign b << 16 | |cc| << 17 | sign c << 21;")
+    out.append("//   linear: dst = ca a + cb b + cc c (+ 2^k p when a coefficient is negative);")
+    out.append("//   bit 28 / 29 of a row's first word: the row holds products / linear operations.")
     out.append("#pragma once")
     out.append("namespace g753 {")
-    out.append("struct CoopProg { const uint32_t* words; unsigned rows; unsigned slots; };")
+    out.append("// Programs live in __constant__ memory behind one accessor type each: the interpreter indexes them with its")
+    out.append("// (warp-uniform) row counter, so a row's flags are a uniform register and its branches are uniform.")
     for fid, p in mods.items():
         f = Field(p)
         out.append("// field %d: K p for K = 2^0 .. 2^%d (24 limbs each), -p^-1 mod 2^96" % (fid, MAX_K_LOG))
@@ -738,8 +845,12 @@ def emit(path):
         slots = max(p.n_slots for p in progs.values())
         for pn, pr in progs.items():
             flat = ", ".join("0x%08xu" % w for row in pr.words for w in row)
+            assert all(len(row) == 8 for row in pr.words)
             out.append("// %s %s: %s" % (nm, pn, pr.info))
-            out.append("static __device__ const uint32_t COOP_%s_%s[] = {%s};" % (nm.upper(), pn.upper(), flat))
+            cname = "COOP_%s_%s" % (nm.upper(), pn.upper())
+            out.append("static __constant__ uint32_t %s[] = {%s};" % (cname, flat))
+            out.append("struct %s_P { static constexpr unsigned ROWS = %d; static __device__ __forceinline__ uint32_t w(unsigned i) "
+                       "{ return %s[i]; } };" % (cname, len(pr.words), cname))
             summary.append((nm, pn, pr.info))
         for tag in ("add",):
             ts = progs[tag + "_head"].test_slots
