@@ -286,9 +286,25 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
     dev, d_h, d_z, sr, ss, sc3, out1, out2 = bufs[:3], bufs[3], bufs[4], bufs[5], bufs[6], bufs[7], bufs[8], bufs[9]
     slot = lambda o, i, k=1: o.at(3 * k * i)
     try:
-        # ---- witness map on the device, then into_repr of h and the assignment (prover.rs:241-267) ----
-        for dv, host in zip(dev, (a, b, c)):
-            dv.put(host)
+        def msm(cx, bases, first, count, d_scalars, d_out):
+            count = max(0, min(count, len(bases) - first))
+            lib.check(lib.msm_dev(cx.handle, bases.handle, first, count, d_scalars, d_out))
+
+        def aux_msm(name, d_vec, base_index, total, d_out, cx=ctx):
+            """one of the five long MSMs (or this rank's shard of it, see ShardedParameters)"""
+            bases, first, off = params.aux[name]
+            msm(cx, bases, first, max(0, total - off), d_vec.at(base_index + off), d_out)
+            if profile is not None:
+                cx.sync()
+                profile[name] = dict(cx.last_msm_phases(), points=max(0, min(total - off, len(bases) - first)),
+                                     plan=cx.last_msm_plan())
+
+        sharder = params.sharder
+        # one GPU: the G2 MSM (the longest, and independent of the witness map) runs on the SECOND context from
+        # the moment the assignment is on the device, beside the witness map and the four G1 MSMs - the blocks of
+        # its accumulation fill the SMs the other stream's low-occupancy phases (sort, reduction, fold) leave idle
+        concurrent = sharder is None
+        # ---- into_repr of the assignment (prover.rs:241-267) and the short scalar vectors ----------------
         dd = np.concatenate([_limbs(d1), _limbs(d2), _limbs(d3), _limbs(r), _limbs(s)])
         dm = np.zeros_like(dd)
         lib.check(lib.field_op(ctx.handle, field, ffi.OP_TO_MONT, ffi.ptr(dd), None, ffi.ptr(dm), 5))
@@ -299,8 +315,6 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
         lib.check(lib.field_op(ctx.handle, field, ffi.OP_SUB, ffi.ptr(zero), ffi.ptr(rs), ffi.ptr(rs), 1))
         lib.check(lib.field_op(ctx.handle, field, ffi.OP_FROM_MONT, ffi.ptr(rs), None, ffi.ptr(rs), 1))
         sc3.put(np.concatenate([_limbs(s), _limbs(r), rs]))
-        lib.check(lib.witness_map_dev(ctx.handle, field, dev[0].p, dev[1].p, dev[2].p, log_n, ffi.ptr(dm), d_h.p))
-        lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_h.p, None, n + 1))
         d_z.put(z)
         lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_z.p, None, n_vars))
         # small scalar vectors [1, inputs..., r|s, 1]: the constant-one slot of the assignment is
@@ -311,25 +325,22 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
                 lib.check(lib.d2d(ctx.handle, dv.at(1), d_z.at(1), (ni - 1) * 96))
             dv.put(_limbs(blind), ni)
             dv.put(ONE, ni + 1)
+        if concurrent:
+            # B in G2 (:302-315) on the second context
+            lib.check(lib.ctx_wait(ctx2.handle, ctx.handle))
+            msm(ctx2, params.b2_small, 0, ni + 2, ss.p, slot(out2, 0, k2))
+            aux_msm("b2", d_z, ni, n_aux, slot(out2, 1, k2), cx=ctx2)
+            lib.check(lib.points_sum_dev(ctx2.handle, g2, slot(out2, 0, k2), 2, slot(out2, 2, k2)))
+        # ---- witness map on the device, then into_repr of h ---------------------------------------------
+        for dv, host in zip(dev, (a, b, c)):
+            dv.put(host)
+        lib.check(lib.witness_map_dev(ctx.handle, field, dev[0].p, dev[1].p, dev[2].p, log_n, ffi.ptr(dm), d_h.p))
+        lib.check(lib.vec_op_dev(ctx.handle, field, ffi.OP_FROM_MONT, d_h.p, None, n + 1))
         if timings is not None:
             ctx.sync()
             timings["witness_map"] = time.perf_counter() - t0
             t0 = time.perf_counter()
 
-        def msm(cx, bases, first, count, d_scalars, d_out):
-            count = max(0, min(count, len(bases) - first))
-            lib.check(lib.msm_dev(cx.handle, bases.handle, first, count, d_scalars, d_out))
-
-        def aux_msm(name, d_vec, base_index, total, d_out):
-            """one of the five long MSMs (or this rank's shard of it, see ShardedParameters)"""
-            bases, first, off = params.aux[name]
-            msm(ctx, bases, first, max(0, total - off), d_vec.at(base_index + off), d_out)
-            if profile is not None:
-                ctx.sync()
-                profile[name] = dict(ctx.last_msm_phases(), points=max(0, min(total - off, len(bases) - first)),
-                                     plan=ctx.last_msm_plan())
-
-        sharder = params.sharder
         # A (prover.rs:270-283) -> slots 0, 1; B in G1 (:286-299) -> slots 2, 3; g_a, g1_b -> slots 8, 9
         aux_msm("a", d_z, ni, n_aux, slot(out1, 1))
         aux_msm("b1", d_z, ni, n_aux, slot(out1, 3))
@@ -339,27 +350,31 @@ def create_proof(params, full_assignment, a, b, c, d1, d2, d3, r, s, timings=Non
         msm(ctx, params.b1_small, 0, ni + 2, ss.p, slot(out1, 2))
         lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 0), 2, slot(out1, 8)))
         lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 2), 2, slot(out1, 9)))
-        lib.check(lib.ctx_wait(ctx2.handle, ctx.handle))
+        if not concurrent:
+            lib.check(lib.ctx_wait(ctx2.handle, ctx.handle))
         # C (:318-337): L, H (zip-truncated against h: n + 1 scalars vs n - 1 bases) -> slots 4..6
         aux_msm("l", d_z, ni, n_aux, slot(out1, 6))
         aux_msm("h", d_h, ni, n + 1 - ni, slot(out1, 5))
         msm(ctx, params.h_head, 0, min(ni, n + 1), d_h.at(0), slot(out1, 4))
-        # B in G2 (:302-315)
-        msm(ctx, params.b2_small, 0, ni + 2, ss.p, slot(out2, 0, k2))
-        aux_msm("b2", d_z, ni, n_aux, slot(out2, 1, k2))
-        if sharder is not None:
+        if not concurrent:
+            # B in G2 (:302-315)
+            msm(ctx, params.b2_small, 0, ni + 2, ss.p, slot(out2, 0, k2))
+            aux_msm("b2", d_z, ni, n_aux, slot(out2, 1, k2))
             sharder.reduce(g1, [slot(out1, 6), slot(out1, 5)])
             sharder.reduce(g2, [slot(out2, 1, k2)])
-        lib.check(lib.points_sum_dev(ctx.handle, g2, slot(out2, 0, k2), 2, slot(out2, 2, k2)))
+            lib.check(lib.points_sum_dev(ctx.handle, g2, slot(out2, 0, k2), 2, slot(out2, 2, k2)))
 
         # second context: s * g_a + r * g1_b - rs * delta_g1 (:322-329) as one MSM over fresh bases
+        # (sharded keys: on the second context, overlapping the remaining large MSMs; one GPU: on the first,
+        # the second is busy with the G2 MSM)
+        cf = ctx if concurrent else ctx2
         ga_b1 = np.empty((2, 3 * LIMBS), dtype=np.uint64)
-        lib.check(lib.d2h(ctx2.handle, ffi.ptr(ga_b1), slot(out1, 8), 2 * 3 * 96))
+        lib.check(lib.d2h(cf.handle, ffi.ptr(ga_b1), slot(out1, 8), 2 * 3 * 96))
         xy = np.zeros((2, 2 * LIMBS), dtype=np.uint64)
         inf = np.zeros(2, dtype=np.uint8)
-        lib.check(lib.batch_normalize(ctx2.handle, g1, ffi.ptr(ga_b1), 2, ffi.ptr(xy), ffi.ptr(inf)))
-        lib.check(lib.bases_update(ctx2.handle, params.fresh.handle, 0, 2, ffi.ptr(xy), ffi.ptr(inf)))
-        msm(ctx2, params.fresh, 0, 3, sc3.p, slot(out1, 7))
+        lib.check(lib.batch_normalize(cf.handle, g1, ffi.ptr(ga_b1), 2, ffi.ptr(xy), ffi.ptr(inf)))
+        lib.check(lib.bases_update(cf.handle, params.fresh.handle, 0, 2, ffi.ptr(xy), ffi.ptr(inf)))
+        msm(cf, params.fresh, 0, 3, sc3.p, slot(out1, 7))
         lib.check(lib.ctx_wait(ctx.handle, ctx2.handle))
         lib.check(lib.points_sum_dev(ctx.handle, g1, slot(out1, 4), 4, slot(out1, 10)))
         gc = out1.get(3 * 10, 3).reshape(1, 3 * LIMBS)

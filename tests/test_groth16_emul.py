@@ -93,7 +93,7 @@ def test_proof_tiny_mnt6(ctx):  # noqa: F811
     check_instance(ctx, 0x6601, 4, 2, 3, 1, 2, 3, O.MNT6_FR.p - 5, 0x77 << 700, engine="mnt6")
 
 
-@pytest.mark.parametrize("engine", ["mnt4", "mnt6"])
+@pytest.mark.parametrize("engine", ["mnt6"])     # MNT4: test_oracle_pairing.py (oracle) and test_gpu_groth16.py (GPU, both engines)
 def test_proof_verifies_with_pairing(ctx, engine):  # noqa: F811
     import shared_checks
     shared_checks.check_proof_verifies_with_pairing(ctx, engine)

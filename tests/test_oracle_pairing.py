@@ -86,7 +86,7 @@ def tiny_groth16(name, num_constraints=5, seed=0x7e57):
     return eng, key, vk, ni, z, ea + [0] * pad, eb + [0] * pad, ec + [0] * pad
 
 
-@pytest.mark.parametrize("name", ["mnt4", "mnt6"])
+@pytest.mark.parametrize("name", ["mnt4"])      # MNT6 goes through the same code in test_groth16_emul.py (CPU) / test_gpu_groth16.py
 def test_generate_prove_verify_on_the_oracle(name):
     eng, key, vk, ni, z, a, b, c = tiny_groth16(name)
     F = eng.fr
