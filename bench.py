@@ -56,6 +56,20 @@ METRIC = "mnt4753_g1_msm_throughput"
 #   G2 / Fq3:  10 tower products, each three lanes x one three-product body (slots.cuh Tw3L: 3 x 576 + 600)
 LIMB_MACS_MUL3 = 3 * 576 + 600
 EXECUTED_MACS_PER_MADD = {0: 8 * 1176 + 2 * 876, 2: 8 * 1176 + 2 * 876, 1: 10 * 2 * 1752, 3: 10 * 3 * LIMB_MACS_MUL3}
+# ... and one AFFINE addition of the pairwise tree (msm.cuh k_tree_round): 3 products for its share of the
+# shared inversion (prefix product, 1 / den, peel), lambda, lambda^2, y3 = 5 products + 1 squaring.  The one
+# safegcd inversion per thread and round (shifts and adds, no limb products) is not counted.
+EXECUTED_MACS_PER_TREE_ADD = {0: 5 * 1176 + 876, 2: 5 * 1176 + 876, 1: 6 * 2 * 1752, 3: 6 * 3 * LIMB_MACS_MUL3}
+
+
+def executed_accumulation(group, n, plan):
+    """(additions, limb-MACs, description) the accumulation phase of an n-point MSM EXECUTES under `plan`"""
+    entries = n * plan["windows"]
+    if plan.get("accumulation") == "affine_tree":
+        # every bucket's run of k entries takes k - 1 additions (all buckets are occupied at these sizes)
+        adds = max(entries - plan["rows"] * (1 << (plan["c"] - 1)), 0)
+        return adds, adds * EXECUTED_MACS_PER_TREE_ADD[group], "affine additions, 5 products + 1 squaring each"
+    return entries, entries * EXECUTED_MACS_PER_MADD[group], "XYZZ mixed additions, 8 products + 2 squarings each"
 
 
 def workload_config(log_n, world, scaling):
@@ -555,8 +569,8 @@ def run_ours(args):
         acc_ms = phases.get("accumulate", 0.0)
         executed = None
         if plan and acc_ms:
-            macs = n_local * plan["windows"] * EXECUTED_MACS_PER_MADD[GROUP]
-            executed = {"plan": plan, "mixed_additions": n_local * plan["windows"], "limb_macs": macs,
+            adds, macs, what = executed_accumulation(GROUP, n_local, plan)
+            executed = {"plan": plan, "additions": adds, "what": what, "limb_macs": macs,
                         "frac": macs / (acc_ms * 1e-3) / peak_mac_per_s}
         traffic = None
         if world == 1 and args.log_n == 22:
@@ -566,9 +580,9 @@ def run_ours(args):
                 pass
         roofline = {
             "bound": "int32-mac",
-            "kernel": "k_bucket_acc",
-            # the fraction of the integer pipe's measured ceiling the kernel sustains on the work it EXECUTES
-            # (n x W signed-digit windows x one XYZZ mixed addition of 8 products + 2 squarings)
+            "kernel": "k_tree_round" if plan and plan.get("accumulation") == "affine_tree" else "k_bucket_acc",
+            # the fraction of the integer pipe's measured ceiling the accumulation sustains on the limb products it
+            # EXECUTES (n x W signed-digit window entries; see executed_accumulation)
             "achieved": executed["limb_macs"] / (acc_ms * 1e-3) / 1e12 if executed else None,
             "peak": peak_mac_per_s / 1e12,
             "unit": "Tlimb-MAC/s",
@@ -854,7 +868,7 @@ def run_config4(ctx, stream, G, ffi, params, args, peak_mac_per_s):
     if not (xy[0] == xy[1]).all():
         raise SystemExit("config 4: MNT6 G2 MSM differs from (sum s_i a_i) * G")
     bases.free()
-    macs = n * plan["windows"] * EXECUTED_MACS_PER_MADD[group]
+    _, macs, what = executed_accumulation(group, n, plan)
     acc_ms = phases.get("accumulate", 0.0)
     # mixed-radix transform
     N = (1 << 15) * 25
@@ -871,7 +885,7 @@ def run_config4(ctx, stream, G, ffi, params, args, peak_mac_per_s):
     return {"msm": {"workload": "MNT6-753 G2 (Fq3) MSM, 2^20 points, resident key with precomputed copies (built in %.1f s)"
                                 % key_s,
                     "ms": min(times) * 1e3, "mpts_per_s": n / min(times) / 1e6, "phases_ms": phases, "plan": plan,
-                    "roofline": {"bound": "int32-mac", "kernel": "k_bucket_acc (Fq3 tower on 3 lanes, one lazily reduced coefficient per lane)", "kernel_ms": acc_ms,
+                    "roofline": {"bound": "int32-mac", "kernel": "accumulation (Fq3 tower on 3 lanes, one lazily reduced coefficient per lane; %s)" % what, "kernel_ms": acc_ms,
                                  "executed_limb_macs": macs, "peak": peak_mac_per_s / 1e12, "unit": "Tlimb-MAC/s",
                                  "frac": macs / (acc_ms * 1e-3) / peak_mac_per_s if acc_ms else None},
                     "verified": "result == (sum s_i a_i mod r) * G2 generator"},

@@ -60,10 +60,11 @@ class Context:
         return int(self.lib.launch_count(self.handle))
 
     def last_msm_plan(self):
-        """window bits, windows, bucket rows and key copies of the last MSM on this context"""
-        buf = (ctypes.c_uint * 4)()
+        """window bits, windows, bucket rows, key copies and accumulation form of the last MSM on this context"""
+        buf = (ctypes.c_uint * 5)()
         self.lib.check(self.lib.last_msm_plan(self.handle, buf))
-        return {"c": int(buf[0]), "windows": int(buf[1]), "rows": int(buf[2]), "copies": int(buf[3])}
+        return {"c": int(buf[0]), "windows": int(buf[1]), "rows": int(buf[2]), "copies": int(buf[3]),
+                "accumulation": "affine_tree" if buf[4] else "xyzz_running_sums"}
 
     def last_msm_phases(self):
         buf = (ctypes.c_float * 8)()

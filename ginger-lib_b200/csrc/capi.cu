@@ -603,6 +603,10 @@ int g753_ctx_create(int device, g753_ctx** out) {
   if (fc) ctx->forced_c = atoi(fc);
   const char* fa = getenv("G753_MSM_AFFINE");
   if (fa) ctx->forced_affine = atoi(fa) ? 1 : 0;
+  const char* tb = getenv("G753_TREE_BATCH");
+  if (tb && atoi(tb) > 0) ctx->tree_batch = atoi(tb);
+  const char* ta = getenv("G753_TREE_AHEAD");
+  if (ta && atoi(ta) > 0) ctx->tree_ahead = atoi(ta);
   *out = ctx;
   return G753_OK;
 }
@@ -1437,9 +1441,9 @@ int g753_last_msm_phases(g753_ctx* ctx, float* ms, int cap) {
   return k;
 }
 
-int g753_last_msm_plan(const g753_ctx* ctx, unsigned* plan4) {
-  if (!ctx || !plan4) return fail(G753_ERR_BAD_ARG, "null pointer");
-  for (int i = 0; i < 4; i++) plan4[i] = ctx->last_plan[i];
+int g753_last_msm_plan(const g753_ctx* ctx, unsigned* plan5) {
+  if (!ctx || !plan5) return fail(G753_ERR_BAD_ARG, "null pointer");
+  for (int i = 0; i < 5; i++) plan5[i] = ctx->last_plan[i];
   return G753_OK;
 }
 

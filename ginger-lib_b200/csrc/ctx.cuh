@@ -24,9 +24,11 @@ struct g753_ctx {
   uint64_t launches = 0;
   float phase_ms[MSM_PHASES] = {0, 0, 0, 0, 0};
   bool phases_valid = false;  // every phase event of the last MSM was recorded (count > 0, this context)
-  unsigned last_plan[4] = {0, 0, 0, 0};  // window bits, windows, bucket rows, key copies of the last MSM
+  unsigned last_plan[5] = {0, 0, 0, 0, 0};  // window bits, windows, bucket rows, key copies, accumulation form of the last MSM
   int forced_c = 0;
-  int forced_affine = -1;  // G753_MSM_AFFINE: 0 / 1 force the accumulation kernel, unset = by size
+  int forced_affine = -1;  // G753_MSM_AFFINE: 0 / 1 force the accumulation form, unset = the group's default
+  int tree_batch = 0;      // G753_TREE_BATCH: output slots per thread of the addition tree (0 = default)
+  int tree_ahead = 0;      // G753_TREE_AHEAD: prefetch distance of the addition tree in slots (0 = default)
   std::mutex mu;
   unsigned scalar_chunks = 1;  // > 1 while g753_msm feeds the scalars of the running MSM in pieces
 #if !defined(G753_HOST_EMUL)

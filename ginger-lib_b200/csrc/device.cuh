@@ -44,6 +44,12 @@ static inline T atomicOr(T* p, T v) {
   *p = old | v;
   return old;
 }
+template <class T>
+static inline T atomicMax(T* p, T v) {
+  T old = *p;
+  if (v > old) *p = v;
+  return old;
+}
 static inline unsigned __brev(unsigned x) {
   unsigned r = 0;
   for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
@@ -72,6 +78,7 @@ static inline int dev_alloc(void** p, size_t bytes) {
   return *p ? G753_OK : G753_ERR_OOM;
 }
 static inline void dev_free(void* p) { free(p); }
+static inline size_t dev_mem_free() { return (size_t)1 << 40; }
 static inline int dev_memset(void* p, int v, size_t bytes, cudaStream_t) {
   memset(p, v, bytes);
   return G753_OK;
@@ -119,6 +126,10 @@ static inline int dev_alloc(void** p, size_t bytes) {
 }
 static inline void dev_free(void* p) {
   if (p) cudaFree(p);
+}
+static inline size_t dev_mem_free() {
+  size_t free_b = 0, total_b = 0;
+  return cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? free_b : 0;
 }
 static inline int dev_memset(void* p, int v, size_t bytes, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(p, v, bytes, s);
@@ -171,6 +182,11 @@ struct Scratch {
     if (rc != G753_OK) return rc;
     cap = want;
     return G753_OK;
+  }
+  // would reserve(bytes) succeed?  (growing frees the current block first)
+  bool can_hold(size_t bytes) const {
+    if (bytes <= cap) return true;
+    return dev_mem_free() + cap > bytes + bytes / 8 + ((size_t)256 << 20);
   }
   void release() {
     dev_free(ptr);

@@ -323,161 +323,488 @@ k_bucket_acc(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
 }
 
 // ------------------------------------------------------------------------------------
-// K5b': bucket accumulation in AFFINE coordinates with shared inversions.
+// K5t: bucket accumulation as a PAIRWISE TREE of affine additions with shared inversions.
 // An affine addition is lambda = (y2 - y1) / (x2 - x1), x3 = lambda^2 - x1 - x2,
-// y3 = lambda (x1 - x3) - y1: 1 inversion + 2 products + 1 squaring.  Every thread runs AFF_G work
-// items in lockstep; at step k it has up to AFF_G independent additions (item g: acc_g += base k of
-// item g), inverts the PRODUCT of their denominators once (Montgomery's trick: 3 products per
-// addition) with the safegcd inversion (~30 products' worth of instructions), so an addition costs
-// 6 products + 30 / AFF_G instead of the 10 of the XYZZ mixed addition.  The reference's
-// batch_normalization uses the same trick for its Z inversions (short_weierstrass_projective.rs:
-// 402-442).  Exceptional pairs take no part in the shared inversion except the doubling
-// (denominator 2 y1): empty accumulator (acc = Q), Q = -acc (acc becomes empty).
-// Accumulators and prefix products live in a global scratch laid out like the slots
-// ([item g][element][16-byte chunk][column], coalesced per chunk); items are length-sorted, so the
-// items of one thread (consecutive positions) have non-increasing lengths.
-// Prime-field curves only (K = 1): G2 keeps the XYZZ kernel.
-// STATUS: correct (parity tests run it with G753_MSM_AFFINE=1) but NOT the default: measured on a
-// B200 at 2^22 it takes 310 ms against the XYZZ kernel's 237 ms.  The arithmetic is ~15 % lighter
-// (6 products + 45 / 16 per addition; the inversion measures 45 products' worth, not 30), but every
-// addition makes two dependent trips to HBM / L2 (base gather, accumulator, prefix product, in both
-// phases) and the 864 B of slots per thread cap the SM at 8 warps, too few to hide them.
+// y3 = lambda (x1 - x3) - y1: 1 inversion + 2 products + 1 squaring.  Inverting the PRODUCT of many
+// denominators once (Montgomery's trick, 3 products per denominator; the reference's
+// batch_normalization does the same for its Z inversions, short_weierstrass_projective.rs:402-442)
+// makes an addition 6 products + (one safegcd inversion ~ 45 products) / batch, against the 10 of the
+// XYZZ mixed addition.  The trick needs many INDEPENDENT additions, which a running bucket sum does not
+// offer; a tree does: level 0 of bucket t is its run of sorted (point, sign) entries, level L + 1 holds
+// the sums of the pairs (2l, 2l + 1) of level L (an odd last element is carried over), and after
+// ceil(log2(count)) rounds one element is left.  The additions of a round are all independent, so a
+// thread takes `batch` consecutive OUTPUT slots whatever buckets they belong to:
+//   phase 1 (forward)   den_j = x2 - x1, the running product of the denominators BEFORE slot j is
+//                       parked in the slot's own output cell;
+//   one inversion of the product of all denominators of the thread;
+//   phase 2 (backward)  1 / den_j = parked prefix * inverse, inverse *= den_j, finish the addition and
+//                       overwrite the cell with (x3, y3).
+// Exceptional pairs take no part in the shared inversion except the doubling (denominator 2 y1):
+// P + (-P) stores the point at infinity as (0, 0) (not on these curves, b != 0), an operand at
+// infinity passes the other one through.
+// No index arrays, no scans: level L of bucket t starts at S_L[t], S_0[t] = row * row_cap + offsets[t],
+// S_{L+1}[t] = floor((S_L[t] + t) / 2) - one slot of padding per bucket and level keeps the runs
+// disjoint (S_L[t+1] - S_L[t] >= count_L[t] implies the same one level up) - and holds
+// count_L[t] = ceil(count_0[t] / 2^L) elements; the bucket of an output slot is found by bisection on
+// S_{L+1}[.].  Level L >= 1 lives in one of two ping-pong arrays of affine points.  The addition of a
+// bucket's LAST pair writes the sum straight to buckets[t] (XYZZ: x, y, 1, 1) and later rounds skip the
+// bucket; k_tree_finish copies the buckets that hold a single entry.  The number of rounds depends on the
+// fullest bucket (known on the device only): the host launches the ceil(log2(row_cap)) rounds a single
+// bucket could need and a round whose input level has no bucket with two elements left returns at once.
 // ------------------------------------------------------------------------------------
-constexpr int AFF_G = 16;
-constexpr int AFF_GSLOTS = 3;  // x, y, prefix product per item
+// output slots per thread when there is enough work for several waves of blocks: the safegcd inversion runs ~170 000
+// instructions against ~9 700 per addition, so a batch of 64 spends a fifth of the instruction stream inverting
+constexpr unsigned TREE_BATCH = 256;
+constexpr uint64_t TREE_MIN_ENTRIES = (uint64_t)1 << 22;   // windows x points from which the tree is the default form
 
-template <class L>
-G753_D void gs_to_slot(int slot, const uint4* gbase, int gslot) {
-  const uint4* p = gbase + (size_t)gslot * SLOT_CHUNKS * L::NC + L::col();
-  uint4* q = slot_ptr<L>(slot);
-#pragma unroll
-  for (int c = 0; c < SLOT_CHUNKS; c++) q[c * L::NC] = p[c * L::NC];
+G753_HD uint32_t tree_start(uint32_t s0, uint32_t t, unsigned level) {
+  uint64_t s = s0;
+  for (unsigned k = 0; k < level; k++) s = (s + t) >> 1;
+  return (uint32_t)s;
 }
-template <class L>
-G753_D void slot_to_gs(uint4* gbase, int gslot, int slot) {
-  uint4* p = gbase + (size_t)gslot * SLOT_CHUNKS * L::NC + L::col();
-  const uint4* q = slot_ptr<L>(slot);
+G753_HD uint32_t tree_count(uint32_t c0, unsigned level) {
+  return level >= 32 ? (c0 ? 1u : 0u) : (uint32_t)(((uint64_t)c0 + ((1ull << level) - 1)) >> level);
+}
+// fullest bucket (grid-stride; one atomic per thread at most)
+static __global__ void k_tree_max(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ends, unsigned NB,
+                                  uint32_t* __restrict__ max_count) {
+  uint32_t m = 0;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < NB; t += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t c = ends[t] - offsets[t];
+    m = c > m ? c : m;
+  }
+  if (m > 1 && m > *(volatile uint32_t*)max_count) atomicMax(max_count, m);
+}
+
+struct TreeGeo {
+  const uint32_t* offsets;   // [NB] start of bucket t's run within its row of sorted[]
+  const uint32_t* ends;      // [NB] end of the run
+  unsigned NB, len;          // buckets in all rows, buckets per row (B + 1)
+  uint32_t row_cap;          // entries per row of sorted[]
+};
+
+// position of output slot j of level `level`: bucket t (largest t with S_level[t] <= j) and that
+// bucket's geometry one level down.  The walk is sequential (up in phase 1, down in phase 2) and the
+// offsets of the NEXT bucket are loaded one bucket ahead, so crossing a bucket boundary does not wait
+// for memory.
+struct TreeWalk {
+  TreeGeo g;
+  unsigned level;            // output level (>= 1)
+  unsigned t;
+  uint32_t s_in, c_in, s_out, c_out;
+  uint32_t s_next;           // walking up: S_level[t + 1] (2^32 - 1 after the last bucket)
+  uint32_t off_next, pre_a, pre_b;   // up: offsets[t+1], ends[t+1], offsets[t+2]; down: -, offsets[t-1], ends[t-1]
+  G753_D uint32_t start_of(unsigned b, uint32_t off, unsigned lv) const {
+    return tree_start((uint32_t)(b / g.len) * g.row_cap + off, b, lv);
+  }
+  G753_D void set(unsigned b, uint32_t off, uint32_t end) {
+    t = b;
+    s_in = start_of(b, off, level - 1);
+    s_out = (uint32_t)(((uint64_t)s_in + b) >> 1);
+    c_in = tree_count(end - off, level - 1);
+    c_out = (c_in + 1) >> 1;
+  }
+  G753_D void preload_up() {
+    pre_a = t + 1 < g.NB ? g.ends[t + 1] : 0u;
+    pre_b = t + 2 < g.NB ? g.offsets[t + 2] : 0u;
+  }
+  G753_D void start_up(uint32_t j) {
+    unsigned lo = 0, hi = g.NB;   // invariant: S[lo] <= j (S[0] = 0), S[hi] > j or hi == NB
+    while (hi - lo > 1) {
+      const unsigned mid = lo + (hi - lo) / 2;
+      if (start_of(mid, g.offsets[mid], level) <= j) lo = mid; else hi = mid;
+    }
+    set(lo, g.offsets[lo], g.ends[lo]);
+    off_next = lo + 1 < g.NB ? g.offsets[lo + 1] : 0u;
+    s_next = lo + 1 < g.NB ? start_of(lo + 1, off_next, level) : 0xffffffffu;
+    preload_up();
+  }
+  G753_D void seek_up(uint32_t j) {
+    while (j >= s_next) {
+      const unsigned b = t + 1;
+      set(b, off_next, pre_a);
+      off_next = pre_b;
+      s_next = b + 1 < g.NB ? start_of(b + 1, off_next, level) : 0xffffffffu;
+      preload_up();
+    }
+  }
+  G753_D void preload_down() {
+    pre_a = t > 0 ? g.offsets[t - 1] : 0u;
+    pre_b = t > 0 ? g.ends[t - 1] : 0u;
+  }
+  G753_D void start_down() { preload_down(); }   // from the bucket the walk up ended in
+  G753_D void seek_down(uint32_t j) {
+    while (j < s_out) {
+      set(t - 1, pre_a, pre_b);
+      preload_down();
+    }
+  }
+};
+
+// what output slot j is made of, in two steps so that the loads of one step are issued an iteration before
+// the next step needs them: TreeIdx (entry indices; at level 1 the two sorted[] entries, in flight) and
+// TreeSlot (operand addresses)
+struct TreeIdx {
+  uint32_t a, b;   // level 1: sorted[src], sorted[src + 1]; above: a = src
+  uint32_t t;      // bucket
+  unsigned kind;   // 0 = nothing to do, 1 = single element carried over, 2 = pair; bit 6: the pair is the last of its bucket
+};
+struct TreeSlot {
+  const Fq* p1;
+  const Fq* p2;
+  uint32_t t;
+  unsigned kind;   // as TreeIdx; bit 4 / bit 5: negate y of p1 / p2
+};
+G753_D TreeIdx tree_idx(const TreeWalk& w, uint32_t j, const uint32_t* __restrict__ sorted) {
+  TreeIdx s;
+  s.a = s.b = 0;
+  s.t = w.t;
+  s.kind = 0;
+  const uint32_t l = j - w.s_out;
+  if (l >= w.c_out || w.c_in <= 1) return s;   // a hole, or a bucket that is finished (its sum is in buckets[t])
+  const uint32_t src = w.s_in + 2 * l;
+  const bool pair = 2 * l + 1 < w.c_in;
+  s.kind = pair ? (w.c_in == 2 ? 66u : 2u) : 1u;
+  if (w.level == 1) {
+    s.a = sorted[src];
+    if (pair) s.b = sorted[src + 1];
+  } else {
+    s.a = src;
+  }
+  return s;
+}
+template <int K>
+G753_D TreeSlot tree_slot(const TreeIdx& i, bool lvl0, const Fq* __restrict__ bases, const Fq* __restrict__ in) {
+  TreeSlot s;
+  s.kind = i.kind;
+  s.t = i.t;
+  s.p1 = s.p2 = nullptr;
+  if (i.kind == 0) return s;
+  if (lvl0) {
+    s.p1 = bases + (size_t)(i.a & 0x7fffffffu) * (2 * K);
+    s.p2 = bases + (size_t)(i.b & 0x7fffffffu) * (2 * K);
+    s.kind |= ((i.a >> 31) << 4) | ((i.b >> 31) << 5);
+  } else {
+    s.p1 = in + (size_t)i.a * (2 * K);
+    s.p2 = s.p1 + 2 * K;
+  }
+  return s;
+}
+template <int BYTES>
+G753_D void tree_prefetch(const void* p) {
+#if defined(__CUDA_ARCH__)
+  const char* q = (const char*)p;
 #pragma unroll
-  for (int c = 0; c < SLOT_CHUNKS; c++) p[c * L::NC] = q[c * L::NC];
+  for (int off = 0; off < BYTES; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + off));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(q + BYTES - 1));
+#else
+  (void)p;
+#endif
+}
+
+// G753_TREE_SYNC = 1: the warps of a block meet at a barrier before every slot, so that they walk the ~22 KB
+// multiplier body together and share its instruction-cache lines (L1.5 is 32 KB per SM); device only
+#ifndef G753_TREE_SYNC
+#define G753_TREE_SYNC 0
+#endif
+G753_D void tree_sync() {
+#if G753_TREE_SYNC && defined(__CUDA_ARCH__)
+  __syncthreads();
+#endif
 }
 
 template <class SC>
 __global__ void __launch_bounds__(SC::M::T::THREADS)
-k_bucket_acc_affine(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                    const MsmItem* __restrict__ items, const uint32_t* __restrict__ item_total,
-                    Fq* __restrict__ points, uint4* __restrict__ scratch) {
-  typedef EcS<SC> E;
-  typedef typename E::M M;
+k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, TreeGeo geo,
+             const uint32_t* __restrict__ max_count, unsigned level, unsigned batch, unsigned far, const Fq* __restrict__ in,
+             Fq* __restrict__ out, Fq* __restrict__ points) {
+  typedef typename SC::M M;
   typedef typename M::T L;
-  static_assert(E::K == 1, "affine accumulation is implemented for the prime-field curves");
-  enum { X1 = 0, Y1 = 1, X2 = 2, Y2 = 3, NUM = 4, DEN = 5, RUN = 6, INV = 7, TMP = 8 };  // Tw1 ops need no scratch
-  const unsigned total = *item_total;
-  const unsigned first = L::item() * AFF_G;
-  if (first >= total) return;
-  const unsigned cnt = total - first < (unsigned)AFF_G ? total - first : (unsigned)AFF_G;
-  uint4* my = scratch + (size_t)blockIdx.x * ((size_t)AFF_G * AFF_GSLOTS * SLOT_CHUNKS * L::NC);
-  const unsigned maxlen = items[first].len;
-  uint32_t empty = 0xffffffffu;  // bit g: accumulator g holds no point yet (or cancelled to infinity)
+  constexpr int K = M::K;
+  enum { X1 = 0, Y1 = K, X2 = 2 * K, Y2 = 3 * K, DEN = 4 * K, T = 5 * K, INV = 6 * K, TMP = 7 * K };
+  constexpr int EL = (int)(K * sizeof(Fq));   // bytes of one coordinate
+  if (tree_count(*max_count, level - 1) <= 1) return;   // every bucket is down to one element already
+  if (L::idle()) return;
+  const uint64_t first64 = (uint64_t)L::item() * batch;
+  TreeWalk w;
+  w.g = geo;
+  w.level = level;
+  bool dead;
+  {
+    const unsigned b = geo.NB - 1;
+    w.set(b, geo.offsets[b], geo.ends[b]);
+    dead = first64 >= (uint64_t)w.s_out + w.c_out;   // beyond the last slot of the level
+  }
+#if !G753_TREE_SYNC
+  if (dead) return;
+#endif
+  const uint32_t first = (uint32_t)first64;
+  const uint64_t stop64 = first64 + batch;
+  const uint32_t last = (uint32_t)(stop64 > 0xfffffffeull ? 0xfffffffeull : stop64);   // exclusive
+  const bool lvl0 = level == 1;   // inputs are key points: never at infinity, y negated by the sign bit
 
-  // loads base k of item g into X2, Y2 (sign applied); returns false when the item has fewer entries
-  auto load_q = [&](unsigned g, unsigned k) -> bool {
-    const MsmItem it = items[first + g];
-    if (k >= it.len) return false;
-    const uint32_t e = sorted[it.start + k];
-    const Fq* q = bases + (size_t)(e & 0x7fffffffu) * 2;
-    M::ldg(X2, q);
-    M::ldg(Y2, q + 1);
-    if (e >> 31) M::neg(Y2, Y2);
-    return true;
+  // with (x1, x2) in X1, X2 (and, when have_y, the sign-corrected y in Y1, Y2):
+  // 0 = ordinary addition, 1 = doubling, 2 = cancellation, 3 = first operand at infinity (result = second),
+  // 4 = second at infinity (result = first); leaves the denominator in DEN (kinds 0, 1)
+  auto fix_y = [&](const TreeSlot& s) {
+    if (s.kind & 16u) M::neg(Y1, Y1);
+    if (s.kind & 32u) M::neg(Y2, Y2);
   };
-  // with acc in X1, Y1 and Q in X2, Y2: 0 = ordinary addition, 1 = doubling, 2 = cancellation;
-  // leaves the denominator in DEN (cases 0, 1)
-  auto classify = [&]() -> int {
+  auto load_y = [&](const TreeSlot& s) {
+    const int d[2] = {Y1, Y2};
+    const Fq* const g[2] = {s.p1 + K, s.p2 + K};
+    t_ldg_many<M, 2>(d, g);
+    fix_y(s);
+  };
+  auto classify = [&](const TreeSlot& s, bool have_y) -> int {
+    if (!lvl0) {
+      const bool z1 = M::is_zero(X1), z2 = M::is_zero(X2);
+      if (z1 || z2) {
+        if (!have_y) load_y(s);
+        if (z1 && M::is_zero(Y1)) return 3;
+        if (z2 && M::is_zero(Y2)) return 4;
+        have_y = true;
+      }
+    }
     M::sub(DEN, X2, X1);
     if (!M::is_zero(DEN)) return 0;
-    M::sub(NUM, Y2, Y1);
-    if (!M::is_zero(NUM) || M::is_zero(Y1)) return 2;
+    if (!have_y) load_y(s);
+    M::sub(DEN, Y2, Y1);
+    if (!M::is_zero(DEN) || M::is_zero(Y1)) return 2;
     M::dbl(DEN, Y1);
     return 1;
   };
-
-  for (unsigned k = 0; k < maxlen; k++) {
-    // ---- phase 1: denominators and their running product -------------------------------------
-    M::set_one(RUN);
-    unsigned active = 0;
-    bool any = false;
-    for (unsigned g = 0; g < cnt; g++) {
-      if (!load_q(g, k)) break;           // lengths are non-increasing within a thread
-      active = g + 1;
-      if ((empty >> g) & 1) continue;
-      gs_to_slot<L>(X1, my, g * AFF_GSLOTS);
-      gs_to_slot<L>(Y1, my, g * AFF_GSLOTS + 1);
-      if (classify() == 2) continue;
-      slot_to_gs<L>(my, g * AFF_GSLOTS + 2, RUN);
-      M::mul(RUN, RUN, DEN, TMP);
-      any = true;
-    }
-    if (any) M::inv(INV, RUN, TMP);
-    // ---- phase 2: walk back, peel the individual inverses off, finish the additions ----------
-    for (int g = (int)active - 1; g >= 0; g--) {
-      load_q((unsigned)g, k);
-      if ((empty >> g) & 1) {
-        slot_to_gs<L>(my, g * AFF_GSLOTS, X2);
-        slot_to_gs<L>(my, g * AFF_GSLOTS + 1, Y2);
-        empty &= ~(1u << g);
-        continue;
-      }
-      gs_to_slot<L>(X1, my, g * AFF_GSLOTS);
-      gs_to_slot<L>(Y1, my, g * AFF_GSLOTS + 1);
-      const int kind = classify();
-      if (kind == 2) {
-        empty |= 1u << g;
-        continue;
-      }
-      if (kind == 1) {                    // lambda = (3 x1^2 + a) / (2 y1)
-        M::sqr(NUM, X1, TMP);
-        M::dbl(TMP, NUM);
-        M::add(NUM, NUM, TMP);
-        M::set_one(TMP);
-        SC::mul_by_a(TMP, TMP);
-        M::add(NUM, NUM, TMP);
+  auto prefetch_x = [&](const TreeSlot& s) {
+    if ((s.kind & 3u) != 2u) return;
+    tree_prefetch<EL>(s.p1);
+    tree_prefetch<EL>(s.p2);
+  };
+  auto prefetch_xy = [&](const TreeSlot& s, const Fq* cell) {
+    if ((s.kind & 3u) == 0u) return;
+    if ((s.kind & 3u) == 2u) {
+      if (lvl0) {
+        tree_prefetch<2 * EL>(s.p1);
+        tree_prefetch<2 * EL>(s.p2);
       } else {
-        M::sub(NUM, Y2, Y1);
+        tree_prefetch<4 * EL>(s.p1);
       }
-      gs_to_slot<L>(TMP, my, g * AFF_GSLOTS + 2);   // product of the denominators before this one
-      M::mul(TMP, TMP, INV, TMP);                // 1 / DEN
-      M::mul(INV, INV, DEN, TMP);                // inverse of the product of the earlier ones
-      M::mul(NUM, NUM, TMP, TMP);                // lambda
-      M::sqr(TMP, NUM, TMP);
-      M::sub(TMP, TMP, X1);
-      M::sub(TMP, TMP, X2);                          // x3
-      M::sub(X1, X1, TMP);
-      M::mul(X1, X1, NUM, TMP);
-      M::sub(Y1, X1, Y1);                            // y3 = lambda (x1 - x3) - y1
-      slot_to_gs<L>(my, g * AFF_GSLOTS, TMP);
-      slot_to_gs<L>(my, g * AFF_GSLOTS + 1, Y1);
+      tree_prefetch<EL>(cell);
+    } else {
+      tree_prefetch<2 * EL>(s.p1);
+    }
+  };
+  TreeIdx none;
+  none.a = none.b = none.t = 0;
+  none.kind = 0;
+  // (x, y) in slots sx, sy: to the cell of the output level, or - the last addition of a bucket - to the bucket
+  // itself as XYZZ (x, y, 1, 1); a sum at infinity leaves the bucket's all-zero limbs (ZZ == 0) alone
+  auto put = [&](const TreeSlot& s, Fq* cell, int sx, int sy, int one, bool maybe_inf) {
+    if (s.kind & 64u) {
+      if (maybe_inf && M::is_zero(sx) && M::is_zero(sy)) return;
+      Fq* o = points + (size_t)s.t * (4 * K);
+      M::set_one(one);
+      M::stg(o, sx);
+      M::stg(o + K, sy);
+      M::stg(o + 2 * K, one);
+      M::stg(o + 3 * K, one);
+    } else {
+      M::stg(cell, sx);
+      M::stg(cell + K, sy);
+    }
+  };
+
+  // ---- phase 1: denominators and their running product -----------------------------------------
+  bool any = false, work = false;
+  uint32_t lead = 0;   // slot of the first denominator: its prefix is 1 and is not stored
+  // Two walks per phase.  The LEADER runs `far` slots ahead and only prefetches operands into L2 (a slot of phase 1
+  // is one product long, ~6 us per warp, less than a trip to HBM under load); the FOLLOWER loads and computes.  Both
+  // read their entry indices one slot before they turn them into addresses.
+  const uint32_t far1 = far ? far : 4u, far2 = (far1 + 1) / 2;
+  {
+    TreeSlot cur = tree_slot<K>(none, lvl0, bases, in);
+    TreeIdx ahead = none, lpend = none;
+    TreeWalk lw = w;
+    if (!dead) {
+      w.start_up(first);
+      lw = w;
+      cur = tree_slot<K>(tree_idx(w, first, sorted), lvl0, bases, in);
+      for (uint32_t jj = first + 1; jj <= first + far1 && jj < last; jj++) {   // the first `far` slots: one burst
+        lw.seek_up(jj);
+        prefetch_x(tree_slot<K>(tree_idx(lw, jj, sorted), lvl0, bases, in));
+      }
+      if (first + far1 + 1 < last) {
+        lw.seek_up(first + far1 + 1);
+        lpend = tree_idx(lw, first + far1 + 1, sorted);
+      }
+    }
+    for (unsigned it = 0; it < batch; it++) {
+      tree_sync();
+      const uint32_t j = first + it;
+      if (dead || j >= last) continue;
+      ahead = none;
+      if (j + 1 < last) {            // entry indices of the next slot: their loads fly during this slot's arithmetic
+        w.seek_up(j + 1);
+        ahead = tree_idx(w, j + 1, sorted);
+      }
+      prefetch_x(tree_slot<K>(lpend, lvl0, bases, in));   // slot j + far + 1
+      lpend = none;
+      if (j + far1 + 2 < last) {
+        lw.seek_up(j + far1 + 2);
+        lpend = tree_idx(lw, j + far1 + 2, sorted);
+      }
+      work = work || (cur.kind & 3u) != 0u;
+      if ((cur.kind & 3u) == 2u) {
+        const int d[2] = {X1, X2};
+        const Fq* const g[2] = {cur.p1, cur.p2};
+        t_ldg_many<M, 2>(d, g);
+        if (classify(cur, false) < 2) {
+          if (!any) {
+            M::copy(INV, DEN);
+            any = true;
+            lead = j;
+          } else {
+            M::stg(out + (size_t)j * (2 * K), INV);
+            M::mul(INV, INV, DEN, TMP);
+          }
+        }
+      }
+      cur = tree_slot<K>(ahead, lvl0, bases, in);
     }
   }
-  // ---- results: XYZZ (x, y, 1, 1), or all-zero limbs for an empty sum ---------------------------
-  for (unsigned g = 0; g < cnt; g++) {
-    const MsmItem it = items[first + g];
-    Fq* out = points + (size_t)it.dest * E::PT;
-    if ((empty >> g) & 1) {
-      M::set_zero(X1);
-      for (int i = 0; i < 4; i++) M::stg(out + i, X1);
-    } else {
-      gs_to_slot<L>(X1, my, g * AFF_GSLOTS);
-      gs_to_slot<L>(Y1, my, g * AFF_GSLOTS + 1);
-      M::set_one(X2);
-      M::stg(out, X1);
-      M::stg(out + 1, Y1);
-      M::stg(out + 2, X2);
-      M::stg(out + 3, X2);
+#if !G753_TREE_SYNC
+  if (!work) return;                 // holes and finished buckets only
+#endif
+  tree_sync();
+  if (any) M::inv(INV, INV, TMP);
+  // ---- phase 2: walk back, peel the individual inverses off, finish the additions ----------------
+  {
+    TreeSlot cur = tree_slot<K>(none, lvl0, bases, in);
+    TreeIdx ahead = none, lpend = none;
+    TreeWalk lw = w;
+    if (!dead) {
+      w.start_down();                // the walk up ended in the bucket of slot last - 1
+      lw = w;
+      cur = tree_slot<K>(tree_idx(w, last - 1, sorted), lvl0, bases, in);
+      for (uint32_t k = 1; k <= far2 && k < last - first; k++) {
+        const uint32_t jj = last - 1 - k;
+        lw.seek_down(jj);
+        prefetch_xy(tree_slot<K>(tree_idx(lw, jj, sorted), lvl0, bases, in), out + (size_t)jj * (2 * K));
+      }
+      if (far2 + 1 < last - first) {
+        lw.seek_down(last - 2 - far2);
+        lpend = tree_idx(lw, last - 2 - far2, sorted);
+      }
+    }
+    for (unsigned it = 0; it < batch; it++) {
+      tree_sync();
+      if (dead || it >= last - first) continue;
+      const uint32_t j = last - 1 - it;
+      Fq* cell = out + (size_t)j * (2 * K);
+      ahead = none;
+      if (j > first) {
+        w.seek_down(j - 1);
+        ahead = tree_idx(w, j - 1, sorted);
+      }
+      if (j - first >= far2 + 1)               // slot j - far - 1
+        prefetch_xy(tree_slot<K>(lpend, lvl0, bases, in), cell - (size_t)(far2 + 1) * (2 * K));
+      lpend = none;
+      if (j - first >= far2 + 2) {
+        lw.seek_down(j - far2 - 2);
+        lpend = tree_idx(lw, j - far2 - 2, sorted);
+      }
+      const unsigned what = cur.kind & 3u;
+      if (what == 1u) {                       // carried over
+        const int d[2] = {X1, Y1};
+        const Fq* const g[2] = {cur.p1, cur.p1 + K};
+        t_ldg_many<M, 2>(d, g);
+        if (cur.kind & 16u) M::neg(Y1, Y1);
+        M::stg(cell, X1);
+        M::stg(cell + K, Y1);
+      } else if (what == 2u) {
+        if (any && j != lead) {               // with the product of the denominators before this one
+          const int d[5] = {X1, Y1, X2, Y2, T};
+          const Fq* const g[5] = {cur.p1, cur.p1 + K, cur.p2, cur.p2 + K, cell};
+          t_ldg_many<M, 5>(d, g);
+        } else {
+          const int d[4] = {X1, Y1, X2, Y2};
+          const Fq* const g[4] = {cur.p1, cur.p1 + K, cur.p2, cur.p2 + K};
+          t_ldg_many<M, 4>(d, g);
+        }
+        fix_y(cur);
+        const int kind = classify(cur, true);
+        if (kind == 2) {
+          if (!(cur.kind & 64u)) {
+            M::set_zero(X1);
+            M::stg(cell, X1);
+            M::stg(cell + K, X1);
+          }
+        } else if (kind == 3) {
+          put(cur, cell, X2, Y2, X1, true);
+        } else if (kind == 4) {
+          put(cur, cell, X1, Y1, X2, true);
+        } else {
+          if (j != lead) {
+            M::mul(T, T, INV, TMP);           // 1 / DEN
+            M::mul(INV, INV, DEN, TMP);       // inverse of the product of the earlier ones
+          } else {
+            M::copy(T, INV);
+          }
+          if (kind == 1) {                    // lambda = (3 x1^2 + a) / (2 y1)
+            M::sqr(Y2, X1, TMP);
+            M::dbl(DEN, Y2);
+            M::add(Y2, Y2, DEN);
+            M::set_one(DEN);
+            SC::mul_by_a(X2, DEN);
+            M::add(Y2, Y2, X2);
+            M::copy(X2, X1);
+          } else {
+            M::sub(Y2, Y2, Y1);
+          }
+          M::mul(T, T, Y2, TMP);              // lambda
+          // prime fields: the dedicated squaring is fewer limb products but MORE instructions (2370 against 1362)
+          // and a second 38 KB body for the instruction cache; the towers' squarings do save products
+          if (K == 1) M::mul(DEN, T, T, TMP); else M::sqr(DEN, T, TMP);
+          M::sub(DEN, DEN, X1);
+          M::sub(DEN, DEN, X2);               // x3
+          M::sub(X1, X1, DEN);
+          M::mul(X1, X1, T, TMP);
+          M::sub(Y1, X1, Y1);                 // y3 = lambda (x1 - x3) - y1
+          put(cur, cell, DEN, Y1, X2, false);
+        }
+      }
+      cur = tree_slot<K>(ahead, lvl0, bases, in);
     }
   }
 }
-constexpr int AFF_SLOTS = 9;   // X1 .. TMP: 864 B per thread, two 128-thread blocks per SM
+template <class M>
+constexpr int tree_slots() { return 7 * M::K + M::NTMP; }
 
+// buckets with ONE entry never enter a round: buckets[t] = that key point (sign applied) as XYZZ (x, y, 1, 1).
+// (Fuller buckets are written by the round that adds their last pair; empty ones keep the all-zero limbs the
+// host wrote, ZZ == 0.)
+template <class SC>
+__global__ void __launch_bounds__(SC::M::T::THREADS)
+k_tree_finish(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, TreeGeo geo, Fq* __restrict__ points) {
+  typedef typename SC::M M;
+  typedef typename M::T L;
+  constexpr int K = M::K;
+  enum { X = 0, Y = K, ONE = 2 * K };
+  if (L::idle()) return;
+  const unsigned t = L::item();
+  if (t >= geo.NB) return;
+  if (geo.ends[t] - geo.offsets[t] != 1) return;
+  const uint32_t e = sorted[(size_t)(t / geo.len) * geo.row_cap + geo.offsets[t]];
+  const Fq* q = bases + (size_t)(e & 0x7fffffffu) * (2 * K);
+  M::ldg(X, q);
+  M::ldg(Y, q + K);
+  if (e >> 31) M::neg(Y, Y);
+  M::set_one(ONE);
+  Fq* o = points + (size_t)t * (4 * K);
+  M::stg(o, X);
+  M::stg(o + K, Y);
+  M::stg(o + 2 * K, ONE);
+  M::stg(o + 3 * K, ONE);
+}
 
 // Buckets that were cut into several items: points[t] = sum of their partial results
 // points[NB + item_off[t] + j], j < item_cnt[t].  A bucket can hold a large share of all points
@@ -733,11 +1060,14 @@ struct MsmWorkspace {
   unsigned n_chunks, nb_chunks, level_entries, max_items;
   size_t tail_points;  // points per ping-pong buffer of the reduction tail
   size_t row_cap;  // entries per row of sorted[]
+  size_t tree_odd, tree_even;  // affine points in the two ping-pong arrays of the addition tree (0: not used)
   size_t total;
 };
+// upper bound on the slots of level L + 1 of the addition tree given the bound on level L
+static inline size_t tree_level_bound(size_t prev, size_t NB) { return (prev + NB) / 2 + 1; }
 
 template <int GID>
-static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n, bool affine = false) {
+static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n, bool tree = false) {
   constexpr size_t PT_BYTES = sizeof(Fq) * 4 * MsmCfg<GID>::K;
   MsmWorkspace s;
   const size_t len = (size_t)pl.B + 1;
@@ -777,9 +1107,14 @@ static inline MsmWorkspace msm_workspace(const MsmPlan& pl, size_t n, bool affin
   t += Carver::pad(PT_BYTES * (NB + s.max_items));                      // buckets + item partials
   t += Carver::pad(PT_BYTES * pl.rows * entries) * 2;                   // reduction levels
   t += Carver::pad(PT_BYTES * (s.tail_points + 1)) * 2;                 // reduction tail
-  if (affine)                                                            // accumulators + prefix products
-    t += Carver::pad((size_t)div_up(div_up(s.max_items, AFF_G), MsmCfg<GID>::NC_ACC) * MsmCfg<GID>::NC_ACC * AFF_G *
-                     AFF_GSLOTS * sizeof(Fq));
+  s.tree_odd = s.tree_even = 0;
+  if (tree) {                                                            // levels 1, 3, ... / 2, 4, ... of the addition tree
+    s.tree_odd = tree_level_bound((size_t)pl.rows * s.row_cap, NB);
+    s.tree_even = tree_level_bound(s.tree_odd, NB);
+    if (s.tree_odd < NB + 4) s.tree_odd = NB + 4;     // the bounds of the later levels tend to NB + 2
+    if (s.tree_even < NB + 4) s.tree_even = NB + 4;
+    t += Carver::pad(PT_BYTES / 2 * s.tree_odd) + Carver::pad(PT_BYTES / 2 * s.tree_even) + 512;
+  }
   s.total = t + 8192;
   return s;
 }
@@ -790,6 +1125,7 @@ struct MsmHooks {  // phase timing hooks; the emulation build leaves them null
   unsigned scalar_chunks = 1;
   void* user = nullptr;
   uint64_t* launches = nullptr;
+  unsigned* form = nullptr;   // out: accumulation form that ran (0 = XYZZ running sums, 1 = affine addition tree)
 };
 
 #define G753_MSM_LAUNCH(hooks, ...)            \
@@ -819,17 +1155,10 @@ struct MsmKey {
   unsigned copies = 1;
   int c = 0;          // window bits the tables were built for (0 = choose per call)
   unsigned rows = 0;  // bucket rows the tables were built for (0 = derive)
-  int affine = -1;    // accumulation kernel: -1 = by size, 0 = XYZZ, 1 = affine with shared inversions
+  int affine = -1;    // accumulation: -1 = the group's default, 0 = XYZZ running sums, 1 = affine addition tree
+  int tree_batch = 0; // output slots per thread of the addition tree (0 = TREE_BATCH)
+  int tree_ahead = 0; // slots by which the L2 prefetch of the tree's operands runs ahead (0 = the kernel's default)
 };
-
-struct MsmHooks;
-template <int GID>
-static inline typename std::enable_if<MsmCfg<GID>::AFFINE>::type msm_launch_affine(
-    MsmHooks& hooks, cudaStream_t stream, unsigned blocks, const Fq* bases, const uint32_t* sorted,
-    const MsmItem* items, const uint32_t* item_total, Fq* points, uint4* scratch);
-template <int GID>
-static inline typename std::enable_if<!MsmCfg<GID>::AFFINE>::type msm_launch_affine(
-    MsmHooks&, cudaStream_t, unsigned, const Fq*, const uint32_t*, const MsmItem*, const uint32_t*, Fq*, uint4*) {}
 
 // out[g * ceil(m_in / 2) + p] = in[g * m_in + 2p] + in[g * m_in + 2p + 1]: one thread per output point while
 // there are many, one warp per point (coop.cuh) once the launch is latency-bound
@@ -875,11 +1204,20 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   const unsigned n = (unsigned)count;
   const MsmPlan pl = msm_plan(msm_cost<GID>(), n, key.copies, key.c, key.rows);
   if (pl.c == 0) return fail(G753_ERR_BAD_ARG, "msm: no window size satisfies the forced plan");
-  const bool affine = Cfg::AFFINE && key.affine > 0;  // opt-in (G753_MSM_AFFINE=1): measured slower, see header
-  const MsmWorkspace ws = msm_workspace<GID>(pl, n, affine);
+  constexpr size_t SMEM_TREE = slot_bytes<EA, CA>(tree_slots<typename EA::M>());
+  static_assert(SMEM_TREE <= 232448, "slot footprint exceeds 227 KB");
+  // the tree pays one inversion per thread and round - ~0.4 ms of latency per round whatever the size - so short
+  // MSMs keep the running sums; G753_MSM_AFFINE=0 / 1 forces one form
+  bool tree = key.affine < 0 ? (Cfg::AFFINE && (uint64_t)pl.W * n >= TREE_MIN_ENTRIES) : key.affine > 0;
+  MsmWorkspace ws = msm_workspace<GID>(pl, n, tree);
+  if (tree && key.affine < 0 && !scratch.can_hold(ws.total)) {   // the tree's level arrays do not fit: running sums
+    tree = false;
+    ws = msm_workspace<GID>(pl, n, false);
+  }
   if ((uint64_t)pl.W * n >= 0xffffffffull || (uint64_t)pl.rows * ws.row_cap >= 0xffffffffull ||
       (uint64_t)(pl.copies - 1) * key.copy_stride + n > 0x7fffffffull)
     return fail(G753_ERR_BAD_ARG, "msm: windows x points exceed the 32-bit index space of the sort");
+  if (hooks.form) *hooks.form = tree ? 1u : 0u;
   G753_TRY(scratch.reserve(ws.total));
   Carver cv(scratch.ptr);
   const size_t len = (size_t)pl.B + 1;
@@ -904,8 +1242,9 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   Fq* lvl_y = cv.take<Fq>(PT * R * ws.level_entries);
   Fq* tail_a = cv.take<Fq>(PT * (ws.tail_points + 1));
   Fq* tail_b = cv.take<Fq>(PT * (ws.tail_points + 1));
-  const unsigned aff_blocks = div_up(div_up(ws.max_items, AFF_G), CA);
-  uint4* aff_scratch = affine ? (uint4*)cv.take<Fq>((size_t)aff_blocks * CA * AFF_G * AFF_GSLOTS) : nullptr;
+  Fq* tree_odd = tree ? cv.take<Fq>(PT / 2 * ws.tree_odd) : nullptr;
+  Fq* tree_even = tree ? cv.take<Fq>(PT / 2 * ws.tree_even) : nullptr;
+  uint32_t* tree_max = cv.take<uint32_t>(64);
 
   if (hooks.mark) hooks.mark(hooks.user, 0);
   G753_TRY(dev_memset(hist, 0, sizeof(uint32_t) * NB, stream));
@@ -933,29 +1272,55 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
                   chunk_sums, (unsigned)len, ws.n_chunks, R, offsets, cursor);
   G753_MSM_LAUNCH(hooks, k_msm_scatter, div_up((size_t)pl.W * n, 256), 256, stream, digits, n, pl.W, pl.B, R,
                   key.copy_stride, ws.row_cap, cursor, sorted);
+  if (tree) {
+    // addition tree (after the scatter, cursor[t] is the end of bucket t's run)
+    G753_TRY(dev_memset(tree_max, 0, sizeof(uint32_t), stream));
+    G753_MSM_LAUNCH(hooks, k_tree_max, (unsigned)(NB < 148u * 1024 ? div_up(NB, 256) : 148u * 4), 256, stream, offsets, cursor,
+                    NB, tree_max);
+    if (hooks.mark) hooks.mark(hooks.user, 2);
+    TreeGeo geo{offsets, cursor, NB, (unsigned)len, (uint32_t)ws.row_cap};
+    size_t bound = (size_t)R * ws.row_cap;   // slots of the level below
+    unsigned rounds = 0;
+    while (((size_t)1 << rounds) < ws.row_cap) rounds++;   // a bucket holds at most row_cap entries
+    const size_t top = key.tree_batch > 0 ? (size_t)key.tree_batch : (size_t)TREE_BATCH;
+    for (unsigned level = 1; level <= rounds; level++) {
+      bound = tree_level_bound(bound, NB);
+      // slots per thread: enough threads for four waves of blocks first (a thread is a serial chain, and levels
+      // end with their slowest thread), then longer batches - one inversion (~113 000 instructions against
+      // ~9 700 per addition) per thread and round.  Measured at 2^22: exact single waves of longer batches on the
+      // short levels lose 5 ms, 256 slots everywhere 40 ms.
+      size_t batch = top;
+      if (key.tree_batch <= 0) {   // (G753_TREE_BATCH fixes the batch)
+        batch = bound / ((size_t)148 * 256 * 4);
+        batch = batch < 4 ? 4 : batch > top ? top : batch;
+      }
+      G753_MSM_LAUNCH_SMEM(hooks, k_tree_round<SCA>, div_up(div_up(bound, batch), CA), TA, SMEM_TREE, stream, key.bases, sorted,
+                           geo, tree_max, level, (unsigned)batch, (unsigned)key.tree_ahead, (level & 1) ? tree_even : tree_odd,
+                           (level & 1) ? tree_odd : tree_even, points);
+    }
+    G753_MSM_LAUNCH_SMEM(hooks, k_tree_finish<SCA>, div_up(NB, CA), TA, SMEM_TREE, stream, key.bases, sorted, geo, points);
+  } else {
   // work items (after the scatter, cursor[t] is the end of bucket t's run)
-  G753_MSM_LAUNCH(hooks, k_item_count, div_up(NB, 256), 256, stream, offsets, cursor, NB, pl.B, item_cnt,
-                  len_hist);
-  G753_MSM_LAUNCH(hooks, k_scan_chunks, div_up(ws.nb_chunks, 128), 128, stream, item_cnt, NB, ws.nb_chunks,
-                  1u, item_chunk_sums);
-  G753_MSM_LAUNCH(hooks, k_scan_tops, 1, 64, stream, item_chunk_sums, ws.nb_chunks, 1u, (uint32_t*)nullptr);
-  G753_MSM_LAUNCH(hooks, k_scan_apply, div_up(ws.nb_chunks, 128), 128, stream, item_cnt, item_chunk_sums,
-                  NB, ws.nb_chunks, 1u, item_off, (uint32_t*)nullptr);
-  G753_MSM_LAUNCH(hooks, k_item_len_scan, 1, 32, stream, len_hist, len_cursor, item_total);
-  G753_MSM_LAUNCH(hooks, k_item_emit, div_up(NB, 256), 256, stream, offsets, cursor, item_cnt, item_off, NB,
-                  pl.B, ws.row_cap, len_cursor, items, part_bucket);
-  if (hooks.mark) hooks.mark(hooks.user, 2);
-  if (affine)
-    msm_launch_affine<GID>(hooks, stream, aff_blocks, key.bases, sorted, items, item_total, points, aff_scratch);
-  else
+    G753_MSM_LAUNCH(hooks, k_item_count, div_up(NB, 256), 256, stream, offsets, cursor, NB, pl.B, item_cnt,
+                    len_hist);
+    G753_MSM_LAUNCH(hooks, k_scan_chunks, div_up(ws.nb_chunks, 128), 128, stream, item_cnt, NB, ws.nb_chunks,
+                    1u, item_chunk_sums);
+    G753_MSM_LAUNCH(hooks, k_scan_tops, 1, 64, stream, item_chunk_sums, ws.nb_chunks, 1u, (uint32_t*)nullptr);
+    G753_MSM_LAUNCH(hooks, k_scan_apply, div_up(ws.nb_chunks, 128), 128, stream, item_cnt, item_chunk_sums,
+                    NB, ws.nb_chunks, 1u, item_off, (uint32_t*)nullptr);
+    G753_MSM_LAUNCH(hooks, k_item_len_scan, 1, 32, stream, len_hist, len_cursor, item_total);
+    G753_MSM_LAUNCH(hooks, k_item_emit, div_up(NB, 256), 256, stream, offsets, cursor, item_cnt, item_off, NB,
+                    pl.B, ws.row_cap, len_cursor, items, part_bucket);
+    if (hooks.mark) hooks.mark(hooks.user, 2);
     G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc<SCA>, div_up(ws.max_items, CA), TA, SMEM_ACC, stream, key.bases,
-                         sorted, items, item_total, points);
-  // a bucket holds at most row_cap points = row_cap / ITEM_LEN + 1 partials
-  for (size_t stride = 1; stride <= ws.row_cap / ITEM_LEN; stride *= FIX_FAN)
-    G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup_level<SCA>, div_up(ws.max_items, CA), TA, SMEM_FIX, stream, item_cnt,
-                         item_off, part_bucket, item_total, NB, (unsigned)stride, points);
-  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup<SCA>, div_up(NB, CA), TA, SMEM_FIX, stream, item_cnt, item_off,
-                       NB, points);
+                           sorted, items, item_total, points);
+    // a bucket holds at most row_cap points = row_cap / ITEM_LEN + 1 partials
+    for (size_t stride = 1; stride <= ws.row_cap / ITEM_LEN; stride *= FIX_FAN)
+      G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup_level<SCA>, div_up(ws.max_items, CA), TA, SMEM_FIX, stream, item_cnt,
+                           item_off, part_bucket, item_total, NB, (unsigned)stride, points);
+    G753_MSM_LAUNCH_SMEM(hooks, k_bucket_fixup<SCA>, div_up(NB, CA), TA, SMEM_FIX, stream, item_cnt, item_off,
+                         NB, points);
+  }
   if (hooks.mark) hooks.mark(hooks.user, 3);
   // reduction levels
   const Fq* X = points;
@@ -1031,17 +1396,6 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
 #endif
   if (hooks.mark) hooks.mark(hooks.user, 5);
   return launch_check("msm_run");
-}
-
-template <int GID>
-static inline typename std::enable_if<MsmCfg<GID>::AFFINE>::type msm_launch_affine(
-    MsmHooks& hooks, cudaStream_t stream, unsigned blocks, const Fq* bases, const uint32_t* sorted,
-    const MsmItem* items, const uint32_t* item_total, Fq* points, uint4* scratch) {
-  typedef MsmCfg<GID> Cfg;
-  constexpr int CA = Cfg::NC_ACC, TA = CA * Cfg::TPA;
-  typedef typename Cfg::template SC<CA, Cfg::TPA> SCA;
-  G753_MSM_LAUNCH_SMEM(hooks, k_bucket_acc_affine<SCA>, blocks, TA, (slot_bytes<EcS<SCA>, CA>(AFF_SLOTS)), stream, bases,
-                       sorted, items, item_total, points, scratch);
 }
 
 }  // namespace g753

@@ -23,6 +23,8 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
   key.inf = b->d_inf ? b->d_inf + first : nullptr;
   key.copy_stride = key.inf_stride = b->n;
   key.affine = ctx->forced_affine;
+  key.tree_batch = ctx->tree_batch;
+  key.tree_ahead = ctx->tree_ahead;
   // the precomputed copies pay off when the slice is a sizeable part of the key they were sized
   // for; short slices (the prover's input-query views) run the plain pipeline on copy 0
   if (b->copies > 1 && count * 4 >= b->n) {
@@ -40,6 +42,7 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
     ctx->last_plan[2] = pl.rows;
     ctx->last_plan[3] = pl.copies;
   }
+  hooks.form = &ctx->last_plan[4];
   return msm_run<GID>(ctx->scratch, ctx->stream, key, d_scalars, count, (Fq*)d_out, hooks);
 }
 

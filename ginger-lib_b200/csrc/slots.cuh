@@ -257,6 +257,35 @@ G753_D void s_stg(Fq* g, int a) {
   for (int k = 0; k < SLOT_CHUNKS; k++) p[k] = q[k * T::NC];
 }
 
+// N tower elements global -> slots with all the loads in flight at once (one trip to L2 / HBM instead of
+// N): element n of tower M goes from g[n] to slot d[n].  Lane roles as in M::ldg.
+template <class M, int N>
+G753_D void t_ldg_many(const int (&d)[N], const Fq* const (&g)[N]) {
+  typedef typename M::T L;
+  auto coefficient = [&](int c) {
+    uint4 v[N][SLOT_CHUNKS];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      const uint4* p = (const uint4*)(g[n] + c);
+#pragma unroll
+      for (int k = 0; k < SLOT_CHUNKS; k++) v[n][k] = p[k];
+    }
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      uint4* q = slot_ptr<L>(d[n] + c);
+#pragma unroll
+      for (int k = 0; k < SLOT_CHUNKS; k++) q[k * L::NC] = v[n][k];
+    }
+  };
+  if (L::TP == 1) {   // one lane per column holds every coefficient
+    for (int c = 0; c < M::K; c++) coefficient(c);
+  } else {
+    const int r = L::role();
+    if (r < M::K) coefficient(r);
+  }
+  L::sync();
+}
+
 // ---- two products under one reduction on slots ---------------------------------------------------
 // returns a * slot[b] + c * slot[e] (fq_mul2).  a and c are in registers; the multipliers are
 // streamed from their slots, one 16-byte chunk every four steps.

@@ -278,10 +278,11 @@ uint64_t g753_launch_count(const g753_ctx* ctx);
 /* per-phase device times (ms) of the last g753_msm* call: digits, sort, accumulate, reduce,
  * combine - CUDA events on the context stream; returns the number of phases written */
 int g753_last_msm_phases(g753_ctx* ctx, float* ms, int cap);
-/* shape of the last g753_msm* call on this context: plan4 = {window bits c, windows W, bucket rows,
- * key copies used}.  The executed work of its accumulation phase is count * W mixed additions
+/* shape of the last g753_msm* call on this context: plan5 = {window bits c, windows W, bucket rows,
+ * key copies used, accumulation form (0 = XYZZ running sums, 1 = pairwise tree of affine additions
+ * with shared inversions)}.  The executed work of its accumulation phase is count * W additions
  * (bench.py reports it beside the reference op count the roofline is scored on). */
-int g753_last_msm_plan(const g753_ctx* ctx, unsigned* plan4);
+int g753_last_msm_plan(const g753_ctx* ctx, unsigned* plan5);
 
 #ifdef __cplusplus
 }

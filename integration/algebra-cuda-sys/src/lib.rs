@@ -123,7 +123,7 @@ extern "C" {
     pub fn g753_debug_scratch(ctx: *mut G753Ctx, h_dst: *mut c_void, bytes: usize, cap: *mut usize) -> c_int;
     pub fn g753_launch_count(ctx: *const G753Ctx) -> u64;
     pub fn g753_last_msm_phases(ctx: *mut G753Ctx, ms: *mut c_float, cap: c_int) -> c_int;
-    pub fn g753_last_msm_plan(ctx: *const G753Ctx, plan4: *mut c_uint) -> c_int;
+    pub fn g753_last_msm_plan(ctx: *const G753Ctx, plan5: *mut c_uint) -> c_int;
 }
 
 /// An error code of the C ABI with the library's thread-local description of it.

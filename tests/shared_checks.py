@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from oracle import g753 as O
-from util753 import G, GROUPS, array_to_ints, ffi, ints_to_array, points_to_arrays, sample_points
+from util753 import (G, GROUPS, array_to_ints, ffi, ints_to_array, points_to_arrays, projective_to_point, sample_points,
+                     sample_scalars)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 KAT = json.load(open(os.path.join(HERE, "golden", "reference_kat.json")))
@@ -154,3 +155,56 @@ def check_proof_verifies_with_pairing(ctx, name, precompute=1):
     assert PR.verify_proof(eng, vk, got, z[1:ni])
     assert not PR.verify_proof(eng, vk, got, [z[1], (z[2] + 1) % F.p])
     assert got == O.groth16_create_proof(key, ni, z, O.witness_map(F, a, b, c, 0, 0, 0), r, s)
+
+
+def check_msm_accumulation_cases(ctx, group):
+    """the exceptional cases of the bucket accumulation, whichever form the environment forces
+    (G753_MSM_AFFINE is read when a context is created): duplicates (doubling), P and -P in one bucket
+    (cancellation, then infinity as an operand one level up the tree), an infinity base, repeated small
+    scalars (long runs in one bucket: several rounds, batches that span buckets), buckets of one entry"""
+    C = GROUPS[group]
+    cx = G.Context(0, library=ctx.lib)
+    n = 60
+    pts = sample_points(C, n, 0x2A0 + group)
+    sc = sample_scalars(C, n, 0x2B0 + group)
+    pts[1] = None
+    pts[6] = pts[5]
+    sc[6] = sc[5]                        # same point twice in the same buckets: doubling branch
+    pts[8] = C.neg(pts[7])
+    sc[8] = sc[7]                        # P and -P with the same scalar: cancellation
+    pts[10] = pts[9]
+    sc[10] = C.r - sc[9]                 # P with s and -s: cancels through the sign bit
+    for i in range(20, 50):
+        sc[i] = 7                        # 30 points in one bucket of window 0
+    pts[30] = pts[29]                    # ... two of them equal
+    coords, inf = points_to_arrays(C, pts)
+    bases = cx.upload_bases(group, coords, inf)
+    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
+    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
+    # all points equal with one scalar: every bucket step is a doubling or a plain chain
+    pts2 = [pts[3]] * 40
+    sc2 = [5] * 40
+    coords, inf = points_to_arrays(C, pts2)
+    b2 = cx.upload_bases(group, coords, inf)
+    got = G.VariableBaseMSM.multi_scalar_mul(b2, ints_to_array(sc2))
+    assert projective_to_point(C, got) == C.mul(pts[3], 200)
+    # infinity as an operand further up the tree: (P - P), (Q + Q'), (A - A), (B - B) pair up as
+    # (inf + QQ') and (inf + inf), then QQ' + inf; the same bucket again through the sign bit
+    P_, Q_, Q2, A_, B_ = pts[11], pts[12], pts[13], pts[14], pts[15]
+    pts3 = [P_, C.neg(P_), Q_, Q2, A_, C.neg(A_), B_, C.neg(B_)]
+    for s3 in (3, C.r - 3):
+        coords, inf = points_to_arrays(C, pts3)
+        b3 = cx.upload_bases(group, coords, inf)
+        got = G.VariableBaseMSM.multi_scalar_mul(b3, ints_to_array([s3] * 8))
+        assert projective_to_point(C, got) == C.mul(C.add(Q_, Q2), s3)
+        b3.free()
+    # no bucket with two entries: no round runs, the finish reads the key itself (sign applied)
+    for s1 in (1, C.r - 1, 0):
+        coords, inf = points_to_arrays(C, [P_])
+        b1 = cx.upload_bases(group, coords, inf)
+        got = G.VariableBaseMSM.multi_scalar_mul(b1, ints_to_array([s1]))
+        assert projective_to_point(C, got) == C.mul(P_, s1)
+        b1.free()
+    bases.free()
+    b2.free()
+    cx.close()

@@ -169,6 +169,21 @@ def test_msm_accumulate_exceptions(ctx, group):
         assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
 
 
+@pytest.mark.parametrize("form", ["1", "0"])
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_msm_accumulation_forms(ctx, monkeypatch, group, form):
+    """both accumulation forms, forced, on every group and on the device's lane-cooperative towers: the
+    pairwise tree of affine additions with shared inversions (k_tree_round) and the XYZZ running sums
+    (k_bucket_acc); doubling, cancellation, infinity operands, long runs, single entries"""
+    import shared_checks
+    monkeypatch.setenv("G753_MSM_AFFINE", form)
+    monkeypatch.setenv("G753_MSM_C", "5")
+    shared_checks.check_msm_accumulation_cases(ctx, group)
+    if form == "1":      # long batches: one thread walks many buckets, the slot roles of the copy pipeline rotate
+        monkeypatch.setenv("G753_TREE_BATCH", "37")
+        shared_checks.check_msm_accumulation_cases(ctx, group)
+
+
 def test_msm_linearity_2e14(ctx):
     """size-independent property: msm(B, s) + msm(B, t) == msm(B, s + t mod r); bases are a
     short list repeated, so the oracle answer is also computable directly."""

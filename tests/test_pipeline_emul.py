@@ -115,7 +115,8 @@ def test_msm_window_sizes(ctx, monkeypatch):
         assert projective_to_point(C, got) == want, c
         # g753_last_msm_plan: W * c covers the 753 scalar bits + the sign carry; a plain key has one row per window
         plan = cx.last_msm_plan()
-        assert plan == {"c": c, "windows": -(-754 // c), "rows": -(-754 // c), "copies": 1}
+        assert plan == {"c": c, "windows": -(-754 // c), "rows": -(-754 // c), "copies": 1,
+                        "accumulation": "xyzz_running_sums"}      # short MSMs keep the running sums
         bases.free()
         cx.close()
 
@@ -396,41 +397,18 @@ def test_mixed_radix_domain_none(ctx):
     assert G.MixedRadixDomain.new(ffi.FIELD_MNT4_FR, (1 << 18) * 5, ctx=ctx) is not None
 
 
-@pytest.mark.parametrize("group", [ffi.MNT4_G1, ffi.MNT6_G1])
-def test_msm_affine_accumulation(ctx, monkeypatch, group):
-    """k_bucket_acc_affine (shared-inversion affine additions, forced on): duplicates (doubling), P and -P
-    in one bucket (cancellation), an infinity base, repeated small scalars (long runs in one bucket)"""
-    C = GROUPS[group]
-    monkeypatch.setenv("G753_MSM_AFFINE", "1")
+@pytest.mark.parametrize("form", ["1", "0"])
+@pytest.mark.parametrize("group", sorted(GROUPS))
+def test_msm_accumulation_forms(ctx, monkeypatch, group, form):
+    """both accumulation forms, forced, on every group: the pairwise tree of affine additions with shared
+    inversions (k_tree_round) and the XYZZ running sums (k_bucket_acc)"""
+    import shared_checks
+    monkeypatch.setenv("G753_MSM_AFFINE", form)
     monkeypatch.setenv("G753_MSM_C", "5")
-    cx = G.Context(0, library=ctx.lib)
-    n = 60
-    pts = sample_points(C, n, 0x2A0 + group)
-    sc = sample_scalars(C, n, 0x2B0 + group)
-    pts[1] = None
-    pts[6] = pts[5]
-    sc[6] = sc[5]                        # same point twice in the same buckets: doubling branch
-    pts[8] = C.neg(pts[7])
-    sc[8] = sc[7]                        # P and -P with the same scalar: cancellation
-    pts[10] = pts[9]
-    sc[10] = C.r - sc[9]                 # P with s and -s: cancels through the sign bit
-    for i in range(20, 50):
-        sc[i] = 7                        # 30 points in one bucket of window 0
-    pts[30] = pts[29]                    # ... two of them equal
-    coords, inf = points_to_arrays(C, pts)
-    bases = cx.upload_bases(group, coords, inf)
-    got = G.VariableBaseMSM.multi_scalar_mul(bases, ints_to_array(sc))
-    assert projective_to_point(C, got) == O.msm_naive(C, pts, sc)
-    # all points equal with one scalar: every bucket step is a doubling or a plain chain
-    pts2 = [pts[3]] * 40
-    sc2 = [5] * 40
-    coords, inf = points_to_arrays(C, pts2)
-    b2 = cx.upload_bases(group, coords, inf)
-    got = G.VariableBaseMSM.multi_scalar_mul(b2, ints_to_array(sc2))
-    assert projective_to_point(C, got) == C.mul(pts[3], 200)
-    bases.free()
-    b2.free()
-    cx.close()
+    shared_checks.check_msm_accumulation_cases(ctx, group)
+    if form == "1":      # long batches: one thread walks many buckets, the slot roles of the copy pipeline rotate
+        monkeypatch.setenv("G753_TREE_BATCH", "37")
+        shared_checks.check_msm_accumulation_cases(ctx, group)
 
 
 @pytest.mark.parametrize("group", sorted(GROUPS))
