@@ -575,7 +575,9 @@ def run_ours(args):
         traffic = None
         if world == 1 and args.log_n == 22:
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_bucket_acc_bytes_2p22")
+                tree_form = bool(plan) and plan.get("accumulation") == "affine_tree"
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                    "k_tree_round_level1_bytes_2p22" if tree_form else "k_bucket_acc_bytes_2p22")
             except (OSError, ValueError):
                 pass
         roofline = {
@@ -589,7 +591,8 @@ def run_ours(args):
             "frac": executed["frac"] if executed else None,
             "traffic": traffic,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at "
-                              "2^22 on one GPU (profiles/); not measured per run, null for other shapes",
+                              "2^22 on one GPU (profiles/; for k_tree_round: its level-1 launch, half of the additions; "
+                              "kernel_ms covers all levels); not measured per run, null for other shapes",
             "peak_source": "measured live: dependent fq_mul stream on 592x256 threads (g753_mac_probe), 1176 limb-MACs per product",
             "kernel_ms": acc_ms,
             "executed": executed,

@@ -605,8 +605,6 @@ int g753_ctx_create(int device, g753_ctx** out) {
   if (fa) ctx->forced_affine = atoi(fa) ? 1 : 0;
   const char* tb = getenv("G753_TREE_BATCH");
   if (tb && atoi(tb) > 0) ctx->tree_batch = atoi(tb);
-  const char* ta = getenv("G753_TREE_AHEAD");
-  if (ta && atoi(ta) > 0) ctx->tree_ahead = atoi(ta);
   *out = ctx;
   return G753_OK;
 }

@@ -62,22 +62,18 @@ template <int GID> struct MsmCfg;
 #define G753_NC_ACC1 128  // columns per block of the prime-field accumulation kernel
 #endif
 template <> struct MsmCfg<0> {
-  static constexpr bool AFFINE = true;
   static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = G753_NC_ACC1, NC_RED = 96;
   template <int NC, int LANES = 1> using SC = SCurveM4G1<Lay<NC, LANES>>;
 };
 template <> struct MsmCfg<1> {
-  static constexpr bool AFFINE = false;
   static constexpr int K = 2, TP = G753_TP2, TPA = G753_TP2A, NC_ACC = 16, NC_RED = 32;
   template <int NC, int LANES = G753_TP2> using SC = SCurveM4G2<Lay<NC, LANES>>;
 };
 template <> struct MsmCfg<2> {
-  static constexpr bool AFFINE = true;
   static constexpr int K = 1, TP = 1, TPA = 1, NC_ACC = G753_NC_ACC1, NC_RED = 96;
   template <int NC, int LANES = 1> using SC = SCurveM6G1<Lay<NC, LANES>>;
 };
 template <> struct MsmCfg<3> {
-  static constexpr bool AFFINE = false;
   static constexpr int K = 3, TP = G753_TP3, TPA = G753_TP3A, NC_ACC = G753_TP3A == 3 ? 40 : 32, NC_RED = 16;
   template <int NC, int LANES = G753_TP3> using SC = SCurveM6G2<Lay<NC, LANES>>;
 };
@@ -502,50 +498,38 @@ G753_D void tree_prefetch(const void* p) {
 #endif
 }
 
-// G753_TREE_SYNC = 1: the warps of a block meet at a barrier before every slot, so that they walk the ~22 KB
-// multiplier body together and share its instruction-cache lines (L1.5 is 32 KB per SM); device only
-#ifndef G753_TREE_SYNC
-#define G753_TREE_SYNC 0
-#endif
-G753_D void tree_sync() {
-#if G753_TREE_SYNC && defined(__CUDA_ARCH__)
-  __syncthreads();
-#endif
-}
-
+// Six element slots per column (x1, y1, x2, y2, T, INV; the denominator overwrites x2, x3 lands in y2's slot): on
+// the prime-field curves 72 KB per 128-thread block, so THREE blocks share an SM (12 warps; the XYZZ kernel's
+// eight slots allow two).  The hot loop calls ONE multiplier body (22 KB; squarings go through it too), which
+// the 32 KB L1.5 instruction cache holds - with the dedicated squaring body beside it ncu showed a quarter of
+// the issue slots waiting for instructions.
 template <class SC>
-__global__ void __launch_bounds__(SC::M::T::THREADS)
+__global__ void __launch_bounds__(SC::M::T::THREADS, SC::M::K == 1 ? 3 : 1)
 k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, TreeGeo geo,
-             const uint32_t* __restrict__ max_count, unsigned level, unsigned batch, unsigned far, const Fq* __restrict__ in,
+             const uint32_t* __restrict__ max_count, unsigned level, unsigned batch, const Fq* __restrict__ in,
              Fq* __restrict__ out, Fq* __restrict__ points) {
   typedef typename SC::M M;
   typedef typename M::T L;
   constexpr int K = M::K;
-  enum { X1 = 0, Y1 = K, X2 = 2 * K, Y2 = 3 * K, DEN = 4 * K, T = 5 * K, INV = 6 * K, TMP = 7 * K };
-  constexpr int EL = (int)(K * sizeof(Fq));   // bytes of one coordinate
+  enum { X1 = 0, Y1 = K, X2 = 2 * K, Y2 = 3 * K, T = 4 * K, INV = 5 * K, TMP = 6 * K };
+  constexpr int ONE = M::NTMP >= K ? TMP : X2;   // where the doubling builds the curve coefficient a
+  constexpr int EL = (int)(K * sizeof(Fq));      // bytes of one coordinate
   if (tree_count(*max_count, level - 1) <= 1) return;   // every bucket is down to one element already
   if (L::idle()) return;
   const uint64_t first64 = (uint64_t)L::item() * batch;
   TreeWalk w;
   w.g = geo;
   w.level = level;
-  bool dead;
   {
     const unsigned b = geo.NB - 1;
     w.set(b, geo.offsets[b], geo.ends[b]);
-    dead = first64 >= (uint64_t)w.s_out + w.c_out;   // beyond the last slot of the level
+    if (first64 >= (uint64_t)w.s_out + w.c_out) return;   // beyond the last slot of the level
   }
-#if !G753_TREE_SYNC
-  if (dead) return;
-#endif
   const uint32_t first = (uint32_t)first64;
   const uint64_t stop64 = first64 + batch;
   const uint32_t last = (uint32_t)(stop64 > 0xfffffffeull ? 0xfffffffeull : stop64);   // exclusive
   const bool lvl0 = level == 1;   // inputs are key points: never at infinity, y negated by the sign bit
 
-  // with (x1, x2) in X1, X2 (and, when have_y, the sign-corrected y in Y1, Y2):
-  // 0 = ordinary addition, 1 = doubling, 2 = cancellation, 3 = first operand at infinity (result = second),
-  // 4 = second at infinity (result = first); leaves the denominator in DEN (kinds 0, 1)
   auto fix_y = [&](const TreeSlot& s) {
     if (s.kind & 16u) M::neg(Y1, Y1);
     if (s.kind & 32u) M::neg(Y2, Y2);
@@ -556,6 +540,9 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
     t_ldg_many<M, 2>(d, g);
     fix_y(s);
   };
+  // with (x1, x2) in X1, X2 (and, when have_y, the sign-corrected y in Y1, Y2):
+  // 0 = ordinary addition, 1 = doubling, 2 = cancellation, 3 = first operand at infinity (result = second),
+  // 4 = second at infinity (result = first).  Kinds 0, 1 leave the DENOMINATOR in X2 (x2 - x1, or 2 y1).
   auto classify = [&](const TreeSlot& s, bool have_y) -> int {
     if (!lvl0) {
       const bool z1 = M::is_zero(X1), z2 = M::is_zero(X2);
@@ -566,12 +553,12 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
         have_y = true;
       }
     }
-    M::sub(DEN, X2, X1);
-    if (!M::is_zero(DEN)) return 0;
+    M::sub(X2, X2, X1);
+    if (!M::is_zero(X2)) return 0;
     if (!have_y) load_y(s);
-    M::sub(DEN, Y2, Y1);
-    if (!M::is_zero(DEN) || M::is_zero(Y1)) return 2;
-    M::dbl(DEN, Y1);
+    M::sub(X2, Y2, Y1);
+    if (!M::is_zero(X2) || M::is_zero(Y1)) return 2;
+    M::dbl(X2, Y1);
     return 1;
   };
   auto prefetch_x = [&](const TreeSlot& s) {
@@ -593,9 +580,11 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
       tree_prefetch<2 * EL>(s.p1);
     }
   };
-  TreeIdx none;
-  none.a = none.b = none.t = 0;
-  none.kind = 0;
+  // prime fields: the dedicated squaring is fewer limb products but MORE instructions (2370 against 1362) and a
+  // second 38 KB body for the instruction cache; the towers' squarings do save products
+  auto square = [&](int d, int a) {
+    if (K == 1) M::mul(d, a, a, TMP); else M::sqr(d, a, TMP);
+  };
   // (x, y) in slots sx, sy: to the cell of the output level, or - the last addition of a bucket - to the bucket
   // itself as XYZZ (x, y, 1, 1); a sum at infinity leaves the bucket's all-zero limbs (ZZ == 0) alone
   auto put = [&](const TreeSlot& s, Fq* cell, int sx, int sy, int one, bool maybe_inf) {
@@ -612,45 +601,30 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
       M::stg(cell + K, sy);
     }
   };
+  TreeIdx none;
+  none.a = none.b = none.t = 0;
+  none.kind = 0;
 
   // ---- phase 1: denominators and their running product -----------------------------------------
+  // Entry indices are read two slots ahead (their loads fly during a slot's arithmetic), turned into addresses
+  // and prefetched into L2 one slot ahead.
   bool any = false, work = false;
   uint32_t lead = 0;   // slot of the first denominator: its prefix is 1 and is not stored
-  // Two walks per phase.  The LEADER runs `far` slots ahead and only prefetches operands into L2 (a slot of phase 1
-  // is one product long, ~6 us per warp, less than a trip to HBM under load); the FOLLOWER loads and computes.  Both
-  // read their entry indices one slot before they turn them into addresses.
-  const uint32_t far1 = far ? far : 4u, far2 = (far1 + 1) / 2;
   {
-    TreeSlot cur = tree_slot<K>(none, lvl0, bases, in);
-    TreeIdx ahead = none, lpend = none;
-    TreeWalk lw = w;
-    if (!dead) {
-      w.start_up(first);
-      lw = w;
-      cur = tree_slot<K>(tree_idx(w, first, sorted), lvl0, bases, in);
-      for (uint32_t jj = first + 1; jj <= first + far1 && jj < last; jj++) {   // the first `far` slots: one burst
-        lw.seek_up(jj);
-        prefetch_x(tree_slot<K>(tree_idx(lw, jj, sorted), lvl0, bases, in));
-      }
-      if (first + far1 + 1 < last) {
-        lw.seek_up(first + far1 + 1);
-        lpend = tree_idx(lw, first + far1 + 1, sorted);
-      }
+    w.start_up(first);
+    TreeSlot cur = tree_slot<K>(tree_idx(w, first, sorted), lvl0, bases, in);
+    TreeIdx ahead = none;
+    if (first + 1 < last) {
+      w.seek_up(first + 1);
+      ahead = tree_idx(w, first + 1, sorted);
     }
-    for (unsigned it = 0; it < batch; it++) {
-      tree_sync();
-      const uint32_t j = first + it;
-      if (dead || j >= last) continue;
+    TreeSlot nxt = tree_slot<K>(ahead, lvl0, bases, in);
+    prefetch_x(nxt);
+    for (uint32_t j = first; j < last; j++) {
       ahead = none;
-      if (j + 1 < last) {            // entry indices of the next slot: their loads fly during this slot's arithmetic
-        w.seek_up(j + 1);
-        ahead = tree_idx(w, j + 1, sorted);
-      }
-      prefetch_x(tree_slot<K>(lpend, lvl0, bases, in));   // slot j + far + 1
-      lpend = none;
-      if (j + far1 + 2 < last) {
-        lw.seek_up(j + far1 + 2);
-        lpend = tree_idx(lw, j + far1 + 2, sorted);
+      if (j + 2 < last) {
+        w.seek_up(j + 2);
+        ahead = tree_idx(w, j + 2, sorted);
       }
       work = work || (cur.kind & 3u) != 0u;
       if ((cur.kind & 3u) == 2u) {
@@ -659,58 +633,39 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
         t_ldg_many<M, 2>(d, g);
         if (classify(cur, false) < 2) {
           if (!any) {
-            M::copy(INV, DEN);
+            M::copy(INV, X2);
             any = true;
             lead = j;
           } else {
             M::stg(out + (size_t)j * (2 * K), INV);
-            M::mul(INV, INV, DEN, TMP);
+            M::mul(INV, INV, X2, TMP);
           }
         }
       }
-      cur = tree_slot<K>(ahead, lvl0, bases, in);
+      cur = nxt;
+      nxt = tree_slot<K>(ahead, lvl0, bases, in);
+      prefetch_x(nxt);
     }
   }
-#if !G753_TREE_SYNC
   if (!work) return;                 // holes and finished buckets only
-#endif
-  tree_sync();
   if (any) M::inv(INV, INV, TMP);
   // ---- phase 2: walk back, peel the individual inverses off, finish the additions ----------------
   {
-    TreeSlot cur = tree_slot<K>(none, lvl0, bases, in);
-    TreeIdx ahead = none, lpend = none;
-    TreeWalk lw = w;
-    if (!dead) {
-      w.start_down();                // the walk up ended in the bucket of slot last - 1
-      lw = w;
-      cur = tree_slot<K>(tree_idx(w, last - 1, sorted), lvl0, bases, in);
-      for (uint32_t k = 1; k <= far2 && k < last - first; k++) {
-        const uint32_t jj = last - 1 - k;
-        lw.seek_down(jj);
-        prefetch_xy(tree_slot<K>(tree_idx(lw, jj, sorted), lvl0, bases, in), out + (size_t)jj * (2 * K));
-      }
-      if (far2 + 1 < last - first) {
-        lw.seek_down(last - 2 - far2);
-        lpend = tree_idx(lw, last - 2 - far2, sorted);
-      }
+    w.start_down();                  // the walk up ended in the bucket of slot last - 1
+    TreeSlot cur = tree_slot<K>(tree_idx(w, last - 1, sorted), lvl0, bases, in);
+    TreeIdx ahead = none;
+    if (last - 1 > first) {
+      w.seek_down(last - 2);
+      ahead = tree_idx(w, last - 2, sorted);
     }
-    for (unsigned it = 0; it < batch; it++) {
-      tree_sync();
-      if (dead || it >= last - first) continue;
-      const uint32_t j = last - 1 - it;
+    TreeSlot nxt = tree_slot<K>(ahead, lvl0, bases, in);
+    prefetch_xy(nxt, out + (size_t)(last - 2) * (2 * K));
+    for (uint32_t j = last; j-- > first;) {
       Fq* cell = out + (size_t)j * (2 * K);
       ahead = none;
-      if (j > first) {
-        w.seek_down(j - 1);
-        ahead = tree_idx(w, j - 1, sorted);
-      }
-      if (j - first >= far2 + 1)               // slot j - far - 1
-        prefetch_xy(tree_slot<K>(lpend, lvl0, bases, in), cell - (size_t)(far2 + 1) * (2 * K));
-      lpend = none;
-      if (j - first >= far2 + 2) {
-        lw.seek_down(j - far2 - 2);
-        lpend = tree_idx(lw, j - far2 - 2, sorted);
+      if (j >= first + 2) {
+        w.seek_down(j - 2);
+        ahead = tree_idx(w, j - 2, sorted);
       }
       const unsigned what = cur.kind & 3u;
       if (what == 1u) {                       // carried over
@@ -744,40 +699,41 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
           put(cur, cell, X1, Y1, X2, true);
         } else {
           if (j != lead) {
-            M::mul(T, T, INV, TMP);           // 1 / DEN
-            M::mul(INV, INV, DEN, TMP);       // inverse of the product of the earlier ones
+            M::mul(T, T, INV, TMP);           // 1 / den
+            M::mul(INV, INV, X2, TMP);        // inverse of the product of the earlier ones
           } else {
             M::copy(T, INV);
           }
-          if (kind == 1) {                    // lambda = (3 x1^2 + a) / (2 y1)
-            M::sqr(Y2, X1, TMP);
-            M::dbl(DEN, Y2);
-            M::add(Y2, Y2, DEN);
-            M::set_one(DEN);
-            SC::mul_by_a(X2, DEN);
+          if (kind == 1) {                    // lambda = (3 x1^2 + a) / (2 y1), x2 = x1
+            square(Y2, X1);
+            M::dbl(X2, Y2);
             M::add(Y2, Y2, X2);
-            M::copy(X2, X1);
+            M::set_one(ONE);
+            SC::mul_by_a(X2, ONE);
+            M::add(Y2, Y2, X2);
+            M::set_zero(X2);                  // "x2 - x1" for the x3 below
           } else {
             M::sub(Y2, Y2, Y1);
           }
           M::mul(T, T, Y2, TMP);              // lambda
-          // prime fields: the dedicated squaring is fewer limb products but MORE instructions (2370 against 1362)
-          // and a second 38 KB body for the instruction cache; the towers' squarings do save products
-          if (K == 1) M::mul(DEN, T, T, TMP); else M::sqr(DEN, T, TMP);
-          M::sub(DEN, DEN, X1);
-          M::sub(DEN, DEN, X2);               // x3
-          M::sub(X1, X1, DEN);
+          square(Y2, T);
+          M::sub(Y2, Y2, X1);
+          M::sub(Y2, Y2, X1);
+          M::sub(Y2, Y2, X2);                 // x3 = lambda^2 - x1 - (x1 + (x2 - x1))
+          M::sub(X1, X1, Y2);
           M::mul(X1, X1, T, TMP);
           M::sub(Y1, X1, Y1);                 // y3 = lambda (x1 - x3) - y1
-          put(cur, cell, DEN, Y1, X2, false);
+          put(cur, cell, Y2, Y1, X2, false);
         }
       }
-      cur = tree_slot<K>(ahead, lvl0, bases, in);
+      cur = nxt;
+      nxt = tree_slot<K>(ahead, lvl0, bases, in);
+      if (j >= first + 2) prefetch_xy(nxt, cell - 2 * (2 * K));
     }
   }
 }
 template <class M>
-constexpr int tree_slots() { return 7 * M::K + M::NTMP; }
+constexpr int tree_slots() { return 6 * M::K + M::NTMP; }
 
 // buckets with ONE entry never enter a round: buckets[t] = that key point (sign applied) as XYZZ (x, y, 1, 1).
 // (Fuller buckets are written by the round that adds their last pair; empty ones keep the all-zero limbs the
@@ -1157,7 +1113,6 @@ struct MsmKey {
   unsigned rows = 0;  // bucket rows the tables were built for (0 = derive)
   int affine = -1;    // accumulation: -1 = the group's default, 0 = XYZZ running sums, 1 = affine addition tree
   int tree_batch = 0; // output slots per thread of the addition tree (0 = TREE_BATCH)
-  int tree_ahead = 0; // slots by which the L2 prefetch of the tree's operands runs ahead (0 = the kernel's default)
 };
 
 // out[g * ceil(m_in / 2) + p] = in[g * m_in + 2p] + in[g * m_in + 2p + 1]: one thread per output point while
@@ -1208,7 +1163,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
   static_assert(SMEM_TREE <= 232448, "slot footprint exceeds 227 KB");
   // the tree pays one inversion per thread and round - ~0.4 ms of latency per round whatever the size - so short
   // MSMs keep the running sums; G753_MSM_AFFINE=0 / 1 forces one form
-  bool tree = key.affine < 0 ? (Cfg::AFFINE && (uint64_t)pl.W * n >= TREE_MIN_ENTRIES) : key.affine > 0;
+  bool tree = key.affine < 0 ? (uint64_t)pl.W * n >= TREE_MIN_ENTRIES : key.affine > 0;
   MsmWorkspace ws = msm_workspace<GID>(pl, n, tree);
   if (tree && key.affine < 0 && !scratch.can_hold(ws.total)) {   // the tree's level arrays do not fit: running sums
     tree = false;
@@ -1283,19 +1238,33 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
     unsigned rounds = 0;
     while (((size_t)1 << rounds) < ws.row_cap) rounds++;   // a bucket holds at most row_cap entries
     const size_t top = key.tree_batch > 0 ? (size_t)key.tree_batch : (size_t)TREE_BATCH;
+    int resident = 2;   // blocks per SM: columns the GPU runs at once = one wave
+#if !defined(G753_HOST_EMUL)
+    cudaFuncSetAttribute(k_tree_round<SCA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TREE);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_tree_round<SCA>, TA, SMEM_TREE) != cudaSuccess || resident < 1)
+      resident = 2;
+#endif
+    const size_t wave = (size_t)148 * (size_t)resident * CA;
     for (unsigned level = 1; level <= rounds; level++) {
       bound = tree_level_bound(bound, NB);
       // slots per thread: enough threads for four waves of blocks first (a thread is a serial chain, and levels
       // end with their slowest thread), then longer batches - one inversion (~113 000 instructions against
-      // ~9 700 per addition) per thread and round.  Measured at 2^22: exact single waves of longer batches on the
-      // short levels lose 5 ms, 256 slots everywhere 40 ms.
+      // ~9 700 per addition) per thread and round.  The upper levels are mostly holes and finished buckets: there
+      // a batch is sized for ~48 expected PAIRS (uniform digits) as long as one wave of threads remains.
+      // Measured at 2^22: exact single waves of longer batches on every short level lose 5 ms, 256 slots
+      // everywhere 40 ms.
       size_t batch = top;
       if (key.tree_batch <= 0) {   // (G753_TREE_BATCH fixes the batch)
-        batch = bound / ((size_t)148 * 256 * 4);
+        const size_t four = bound / (4 * wave), one = bound / wave;
+        size_t pairs = ((size_t)pl.W * n) >> level;
+        if (pairs < 1) pairs = 1;
+        size_t by_pairs = 48 * bound / pairs;
+        if (by_pairs > one) by_pairs = one;
+        batch = four > by_pairs ? four : by_pairs;
         batch = batch < 4 ? 4 : batch > top ? top : batch;
       }
       G753_MSM_LAUNCH_SMEM(hooks, k_tree_round<SCA>, div_up(div_up(bound, batch), CA), TA, SMEM_TREE, stream, key.bases, sorted,
-                           geo, tree_max, level, (unsigned)batch, (unsigned)key.tree_ahead, (level & 1) ? tree_even : tree_odd,
+                           geo, tree_max, level, (unsigned)batch, (level & 1) ? tree_even : tree_odd,
                            (level & 1) ? tree_odd : tree_even, points);
     }
     G753_MSM_LAUNCH_SMEM(hooks, k_tree_finish<SCA>, div_up(NB, CA), TA, SMEM_TREE, stream, key.bases, sorted, geo, points);
