@@ -605,6 +605,8 @@ int g753_ctx_create(int device, g753_ctx** out) {
   if (fa) ctx->forced_affine = atoi(fa) ? 1 : 0;
   const char* tb = getenv("G753_TREE_BATCH");
   if (tb && atoi(tb) > 0) ctx->tree_batch = atoi(tb);
+  const char* tw = getenv("G753_TREE_WAVES");
+  if (tw && atoi(tw) > 0) ctx->tree_waves = atoi(tw);
   *out = ctx;
   return G753_OK;
 }

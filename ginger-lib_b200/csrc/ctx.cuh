@@ -28,6 +28,7 @@ struct g753_ctx {
   int forced_c = 0;
   int forced_affine = -1;  // G753_MSM_AFFINE: 0 / 1 force the accumulation form, unset = the group's default
   int tree_batch = 0;      // G753_TREE_BATCH: output slots per thread of the addition tree (0 = default)
+  int tree_waves = 0;      // G753_TREE_WAVES: waves of blocks per level before batches grow (0 = default)
   std::mutex mu;
   unsigned scalar_chunks = 1;  // > 1 while g753_msm feeds the scalars of the running MSM in pieces
 #if !defined(G753_HOST_EMUL)

@@ -607,44 +607,59 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
 
   // ---- phase 1: denominators and their running product -----------------------------------------
   // Entry indices are read two slots ahead (their loads fly during a slot's arithmetic), turned into addresses
-  // and prefetched into L2 one slot ahead.
+  // and prefetched into L2 one slot ahead.  A lane steps over the slots that are no pair (holes, finished buckets,
+  // carried elements) on its own and meets the other lanes of its warp again at its next PAIR: on the upper levels
+  // most slots are no pair, and a warp that walked them in lockstep paid a full addition for every slot in which
+  // any of its lanes had one (measured: 1 ns per slot on every level, whatever the share of pairs).
   bool any = false, work = false;
   uint32_t lead = 0;   // slot of the first denominator: its prefix is 1 and is not stored
   {
     w.start_up(first);
     TreeSlot cur = tree_slot<K>(tree_idx(w, first, sorted), lvl0, bases, in);
+    TreeSlot nxt = tree_slot<K>(none, lvl0, bases, in);
     TreeIdx ahead = none;
     if (first + 1 < last) {
       w.seek_up(first + 1);
-      ahead = tree_idx(w, first + 1, sorted);
+      nxt = tree_slot<K>(tree_idx(w, first + 1, sorted), lvl0, bases, in);
+      prefetch_x(nxt);
     }
-    TreeSlot nxt = tree_slot<K>(ahead, lvl0, bases, in);
-    prefetch_x(nxt);
-    for (uint32_t j = first; j < last; j++) {
+    if (first + 2 < last) {
+      w.seek_up(first + 2);
+      ahead = tree_idx(w, first + 2, sorted);
+    }
+    uint32_t j = first;
+    auto advance = [&]() {
+      cur = nxt;
+      nxt = tree_slot<K>(ahead, lvl0, bases, in);
+      prefetch_x(nxt);
+      j++;
       ahead = none;
       if (j + 2 < last) {
         w.seek_up(j + 2);
         ahead = tree_idx(w, j + 2, sorted);
       }
-      work = work || (cur.kind & 3u) != 0u;
-      if ((cur.kind & 3u) == 2u) {
-        const int d[2] = {X1, X2};
-        const Fq* const g[2] = {cur.p1, cur.p2};
-        t_ldg_many<M, 2>(d, g);
-        if (classify(cur, false) < 2) {
-          if (!any) {
-            M::copy(INV, X2);
-            any = true;
-            lead = j;
-          } else {
-            M::stg(out + (size_t)j * (2 * K), INV);
-            M::mul(INV, INV, X2, TMP);
-          }
+    };
+    for (;;) {
+      while (j < last && (cur.kind & 3u) != 2u) {
+        work = work || (cur.kind & 3u) != 0u;
+        advance();
+      }
+      if (j >= last) break;
+      work = true;
+      const int d[2] = {X1, X2};
+      const Fq* const g[2] = {cur.p1, cur.p2};
+      t_ldg_many<M, 2>(d, g);
+      if (classify(cur, false) < 2) {
+        if (!any) {
+          M::copy(INV, X2);
+          any = true;
+          lead = j;
+        } else {
+          M::stg(out + (size_t)j * (2 * K), INV);
+          M::mul(INV, INV, X2, TMP);
         }
       }
-      cur = nxt;
-      nxt = tree_slot<K>(ahead, lvl0, bases, in);
-      prefetch_x(nxt);
+      advance();
     }
   }
   if (!work) return;                 // holes and finished buckets only
@@ -653,82 +668,95 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
   {
     w.start_down();                  // the walk up ended in the bucket of slot last - 1
     TreeSlot cur = tree_slot<K>(tree_idx(w, last - 1, sorted), lvl0, bases, in);
+    TreeSlot nxt = tree_slot<K>(none, lvl0, bases, in);
     TreeIdx ahead = none;
-    if (last - 1 > first) {
+    if (last - first >= 2) {
       w.seek_down(last - 2);
-      ahead = tree_idx(w, last - 2, sorted);
+      nxt = tree_slot<K>(tree_idx(w, last - 2, sorted), lvl0, bases, in);
+      prefetch_xy(nxt, out + (size_t)(last - 2) * (2 * K));
     }
-    TreeSlot nxt = tree_slot<K>(ahead, lvl0, bases, in);
-    prefetch_xy(nxt, out + (size_t)(last - 2) * (2 * K));
-    for (uint32_t j = last; j-- > first;) {
-      Fq* cell = out + (size_t)j * (2 * K);
-      ahead = none;
-      if (j >= first + 2) {
-        w.seek_down(j - 2);
-        ahead = tree_idx(w, j - 2, sorted);
-      }
-      const unsigned what = cur.kind & 3u;
-      if (what == 1u) {                       // carried over
-        const int d[2] = {X1, Y1};
-        const Fq* const g[2] = {cur.p1, cur.p1 + K};
-        t_ldg_many<M, 2>(d, g);
-        if (cur.kind & 16u) M::neg(Y1, Y1);
-        M::stg(cell, X1);
-        M::stg(cell + K, Y1);
-      } else if (what == 2u) {
-        if (any && j != lead) {               // with the product of the denominators before this one
-          const int d[5] = {X1, Y1, X2, Y2, T};
-          const Fq* const g[5] = {cur.p1, cur.p1 + K, cur.p2, cur.p2 + K, cell};
-          t_ldg_many<M, 5>(d, g);
-        } else {
-          const int d[4] = {X1, Y1, X2, Y2};
-          const Fq* const g[4] = {cur.p1, cur.p1 + K, cur.p2, cur.p2 + K};
-          t_ldg_many<M, 4>(d, g);
-        }
-        fix_y(cur);
-        const int kind = classify(cur, true);
-        if (kind == 2) {
-          if (!(cur.kind & 64u)) {
-            M::set_zero(X1);
-            M::stg(cell, X1);
-            M::stg(cell + K, X1);
-          }
-        } else if (kind == 3) {
-          put(cur, cell, X2, Y2, X1, true);
-        } else if (kind == 4) {
-          put(cur, cell, X1, Y1, X2, true);
-        } else {
-          if (j != lead) {
-            M::mul(T, T, INV, TMP);           // 1 / den
-            M::mul(INV, INV, X2, TMP);        // inverse of the product of the earlier ones
-          } else {
-            M::copy(T, INV);
-          }
-          if (kind == 1) {                    // lambda = (3 x1^2 + a) / (2 y1), x2 = x1
-            square(Y2, X1);
-            M::dbl(X2, Y2);
-            M::add(Y2, Y2, X2);
-            M::set_one(ONE);
-            SC::mul_by_a(X2, ONE);
-            M::add(Y2, Y2, X2);
-            M::set_zero(X2);                  // "x2 - x1" for the x3 below
-          } else {
-            M::sub(Y2, Y2, Y1);
-          }
-          M::mul(T, T, Y2, TMP);              // lambda
-          square(Y2, T);
-          M::sub(Y2, Y2, X1);
-          M::sub(Y2, Y2, X1);
-          M::sub(Y2, Y2, X2);                 // x3 = lambda^2 - x1 - (x1 + (x2 - x1))
-          M::sub(X1, X1, Y2);
-          M::mul(X1, X1, T, TMP);
-          M::sub(Y1, X1, Y1);                 // y3 = lambda (x1 - x3) - y1
-          put(cur, cell, Y2, Y1, X2, false);
-        }
-      }
+    if (last - first >= 3) {
+      w.seek_down(last - 3);
+      ahead = tree_idx(w, last - 3, sorted);
+    }
+    uint32_t left = last - first;    // slots not yet done; the current one is first + left - 1
+    auto advance = [&]() {
       cur = nxt;
       nxt = tree_slot<K>(ahead, lvl0, bases, in);
-      if (j >= first + 2) prefetch_xy(nxt, cell - 2 * (2 * K));
+      left--;
+      if (left >= 2) prefetch_xy(nxt, out + (size_t)(first + left - 2) * (2 * K));
+      ahead = none;
+      if (left >= 3) {
+        w.seek_down(first + left - 3);
+        ahead = tree_idx(w, first + left - 3, sorted);
+      }
+    };
+    for (;;) {
+      while (left > 0 && (cur.kind & 3u) != 2u) {
+        if ((cur.kind & 3u) == 1u) {          // carried over
+          Fq* cell = out + (size_t)(first + left - 1) * (2 * K);
+          const int d[2] = {X1, Y1};
+          const Fq* const g[2] = {cur.p1, cur.p1 + K};
+          t_ldg_many<M, 2>(d, g);
+          if (cur.kind & 16u) M::neg(Y1, Y1);
+          M::stg(cell, X1);
+          M::stg(cell + K, Y1);
+        }
+        advance();
+      }
+      if (left == 0) break;
+      const uint32_t j = first + left - 1;
+      Fq* cell = out + (size_t)j * (2 * K);
+      if (any && j != lead) {                 // with the product of the denominators before this one
+        const int d[5] = {X1, Y1, X2, Y2, T};
+        const Fq* const g[5] = {cur.p1, cur.p1 + K, cur.p2, cur.p2 + K, cell};
+        t_ldg_many<M, 5>(d, g);
+      } else {
+        const int d[4] = {X1, Y1, X2, Y2};
+        const Fq* const g[4] = {cur.p1, cur.p1 + K, cur.p2, cur.p2 + K};
+        t_ldg_many<M, 4>(d, g);
+      }
+      fix_y(cur);
+      const int kind = classify(cur, true);
+      if (kind == 2) {
+        if (!(cur.kind & 64u)) {
+          M::set_zero(X1);
+          M::stg(cell, X1);
+          M::stg(cell + K, X1);
+        }
+      } else if (kind == 3) {
+        put(cur, cell, X2, Y2, X1, true);
+      } else if (kind == 4) {
+        put(cur, cell, X1, Y1, X2, true);
+      } else {
+        if (j != lead) {
+          M::mul(T, T, INV, TMP);             // 1 / den
+          M::mul(INV, INV, X2, TMP);          // inverse of the product of the earlier ones
+        } else {
+          M::copy(T, INV);
+        }
+        if (kind == 1) {                      // lambda = (3 x1^2 + a) / (2 y1), x2 = x1
+          square(Y2, X1);
+          M::dbl(X2, Y2);
+          M::add(Y2, Y2, X2);
+          M::set_one(ONE);
+          SC::mul_by_a(X2, ONE);
+          M::add(Y2, Y2, X2);
+          M::set_zero(X2);                    // "x2 - x1" for the x3 below
+        } else {
+          M::sub(Y2, Y2, Y1);
+        }
+        M::mul(T, T, Y2, TMP);                // lambda
+        square(Y2, T);
+        M::sub(Y2, Y2, X1);
+        M::sub(Y2, Y2, X1);
+        M::sub(Y2, Y2, X2);                   // x3 = lambda^2 - x1 - (x1 + (x2 - x1))
+        M::sub(X1, X1, Y2);
+        M::mul(X1, X1, T, TMP);
+        M::sub(Y1, X1, Y1);                   // y3 = lambda (x1 - x3) - y1
+        put(cur, cell, Y2, Y1, X2, false);
+      }
+      advance();
     }
   }
 }
@@ -1113,6 +1141,7 @@ struct MsmKey {
   unsigned rows = 0;  // bucket rows the tables were built for (0 = derive)
   int affine = -1;    // accumulation: -1 = the group's default, 0 = XYZZ running sums, 1 = affine addition tree
   int tree_batch = 0; // output slots per thread of the addition tree (0 = TREE_BATCH)
+  int tree_waves = 0; // waves of blocks a level is cut into before its batches grow (0 = 4)
 };
 
 // out[g * ceil(m_in / 2) + p] = in[g * m_in + 2p] + in[g * m_in + 2p + 1]: one thread per output point while
@@ -1255,7 +1284,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
       // everywhere 40 ms.
       size_t batch = top;
       if (key.tree_batch <= 0) {   // (G753_TREE_BATCH fixes the batch)
-        const size_t four = bound / (4 * wave), one = bound / wave;
+        const size_t four = bound / ((key.tree_waves > 0 ? (size_t)key.tree_waves : 4) * wave), one = bound / wave;
         size_t pairs = ((size_t)pl.W * n) >> level;
         if (pairs < 1) pairs = 1;
         size_t by_pairs = 48 * bound / pairs;

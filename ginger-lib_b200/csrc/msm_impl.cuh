@@ -24,6 +24,7 @@ int msm_dispatch(g753_ctx* ctx, const g753_bases* b, size_t first, size_t count,
   key.copy_stride = key.inf_stride = b->n;
   key.affine = ctx->forced_affine;
   key.tree_batch = ctx->tree_batch;
+  key.tree_waves = ctx->tree_waves;
   // the precomputed copies pay off when the slice is a sizeable part of the key they were sized
   // for; short slices (the prover's input-query views) run the plain pipeline on copy 0
   if (b->copies > 1 && count * 4 >= b->n) {

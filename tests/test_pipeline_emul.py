@@ -91,7 +91,7 @@ def ctx_optin():
     c.close()
 
 
-@pytest.mark.parametrize("group", sorted(GROUPS))
+@pytest.mark.parametrize("group", [ffi.MNT4_G1, ffi.MNT6_G2])     # one prime-field curve, one tower (CPU suite time)
 def test_msm_optin_forms(ctx_optin, group):
     """-DG753_ACC6=1 -DG753_ROLLED=1: same results from the six-slot addition and the rolled multiplier"""
     test_msm_small(ctx_optin, group)
@@ -397,11 +397,11 @@ def test_mixed_radix_domain_none(ctx):
     assert G.MixedRadixDomain.new(ffi.FIELD_MNT4_FR, (1 << 18) * 5, ctx=ctx) is not None
 
 
-@pytest.mark.parametrize("form", ["1", "0"])
-@pytest.mark.parametrize("group", sorted(GROUPS))
+@pytest.mark.parametrize("group,form", [(g, "1") for g in sorted(GROUPS)] + [(ffi.MNT4_G1, "0"), (ffi.MNT4_G2, "0")])
 def test_msm_accumulation_forms(ctx, monkeypatch, group, form):
-    """both accumulation forms, forced, on every group: the pairwise tree of affine additions with shared
-    inversions (k_tree_round) and the XYZZ running sums (k_bucket_acc)"""
+    """both accumulation forms, forced: the pairwise tree of affine additions with shared inversions
+    (k_tree_round) on every group and the XYZZ running sums (k_bucket_acc; the form every short MSM of this
+    suite runs anyway) on one curve of each kind; the GPU tier runs all eight combinations"""
     import shared_checks
     monkeypatch.setenv("G753_MSM_AFFINE", form)
     monkeypatch.setenv("G753_MSM_C", "5")
