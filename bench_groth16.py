@@ -164,8 +164,9 @@ def run(ctx, log_n=20, steps=3, warmup=1, copies=0, verify=True, rank=0, world=1
     groth16.create_proof(P, z, a, b, c, 0, 0, 0, r, s, profile=prof)
     for name, ph in prof.items():
         grp = g2 if name == "b2" else g1
-        macs = ph["points"] * ph["plan"]["windows"] * bench.EXECUTED_MACS_PER_MADD[grp]
+        _, macs, what = bench.executed_accumulation(grp, ph["points"], ph["plan"])
         ph["accumulate_executed_limb_macs"] = macs
+        ph["accumulate_executed"] = what
         if peak_mac_per_s and ph.get("accumulate"):
             ph["accumulate_frac_of_int_peak"] = macs / (ph["accumulate"] * 1e-3) / peak_mac_per_s
     ok = None

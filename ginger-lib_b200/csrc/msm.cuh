@@ -503,10 +503,34 @@ G753_D void tree_prefetch(const void* p) {
 // eight slots allow two).  The hot loop calls ONE multiplier body (22 KB; squarings go through it too), which
 // the 32 KB L1.5 instruction cache holds - with the dedicated squaring body beside it ncu showed a quarter of
 // the issue slots waiting for instructions.
+// warp votes of the round's loops (the TEST-ONLY host build runs one lane at a time)
+G753_D unsigned tree_lanes() {
+#if defined(__CUDA_ARCH__)
+  return __activemask();
+#else
+  return 1u;
+#endif
+}
+G753_D bool tree_any(unsigned lanes, bool v) {
+#if defined(__CUDA_ARCH__)
+  return __any_sync(lanes, v) != 0;
+#else
+  (void)lanes;
+  return v;
+#endif
+}
+G753_D void tree_join(unsigned lanes) {
+#if defined(__CUDA_ARCH__)
+  __syncwarp(lanes);
+#else
+  (void)lanes;
+#endif
+}
+
 template <class SC>
 __global__ void __launch_bounds__(SC::M::T::THREADS, SC::M::K == 1 ? 3 : 1)
 k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, TreeGeo geo,
-             const uint32_t* __restrict__ max_count, unsigned level, unsigned batch, const Fq* __restrict__ in,
+             const uint32_t* max_count, unsigned level, unsigned batch, const Fq* __restrict__ in,
              Fq* __restrict__ out, Fq* __restrict__ points) {
   typedef typename SC::M M;
   typedef typename M::T L;
@@ -529,6 +553,11 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
   const uint64_t stop64 = first64 + batch;
   const uint32_t last = (uint32_t)(stop64 > 0xfffffffeull ? 0xfffffffeull : stop64);   // exclusive
   const bool lvl0 = level == 1;   // inputs are key points: never at infinity, y negated by the sign bit
+  // max_count[1 + L] != 0: level L holds a point at infinity, stored as (0, 0) (a cancellation - with real keys
+  // practically never); only then are the operands of the next level tested for it
+  uint32_t* const inf_seen = (uint32_t*)max_count + 1;
+  const bool may_inf = !lvl0 && inf_seen[level - 1] != 0;
+  if (may_inf) inf_seen[level] = 1;   // infinity operands pass through
 
   auto fix_y = [&](const TreeSlot& s) {
     if (s.kind & 16u) M::neg(Y1, Y1);
@@ -544,7 +573,7 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
   // 0 = ordinary addition, 1 = doubling, 2 = cancellation, 3 = first operand at infinity (result = second),
   // 4 = second at infinity (result = first).  Kinds 0, 1 leave the DENOMINATOR in X2 (x2 - x1, or 2 y1).
   auto classify = [&](const TreeSlot& s, bool have_y) -> int {
-    if (!lvl0) {
+    if (may_inf) {
       const bool z1 = M::is_zero(X1), z2 = M::is_zero(X2);
       if (z1 || z2) {
         if (!have_y) load_y(s);
@@ -613,6 +642,7 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
   // any of its lanes had one (measured: 1 ns per slot on every level, whatever the share of pairs).
   bool any = false, work = false;
   uint32_t lead = 0;   // slot of the first denominator: its prefix is 1 and is not stored
+  const unsigned lanes = tree_lanes();   // the lanes of this warp that have slots
   {
     w.start_up(first);
     TreeSlot cur = tree_slot<K>(tree_idx(w, first, sorted), lvl0, bases, in);
@@ -639,31 +669,40 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
         ahead = tree_idx(w, j + 2, sorted);
       }
     };
-    for (;;) {
+    // every lane of the warp stays in the loop until the last one is through, and the lanes JOIN before each pair:
+    // left to itself the compiler does not reconverge the lanes after the stepping loop, and a warp in pieces
+    // runs the multiplier once per piece
+    while (tree_any(lanes, j < last)) {
       while (j < last && (cur.kind & 3u) != 2u) {
         work = work || (cur.kind & 3u) != 0u;
         advance();
       }
-      if (j >= last) break;
-      work = true;
-      const int d[2] = {X1, X2};
-      const Fq* const g[2] = {cur.p1, cur.p2};
-      t_ldg_many<M, 2>(d, g);
-      if (classify(cur, false) < 2) {
-        if (!any) {
-          M::copy(INV, X2);
-          any = true;
-          lead = j;
-        } else {
-          M::stg(out + (size_t)j * (2 * K), INV);
-          M::mul(INV, INV, X2, TMP);
+      tree_join(lanes);
+      if (j < last) {
+        work = true;
+        const int d[2] = {X1, X2};
+        const Fq* const g[2] = {cur.p1, cur.p2};
+        t_ldg_many<M, 2>(d, g);
+        if (classify(cur, false) < 2) {
+          if (!any) {
+            M::copy(INV, X2);
+            any = true;
+            lead = j;
+          } else {
+            M::stg(out + (size_t)j * (2 * K), INV);
+            M::mul(INV, INV, X2, TMP);
+          }
         }
+        advance();
       }
-      advance();
     }
   }
-  if (!work) return;                 // holes and finished buckets only
-  if (any) M::inv(INV, INV, TMP);
+  tree_join(lanes);
+  if (tree_any(lanes, any)) {        // (together: the lanes that returned early would split the warp for good)
+    if (!any) M::set_one(INV);
+    M::inv(INV, INV, TMP);
+  }
+  if (!tree_any(lanes, work)) return;   // holes and finished buckets only
   // ---- phase 2: walk back, peel the individual inverses off, finish the additions ----------------
   {
     w.start_down();                  // the walk up ended in the bucket of slot last - 1
@@ -679,7 +718,8 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
       w.seek_down(last - 3);
       ahead = tree_idx(w, last - 3, sorted);
     }
-    uint32_t left = last - first;    // slots not yet done; the current one is first + left - 1
+    uint32_t left = work ? last - first : 0u;   // slots not yet done (the current one is first + left - 1); a lane
+                                                // without pairs or carried elements only keeps its warp company
     auto advance = [&]() {
       cur = nxt;
       nxt = tree_slot<K>(ahead, lvl0, bases, in);
@@ -691,7 +731,7 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
         ahead = tree_idx(w, first + left - 3, sorted);
       }
     };
-    for (;;) {
+    while (tree_any(lanes, left > 0)) {
       while (left > 0 && (cur.kind & 3u) != 2u) {
         if ((cur.kind & 3u) == 1u) {          // carried over
           Fq* cell = out + (size_t)(first + left - 1) * (2 * K);
@@ -704,7 +744,8 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
         }
         advance();
       }
-      if (left == 0) break;
+      tree_join(lanes);
+      if (left == 0) continue;
       const uint32_t j = first + left - 1;
       Fq* cell = out + (size_t)j * (2 * K);
       if (any && j != lead) {                 // with the product of the denominators before this one
@@ -723,6 +764,7 @@ k_tree_round(const Fq* __restrict__ bases, const uint32_t* __restrict__ sorted, 
           M::set_zero(X1);
           M::stg(cell, X1);
           M::stg(cell + K, X1);
+          inf_seen[level] = 1;
         }
       } else if (kind == 3) {
         put(cur, cell, X2, Y2, X1, true);
@@ -1258,7 +1300,7 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
                   key.copy_stride, ws.row_cap, cursor, sorted);
   if (tree) {
     // addition tree (after the scatter, cursor[t] is the end of bucket t's run)
-    G753_TRY(dev_memset(tree_max, 0, sizeof(uint32_t), stream));
+    G753_TRY(dev_memset(tree_max, 0, sizeof(uint32_t) * 64, stream));   // fullest bucket + one "infinity stored" flag per level
     G753_MSM_LAUNCH(hooks, k_tree_max, (unsigned)(NB < 148u * 1024 ? div_up(NB, 256) : 148u * 4), 256, stream, offsets, cursor,
                     NB, tree_max);
     if (hooks.mark) hooks.mark(hooks.user, 2);
@@ -1284,13 +1326,18 @@ static int msm_run(Scratch& scratch, cudaStream_t stream, const MsmKey& key, con
       // everywhere 40 ms.
       size_t batch = top;
       if (key.tree_batch <= 0) {   // (G753_TREE_BATCH fixes the batch)
-        const size_t four = bound / ((key.tree_waves > 0 ? (size_t)key.tree_waves : 4) * wave), one = bound / wave;
+        const size_t four = div_up(bound, (key.tree_waves > 0 ? (size_t)key.tree_waves : 4) * wave), one = div_up(bound, wave);
         size_t pairs = ((size_t)pl.W * n) >> level;
         if (pairs < 1) pairs = 1;
         size_t by_pairs = 48 * bound / pairs;
         if (by_pairs > one) by_pairs = one;
         batch = four > by_pairs ? four : by_pairs;
         batch = batch < 4 ? 4 : batch > top ? top : batch;
+        // ... and WHOLE waves: a few blocks more than the GPU holds run as one more wave (measured: 446 blocks on
+        // 444 block slots took twice the time; at 2^22 levels 2 and 3 ran 4.01 waves)
+        const size_t waves = div_up(bound, batch * wave);
+        batch = div_up(bound, waves * wave);
+        if (batch < 4) batch = 4;
       }
       G753_MSM_LAUNCH_SMEM(hooks, k_tree_round<SCA>, div_up(div_up(bound, batch), CA), TA, SMEM_TREE, stream, key.bases, sorted,
                            geo, tree_max, level, (unsigned)batch, (level & 1) ? tree_even : tree_odd,
