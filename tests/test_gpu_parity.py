@@ -179,7 +179,7 @@ def test_msm_accumulation_forms(ctx, monkeypatch, group, form):
     monkeypatch.setenv("G753_MSM_AFFINE", form)
     monkeypatch.setenv("G753_MSM_C", "5")
     shared_checks.check_msm_accumulation_cases(ctx, group)
-    if form == "1":      # long batches: one thread walks many buckets, the slot roles of the copy pipeline rotate
+    if form == "1":      # long batches: one thread walks many buckets
         monkeypatch.setenv("G753_TREE_BATCH", "37")
         shared_checks.check_msm_accumulation_cases(ctx, group)
 

@@ -91,7 +91,7 @@ def ctx_optin():
     c.close()
 
 
-@pytest.mark.parametrize("group", [ffi.MNT4_G1, ffi.MNT6_G2])     # one prime-field curve, one tower (CPU suite time)
+@pytest.mark.parametrize("group", [ffi.MNT4_G1])     # (CPU suite time; the forms only differ on the prime-field curves)
 def test_msm_optin_forms(ctx_optin, group):
     """-DG753_ACC6=1 -DG753_ROLLED=1: same results from the six-slot addition and the rolled multiplier"""
     test_msm_small(ctx_optin, group)
@@ -406,7 +406,7 @@ def test_msm_accumulation_forms(ctx, monkeypatch, group, form):
     monkeypatch.setenv("G753_MSM_AFFINE", form)
     monkeypatch.setenv("G753_MSM_C", "5")
     shared_checks.check_msm_accumulation_cases(ctx, group)
-    if form == "1":      # long batches: one thread walks many buckets, the slot roles of the copy pipeline rotate
+    if form == "1" and group in (ffi.MNT4_G1, ffi.MNT4_G2):      # long batches: one thread walks many buckets
         monkeypatch.setenv("G753_TREE_BATCH", "37")
         shared_checks.check_msm_accumulation_cases(ctx, group)
 
