@@ -5,8 +5,9 @@
 //   reference: unsigned c-bit windows, 2^c - 1 buckets, one CPU task per window, serial
 //              running-sum reduction, c from scalars.len() (variable_base.rs:14-18);
 //   here:      signed-digit windows (2^(c-1) buckets), a counting sort of (digit, point)
-//              pairs per window, length-balanced accumulation of the sorted runs, a multi-level
-//              parallel running-sum reduction, Horner window fold.
+//              pairs per window, accumulation of the sorted runs - a pairwise tree of affine
+//              additions with shared inversions, or length-balanced XYZZ running sums for short
+//              inputs -, a multi-level parallel running-sum reduction, Horner window fold.
 // Reference semantics preserved: zero scalars and infinity bases contribute
 // nothing, duplicate bases hit the doubling branch, P + (-P) gives infinity, count == 0
 // returns infinity.  (The reference's scalar == 1 fast path is an optimisation, not a
@@ -16,7 +17,9 @@
 //   k_msm_digits      K4  scalar -> signed window digits + per-window histogram
 //   k_scan_*          K4  exclusive scan of the histograms (bucket offsets)
 //   k_msm_scatter     K4  counting-sort scatter of point indices into bucket order
-//   k_item_*          K5  cut every bucket's run into work items of <= ITEM_LEN points and order
+//   k_tree_max/_round/_finish  K5t  the runs summed level by level, 6 products per addition (the default
+//                         from 2^22 window entries)
+//   k_item_*          K5  (short inputs) cut every bucket's run into work items of <= ITEM_LEN points and order
 //                         the items by length (longest first), so the 32 lanes of a warp run
 //                         the same number of mixed additions
 //   k_bucket_acc      K5  one thread per item: XYZZ accumulator in shared-memory slots
