@@ -319,11 +319,15 @@ def test_bad_arguments(ctx):
     assert array_field(F, out) == [O.EvaluationDomain(F, 1 << 29).group_gen]
 
 
-@pytest.mark.parametrize("group,c,copies", [(ffi.MNT4_G1, 7, 4), (ffi.MNT4_G1, 0, 8), (ffi.MNT6_G2, 9, 3)])
-def test_msm_precomputed_key_copies(ctx, monkeypatch, group, c, copies):
+@pytest.mark.parametrize("group,c,copies,form", [(ffi.MNT4_G1, 7, 4, None), (ffi.MNT4_G1, 0, 8, None), (ffi.MNT6_G2, 9, 3, None),
+                                                 (ffi.MNT4_G1, 5, 4, "1"), (ffi.MNT4_G2, 6, 3, "1")])
+def test_msm_precomputed_key_copies(ctx, monkeypatch, group, c, copies, form):
     """g753_bases_precompute: copy j holds 2^(j*rows*c) * P_i; the MSM over the key (and over
-    slices of it) must give the same group element as the plain pipeline / the naive sum"""
+    slices of it) must give the same group element as the plain pipeline / the naive sum.  form "1": the
+    addition tree forced on the copies (several windows per bucket row, entries that point into different copies)"""
     C = GROUPS[group]
+    if form is not None:
+        monkeypatch.setenv("G753_MSM_AFFINE", form)
     n = 24 if C.F.k == 1 else 8
     pts = sample_points(C, n, 0x1A0 + group)
     sc = sample_scalars(C, n, 0x1B0 + group)
