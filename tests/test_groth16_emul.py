@@ -93,6 +93,15 @@ def test_proof_tiny_mnt6(ctx):  # noqa: F811
     check_instance(ctx, 0x6601, 4, 2, 3, 1, 2, 3, O.MNT6_FR.p - 5, 0x77 << 700, engine="mnt6")
 
 
+def test_proof_tiny_with_the_addition_tree(ctx, monkeypatch):  # noqa: F811
+    """the form every MSM of a full-size proof runs (msm.cuh k_tree_round), forced on the tiny instance: G1 and
+    G2 (Fq2) queries, the duplicate / zero assignments of tiny_instance included"""
+    monkeypatch.setenv("G753_MSM_AFFINE", "1")
+    cx = G.Context(0, library=ctx.lib)
+    check_instance(cx, 0x6109, 4, 2, 3, 5, 7, 11, 3, 4)
+    cx.close()
+
+
 @pytest.mark.parametrize("engine", ["mnt6"])     # MNT4: test_oracle_pairing.py (oracle) and test_gpu_groth16.py (GPU, both engines)
 def test_proof_verifies_with_pairing(ctx, engine):  # noqa: F811
     import shared_checks
